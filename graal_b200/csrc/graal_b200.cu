@@ -1,0 +1,1058 @@
+// graal_b200 -- B200-native GRAAL MCMC scoring path (sm_100a).  See include/graal_b200.h for the ABI
+// and DESIGN.md for the formulation.  Compile with -fmad=false: the float32 geometry (mid-points,
+// distances, norm factors) must round exactly like the reference's separate mul/add sequence;
+// fused operations are written explicitly (fma()) where they are wanted.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+#include <map>
+#include <algorithm>
+
+#include "../../include/graal_b200.h"
+#include "moves.cuh"
+
+#define GRAAL_VERSION "graal_b200 0.1 (sm_100a)"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
+#define CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
+    return set_err(-2, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); } while (0)
+#define CHECK_LAUNCH(ctx) do { (ctx)->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) \
+    return set_err(-3, "%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------------
+struct Params { float kuhn, lm, c1, slope, d, d_max, fact, v_inter, nfpb; };
+
+// per-sub-frag geometry record of one slot (16 B, one 128-bit load):
+//   mid  : mid-point in kb (float32, reference op order kernels3.cu:2997-3060)
+//   id_c : contig id
+//   stot : contig length in kb (float32 of l_cont_bp / 1000) -- used by circular contigs only
+//   pk   : accu_true[0:13) | accu_quirk[13:26) | local sub index[26:28) | circ[28]
+struct __align__(16) Geo { float mid; int id_c; float stot; unsigned pk; };
+#define PK_ACCU_BITS 13
+#define PK_ACCU_MAX ((1 << PK_ACCU_BITS) - 1)
+__device__ __forceinline__ int pk_true(unsigned pk) { return pk & PK_ACCU_MAX; }
+__device__ __forceinline__ int pk_quirk(unsigned pk) { return (pk >> PK_ACCU_BITS) & PK_ACCU_MAX; }
+__device__ __forceinline__ int pk_local(unsigned pk) { return (pk >> 26) & 3; }
+__device__ __forceinline__ int pk_circ(unsigned pk) { return (pk >> 28) & 1; }
+__device__ __forceinline__ bool geo_eq(const Geo& a, const Geo& b) {
+    return __float_as_int(a.mid) == __float_as_int(b.mid) && a.id_c == b.id_c &&
+           __float_as_int(a.stot) == __float_as_int(b.stot) && a.pk == b.pk;
+}
+__device__ __forceinline__ Geo ld_geo(const Geo* p) {
+    int4 v = __ldg(reinterpret_cast<const int4*>(p));
+    Geo g; g.mid = __int_as_float(v.x); g.id_c = v.y; g.stot = __int_as_float(v.z); g.pk = (unsigned)v.w;
+    return g;
+}
+
+// rippe_contacts (kernels3.cu:120-133)
+__device__ __forceinline__ float rippe_contacts(float s, const Params& p) {
+    float r = 0.0f;
+    if (s > 0.0f && s < p.d_max) {
+        float x = s * p.lm / p.kuhn;
+        r = (p.c1 * powf(s, p.slope) * expf((p.d - 2.0f) / (powf(x, 2.0f) + p.d))) * p.fact;
+    }
+    return fmaxf(r, p.v_inter);
+}
+
+// rippe_contacts_circ (kernels3.cu:135-166)
+__device__ __noinline__ float rippe_contacts_circ(float s, float s_tot, const Params& p) {
+    float result = 0.0f;
+    if (s > 0.0f && s < p.d_max) {
+        float K = p.lm / p.kuhn;
+        float nmax = K * 1.0f;
+        float n = K * s * (s_tot - s) / s_tot;
+        float norm_lin = rippe_contacts(s, p);
+        float k3 = powf(p.kuhn, -3.0f);
+        float norm_circ = (k3 * powf(nmax, p.slope) * expf((p.d - 2.0f) / (powf(nmax, 2.0f) + p.d))) * p.fact;
+        float val = (k3 * powf(n, p.slope) * expf((p.d - 2.0f) / (powf(n, 2.0f) + p.d))) * p.fact;
+        result = val * norm_lin / norm_circ;
+    }
+    return fmaxf(result, p.v_inter);
+}
+
+// expected contacts of the sub-frag pair (a, b); a belongs to the LOWER data bin (quirk Q1 side).
+__device__ __forceinline__ float expected_pair(const Geo& a, const Geo& b, const Params& p) {
+    if (a.id_c == b.id_c) {
+        float s = fabsf(b.mid - a.mid);
+        float norm = __int2float_rn(pk_true(a.pk) * pk_true(b.pk)) / p.nfpb;
+        float r = pk_circ(a.pk) ? rippe_contacts_circ(s, a.stot, p) : rippe_contacts(s, p);
+        return r * norm;
+    }
+    float norm = __int2float_rn(pk_quirk(a.pk) * pk_true(b.pk)) / p.nfpb;
+    return p.v_inter * norm;
+}
+
+// the value every clamped / trans pixel takes: f32(v_inter * f32(f32(P)/nfpb))
+__host__ __device__ __forceinline__ float g_clamp(int P, float v_inter, float nfpb) {
+    float norm = (float)P / nfpb;
+    return v_inter * norm;
+}
+
+// factorial (kernels3.cu:80-93) and the observation-only part of evaluate_likelihood_double (:198-203)
+__device__ __forceinline__ float factorial_f32(float n) {
+    float result = 1.0f;
+    n = floorf(n);
+    if (n < 10.0f) { for (int c = 1; c <= (int)n; c++) result = result * (float)c; }
+    else result = powf(n, n) * expf(-n) * sqrtf((float)(2.0 * M_PI * (double)n));
+    return result;
+}
+__device__ __forceinline__ double log_fact_term(float obf) {
+    double ob = (double)obf;
+    if (ob >= 15.0) return ob * log(ob) - ob + log(sqrt(ob * 2.0 * M_PI));
+    if (ob > 0.0) return log((double)factorial_f32(obf));
+    return 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reductions (deterministic two-stage: per-block partials, then one block sums them in order)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double block_sum(double v) {   // result valid in thread 0
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+    if (w == 0) v = warp_sum(v);
+    __syncthreads();
+    return v;
+}
+
+// out[k] (op)= scale * sum_j partials[k * stride + j], j < n;  op: 0 set, 1 add
+__global__ void k_reduce_partials(const double* __restrict__ partials, int n, int stride, double scale,
+                                  double* __restrict__ out, int accumulate) {
+    const int k = blockIdx.x;
+    double v = 0.0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) v += partials[(size_t)k * stride + j];
+    v = block_sum(v);
+    if (threadIdx.x == 0) out[k] = (accumulate ? out[k] : 0.0) + scale * v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// structure mutations
+// ------------------------------------------------------------------------------------------------
+__global__ void k_apply_move(const int* __restrict__ src, int* __restrict__ dst, int ld, int n,
+                             int op, int fA, int fB, int aux, int max_id) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Bin s = load_bin(src, ld, i);
+    bool written = true;
+    switch (op) {
+        case GRAAL_OP_COPY: break;
+        case GRAAL_OP_FLIP: s = op_flip(s, i, fA); break;
+        case GRAAL_OP_SWAP_ACTIV: s = op_swap_activity(s, i, fA, max_id); break;
+        case GRAAL_OP_POP_OUT: { Bin P = load_bin(src, ld, fA); s = op_pop_out(s, i, P, max_id); } break;
+        case GRAAL_OP_POP_IN_1: case GRAAL_OP_POP_IN_2: case GRAAL_OP_POP_IN_3: case GRAAL_OP_POP_IN_4: {
+            Bin Pp = load_bin(src, ld, fA), Pi = load_bin(src, ld, fB);
+            s = op_pop_in(op - GRAAL_OP_POP_IN_1 + 1, s, i, Pp, Pi, fA, fB, max_id, aux);
+        } break;
+        case GRAAL_OP_SPLIT: { Bin Pc = load_bin(src, ld, fA); s = op_split(s, i, Pc, aux, max_id); } break;
+        case GRAAL_OP_PASTE: {
+            Bin PA = load_bin(src, ld, fA), PB = load_bin(src, ld, fB);
+            written = op_paste(s, i, PA, PB, fA, fB);
+        } break;
+    }
+    if (written) store_bin(dst, ld, i, s);
+}
+
+__global__ void k_max_field(const int* __restrict__ v, int n, int* __restrict__ out) {
+    int m = INT_MIN;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, v[i]);
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+__global__ void k_set_int(int* p, int v) { *p = v; }
+__global__ void k_set_double(double* p, double v) { *p = v; }
+__global__ void k_init_stats(unsigned long long* a) { a[0] = 0ull; a[1] = 0ull; a[2] = (unsigned long long)(unsigned)INT_MAX; a[3] = (unsigned long long)(unsigned)INT_MIN; }
+
+// the 13 candidates of new_perform_modificationS (cuda_lib_gl.py:841-954) in one pass.
+__global__ void k_build_candidates(const int* __restrict__ src, int* __restrict__ dst0, size_t slot_stride,
+                                   int ld, int n, int fA, int fB, const int* __restrict__ d_max_id,
+                                   int max_id_host, unsigned mask) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int M = (max_id_host >= 0) ? max_id_host : *d_max_id;
+    const Bin C = load_bin(src, ld, i);
+    const Bin CA = load_bin(src, ld, fA);
+    const Bin CB = load_bin(src, ld, fB);
+    if (mask & 0x1FDu) {   // anything that needs the popped-out structure (modes 0, 2..8)
+        const Bin P = op_pop_out(C, i, CA, M);
+        const Bin PA = op_pop_out(CA, fA, CA, M);
+        const Bin PB = op_pop_out(CB, fB, CA, M);
+        const int M2 = M + pop_out_new_ids(CA);
+        if (mask & 1u) store_bin(dst0, ld, i, P);
+        #pragma unroll
+        for (int m = 2; m < 8; m++) {
+            if (mask & (1u << m)) {
+                Bin r = op_pop_in(1 + (m - 2) / 2, P, i, PA, PB, fA, fB, M2, (m & 1) ? -1 : 1);
+                store_bin(dst0 + (size_t)m * slot_stride, ld, i, r);
+            }
+        }
+        if (mask & (1u << 8)) store_bin(dst0 + 8 * slot_stride, ld, i, op_swap_activity(P, i, fA, M2));
+    }
+    if (mask & 2u) store_bin(dst0 + slot_stride, ld, i, op_flip(C, i, fA));
+    if (mask & 0x1E00u) {
+        #pragma unroll
+        for (int uA = 0; uA < 2; uA++) {
+            const Bin T1 = op_split(C, i, CA, uA, M);
+            const Bin T1A = op_split(CA, fA, CA, uA, M);
+            const Bin T1B = op_split(CB, fB, CA, uA, M);
+            const int M1 = M + split_new_ids(CA, uA);
+            #pragma unroll
+            for (int uB = 0; uB < 2; uB++) {
+                const int m = 9 + 2 * uA + uB;
+                if (!(mask & (1u << m))) continue;
+                Bin T2 = op_split(T1, i, T1B, uB, M1);
+                const Bin T2A = op_split(T1A, fA, T1B, uB, M1);
+                const Bin T2B = op_split(T1B, fB, T1B, uB, M1);
+                if (op_paste(T2, i, T2A, T2B, fA, fB)) store_bin(dst0 + (size_t)m * slot_stride, ld, i, T2);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// contig relabel
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fill_int(int* p, int n, int v) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_first_index(const int* __restrict__ id_c, int n, int cap, int* __restrict__ first, int* __restrict__ err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = id_c[i];
+    if (c < 0 || c >= cap) { atomicExch(err, 1); return; }
+    atomicMin(&first[c], i);
+}
+__global__ void k_relabel_keys(const int* __restrict__ first, const int* __restrict__ l_cont, int cap,
+                               unsigned long long* __restrict__ keys) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cap) return;
+    const int f = first[c];
+    keys[c] = (f == INT_MAX) ? ~0ull : (((unsigned long long)(unsigned)l_cont[f]) << 32) | (unsigned)c;
+}
+__global__ void k_relabel_map(const unsigned long long* __restrict__ sorted, int cap, int* __restrict__ map,
+                              int* __restrict__ n_contigs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= cap) return;
+    const unsigned long long k = sorted[r];
+    if (k == ~0ull) return;
+    map[(int)(k & 0xffffffffull)] = r;
+    if (r + 1 == cap || sorted[r + 1] == ~0ull) *n_contigs = r + 1;
+}
+__global__ void k_relabel_apply(int* __restrict__ id_c, int n, const int* __restrict__ map,
+                                const int* __restrict__ n_contigs, int* __restrict__ max_id_a, int* __restrict__ max_id_b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { const int m = *n_contigs - 1; *max_id_a = m; if (max_id_b) *max_id_b = m; }
+    if (i >= n) return;
+    id_c[i] = map[id_c[i]];
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry: per-sub-frag records of a slot (unique bins: frag index == data bin index)
+// ------------------------------------------------------------------------------------------------
+struct LevelView {
+    const int4* sub_id; const float* sub_len; const int* sub_accu;   // [N] int4, [N*3], [N*3]
+};
+
+__device__ __forceinline__ void bin_geometry(const int* __restrict__ slot, int ld, int bin, const LevelView& lv,
+                                             Geo* __restrict__ geo) {
+    const int id_d = slot[F_ID_D * ld + bin];
+    const int4 sid = lv.sub_id[id_d];
+    const int lim = sid.w - 1;
+    const float len[3] = { lv.sub_len[id_d * 3], lv.sub_len[id_d * 3 + 1], lv.sub_len[id_d * 3 + 2] };
+    const int acc[3] = { lv.sub_accu[id_d * 3], lv.sub_accu[id_d * 3 + 1], lv.sub_accu[id_d * 3 + 2] };
+    const int ori = slot[F_ORI * ld + bin];
+    const float start_kb = __int2float_rn(slot[F_START_BP * ld + bin]) / 1000.0f;
+    const int id_c = slot[F_ID_C * ld + bin];
+    const unsigned circ = slot[F_CIRC * ld + bin] == 1 ? 1u : 0u;
+    const float stot = __int2float_rn(slot[F_L_CONT_BP * ld + bin]) / 1000.0f;
+    const int acc_last = acc[lim];
+    float accu = 0.0f;
+    #pragma unroll
+    for (int i = 0; i < 3; i++) {
+        if (i > lim) break;
+        const int loc = (ori == 1) ? i : lim - i;           // list order -> local sub index
+        const float l = (loc == 0) ? len[0] : (loc == 1 ? len[1] : len[2]);
+        float mid;
+        if (i == 0) { mid = start_kb + l / 2.0f; accu = start_kb + l; }
+        else { mid = accu + l / 2.0f; accu = accu + l; }
+        const int at = (loc == 0) ? acc[0] : (loc == 1 ? acc[1] : acc[2]);
+        const int aq = (ori == 1) ? at : acc_last;
+        Geo g; g.mid = mid; g.id_c = id_c; g.stot = stot;
+        g.pk = (unsigned)at | ((unsigned)aq << PK_ACCU_BITS) | ((unsigned)loc << 26) | (circ << 28);
+        const int sub = (loc == 0) ? sid.x : (loc == 1 ? sid.y : sid.z);
+        geo[sub] = g;
+    }
+}
+
+__global__ void k_geometry_all(const int* __restrict__ slot, int ld, int n, LevelView lv, Geo* __restrict__ geo) {
+    const int bin = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bin < n) bin_geometry(slot, ld, bin, lv, geo);
+}
+
+// ------------------------------------------------------------------------------------------------
+// full likelihood, contact part: stream the row-segmented contact list once
+// ------------------------------------------------------------------------------------------------
+#define CHUNK 2048       // entries per warp-chunk
+
+__global__ void __launch_bounds__(256)
+k_full_contacts(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, long long E, int W,
+                const Geo* __restrict__ geo, Params p, double* __restrict__ partials) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long n_chunks = (E + CHUNK - 1) / CHUNK;
+    double acc = 0.0;
+    for (long long ch = warp; ch < n_chunks; ch += n_warps) {
+        const long long e0 = ch * CHUNK, e1 = min(E, e0 + (long long)CHUNK);
+        // first row whose segment ends after e0 (binary search, same result in every lane)
+        int lo = 0, hi = W;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(&rowptr[mid + 1]) > e0) hi = mid; else lo = mid + 1; }
+        int row = lo;
+        long long row_end = (row < W) ? __ldg(&rowptr[row + 1]) : E;
+        Geo gr = ld_geo(&geo[min(row, W - 1)]);
+        for (long long e = e0 + lane; e < e1; e += 32) {
+            if (e >= row_end) {
+                do { row++; row_end = __ldg(&rowptr[row + 1]); } while (e >= row_end);
+                gr = ld_geo(&geo[row]);
+            }
+            const int2 ce = __ldg(&contacts[e]);
+            const Geo gc = ld_geo(&geo[ce.x]);
+            const float ob = __int_as_float(ce.y);
+            const float ex = expected_pair(gr, gc, p);
+            if (ex != 0.0f) acc += (double)ob * log((double)ex);
+            else acc += log_fact_term(ob);          // pixel contributes 0: undo the precomputed -lf(ob)
+        }
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+// sum of lf(ob) over all stored contacts (level constant)
+__global__ void k_lf_total(const int2* __restrict__ contacts, long long E, double* __restrict__ partials) {
+    double acc = 0.0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x)
+        acc += log_fact_term(__int_as_float(contacts[e].y));
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// position order of bins (contig by contig) and the band-limited expected mass
+// ------------------------------------------------------------------------------------------------
+__global__ void k_contig_lengths(const int* __restrict__ slot, int ld, int n, int cap, int* __restrict__ cont_len) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (slot[F_POS * ld + i] == 0) { const int c = slot[F_ID_C * ld + i]; if (c >= 0 && c < cap) cont_len[c] = slot[F_L_CONT * ld + i]; }
+}
+__global__ void k_order_fill(const int* __restrict__ slot, int ld, int n, int cap, const int* __restrict__ cont_off,
+                             int* __restrict__ order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = slot[F_ID_C * ld + i];
+    if (c < 0 || c >= cap) return;
+    const int k = cont_off[c] + slot[F_POS * ld + i];
+    if (k >= 0 && k < n) order[k] = i;
+}
+
+// B(S): sum over cis sub-frag pairs within d_max of  ex - g(true product).
+// One warp per bin x (in position order); lanes take the following bins y of the same contig.
+//   DELTA = false: all pairs, same-bin pairs included (full likelihood)
+//   DELTA = true : pairs of distinct bins whose records differ between geo and geo_other
+template <bool DELTA>
+__global__ void __launch_bounds__(256)
+k_band(const int* __restrict__ order, const int* __restrict__ d_count, int count_host,
+       const int* __restrict__ slot, int ld, LevelView lv, const Geo* __restrict__ geo,
+       const Geo* __restrict__ geo_other, size_t cand_geo_stride, size_t cand_slot_stride, int order_stride,
+       int eval_is_cand, Params p, double* __restrict__ partials, int partial_stride) {
+    // blockIdx.y = candidate index (delta mode); the evaluated table is either the candidate's
+    // (eval_is_cand = 1, compared against the base table geo_other) or the base table (compared
+    // against the candidate's)
+    const int k = blockIdx.y;
+    const int count = (count_host >= 0) ? count_host : *d_count;
+    const Geo* gE = geo; const Geo* gO = geo_other;
+    const int* sl = slot;
+    const int* ord = order;
+    if (DELTA) {
+        if (eval_is_cand) { gE = geo + (size_t)k * cand_geo_stride; sl = slot + (size_t)k * cand_slot_stride; ord = order + (size_t)k * order_stride; }
+        else { gO = geo_other + (size_t)k * cand_geo_stride; }
+    }
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    double acc = 0.0;
+    for (int ix = warp; ix < count; ix += n_warps) {
+        const int x = ord[ix];
+        const int4 sx = lv.sub_id[sl[F_ID_D * ld + x]];
+        Geo gx[3]; bool chx[3];
+        float xmax = -1e30f;
+        #pragma unroll
+        for (int a = 0; a < 3; a++) if (a < sx.w) {
+            const int sub = (a == 0) ? sx.x : (a == 1 ? sx.y : sx.z);
+            gx[a] = ld_geo(&gE[sub]);
+            if (DELTA) chx[a] = !geo_eq(gx[a], ld_geo(&gO[sub]));
+            xmax = fmaxf(xmax, gx[a].mid);
+        }
+        const int cx = gx[0].id_c;
+        if (!DELTA && lane == 0) {        // same-bin pairs a < b (diagonal pixel, Q4)
+            #pragma unroll
+            for (int a = 0; a < 3; a++) for (int b = a + 1; b < 3; b++) if (b < sx.w) {
+                const float ex = expected_pair(gx[a], gx[b], p);
+                acc += (double)ex - (double)g_clamp(pk_true(gx[a].pk) * pk_true(gx[b].pk), p.v_inter, p.nfpb);
+            }
+        }
+        for (int base = ix + 1; base < count; base += 32) {
+            const int iy = base + lane;
+            bool live = iy < count;
+            if (live) {
+                const int y = ord[iy];
+                const float ystart = __int2float_rn(sl[F_START_BP * ld + y]) / 1000.0f;
+                const int4 sy = lv.sub_id[sl[F_ID_D * ld + y]];
+                const Geo gy0 = ld_geo(&gE[sy.x]);
+                // beyond the band (or next contig): every remaining pair evaluates to the clamp value
+                if (gy0.id_c != cx || (double)ystart - (double)xmax > (double)p.d_max * 1.00001 + 0.05) live = false;
+                else {
+                    #pragma unroll
+                    for (int b = 0; b < 3; b++) if (b < sy.w) {
+                        const int sub = (b == 0) ? sy.x : (b == 1 ? sy.y : sy.z);
+                        const Geo gy = (b == 0) ? gy0 : ld_geo(&gE[sub]);
+                        bool chy = false;
+                        if (DELTA) chy = !geo_eq(gy, ld_geo(&gO[sub]));
+                        #pragma unroll
+                        for (int a = 0; a < 3; a++) if (a < sx.w) {
+                            if (DELTA && !(chx[a] || chy)) continue;
+                            const float s = fabsf(gy.mid - gx[a].mid);
+                            if (!(s > 0.0f && s < p.d_max)) continue;
+                            const float ex = expected_pair(gx[a], gy, p);
+                            acc += (double)ex - (double)g_clamp(pk_true(gx[a].pk) * pk_true(gy.pk), p.v_inter, p.nfpb);
+                        }
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, live)) break;
+        }
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[(size_t)k * partial_stride + blockIdx.x] = acc;
+}
+
+// Q(S): quirk-Q1 correction of trans pairs (bi < bj) whose lower bin is flipped and has non-uniform accu.
+// One block per quirky bin of the list; bins_u == nullptr: all bins j > bi, else the members of bins_u.
+__global__ void __launch_bounds__(256)
+k_quirk(const int* __restrict__ quirky, int n_quirky, const int* __restrict__ slot, int ld, int n,
+        size_t cand_slot_stride, LevelView lv, const int* __restrict__ bins_u, const int* __restrict__ d_count_u,
+        Params p, double* __restrict__ partials, int partial_stride) {
+    const int k = blockIdx.y;
+    const int* sl = slot + (size_t)k * cand_slot_stride;
+    const int bi = quirky[blockIdx.x];
+    double acc = 0.0;
+    const bool act = sl[F_ORI * ld + bi] != 1;
+    if (act) {
+        const int cnt = bins_u ? *d_count_u : n;
+        const int ci = sl[F_ID_C * ld + bi];
+        const int4 si = lv.sub_id[bi];
+        const int li = si.w - 1;
+        const int ai[3] = { lv.sub_accu[bi * 3], lv.sub_accu[bi * 3 + 1], lv.sub_accu[bi * 3 + 2] };
+        const int alast = ai[li];
+        bool in_u = bins_u == nullptr;
+        if (bins_u) { for (int j = threadIdx.x; j < cnt; j += blockDim.x) if (bins_u[j] == bi) in_u = true; in_u = __syncthreads_or(in_u); }
+        if (in_u) {
+            for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+                const int bj = bins_u ? bins_u[j] : j;
+                if (bj <= bi || sl[F_ID_C * ld + bj] == ci) continue;
+                const int lj = lv.sub_id[bj].w - 1;
+                for (int b = 0; b <= lj; b++) {
+                    const int aj = lv.sub_accu[bj * 3 + b];
+                    for (int a = 0; a <= li; a++)
+                        acc += (double)g_clamp(alast * aj, p.v_inter, p.nfpb) - (double)g_clamp(ai[a] * aj, p.v_inter, p.nfpb);
+                }
+            }
+        }
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[(size_t)k * partial_stride + blockIdx.x] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// delta likelihood of candidate slots against the base slot (sub_compute_likelihood, range 1)
+// ------------------------------------------------------------------------------------------------
+// meta[0]=contig A, [1]=contig B, [2]=len A, [3]=len B (0 if same contig), [4]=m = |U|, [5]=max_id
+__global__ void k_delta_setup(const int* __restrict__ base, int ld, int fA, int fB, const int* __restrict__ d_max_id,
+                              int max_id_host, int* __restrict__ meta) {
+    const int cA = base[F_ID_C * ld + fA], cB = base[F_ID_C * ld + fB];
+    const int lA = base[F_L_CONT * ld + fA], lB = (cB != cA) ? base[F_L_CONT * ld + fB] : 0;
+    meta[0] = cA; meta[1] = cB; meta[2] = lA; meta[3] = lB; meta[4] = lA + lB; meta[5] = (max_id_host >= 0) ? max_id_host : *d_max_id;
+}
+// fill_sub_index_fA / fB (kernels3.cu:3225-3249): U in the base slot's position order
+__global__ void k_fill_sub_index(const int* __restrict__ base, int ld, int n, const int* __restrict__ meta,
+                                 int* __restrict__ sub_index) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = base[F_ID_C * ld + i];
+    const int pos = base[F_POS * ld + i];
+    if (c == meta[0]) { if (pos >= 0 && pos < n) sub_index[pos] = i; }
+    else if (c == meta[1]) { const int k = meta[2] + pos; if (k >= 0 && k < n) sub_index[k] = i; }
+}
+// candidate geometry (members of U only) + contig lengths of the candidate's pieces of U
+__device__ __forceinline__ int piece_slot(int id_c, const int* meta) {
+    if (id_c == meta[0]) return 0;
+    if (id_c == meta[1]) return 1;
+    const int d = id_c - meta[5];
+    return (d >= 1 && d <= 3) ? 1 + d : -1;
+}
+__global__ void k_cand_geometry(const int* __restrict__ cand0, size_t slot_stride, int ld, LevelView lv,
+                                const int* __restrict__ sub_index, const int* __restrict__ meta,
+                                Geo* __restrict__ geo0, size_t geo_stride, int* __restrict__ piece_len) {
+    const int k = blockIdx.y;
+    const int m = meta[4];
+    const int* sl = cand0 + (size_t)k * slot_stride;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < m; u += gridDim.x * blockDim.x) {
+        const int bin = sub_index[u];
+        bin_geometry(sl, ld, bin, lv, geo0 + (size_t)k * geo_stride);
+        if (sl[F_POS * ld + bin] == 0) {
+            const int ps = piece_slot(sl[F_ID_C * ld + bin], meta);
+            if (ps >= 0) piece_len[k * 8 + ps] = sl[F_L_CONT * ld + bin];
+        }
+    }
+}
+__global__ void k_cand_order(const int* __restrict__ cand0, size_t slot_stride, int ld,
+                             const int* __restrict__ sub_index, const int* __restrict__ meta,
+                             const int* __restrict__ piece_len, int* __restrict__ order0, int order_stride) {
+    const int k = blockIdx.y;
+    const int m = meta[4];
+    const int* sl = cand0 + (size_t)k * slot_stride;
+    int off[5]; int run = 0;
+    #pragma unroll
+    for (int s = 0; s < 5; s++) { off[s] = run; run += piece_len[k * 8 + s]; }
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < m; u += gridDim.x * blockDim.x) {
+        const int bin = sub_index[u];
+        const int ps = piece_slot(sl[F_ID_C * ld + bin], meta);
+        if (ps < 0) continue;
+        const int idx = off[ps] + sl[F_POS * ld + bin];
+        if (idx >= 0 && idx < m) order0[(size_t)k * order_stride + idx] = bin;
+    }
+}
+
+// contact part of the delta: one warp per member bin of U, lanes stride over its (<= 3 rows of) contacts
+__global__ void __launch_bounds__(256)
+k_delta_contacts(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, LevelView lv,
+                 const int* __restrict__ sub_index, const int* __restrict__ meta,
+                 const Geo* __restrict__ geo_base, const Geo* __restrict__ geo_cand0, size_t geo_stride,
+                 Params p, double* __restrict__ partials, int partial_stride) {
+    const int k = blockIdx.y;
+    const Geo* gK = geo_cand0 + (size_t)k * geo_stride;
+    const int m = meta[4], cA = meta[0], cB = meta[1];
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    double acc = 0.0;
+    for (int u = warp; u < m; u += n_warps) {
+        const int bin = sub_index[u];
+        const int4 sid = lv.sub_id[bin];
+        const int sub0 = sid.x;
+        const long long e0 = __ldg(&rowptr[sub0]);
+        const long long b1 = __ldg(&rowptr[sub0 + 1]);
+        const long long b2 = (sid.w > 1) ? __ldg(&rowptr[sub0 + 2]) : b1;
+        const long long e1 = (sid.w > 2) ? __ldg(&rowptr[sub0 + 3]) : b2;
+        Geo g0r[3], gkr[3];
+        #pragma unroll
+        for (int a = 0; a < 3; a++) if (a < sid.w) { g0r[a] = ld_geo(&geo_base[sub0 + a]); gkr[a] = ld_geo(&gK[sub0 + a]); }
+        for (long long e = e0 + lane; e < e1; e += 32) {
+            const int a = (e >= b1) + (e >= b2);
+            const int2 ce = __ldg(&contacts[e]);
+            const Geo g0c = ld_geo(&geo_base[ce.x]);
+            if (g0c.id_c != cA && g0c.id_c != cB) continue;              // partner outside U
+            if (ce.x - pk_local(g0c.pk) == sub0) continue;               // same bin: diagonal pixel, not re-scored
+            const Geo gkc = ld_geo(&gK[ce.x]);
+            const Geo r0 = (a == 0) ? g0r[0] : (a == 1 ? g0r[1] : g0r[2]);
+            const Geo rk = (a == 0) ? gkr[0] : (a == 1 ? gkr[1] : gkr[2]);
+            if (geo_eq(r0, rk) && geo_eq(g0c, gkc)) continue;            // bitwise unchanged pair
+            const float ob = __int_as_float(ce.y);
+            const float ex0 = expected_pair(r0, g0c, p);
+            const float exk = expected_pair(rk, gkc, p);
+            double t = 0.0;
+            if (exk != 0.0f) t += (double)ob * log((double)exk); else t += log_fact_term(ob);
+            if (ex0 != 0.0f) t -= (double)ob * log((double)ex0); else t -= log_fact_term(ob);
+            acc += t;
+        }
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[(size_t)k * partial_stride + blockIdx.x] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// statistics and the distance histogram
+// ------------------------------------------------------------------------------------------------
+__global__ void k_stats(const int* __restrict__ slot, int ld, int n, unsigned long long* __restrict__ acc) {
+    // acc[0] = #heads (start_bp == 0), acc[1] = sum l_cont_bp over heads, acc[2] = min l_cont, acc[3] = max l_cont
+    unsigned long long heads = 0, sum = 0; int mn = INT_MAX, mx = INT_MIN;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int lc = slot[F_L_CONT * ld + i];
+        mn = min(mn, lc); mx = max(mx, lc);
+        if (slot[F_START_BP * ld + i] == 0) { heads++; sum += (unsigned long long)(long long)slot[F_L_CONT_BP * ld + i]; }
+    }
+    atomicAdd(&acc[0], heads); atomicAdd(&acc[1], sum);
+    atomicMin((int*)&acc[2], mn); atomicMax((int*)&acc[3], mx);
+}
+__global__ void k_stats_final(const unsigned long long* __restrict__ acc, const int* __restrict__ n_contigs, double* __restrict__ out) {
+    out[0] = (double)*n_contigs;
+    out[1] = (double)*(const int*)&acc[2];
+    out[2] = acc[0] ? (double)acc[1] / (double)acc[0] : 0.0;
+    out[3] = (double)*(const int*)&acc[3];
+}
+__global__ void k_count_contigs(const int* __restrict__ first, int cap, int* __restrict__ n_contigs) {
+    int c = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) c += first[i] != INT_MAX;
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(n_contigs, c);
+}
+
+// distance histogram of estimate_parameters (cuda_lib_gl.py:1236-1270).  The initial sub-level layout
+// is contig-contiguous and position-ordered, so the cis partners of sub-frag i are i+1 .. end of contig.
+// One warp per sub-frag i: pair counts per bin over j > i (zeros included), contacts from row i.
+__global__ void __launch_bounds__(256)
+k_dist_hist(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, int W,
+            const int* __restrict__ id_c, const int* __restrict__ st, const int* __restrict__ ln, const int* __restrict__ pos,
+            double max_kb, double bin_kb, int n_bins, double* __restrict__ d_sum, unsigned long long* __restrict__ d_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < W - 1; i += n_warps) {
+        const int ci = id_c[i], sti = st[i], lni = ln[i], pi = pos[i];
+        for (int base = i + 1; base < W; base += 32) {
+            const int j = base + lane;
+            bool live = j < W && id_c[j] == ci;
+            if (live) {
+                double d = (pi < pos[j]) ? ((double)(st[j] - sti - lni) + (double)(lni + ln[j]) / 2.) / 1000.
+                                         : ((double)(sti - st[j] - ln[j]) + (double)(ln[j] + lni) / 2.) / 1000.;
+                if (d < max_kb) { const int b = (int)(d / bin_kb); if (b >= 0 && b < n_bins) atomicAdd(&d_cnt[b], 1ull); }
+            }
+            if (!__any_sync(0xffffffffu, live)) break;      // contig-contiguous layout
+        }
+        for (long long e = rowptr[i] + lane; e < rowptr[i + 1]; e += 32) {
+            const int2 ce = contacts[e];
+            const int j = ce.x;
+            if (id_c[j] != ci) continue;
+            double d = (pi < pos[j]) ? ((double)(st[j] - sti - lni) + (double)(lni + ln[j]) / 2.) / 1000.
+                                     : ((double)(sti - st[j] - ln[j]) + (double)(ln[j] + lni) / 2.) / 1000.;
+            if (d < max_kb) { const int b = (int)(d / bin_kb); if (b >= 0 && b < n_bins) atomicAdd(&d_sum[b], (double)__int_as_float(ce.y)); }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct graal_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int n_sm = 148;
+    int64_t launches = 0;
+    // level
+    int N = 0, n_new = 0, W = 0;
+    long long E = 0;
+    LevelView lv{};
+    const int* collector = nullptr; const int* dispatcher = nullptr;
+    const long long* rowptr = nullptr; const int2* contacts = nullptr;
+    float nfpb = 1.0f;
+    std::vector<std::pair<int, long long>> accu_hist;   // (accu value, count) over all sub-frags
+    int* d_quirky = nullptr; int n_quirky = 0;
+    double lf_total = 0.0;
+    // params
+    Params p{}; bool have_params = false;
+    // state
+    int* slots = nullptr; int ld = 0, n_slots = 0;
+    // scratch
+    Geo* geo_base = nullptr; int geo_base_slot = -1;
+    Geo* geo_cand = nullptr;                 // [13][W]
+    int* order = nullptr;                    // [n]
+    int* cand_order = nullptr;               // [13][n]
+    int* sub_index = nullptr;                // [n]
+    int* cont_len = nullptr; int* cont_off = nullptr; int cap = 0;   // [cap]
+    int* first_idx = nullptr; int* map = nullptr;
+    unsigned long long* keys = nullptr; unsigned long long* keys_sorted = nullptr;
+    void* cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
+    int* d_ints = nullptr;                   // [0]=max_id [1]=n_contigs [2]=err [3]=tmp max  [8..16)=delta meta  [16..16+13*8)=piece_len
+    unsigned long long* d_stats = nullptr;   // [4]
+    double* partials = nullptr; int partial_stride = 0;   // [14][partial_stride]
+    double* d_scalars = nullptr;             // [16] device doubles: [0]=contacts [1]=band [2]=quirk ...
+};
+
+static size_t slot_stride(const graal_ctx* c) { return (size_t)N_FIELDS * c->ld; }
+static int* slot_ptr(const graal_ctx* c, int s) { return c->slots + (size_t)s * slot_stride(c); }
+
+static double host_g0(const graal_ctx* c, const Params& p) {
+    // sum over all unordered sub-frag pairs of g(a*b), grouped by the distinct accu values
+    double tot = 0.0;
+    const auto& h = c->accu_hist;
+    for (size_t i = 0; i < h.size(); i++) {
+        const double ci = (double)h[i].second;
+        tot += ci * (ci - 1.0) / 2.0 * (double)g_clamp(h[i].first * h[i].first, p.v_inter, p.nfpb);
+        for (size_t j = i + 1; j < h.size(); j++)
+            tot += ci * (double)h[j].second * (double)g_clamp(h[i].first * h[j].first, p.v_inter, p.nfpb);
+    }
+    return tot;
+}
+
+extern "C" {
+
+const char* graal_last_error(void) { return g_err; }
+const char* graal_version(void) { return GRAAL_VERSION; }
+
+int graal_ctx_create(int device, graal_ctx** out) {
+    if (!out) return set_err(-1, "null out pointer");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev <= 0) return set_err(-2, "no CUDA device available (%s): this library has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= n_dev) return set_err(-1, "device %d out of range (0..%d)", device, n_dev - 1);
+    CUDA_OK(cudaSetDevice(device));
+    graal_ctx* c = new graal_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    c->n_sm = prop.multiProcessorCount;
+    CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    CUDA_OK(cudaMalloc(&c->d_ints, 256 * sizeof(int)));
+    CUDA_OK(cudaMemset(c->d_ints, 0, 256 * sizeof(int)));
+    CUDA_OK(cudaMalloc(&c->d_stats, 4 * sizeof(unsigned long long)));
+    CUDA_OK(cudaMalloc(&c->d_scalars, 64 * sizeof(double)));
+    c->partial_stride = c->n_sm * 8;
+    CUDA_OK(cudaMalloc(&c->partials, (size_t)16 * c->partial_stride * sizeof(double)));
+    *out = c;
+    return 0;
+}
+
+static void free_level_scratch(graal_ctx* c) {
+    cudaFree(c->geo_base); cudaFree(c->geo_cand); cudaFree(c->order); cudaFree(c->cand_order); cudaFree(c->sub_index);
+    cudaFree(c->cont_len); cudaFree(c->cont_off); cudaFree(c->first_idx); cudaFree(c->map); cudaFree(c->keys);
+    cudaFree(c->keys_sorted); cudaFree(c->cub_tmp); cudaFree(c->d_quirky);
+    c->geo_base = c->geo_cand = nullptr; c->order = c->cand_order = c->sub_index = c->cont_len = c->cont_off = nullptr;
+    c->first_idx = c->map = nullptr; c->keys = c->keys_sorted = nullptr; c->cub_tmp = nullptr; c->d_quirky = nullptr;
+}
+
+void graal_ctx_destroy(graal_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_level_scratch(c);
+    cudaFree(c->d_ints); cudaFree(c->d_stats); cudaFree(c->d_scalars); cudaFree(c->partials);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int graal_set_stream(graal_ctx* c, void* s) {
+    if (!c) return set_err(-1, "null context");
+    if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    c->stream = (cudaStream_t)s; c->own_stream = false;
+    return 0;
+}
+int graal_sync(graal_ctx* c) { if (!c) return set_err(-1, "null context"); CUDA_OK(cudaStreamSynchronize(c->stream)); return 0; }
+int64_t graal_launch_count(graal_ctx* c) { return c ? c->launches : -1; }
+
+int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags,
+                     const int32_t* sub_id, const float* sub_len_kb, const int32_t* sub_accu,
+                     const int32_t* collector, const int32_t* dispatcher,
+                     const int64_t* rowptr, const void* contacts, int64_t n_contacts, float nfpb) {
+    if (!c) return set_err(-1, "null context");
+    if (n_frags <= 0 || n_sub_frags <= 0 || n_new_frags < n_frags) return set_err(-1, "bad level sizes");
+    if (!sub_id || !sub_len_kb || !sub_accu || !rowptr || (n_contacts > 0 && !contacts)) return set_err(-1, "null level pointer");
+    if (n_new_frags != n_frags)
+        return set_err(-4, "levels with repeat copies (n_new_frags %d != n_frags %d) are not supported by the device path yet", n_new_frags, n_frags);
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    free_level_scratch(c);
+    c->N = n_frags; c->n_new = n_new_frags; c->W = n_sub_frags; c->E = n_contacts; c->nfpb = nfpb;
+    c->lv.sub_id = reinterpret_cast<const int4*>(sub_id); c->lv.sub_len = sub_len_kb; c->lv.sub_accu = sub_accu;
+    c->collector = collector; c->dispatcher = dispatcher;
+    c->rowptr = reinterpret_cast<const long long*>(rowptr); c->contacts = reinterpret_cast<const int2*>(contacts);
+    // derived host tables: accu histogram (for G0) and the list of quirky bins (non-uniform accu, Q1)
+    std::vector<int> h_sid((size_t)n_frags * 4), h_acc((size_t)n_frags * 3);
+    CUDA_OK(cudaMemcpy(h_sid.data(), sub_id, h_sid.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(h_acc.data(), sub_accu, h_acc.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    std::map<int, long long> hist; std::vector<int> quirky; long long w_check = 0;
+    for (int b = 0; b < n_frags; b++) {
+        const int cnt = h_sid[(size_t)b * 4 + 3];
+        if (cnt < 1 || cnt > 3) return set_err(-1, "bin %d has %d sub-frags (1..3 supported)", b, cnt);
+        if (h_sid[(size_t)b * 4] != (int)w_check) return set_err(-1, "sub-frag ids of bin %d are not consecutive in bin order", b);
+        bool q = false;
+        for (int a = 0; a < cnt; a++) {
+            const int v = h_acc[(size_t)b * 3 + a];
+            if (h_sid[(size_t)b * 4 + a] != (int)w_check + a) return set_err(-1, "sub-frag ids of bin %d are not consecutive", b);
+            if (v < 0 || v > PK_ACCU_MAX) return set_err(-1, "accu %d of bin %d outside 0..%d", v, b, PK_ACCU_MAX);
+            hist[v]++; if (v != h_acc[(size_t)b * 3 + cnt - 1]) q = true;
+        }
+        if (q) quirky.push_back(b);
+        w_check += cnt;
+    }
+    if (w_check != n_sub_frags) return set_err(-1, "sub-frag count mismatch: %lld vs %d", w_check, n_sub_frags);
+    c->accu_hist.assign(hist.begin(), hist.end());
+    c->n_quirky = (int)quirky.size();
+    if (c->n_quirky) {
+        CUDA_OK(cudaMalloc(&c->d_quirky, quirky.size() * sizeof(int)));
+        CUDA_OK(cudaMemcpy(c->d_quirky, quirky.data(), quirky.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    const int n = n_new_frags;
+    c->cap = 2 * n + 16;
+    CUDA_OK(cudaMalloc(&c->geo_base, (size_t)c->W * sizeof(Geo)));
+    CUDA_OK(cudaMalloc(&c->geo_cand, (size_t)GRAAL_N_CANDIDATES * c->W * sizeof(Geo)));
+    CUDA_OK(cudaMemset(c->geo_cand, 0, (size_t)GRAAL_N_CANDIDATES * c->W * sizeof(Geo)));
+    CUDA_OK(cudaMalloc(&c->order, (size_t)n * sizeof(int)));
+    CUDA_OK(cudaMalloc(&c->cand_order, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int)));
+    CUDA_OK(cudaMalloc(&c->sub_index, (size_t)n * sizeof(int)));
+    CUDA_OK(cudaMemset(c->sub_index, 0, (size_t)n * sizeof(int)));
+    CUDA_OK(cudaMemset(c->cand_order, 0, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int)));
+    CUDA_OK(cudaMalloc(&c->cont_len, (size_t)c->cap * sizeof(int)));
+    CUDA_OK(cudaMalloc(&c->cont_off, (size_t)c->cap * sizeof(int)));
+    CUDA_OK(cudaMalloc(&c->first_idx, (size_t)c->cap * sizeof(int)));
+    CUDA_OK(cudaMalloc(&c->map, (size_t)c->cap * sizeof(int)));
+    CUDA_OK(cudaMalloc(&c->keys, (size_t)c->cap * sizeof(unsigned long long)));
+    CUDA_OK(cudaMalloc(&c->keys_sorted, (size_t)c->cap * sizeof(unsigned long long)));
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, b1, c->keys, c->keys_sorted, c->cap);
+    cub::DeviceScan::ExclusiveSum(nullptr, b2, c->cont_len, c->cont_off, c->cap);
+    c->cub_tmp_bytes = std::max(b1, b2);
+    CUDA_OK(cudaMalloc(&c->cub_tmp, c->cub_tmp_bytes));
+    c->geo_base_slot = -1;
+    // level constant: sum of lf(ob)
+    c->lf_total = 0.0;
+    if (c->E > 0) {
+        const int grid = c->partial_stride;
+        k_lf_total<<<grid, 256, 0, c->stream>>>(c->contacts, c->E, c->partials);
+        CHECK_LAUNCH(c);
+        k_reduce_partials<<<1, 256, 0, c->stream>>>(c->partials, grid, 0, 1.0, c->d_scalars + 15, 0);
+        CHECK_LAUNCH(c);
+        CUDA_OK(cudaMemcpyAsync(&c->lf_total, c->d_scalars + 15, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int graal_set_params(graal_ctx* c, const float q[8]) {
+    if (!c || !q) return set_err(-1, "null argument");
+    c->p.kuhn = q[0]; c->p.lm = q[1]; c->p.c1 = q[2]; c->p.slope = q[3]; c->p.d = q[4];
+    c->p.d_max = q[5]; c->p.fact = q[6]; c->p.v_inter = q[7]; c->p.nfpb = c->nfpb;
+    c->have_params = true;
+    return 0;
+}
+
+int graal_state_bind(graal_ctx* c, int32_t* base, int ld, int n_slots) {
+    if (!c || !base) return set_err(-1, "null argument");
+    if (c->n_new <= 0) return set_err(-1, "bind the level first");
+    if (ld < c->n_new || n_slots < 1) return set_err(-1, "bad slot geometry (ld %d < n %d)", ld, c->n_new);
+    c->slots = base; c->ld = ld; c->n_slots = n_slots; c->geo_base_slot = -1;
+    return 0;
+}
+
+#define NEED_STATE(c) do { if (!(c) || !(c)->slots) return set_err(-1, "state not bound"); CUDA_OK(cudaSetDevice((c)->device)); } while (0)
+#define NEED_SLOT(c, s) do { if ((s) < 0 || (s) >= (c)->n_slots) return set_err(-1, "slot %d out of range", (s)); } while (0)
+static inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
+
+int graal_relabel_contigs(graal_ctx* c, int slot, int32_t* d_max_id) {
+    NEED_STATE(c); NEED_SLOT(c, slot);
+    const int n = c->n_new, cap = c->cap, ld = c->ld;
+    int* s = slot_ptr(c, slot);
+    cudaStream_t st = c->stream;
+    k_fill_int<<<nblk(cap, 256), 256, 0, st>>>(c->first_idx, cap, INT_MAX); CHECK_LAUNCH(c);
+    k_first_index<<<nblk(n, 256), 256, 0, st>>>(s + F_ID_C * ld, n, cap, c->first_idx, c->d_ints + 2); CHECK_LAUNCH(c);
+    k_relabel_keys<<<nblk(cap, 256), 256, 0, st>>>(c->first_idx, s + F_L_CONT * ld, cap, c->keys); CHECK_LAUNCH(c);
+    size_t tb = c->cub_tmp_bytes;
+    CUDA_OK(cub::DeviceRadixSort::SortKeys(c->cub_tmp, tb, c->keys, c->keys_sorted, cap, 0, 64, st)); c->launches += 8;
+    k_relabel_map<<<nblk(cap, 256), 256, 0, st>>>(c->keys_sorted, cap, c->map, c->d_ints + 1); CHECK_LAUNCH(c);
+    k_relabel_apply<<<nblk(n, 256), 256, 0, st>>>(s + F_ID_C * ld, n, c->map, c->d_ints + 1, c->d_ints + 0, d_max_id); CHECK_LAUNCH(c);
+    if (c->geo_base_slot == slot) c->geo_base_slot = -1;
+    return 0;
+}
+
+int graal_apply_move(graal_ctx* c, int src_slot, int dst_slot, int op, int id_fA, int id_fB, int aux,
+                     int max_id_in, int32_t* d_max_id_out) {
+    NEED_STATE(c); NEED_SLOT(c, src_slot); NEED_SLOT(c, dst_slot);
+    if (op < 0 || op >= GRAAL_N_OPS) return set_err(-1, "unknown op %d", op);
+    const int n = c->n_new;
+    if (id_fA < 0 || id_fA >= n || id_fB < 0 || id_fB >= n) return set_err(-1, "bin id out of range");
+    if (src_slot == dst_slot) return set_err(-1, "in-place moves are not supported (src == dst)");
+    k_apply_move<<<nblk(n, 128), 128, 0, c->stream>>>(slot_ptr(c, src_slot), slot_ptr(c, dst_slot), c->ld, n, op, id_fA, id_fB, aux, max_id_in);
+    CHECK_LAUNCH(c);
+    if (d_max_id_out) {
+        k_set_int<<<1, 1, 0, c->stream>>>(d_max_id_out, INT_MIN); CHECK_LAUNCH(c);
+        k_max_field<<<std::min(nblk(n, 256), c->n_sm * 4), 256, 0, c->stream>>>(slot_ptr(c, dst_slot) + F_ID_C * c->ld, n, d_max_id_out);
+        CHECK_LAUNCH(c);
+    }
+    if (c->geo_base_slot == dst_slot) c->geo_base_slot = -1;
+    return 0;
+}
+
+int graal_build_candidates(graal_ctx* c, int src_slot, int first_dst_slot, int id_fA, int id_fB, int max_id, unsigned mask) {
+    NEED_STATE(c); NEED_SLOT(c, src_slot); NEED_SLOT(c, first_dst_slot); NEED_SLOT(c, first_dst_slot + GRAAL_N_CANDIDATES - 1);
+    const int n = c->n_new;
+    if (id_fA < 0 || id_fA >= n || id_fB < 0 || id_fB >= n) return set_err(-1, "bin id out of range");
+    if (src_slot >= first_dst_slot && src_slot < first_dst_slot + GRAAL_N_CANDIDATES) return set_err(-1, "source slot inside the destination range");
+    k_build_candidates<<<nblk(n, 128), 128, 0, c->stream>>>(slot_ptr(c, src_slot), slot_ptr(c, first_dst_slot), slot_stride(c), c->ld, n,
+                                                           id_fA, id_fB, c->d_ints + 0, max_id, mask & 0x1FFFu);
+    CHECK_LAUNCH(c);
+    if (c->geo_base_slot >= first_dst_slot && c->geo_base_slot < first_dst_slot + GRAAL_N_CANDIDATES) c->geo_base_slot = -1;
+    return 0;
+}
+
+int graal_commit(graal_ctx* c, int dst_slot, int src_slot) {
+    NEED_STATE(c); NEED_SLOT(c, src_slot); NEED_SLOT(c, dst_slot);
+    if (src_slot == dst_slot) return 0;
+    k_apply_move<<<nblk(c->n_new, 128), 128, 0, c->stream>>>(slot_ptr(c, src_slot), slot_ptr(c, dst_slot), c->ld, c->n_new, GRAAL_OP_COPY, 0, 0, 0, 0);
+    CHECK_LAUNCH(c);
+    if (c->geo_base_slot == dst_slot) c->geo_base_slot = -1;
+    return 0;
+}
+
+static int ensure_base_geometry(graal_ctx* c, int slot) {
+    if (c->geo_base_slot == slot) return 0;
+    k_geometry_all<<<nblk(c->n_new, 128), 128, 0, c->stream>>>(slot_ptr(c, slot), c->ld, c->n_new, c->lv, c->geo_base);
+    CHECK_LAUNCH(c);
+    c->geo_base_slot = slot;
+    return 0;
+}
+
+int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d_out) {
+    NEED_STATE(c); NEED_SLOT(c, slot);
+    if (!d_out) return set_err(-1, "null output");
+    if (!c->have_params && !p_override) return set_err(-1, "parameters not set");
+    Params p = c->p;
+    if (p_override) { p.kuhn = p_override[0]; p.lm = p_override[1]; p.c1 = p_override[2]; p.slope = p_override[3];
+                      p.d = p_override[4]; p.d_max = p_override[5]; p.fact = p_override[6]; p.v_inter = p_override[7]; p.nfpb = c->nfpb; }
+    cudaStream_t st = c->stream;
+    const int n = c->n_new, ld = c->ld;
+    int* s = slot_ptr(c, slot);
+    int rc = ensure_base_geometry(c, slot); if (rc) return rc;
+    // position order of the bins, contig by contig
+    CUDA_OK(cudaMemsetAsync(c->cont_len, 0, (size_t)c->cap * sizeof(int), st));
+    k_contig_lengths<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_len); CHECK_LAUNCH(c);
+    size_t tb = c->cub_tmp_bytes;
+    CUDA_OK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, tb, c->cont_len, c->cont_off, c->cap, st)); c->launches += 2;
+    k_order_fill<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_off, c->order); CHECK_LAUNCH(c);
+    const int ps = c->partial_stride;
+    // contacts
+    const int g1 = c->E > 0 ? std::min<long long>(ps, (c->E + CHUNK * 8 - 1) / (CHUNK * 8)) : 0;
+    const double g0 = host_g0(c, p);
+    // d_out = -(lf_total + G0)   then accumulate the three device sums
+    const double init = -(c->lf_total + g0);
+    k_set_double<<<1, 1, 0, st>>>(d_out, init); CHECK_LAUNCH(c);
+    if (g1 > 0) {
+        k_full_contacts<<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->W, c->geo_base, p, c->partials); CHECK_LAUNCH(c);
+        k_reduce_partials<<<1, 256, 0, st>>>(c->partials, g1, 0, 1.0, d_out, 1); CHECK_LAUNCH(c);
+    }
+    const int g2 = std::min(ps, nblk(n, 8));
+    k_band<false><<<dim3(g2, 1), 256, 0, st>>>(c->order, nullptr, n, s, ld, c->lv, c->geo_base, nullptr, 0, 0, 0, 0, p,
+                                              c->partials + (size_t)1 * ps, ps); CHECK_LAUNCH(c);
+    k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)1 * ps, g2, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
+    if (c->n_quirky > 0) {
+        if (c->n_quirky > ps) return set_err(-5, "too many quirky bins (%d > %d)", c->n_quirky, ps);
+        k_quirk<<<dim3(c->n_quirky, 1), 256, 0, st>>>(c->d_quirky, c->n_quirky, s, ld, n, 0, c->lv, nullptr, nullptr, p,
+                                                      c->partials + (size_t)2 * ps, ps); CHECK_LAUNCH(c);
+        k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)2 * ps, c->n_quirky, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
+    }
+    return 0;
+}
+
+int graal_delta_loglik(graal_ctx* c, int base_slot, int first_cand_slot, int n_cand, int id_fA, int id_fB, int max_id, double* d_out) {
+    NEED_STATE(c); NEED_SLOT(c, base_slot); NEED_SLOT(c, first_cand_slot);
+    if (n_cand < 1 || n_cand > GRAAL_N_CANDIDATES) return set_err(-1, "n_cand must be 1..13");
+    NEED_SLOT(c, first_cand_slot + n_cand - 1);
+    if (!d_out) return set_err(-1, "null output");
+    if (!c->have_params) return set_err(-1, "parameters not set");
+    const int n = c->n_new, ld = c->ld;
+    if (id_fA < 0 || id_fA >= n || id_fB < 0 || id_fB >= n) return set_err(-1, "bin id out of range");
+    cudaStream_t st = c->stream;
+    const Params p = c->p;
+    int rc = ensure_base_geometry(c, base_slot); if (rc) return rc;
+    int* base = slot_ptr(c, base_slot);
+    int* cand0 = slot_ptr(c, first_cand_slot);
+    int* meta = c->d_ints + 8;
+    int* piece_len = c->d_ints + 16;
+    const int ps = c->partial_stride;
+    k_delta_setup<<<1, 1, 0, st>>>(base, ld, id_fA, id_fB, c->d_ints + 0, max_id, meta); CHECK_LAUNCH(c);
+    k_fill_sub_index<<<nblk(n, 256), 256, 0, st>>>(base, ld, n, meta, c->sub_index); CHECK_LAUNCH(c);
+    CUDA_OK(cudaMemsetAsync(piece_len, 0, GRAAL_N_CANDIDATES * 8 * sizeof(int), st));
+    const int gu = std::min(c->n_sm * 2, nblk(n, 256));
+    k_cand_geometry<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->lv, c->sub_index, meta, c->geo_cand, (size_t)c->W, piece_len); CHECK_LAUNCH(c);
+    k_cand_order<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->sub_index, meta, piece_len, c->cand_order, n); CHECK_LAUNCH(c);
+    const int gw = std::min(ps, std::max(1, nblk(n, 8)));
+    // contacts: + sum over changed contacts of ob*(log ex_k - log ex_0)
+    k_delta_contacts<<<dim3(gw, n_cand), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, c->sub_index, meta, c->geo_base, c->geo_cand, (size_t)c->W,
+                                                      p, c->partials, ps); CHECK_LAUNCH(c);
+    k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, 1.0, d_out, 0); CHECK_LAUNCH(c);
+    // band mass: - [B_U(S_k) - B_U(S_0)] over changed pairs
+    k_band<true><<<dim3(gw, n_cand), 256, 0, st>>>(c->cand_order, meta + 4, -1, cand0, ld, c->lv, c->geo_cand, c->geo_base, (size_t)c->W, slot_stride(c), n, 1, p,
+                                                  c->partials, ps); CHECK_LAUNCH(c);
+    k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, -1.0, d_out, 1); CHECK_LAUNCH(c);
+    k_band<true><<<dim3(gw, n_cand), 256, 0, st>>>(c->sub_index, meta + 4, -1, base, ld, c->lv, c->geo_base, c->geo_cand, (size_t)c->W, 0, 0, 0, p,
+                                                  c->partials, ps); CHECK_LAUNCH(c);
+    k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, 1.0, d_out, 1); CHECK_LAUNCH(c);
+    if (c->n_quirky > 0) {
+        // quirk mass: - [Q_U(S_k) - Q_U(S_0)]
+        k_quirk<<<dim3(c->n_quirky, n_cand), 256, 0, st>>>(c->d_quirky, c->n_quirky, cand0, ld, n, slot_stride(c), c->lv, c->sub_index, meta + 4, p,
+                                                          c->partials, ps); CHECK_LAUNCH(c);
+        k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, c->n_quirky, ps, -1.0, d_out, 1); CHECK_LAUNCH(c);
+        // the base slot's term is the same for every candidate: computed once, added to all
+        k_quirk<<<dim3(c->n_quirky, 1), 256, 0, st>>>(c->d_quirky, c->n_quirky, base, ld, n, 0, c->lv, c->sub_index, meta + 4, p,
+                                                     c->partials + (size_t)13 * ps, ps); CHECK_LAUNCH(c);
+        for (int k = 0; k < n_cand; k++) {
+            k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)13 * ps, c->n_quirky, 0, 1.0, d_out + k, 1); CHECK_LAUNCH(c);
+        }
+    }
+    return 0;
+}
+
+int graal_state_stats(graal_ctx* c, int slot, double* d_out) {
+    NEED_STATE(c); NEED_SLOT(c, slot);
+    if (!d_out) return set_err(-1, "null output");
+    const int n = c->n_new, ld = c->ld, cap = c->cap;
+    int* s = slot_ptr(c, slot);
+    cudaStream_t st = c->stream;
+    k_init_stats<<<1, 1, 0, st>>>(c->d_stats); CHECK_LAUNCH(c);
+    k_stats<<<std::min(nblk(n, 256), c->n_sm * 4), 256, 0, st>>>(s, ld, n, c->d_stats); CHECK_LAUNCH(c);
+    k_fill_int<<<nblk(cap, 256), 256, 0, st>>>(c->first_idx, cap, INT_MAX); CHECK_LAUNCH(c);
+    k_first_index<<<nblk(n, 256), 256, 0, st>>>(s + F_ID_C * ld, n, cap, c->first_idx, c->d_ints + 2); CHECK_LAUNCH(c);
+    k_set_int<<<1, 1, 0, st>>>(c->d_ints + 3, 0); CHECK_LAUNCH(c);
+    k_count_contigs<<<std::min(nblk(cap, 256), c->n_sm * 4), 256, 0, st>>>(c->first_idx, cap, c->d_ints + 3); CHECK_LAUNCH(c);
+    k_stats_final<<<1, 1, 0, st>>>(c->d_stats, c->d_ints + 3, d_out); CHECK_LAUNCH(c);
+    return 0;
+}
+
+int graal_dist_histogram(graal_ctx* c, const int32_t* sub_id_c, const int32_t* sub_start_bp, const int32_t* sub_len_bp,
+                         const int32_t* sub_pos, double max_dist_kb, double bin_kb, int n_bins, double* d_sum, int64_t* d_cnt) {
+    if (!c || !c->rowptr) return set_err(-1, "level not bound");
+    if (!sub_id_c || !sub_start_bp || !sub_len_bp || !sub_pos || !d_sum || !d_cnt || n_bins <= 0) return set_err(-1, "bad argument");
+    CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    CUDA_OK(cudaMemsetAsync(d_sum, 0, (size_t)n_bins * sizeof(double), st));
+    CUDA_OK(cudaMemsetAsync(d_cnt, 0, (size_t)n_bins * sizeof(int64_t), st));
+    k_dist_hist<<<c->n_sm * 8, 256, 0, st>>>(c->rowptr, c->contacts, c->W, sub_id_c, sub_start_bp, sub_len_bp, sub_pos,
+                                            max_dist_kb, bin_kb, n_bins, d_sum, reinterpret_cast<unsigned long long*>(d_cnt));
+    CHECK_LAUNCH(c);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,581 @@
+"""Headless ``sampler``: the Python surface of /root/reference/cuda_lib_gl.py (class sampler) over the
+sm_100a C-ABI.  Same method names, argument meaning and return tuples as the reference, minus the
+PyCUDA / OpenGL objects (gl_window, pos_vbo, col_vbo, vel, pos, raw_im_init, pbo_im_buffer).
+
+Host code is NumPy; torch only owns the device buffers (slots, level tables, outputs) whose raw
+pointers go through ctypes.  There is no CPU fallback: constructing a sampler without the CUDA
+library or without a GPU raises ``GraalError``.
+
+Reference map (cuda_lib_gl.py): __init__ :33-446, init_likelihood :448, dist_inter_genome :475-541,
+eval_likelihood :543-631, setup_texture :637-665, test_copy_struct :1156-1183,
+setup_rippe_parameters :1203-1214, estimate_parameters :1229-1294, explode_genome :1539-1557,
+apply_replay_simu :1559-1578, modify_gl_cuda_buffer :1695-1788, step_max_likelihood :1793-1980,
+step_nuisance_parameters :2022-2107, return_neighbours :2295-2331, setup_distri_frags :2363-2390,
+stream_likelihood :2392-2546, temperature :2590-2603, free_gpu :2605-2613.
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+from ._lib import GraalError, check
+from . import rippe as opti
+from .level import FRAG_FIELDS
+
+F32, I32 = np.float32, np.int32
+N_TMP_STRUCT = 13
+CUR = 0            # slot of the current genome (reference: gpu_vect_frags)
+CAND0 = 1          # first of the 13 collector slots (reference: collector_gpu_vect_frags)
+PARAM_FIELDS = ("kuhn", "lm", "c1", "slope", "d", "d_max", "fact", "v_inter")
+PARAM_DTYPE = np.dtype([(k if k != "d_max" else "l_max", F32) for k in PARAM_FIELDS], align=True)
+
+MODIFICATION_STR = ['eject frag', 'flip frag',
+                    'pop out split insert @ left or 1', 'pop out split insert @ left or -1',
+                    'pop out split insert @ right or 1', 'pop out split insert @ right or -1',
+                    'pop out insert @ right or 1', 'pop out insert @ right or -1',
+                    'swap activity', 'transloc_1', 'transloc_2', 'transloc_3', 'transloc_4',
+                    'local_scramble d1', 'local_scramble d2', 'local_scramble d3', 'local_scramble d4']
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class _VectFrags:
+    """Stand-in for the reference GPUStruct ``gpu_vect_frags``: ``copy_from_gpu()`` then ``.pos``,
+    ``.id_c`` ... as NumPy arrays (gpustruct.py:173-211)."""
+
+    def __init__(self, owner, slot):
+        self._o, self._slot = owner, slot
+        for k in FRAG_FIELDS:
+            setattr(self, k, None)
+
+    def copy_from_gpu(self):
+        h = self._o.slot_to_host(self._slot)
+        for k in FRAG_FIELDS:
+            setattr(self, k, h[k])
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k in FRAG_FIELDS}
+
+
+def build_contact_lists(sub_coo, W, blacklisted_subs=(), mean_value_trans=0.0):
+    """Upper triangle (row < col) of the prepared sub-level matrix as row-segmented contact lists.
+    Restates sampler.__init__ (cuda_lib_gl.py:153-172): csr + csr.T, diagonal zeroed, the rows and
+    columns of blacklisted sub-frags overwritten with mean_value_trans."""
+    r, c, v = (np.asarray(a) for a in sub_coo)
+    keep = r != c
+    r, c, v = r[keep].astype(np.int64), c[keep].astype(np.int64), v[keep].astype(F32)
+    lo, hi = np.minimum(r, c), np.maximum(r, c)
+    bl = np.unique(np.asarray(list(blacklisted_subs), dtype=np.int64))
+    if bl.size:
+        isb = np.zeros(W, dtype=bool)
+        isb[bl] = True
+        keep = ~(isb[lo] | isb[hi])
+        lo, hi, v = lo[keep], hi[keep], v[keep]
+        al, ah = [], []
+        for s in bl:
+            j = np.arange(W, dtype=np.int64)
+            j = j[(j != s) & ~(isb[j] & (j < s))]          # pairs among blacklisted ones counted once
+            al.append(np.minimum(s, j)); ah.append(np.maximum(s, j))
+        al, ah = np.concatenate(al), np.concatenate(ah)
+        lo = np.concatenate([lo, al]); hi = np.concatenate([hi, ah])
+        v = np.concatenate([v, np.full(al.shape[0], F32(mean_value_trans), dtype=F32)])
+    order = np.lexsort((hi, lo))
+    lo, hi, v = lo[order], hi[order], v[order]
+    nz = v != 0
+    lo, hi, v = lo[nz], hi[nz], v[nz]
+    rowptr = np.zeros(W + 1, dtype=np.int64)
+    np.add.at(rowptr, lo + 1, 1)
+    rowptr = np.cumsum(rowptr)
+    contacts = np.empty((lo.shape[0], 2), dtype=I32)
+    contacts[:, 0] = hi.astype(I32)
+    contacts[:, 1] = v.view(I32)
+    return rowptr, contacts
+
+
+def neighbour_tables(level_coo, N, blacklisted_bins=(), n_neighbors=10):
+    """setup_distri_frags (cuda_lib_gl.py:2363-2390) from the sparse LEVEL matrix: for every bin the
+    10 columns of its row with the largest contact counts (reversed argsort; ties are DEFINED by a
+    stable sort, i.e. equal values come in decreasing column order) and p ~ v**3 (uniform when the
+    row is empty)."""
+    r, c, v = (np.asarray(a) for a in level_coo)
+    keep = r != c
+    r, c, v = r[keep].astype(np.int64), c[keep].astype(np.int64), v[keep].astype(F32)
+    rows = np.concatenate([r, c]); cols = np.concatenate([c, r]); vals = np.concatenate([v, v])
+    if len(blacklisted_bins):
+        isb = np.zeros(N, dtype=bool)
+        isb[np.asarray(list(blacklisted_bins), dtype=np.int64)] = True
+        keep = ~(isb[rows] | isb[cols])
+        rows, cols, vals = rows[keep], cols[keep], vals[keep]
+    keep = vals != 0
+    rows, cols, vals = rows[keep], cols[keep], vals[keep]
+    order = np.lexsort((-cols, -vals.astype(np.float64), rows))
+    rows, cols, vals = rows[order], cols[order], vals[order]
+    start = np.searchsorted(rows, np.arange(N), side="left")
+    end = np.searchsorted(rows, np.arange(N), side="right")
+    xk = np.zeros((N, n_neighbors), dtype=I32)
+    pk = np.zeros((N, n_neighbors), dtype=F32)
+    nn = min(n_neighbors, N)
+    for i in range(N):
+        k = min(end[i] - start[i], nn)
+        x = cols[start[i]:start[i] + k]
+        val = vals[start[i]:start[i] + k]
+        if k < nn:          # pad with zero-valued columns: largest indices first (reversed stable argsort)
+            have = set(int(a) for a in cols[start[i]:end[i]])
+            pad, j = [], N - 1
+            while len(pad) < nn - k and j >= 0:
+                if j not in have:
+                    pad.append(j)
+                j -= 1
+            x = np.concatenate([x, np.array(pad, dtype=np.int64)])
+            val = np.concatenate([val, np.zeros(len(pad), dtype=F32)])
+        dat = val.astype(F32) ** 3
+        if dat.sum() > 0:
+            p = dat / dat.sum()
+        else:
+            tmp = np.ones_like(dat, dtype=F32)
+            p = tmp / tmp.sum()
+        xk[i, :nn] = x
+        pk[i, :nn] = p
+    return xk[:, :nn], pk[:, :nn]
+
+
+def dist_inter_genome(prev, next_, ori, id_d, init_prev, init_next, init_ori, init_orientable,
+                      blacklisted, is_repeat, n_new_frags, n_frags_4_dist):
+    """Normalised neighbour / orientation distance to the initial genome (cuda_lib_gl.py:475-541),
+    vectorised over bins (the reference loops in Python)."""
+    n = int(n_new_frags)
+    norm_distance = 3.0 * (n - n_frags_4_dist)
+    keep = ~np.asarray(is_repeat, dtype=bool)
+    if len(blacklisted):
+        keep = keep.copy()
+        keep[np.asarray(list(blacklisted), dtype=np.int64)] = False
+    f = np.nonzero(keep)[0]
+    p0, n0 = init_prev[f], init_next[f]
+    tp, tn = prev[f], next_[f]
+    p1 = np.where(tp != -1, id_d[np.maximum(tp, 0)], tp)
+    n1 = np.where(tn != -1, id_d[np.maximum(tn, 0)], tn)
+    d = np.full(f.shape[0], 3.0)
+    d -= ((p1 == p0) & (n1 == n0)) | ((p1 == n0) & (n1 == p0))
+    orientable = init_orientable[f] == 1
+    flipped = orientable & (init_ori[f] != ori[f])
+    swap = np.where(flipped, -1, 1)
+    p1s, n1s = np.where(flipped, n1, p1), np.where(flipped, p1, n1)
+
+    def side(t0, t1):
+        same = t0 == t1
+        end = same & (t0 == -1)
+        t1c = np.maximum(t1, 0)
+        rigid = same & ~end & (init_orientable[t1c] == 0)
+        soft = same & ~end & ~rigid
+        agree = soft & (init_ori[np.maximum(t0, 0)] == swap * ori[t1c])
+        return 1.0 * end + 1.0 * rigid + 0.5 * soft + 0.5 * agree
+    d -= np.where(orientable, side(p0, p1s) + side(n0, n1s),
+                  1.0 * ((p1 == p0) | (p1 == n0)) + 1.0 * ((n1 == n0) | (n1 == p0)))
+    return float(d.sum()) / norm_distance if norm_distance != 0 else 0.0
+
+
+class sampler:
+    def __init__(self, use_rippe, S_o_A_frags, collector_id_repeats, frag_dispatcher,
+                 id_frag_duplicated, id_frags_blacklisted,
+                 n_frags, n_new_frags, init_n_sub_frags, n_new_sub_frags, np_rep_sub_frags_id,
+                 hic_matrix_sub_sampled,
+                 np_sub_frags_len_bp, np_sub_frags_id, np_sub_frags_accu,
+                 mean_squared_frags_per_bin, norm_vect_accu,
+                 S_o_A_sub_frags,
+                 hic_matrix, mean_value_trans, n_iterations=0, is_simu=False,
+                 device=0, rng=None, sub_sample_factor=0):
+        """Arguments as in cuda_lib_gl.py:33-42 without the GL objects.  ``hic_matrix_sub_sampled``
+        (current level) and ``hic_matrix`` (sub level) are upper-triangle COO triples
+        (rows, cols, counts) instead of dense arrays.  ``rng``: np.random.RandomState (default: the
+        global np.random module, as the reference)."""
+        if not use_rippe:
+            raise GraalError("only the Rippe model exists (kernels4.cu is not part of the reference tree)")
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise GraalError("no CUDA device: graal_b200 has no CPU path")
+        self.lib = _lib.load()
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        self.rng = np.random if rng is None else rng
+        self.o = 0
+        self.use_rippe = use_rippe
+        self.n_tmp_struct = self.n_modif_metropolis = N_TMP_STRUCT
+        self.modification_str = MODIFICATION_STR
+        self.n_iterations = n_iterations
+        self.is_simu = is_simu
+        self.id_frags_blacklisted = list(id_frags_blacklisted)
+        self.id_frag_duplicated = id_frag_duplicated
+        self.np_id_frag_duplicated = np.asarray(id_frag_duplicated, dtype=I32)
+        self.n_frags, self.n_new_frags = I32(n_frags), I32(n_new_frags)
+        self.init_n_sub_frags, self.n_new_sub_frags = I32(init_n_sub_frags), I32(n_new_sub_frags)
+        self.uniq_frags = np.setdiff1d(np.arange(n_frags, dtype=I32), self.np_id_frag_duplicated).astype(I32)
+        self.n_frags_uniq = I32(len(self.uniq_frags))
+        self.collector_id_repeats = np.asarray(collector_id_repeats, dtype=I32)
+        self.frag_dispatcher = np.asarray(frag_dispatcher, dtype=I32).reshape(-1, 2)
+        self.S_o_A_frags, self.S_o_A_sub_frags = S_o_A_frags, S_o_A_sub_frags
+        self.mean_value_trans = mean_value_trans
+        self.np_sub_frags_len_bp = np.ascontiguousarray(np_sub_frags_len_bp, dtype=F32).reshape(-1, 3)
+        self.np_sub_frags_id = np.ascontiguousarray(np_sub_frags_id, dtype=I32).reshape(-1, 4)
+        self.np_sub_frags_accu = np.ascontiguousarray(np_sub_frags_accu, dtype=I32).reshape(-1, 3)
+        self.mean_squared_frags_per_bin = F32(mean_squared_frags_per_bin)
+        self.norm_vect_accu = norm_vect_accu
+        n = int(n_new_frags)
+        # ---- sub-level matrix -> contact lists (cuda_lib_gl.py:153-172, 194)
+        black_subs = []
+        for f in self.id_frags_blacklisted:
+            da = self.np_sub_frags_id[S_o_A_frags["id_d"][f]]
+            black_subs.extend(int(da[k]) for k in range(da[3]))
+        rowptr, contacts = build_contact_lists(hic_matrix, int(init_n_sub_frags), black_subs, mean_value_trans)
+        self.n_contacts = int(contacts.shape[0])
+        self.max_obs = float(contacts[:, 1].view(F32).max()) if self.n_contacts else 0.0
+        # ---- proposal tables (cuda_lib_gl.py:444-445)
+        self.n_neighbors = 10
+        black_bins = [int(S_o_A_frags["id_d"][f]) for f in self.id_frags_blacklisted]
+        self.distri_xk, self.distri_pk = neighbour_tables(hic_matrix_sub_sampled, int(n_frags), black_bins, self.n_neighbors)
+        # ---- device buffers (torch owns them)
+        dev = self.device
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self.d_sub_id, self.d_sub_len, self.d_sub_accu = t(self.np_sub_frags_id), t(self.np_sub_frags_len_bp), t(self.np_sub_frags_accu)
+        self.d_collector, self.d_dispatcher = t(self.collector_id_repeats), t(self.frag_dispatcher)
+        self.d_rowptr, self.d_contacts = t(rowptr), t(contacts)
+        self.ld = (n + 31) // 32 * 32
+        self.n_slots = 1 + N_TMP_STRUCT
+        host = np.zeros((self.n_slots, len(FRAG_FIELDS), self.ld), dtype=I32)
+        for fi, k in enumerate(FRAG_FIELDS):
+            host[CUR, fi, :n] = np.ones(n, dtype=I32) if k == "ori" else np.asarray(S_o_A_frags[k], dtype=I32)   # Q5
+        host[CAND0:, FRAG_FIELDS.index("ori"), :] = 1           # collector initial content (cuda_lib_gl.py:269-287)
+        host[CAND0:, FRAG_FIELDS.index("activ"), :] = 1
+        self.d_slots = t(host)
+        self.d_out = torch.zeros(64 + 16 * N_TMP_STRUCT, dtype=torch.float64, device=dev)   # [0] full, [1] test, [4:8] stats, [16:] deltas
+        self.d_max_id = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.h_out = torch.zeros_like(self.d_out, device="cpu").pin_memory()
+        # ---- context
+        ctx = C.c_void_p()
+        check(self.lib.graal_ctx_create(device, C.byref(ctx)))
+        self.ctx = ctx
+        self.stream = torch.cuda.Stream(device=dev)
+        check(self.lib.graal_set_stream(self.ctx, C.c_void_p(self.stream.cuda_stream)))
+        torch.cuda.synchronize(dev)
+        check(self.lib.graal_level_bind(self.ctx, int(n_frags), n, int(init_n_sub_frags),
+                                        self.d_sub_id.data_ptr(), self.d_sub_len.data_ptr(), self.d_sub_accu.data_ptr(),
+                                        self.d_collector.data_ptr(), self.d_dispatcher.data_ptr(),
+                                        self.d_rowptr.data_ptr(), self.d_contacts.data_ptr(), self.n_contacts,
+                                        float(self.mean_squared_frags_per_bin)))
+        check(self.lib.graal_state_bind(self.ctx, self.d_slots.data_ptr(), self.ld, self.n_slots))
+        # ---- bookkeeping for dist_inter_genome (cuda_lib_gl.py:226-233, 452-469)
+        self.np_init_prev = np.copy(S_o_A_frags['prev'])
+        self.np_init_next = np.copy(S_o_A_frags['next'])
+        self.np_init_ori = np.ones(n, dtype=I32)
+        self.np_init_orientable = (self.np_sub_frags_id[S_o_A_frags['id_d'], 3] > 1).astype(I32)
+        self.h_id_d = np.asarray(S_o_A_frags["id_d"], dtype=I32).copy()      # never modified by any kernel
+        self.gpu_vect_frags = _VectFrags(self, CUR)
+        self.collector_gpu_vect_frags = [_VectFrags(self, CAND0 + k) for k in range(N_TMP_STRUCT)]
+        self.define_repeats()
+        self.param_simu = None
+        self.likelihood_t = None
+        self.score = np.zeros(0)
+        self.delta_scores = np.zeros(0)
+        self.gpu_launches_at_start = self.lib.graal_launch_count(self.ctx)
+
+    @classmethod
+    def from_inputs(cls, inp, device=0, rng=None):
+        """Build from ``graal_b200.level.SamplerInputs`` (what simulation.__init__ assembles)."""
+        return cls(True, inp.S_o_A_frags, inp.collector_id_repeats, inp.frag_dispatcher, inp.id_frag_duplicated,
+                   inp.id_frags_blacklisted, inp.n_frags, inp.n_new_frags, inp.init_n_sub_frags, inp.n_new_sub_frags,
+                   inp.np_rep_sub_frags_id, inp.level_coo, inp.np_sub_frags_len_bp, inp.np_sub_frags_id,
+                   inp.np_sub_frags_accu, inp.mean_squared_frags_per_bin, inp.norm_vect_accu, inp.S_o_A_sub_frags,
+                   inp.sub_coo, inp.mean_value_trans, device=device, rng=rng)
+
+    # ------------------------------------------------------------------ plumbing
+    def sync(self):
+        check(self.lib.graal_sync(self.ctx))
+
+    def _ptr(self, tensor, offset=0):
+        return C.c_void_p(tensor.data_ptr() + offset * tensor.element_size())
+
+    def _fetch(self):
+        """One D2H of the whole output block (pinned), after the stream has drained."""
+        with self.torch.cuda.stream(self.stream):
+            self.h_out.copy_(self.d_out, non_blocking=True)
+        self.stream.synchronize()
+        return self.h_out.numpy()
+
+    def slot_to_host(self, slot):
+        self.sync()
+        n = int(self.n_new_frags)
+        a = self.d_slots[slot, :, :n].cpu().numpy()
+        return {k: a[i].copy() for i, k in enumerate(FRAG_FIELDS)}
+
+    def slot_from_host(self, slot, arrays):
+        n = int(self.n_new_frags)
+        self.sync()
+        for i, k in enumerate(FRAG_FIELDS):
+            self.d_slots[slot, i, :n] = self.torch.from_numpy(np.ascontiguousarray(arrays[k], dtype=I32)).to(self.device)
+        self.torch.cuda.synchronize(self.device)
+        check(self.lib.graal_state_bind(self.ctx, self.d_slots.data_ptr(), self.ld, self.n_slots))   # drops cached geometry
+
+    @property
+    def gpu_launches(self):
+        return int(self.lib.graal_launch_count(self.ctx))
+
+    # ------------------------------------------------------------------ cuda_lib_gl.py:452-469
+    def define_repeats(self):
+        s = self.S_o_A_frags
+        rep_ids = np.unique(np.asarray(s["id_d"])[np.asarray(s["id"]) != np.asarray(s["id_d"])])
+        self.is_repeat = np.isin(s["id_d"], rep_ids)
+        self.n_frags_duplicated = int(self.is_repeat.sum())
+        self.n_frags_4_dist = len(np.unique(list(self.id_frags_blacklisted) + list(np.nonzero(self.is_repeat)[0])))
+
+    def setup_texture(self):
+        """cuda_lib_gl.py:637-665: selects the data matrix; the contact lists are already resident."""
+        self.data = self.d_contacts
+
+    # ------------------------------------------------------------------ parameters
+    def setup_rippe_parameters(self, param, d_max):
+        """cuda_lib_gl.py:1203-1214."""
+        kuhn, lm, slope, d, fact = param
+        kuhn, lm = F32(kuhn), F32(lm)
+        c1 = F32((0.53 * np.power(lm / kuhn, slope)) * np.power(kuhn, -3))
+        return np.array([(kuhn, lm, c1, F32(slope), F32(d), F32(d_max), F32(fact), self.mean_value_trans)], dtype=PARAM_DTYPE)
+
+    def _set_device_params(self, p):
+        arr = (C.c_float * 8)(*[float(x) for x in p[0]])
+        check(self.lib.graal_set_params(self.ctx, arr))
+
+    def set_parameters(self, param, d_max):
+        self.param_simu = self.setup_rippe_parameters(param, d_max)
+        self._set_device_params(self.param_simu)
+
+    def distance_histogram(self, max_dist_kb, size_bin_kb):
+        """Device reduction of the O(W^2) loop of estimate_parameters (cuda_lib_gl.py:1236-1270)."""
+        torch = self.torch
+        bins = np.arange(size_bin_kb, max_dist_kb + size_bin_kb, size_bin_kb)
+        nb = len(bins)
+        sub = self.S_o_A_sub_frags
+        t = lambda k: torch.from_numpy(np.ascontiguousarray(sub[k], dtype=I32)).to(self.device)
+        d_idc, d_st, d_ln, d_pos = t("id_c"), t("start_bp"), t("len_bp"), t("pos")
+        d_sum = torch.zeros(nb, dtype=torch.float64, device=self.device)
+        d_cnt = torch.zeros(nb, dtype=torch.int64, device=self.device)
+        torch.cuda.synchronize(self.device)
+        check(self.lib.graal_dist_histogram(self.ctx, self._ptr(d_idc), self._ptr(d_st), self._ptr(d_ln), self._ptr(d_pos),
+                                            float(max_dist_kb), float(size_bin_kb), nb, self._ptr(d_sum), self._ptr(d_cnt)))
+        self.sync()
+        sums, cnts = d_sum.cpu().numpy(), d_cnt.cpu().numpy()
+        mean = np.full(nb, 1e-10, dtype=F32)
+        ok = (cnts > 0) & (sums > 0)
+        mean[ok] = (sums[ok] / cnts[ok]).astype(F32)
+        return bins, mean, sums, cnts
+
+    def estimate_parameters(self, max_dist_kb, size_bin_kb):
+        """cuda_lib_gl.py:1229-1294."""
+        self.bins, self.mean_contacts, _, _ = self.distance_histogram(max_dist_kb, size_bin_kb)
+        p, self.y_estim = opti.estimate_param_rippe(self.mean_contacts, self.bins)
+        estim_max_dist = opti.estimate_max_dist_intra(p, self.mean_value_trans)
+        self.set_parameters(p, estim_max_dist)
+
+    # ------------------------------------------------------------------ likelihood
+    def eval_likelihood(self, test_params=None):
+        """cuda_lib_gl.py:543-631 (and :1986-2019 with test parameters): full log-likelihood."""
+        arr = None
+        if test_params is not None:
+            arr = (C.c_float * 8)(*[float(x) for x in test_params[0]])
+        check(self.lib.graal_full_loglik(self.ctx, CUR, arr, self._ptr(self.d_out, 0)))
+        return np.float64(self._fetch()[0])
+
+    def init_likelihood(self):
+        self.likelihood_t = self.eval_likelihood()
+
+    def modify_gl_cuda_buffer(self, id_fi=0, dt=0):
+        """cuda_lib_gl.py:1695-1788, structure part only: relabel contig ids, return max_id."""
+        check(self.lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
+        self.sync()
+        return I32(int(self.d_max_id[0].item()))
+
+    relabel_contigs = modify_gl_cuda_buffer
+
+    def perform_modifications(self, id_fA, id_fB, max_id=-1, mask=0x1FFF):
+        """new_perform_modificationS (cuda_lib_gl.py:1045-1048): the 13 candidates into the collector slots."""
+        check(self.lib.graal_build_candidates(self.ctx, CUR, CAND0, int(id_fA), int(id_fB), int(max_id), mask))
+
+    def test_copy_struct(self, id_fA, id_f_sampled, mode, max_id):
+        """cuda_lib_gl.py:1156-1183: rebuild the sampled candidate, commit it to the current slot."""
+        mode = int(mode)
+        mask = (1 << mode) if mode < 9 else 0x1E00
+        self.perform_modifications(id_fA, id_f_sampled, max_id, mask)
+        check(self.lib.graal_commit(self.ctx, CUR, CAND0 + mode))
+
+    def explode_genome(self, dt=0):
+        """cuda_lib_gl.py:1539-1557."""
+        for i in range(int(self.n_new_frags)):
+            check(self.lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
+            self.test_copy_struct(i, 0, 0, -1)
+        self.sync()
+
+    def apply_replay_simu(self, id_fA, id_fB, op_sampled, dt=0):
+        """cuda_lib_gl.py:1559-1578."""
+        check(self.lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
+        self.test_copy_struct(id_fA, id_fB, op_sampled, -1)
+
+    # ------------------------------------------------------------------ proposals
+    def return_neighbours(self, id_fA, delta0):
+        """cuda_lib_gl.py:2295-2331."""
+        ori_id = int(self.h_id_d[id_fA])
+        delta = min(self.n_neighbors, delta0)
+        distri = self.distri_pk[ori_id]
+        n_max_candidates = min(delta, np.nonzero(distri != 0)[0].shape[0])
+        init_id = self.rng.choice(self.distri_xk[ori_id], n_max_candidates, p=distri, replace=False)
+        out = []
+        if ori_id in self.np_id_frag_duplicated:
+            d = self.frag_dispatcher[ori_id]
+            out.extend(np.setdiff1d(self.collector_id_repeats[d[0]:d[1]], id_fA))
+        for id_fB in init_id:
+            d = self.frag_dispatcher[id_fB]
+            out.extend(self.collector_id_repeats[d[0]:d[1]])
+        return [int(e) for e in out if e not in self.id_frags_blacklisted]
+
+    def temperature(self, t, n_step):
+        return 1.0
+
+    def score_neighbours(self, id_fA, id_neighbours):
+        """stream_likelihood (cuda_lib_gl.py:2392-2546) for every neighbour: candidates + deltas, queued
+        on the stream; results land in d_out[16 + 13*x + j]."""
+        for x, id_fB in enumerate(id_neighbours):
+            self.perform_modifications(id_fA, id_fB)
+            check(self.lib.graal_delta_loglik(self.ctx, CUR, CAND0, N_TMP_STRUCT, int(id_fA), int(id_fB), -1,
+                                              self._ptr(self.d_out, 16 + N_TMP_STRUCT * x)))
+
+    def step_max_likelihood(self, id_fA, delta, size_block=512, dt=0, t=0, n_step=1):
+        """cuda_lib_gl.py:1793-1980.  Returns (o, n_contigs, min_len, mean_len_bp, max_len, op_sampled,
+        id_f_sampled, dist, F_t)."""
+        lib = self.lib
+        if id_fA not in self.id_frags_blacklisted:
+            check(lib.graal_state_stats(self.ctx, CUR, self._ptr(self.d_out, 4)))
+            check(lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
+            check(lib.graal_full_loglik(self.ctx, CUR, None, self._ptr(self.d_out, 0)))
+            id_neighbours = self.return_neighbours(id_fA, delta)
+            n_neighbours = len(id_neighbours)
+            if n_neighbours > 16:
+                raise GraalError("more than 16 neighbours in one step")
+            id_neighbours.sort()
+            self.id_neighbours = id_neighbours
+            self.score_neighbours(id_fA, id_neighbours)
+            out = self._fetch()
+            likelihood_t = np.float64(out[0])
+            self.likelihood_t = likelihood_t
+            n_contigs, min_len, mean_len_bp, max_len = int(out[4]), int(out[5]), out[6], int(out[7])
+            self.delta_scores = np.array(out[16:16 + n_neighbours * N_TMP_STRUCT], dtype=np.float64)
+            self.score = self.delta_scores + likelihood_t
+            sample_out = self._sample(self.score, self.temperature(t, n_step))
+            id_f_sampled = id_neighbours[sample_out // N_TMP_STRUCT]
+            op_sampled = sample_out % N_TMP_STRUCT
+            self.test_copy_struct(id_fA, id_f_sampled, op_sampled, -1)
+            o = self.score[sample_out]
+            self.o = o
+        else:
+            o = self.o
+            check(lib.graal_state_stats(self.ctx, CUR, self._ptr(self.d_out, 4)))
+            check(lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
+            out = self._fetch()
+            n_contigs, min_len, mean_len_bp, max_len = int(out[4]), int(out[5]), out[6], int(out[7])
+            op_sampled, id_f_sampled = -1, id_fA
+        F_t = self.temperature(t, n_step)
+        dist = self.dist_inter_genome(self.gpu_vect_frags)
+        self.likelihood_t = o
+        return o, n_contigs, min_len, mean_len_bp, max_len, op_sampled, id_f_sampled, dist, F_t
+
+    def _sample(self, score, F_t):
+        """Candidate filtering and draw (cuda_lib_gl.py:1899-1947)."""
+        nt = N_TMP_STRUCT
+        scores_2_remove = list(range(nt, len(score), nt)) + list(range(nt + 1, len(score), nt))
+        id_max = int(score.argmax())
+        filtered_score = score - score.min()
+        filtered_score[scores_2_remove] = 0
+        max_score = filtered_score.max()
+        thresh_overflow = 30
+        filtered_score = filtered_score - (max_score - thresh_overflow)
+        filtered_score[filtered_score < 0] = 0
+        id_ok = np.nonzero(filtered_score > 0)[0]
+        sub_score = filtered_score[id_ok]
+        with np.errstate(all="ignore"):
+            sub_score = sub_score / sub_score.sum()
+            sub_score[sub_score > 0] = np.power(sub_score[sub_score > 0], 1. / F_t)
+            sub_score = sub_score / sub_score.sum()
+        self.sub_score = sub_score
+        if len(id_ok) <= 1:
+            return id_max
+        return int(self.rng.choice(id_ok, 1, p=sub_score)[0])
+
+    # ------------------------------------------------------------------ cuda_lib_gl.py:2022-2107
+    def step_nuisance_parameters(self, dt=0, t=0, n_step=1):
+        curr_param = np.copy(self.param_simu)
+        kuhn, lm, c1, slope, d, d_max, fact, d_nuc = curr_param[0]
+        self.sigma_fact = 10 ** (np.log10(fact) - 2)
+        self.sigma_slope, self.sigma_d_max, self.sigma_d_nuc = 0.05, 100, 0.5
+        id_modif = self.rng.choice(4)
+        c1f = lambda sl: F32((0.53 * np.power(lm / kuhn, sl)) * np.power(kuhn, -3))
+        if id_modif == 0:
+            new_fact = fact + self.rng.normal(loc=0.0, scale=self.sigma_fact)
+            new_d_max = opti.estimate_max_dist_intra([kuhn, lm, slope, d, new_fact], d_nuc)
+            out_test_param = [(kuhn, lm, c1f(slope), slope, d, new_d_max, new_fact, d_nuc)]
+        elif id_modif == 1:
+            new_slope = slope + self.rng.normal(loc=0.0, scale=self.sigma_slope)
+            new_d_max = opti.estimate_max_dist_intra([kuhn, lm, new_slope, d, fact], d_nuc)
+            out_test_param = [(kuhn, lm, c1f(new_slope), new_slope, d, new_d_max, fact, d_nuc)]
+        elif id_modif == 2:
+            new_d_max = d_max + self.rng.normal(loc=0.0, scale=self.sigma_d_max)
+            new_d_nuc = opti.peval(new_d_max, [kuhn, lm, slope, d, fact])
+            out_test_param = [(kuhn, lm, c1f(slope), slope, d, new_d_max, fact, new_d_nuc)]
+        else:
+            new_d_nuc = d_nuc + self.rng.normal(loc=0.0, scale=self.sigma_d_nuc)
+            new_d_max = opti.estimate_max_dist_intra([kuhn, lm, slope, d, fact], new_d_nuc)
+            out_test_param = [(kuhn, lm, c1f(slope), slope, d, new_d_max, fact, new_d_nuc)]
+        out_test_param = np.array(out_test_param, dtype=PARAM_DTYPE)
+        test_likelihood = self.eval_likelihood(out_test_param)
+        F_t = self.temperature(t, n_step)
+        with np.errstate(over="ignore"):
+            ratio = np.exp((test_likelihood - self.likelihood_t) / F_t)
+        u = self.rng.rand()
+        success = 0
+        if ratio >= u:
+            success = 1
+            self.param_simu = out_test_param
+            self._set_device_params(self.param_simu)
+            self.likelihood_t = test_likelihood
+        kuhn, lm, c1, slope, d, d_max, fact, d_nuc = self.param_simu[0]
+        y_rippe = opti.peval(self.bins, [kuhn, lm, slope, d, fact]) if hasattr(self, "bins") else None
+        return fact, d, d_max, d_nuc, slope, self.likelihood_t, success, y_rippe
+
+    # ------------------------------------------------------------------ cuda_lib_gl.py:475-541
+    def dist_inter_genome(self, tmp_gpu_vect_frags):
+        tmp_gpu_vect_frags.copy_from_gpu()
+        g1 = tmp_gpu_vect_frags
+        return dist_inter_genome(g1.prev, g1.next, g1.ori, g1.id_d, self.np_init_prev, self.np_init_next,
+                                 self.np_init_ori, self.np_init_orientable, self.id_frags_blacklisted,
+                                 self.is_repeat, int(self.n_new_frags), self.n_frags_4_dist)
+
+    def genome_content(self):
+        """Contigs of the current genome as lists of (bin id, orientation), in position order."""
+        self.gpu_vect_frags.copy_from_gpu()
+        c = self.gpu_vect_frags
+        out = {}
+        for cid in np.unique(c.id_c):
+            m = np.nonzero(c.id_c == cid)[0]
+            m = m[np.argsort(c.pos[m], kind="stable")]
+            out[int(cid)] = [(int(i), int(c.ori[i])) for i in m]
+        return out
+
+    def free_gpu(self):
+        """cuda_lib_gl.py:2605-2613."""
+        if getattr(self, "ctx", None) is not None:
+            self.lib.graal_ctx_destroy(self.ctx)
+            self.ctx = None
+        for k in [a for a in vars(self) if a.startswith("d_")]:
+            setattr(self, k, None)
+
+    def __del__(self):
+        try:
+            self.free_gpu()
+        except Exception:
+            pass

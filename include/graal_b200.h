@@ -1,0 +1,130 @@
+/*
+ * graal_b200 -- C-ABI of the B200-native GRAAL MCMC scoring path.
+ *
+ * Drop-in boundary: today this path sits behind PyCUDA function handles obtained with
+ * module.get_function(name) (reference cuda_lib_gl.py:378-402) and launched with raw device
+ * pointers.  Every entry point below names the reference kernel(s) / host routine it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative code on error; the message is available
+ *     through graal_last_error() (thread-local).  No exceptions or C++ types cross the ABI.
+ *   - all bulk buffers are caller-owned DEVICE pointers (torch tensors on the Python side); the
+ *     library owns only its scratch (geometry tables, partial sums, derived level tables).
+ *   - a context is bound to one GPU and one CUDA stream and must be used from one thread at a time
+ *     (the reference owns its CUDA context from a single Python thread, main_gl.py:690-706).
+ *   - results written to device pointers are valid after the context's stream is synchronised.
+ *
+ * State layout ("slots"): the reference keeps the genome in a struct of 14 int* (kernels3.cu:9-24,
+ * packed by gpustruct.py).  Here a slot is one SoA block of 14 x ld int32, field f of slot s at
+ * base + (s*14 + f)*ld, field order = GRAAL_F_* below (same order as the reference struct).
+ */
+#ifndef GRAAL_B200_H
+#define GRAAL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct graal_ctx graal_ctx;
+
+enum {
+    GRAAL_F_POS = 0, GRAAL_F_ID_C, GRAAL_F_START_BP, GRAAL_F_LEN_BP, GRAAL_F_CIRC, GRAAL_F_ID,
+    GRAAL_F_PREV, GRAAL_F_NEXT, GRAAL_F_L_CONT, GRAAL_F_L_CONT_BP, GRAAL_F_ORI, GRAAL_F_REP,
+    GRAAL_F_ACTIV, GRAAL_F_ID_D, GRAAL_N_FIELDS
+};
+
+/* single structure mutations (graal_apply_move); aux = orientation (+1/-1) or `upstream` flag */
+enum {
+    GRAAL_OP_COPY = 0,      /* simple_copy          kernels3.cu:3755-3774 */
+    GRAAL_OP_FLIP,          /* flip_frag            kernels3.cu:239-279   */
+    GRAAL_OP_SWAP_ACTIV,    /* swap_activity_frag   kernels3.cu:283-326   */
+    GRAAL_OP_POP_OUT,       /* pop_out_frag         kernels3.cu:329-563   */
+    GRAAL_OP_POP_IN_1,      /* pop_in_frag_1        kernels3.cu:565-812   */
+    GRAAL_OP_POP_IN_2,      /* pop_in_frag_2        kernels3.cu:814-1079  */
+    GRAAL_OP_POP_IN_3,      /* pop_in_frag_3        kernels3.cu:1081-1265 */
+    GRAAL_OP_POP_IN_4,      /* pop_in_frag_4        kernels3.cu:1267-1448 */
+    GRAAL_OP_SPLIT,         /* split_contig         kernels3.cu:1451-1784 */
+    GRAAL_OP_PASTE,         /* paste_contigs        kernels3.cu:1786-2070 */
+    GRAAL_N_OPS
+};
+
+#define GRAAL_N_CANDIDATES 13   /* n_tmp_struct, cuda_lib_gl.py:111-112 */
+
+/* ---- context -------------------------------------------------------------------------------- */
+int  graal_ctx_create(int device, graal_ctx** out);
+void graal_ctx_destroy(graal_ctx* ctx);
+const char* graal_last_error(void);
+int  graal_set_stream(graal_ctx* ctx, void* cuda_stream);       /* cudaStream_t; default: own stream */
+int  graal_sync(graal_ctx* ctx);
+const char* graal_version(void);
+
+/* ---- level (read-only inputs of the likelihood kernels) ---------------------------------------
+ * Replaces the uploads of sampler.__init__ (cuda_lib_gl.py:123-130, 194, 210-215): collector_id,
+ * dispatcher (int2[N]), id_sub_frags (int4[N]: 3 sub ids + count), len_bp_sub_frags (float3[N], kb),
+ * accu_sub_frags (int3[N]) and the DENSE obsData2D, which becomes the upper triangle (row < col) of
+ * the same symmetric, zero-diagonal matrix as row-segmented contact lists:
+ * rowptr int64[W+1], contacts = E records {int32 col, float32 count}.
+ * nfpb = mean_squared_frags_per_bin (simulation_loader.py:73). */
+int graal_level_bind(graal_ctx* ctx, int n_frags, int n_new_frags, int n_sub_frags,
+                     const int32_t* sub_id, const float* sub_len_kb, const int32_t* sub_accu,
+                     const int32_t* collector, const int32_t* dispatcher,
+                     const int64_t* rowptr, const void* contacts, int64_t n_contacts, float nfpb);
+
+/* param_simu (kernels3.cu:26-35): kuhn, lm, c1, slope, d, d_max, fact, v_inter */
+int graal_set_params(graal_ctx* ctx, const float p[8]);
+
+/* ---- state ---------------------------------------------------------------------------------- */
+int graal_state_bind(graal_ctx* ctx, int32_t* slots_base, int ld, int n_slots);
+
+/* relabel side effect of gl_update_pos (kernels3.cu:3848-3851) + host map of modify_gl_cuda_buffer
+ * (cuda_lib_gl.py:1697-1722): ids become 0..n_contigs-1 by increasing contig length, ties by old id.
+ * d_max_id (device int32, may be NULL) receives n_contigs-1; also kept inside the context. */
+int graal_relabel_contigs(graal_ctx* ctx, int slot, int32_t* d_max_id);
+
+/* one mutation kernel, src_slot -> dst_slot (persistent destination: unwritten bins keep their
+ * content).  d_max_id_out (device int32, may be NULL) receives max(id_c) of the destination, i.e. the
+ * ga.max(...) that follows pop_out / split in the reference (cuda_lib_gl.py:857,934,943). */
+int graal_apply_move(graal_ctx* ctx, int src_slot, int dst_slot, int op, int id_fA, int id_fB,
+                     int aux, int max_id_in, int32_t* d_max_id_out);
+
+/* fused new_perform_modificationS (cuda_lib_gl.py:841-954,1045-1048): the 13 candidate structures of
+ * (id_fA, id_fB) from src_slot into slots first_dst_slot .. first_dst_slot+12; bit m of mode_mask
+ * enables candidate m.  max_id < 0: use the value left by the last graal_relabel_contigs. */
+int graal_build_candidates(graal_ctx* ctx, int src_slot, int first_dst_slot, int id_fA, int id_fB,
+                           int max_id, unsigned mode_mask);
+
+/* copy_struct (kernels3.cu:3720-3742): commit slot src into slot dst. */
+int graal_commit(graal_ctx* ctx, int dst_slot, int src_slot);
+
+/* evaluate_likelihood (kernels3.cu:2802-3222) + ga.sum (cuda_lib_gl.py:629,1848): full
+ * log-likelihood of a slot -> d_out[0] (device double).  p_override (host, 8 floats, may be NULL)
+ * evaluates with test parameters (compute_likelihood_4_nuisance, cuda_lib_gl.py:1986-2019). */
+int graal_full_loglik(graal_ctx* ctx, int slot, const float* p_override, double* d_out);
+
+/* fill_sub_index_fA/fB (kernels3.cu:3225-3249) + sub_compute_likelihood (kernels3.cu:3259-3718)
+ * for n_cand candidate slots against base_slot -> d_out[n_cand] (device doubles).
+ * max_id: max(id_c) of base_slot (< 0: the value left by the last graal_relabel_contigs). */
+int graal_delta_loglik(graal_ctx* ctx, int base_slot, int first_cand_slot, int n_cand,
+                       int id_fA, int id_fB, int max_id, double* d_out);
+
+/* per-step statistics of step_max_likelihood (cuda_lib_gl.py:1809-1816) -> d_out[4] (device doubles):
+ * n_contigs, min l_cont, mean l_cont_bp over contig heads, max l_cont. */
+int graal_state_stats(graal_ctx* ctx, int slot, double* d_out);
+
+/* distance histogram of estimate_parameters (cuda_lib_gl.py:1236-1270) on the INITIAL sub-level
+ * layout: for cis sub-frag pairs with mid-to-mid distance d < max_dist_kb, bin int(d/bin_kb):
+ * d_sum[b] += contacts (zeros included through d_cnt), d_cnt[b] += 1.
+ * sub_id_c / sub_start_bp / sub_len_bp / sub_pos: int32[W] device arrays (S_o_A_sub_frags). */
+int graal_dist_histogram(graal_ctx* ctx, const int32_t* sub_id_c, const int32_t* sub_start_bp,
+                         const int32_t* sub_len_bp, const int32_t* sub_pos,
+                         double max_dist_kb, double bin_kb, int n_bins, double* d_sum, int64_t* d_cnt);
+
+/* instrumentation: number of kernel launches issued by this context so far */
+int64_t graal_launch_count(graal_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
