@@ -666,7 +666,40 @@ k_dist_hist(const long long* __restrict__ rowptr, const int2* __restrict__ conta
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
+// per-kernel device timers (CUDA event pairs on the context's stream), enabled on demand
+#define PROF_KERNELS 8
+#define PROF_RING 4096
+struct Profiler {
+    bool on = false;
+    std::vector<cudaEvent_t> ev[PROF_KERNELS];      // 2 * PROF_RING events per kernel id, created lazily
+    int head[PROF_KERNELS] = {0}, pending[PROF_KERNELS] = {0};
+    double total_ms[PROF_KERNELS] = {0};
+    long long count[PROF_KERNELS] = {0};
+    void resolve(int k) {
+        for (int i = 0; i < pending[k]; i++) {
+            const int slot = (head[k] - pending[k] + i + PROF_RING) % PROF_RING;
+            float ms = 0.f;
+            cudaEventSynchronize(ev[k][2 * slot + 1]);
+            if (cudaEventElapsedTime(&ms, ev[k][2 * slot], ev[k][2 * slot + 1]) == cudaSuccess) { total_ms[k] += ms; count[k]++; }
+        }
+        pending[k] = 0;
+    }
+    void begin(int k, cudaStream_t st) {
+        if (!on) return;
+        if (ev[k].empty()) { ev[k].resize(2 * PROF_RING); for (auto& e : ev[k]) cudaEventCreate(&e); }
+        if (pending[k] == PROF_RING) resolve(k);
+        cudaEventRecord(ev[k][2 * head[k]], st);
+    }
+    void end(int k, cudaStream_t st) {
+        if (!on) return;
+        cudaEventRecord(ev[k][2 * head[k] + 1], st);
+        head[k] = (head[k] + 1) % PROF_RING; pending[k]++;
+    }
+    void destroy() { for (int k = 0; k < PROF_KERNELS; k++) { for (auto& e : ev[k]) cudaEventDestroy(e); ev[k].clear(); } }
+};
+
 struct graal_ctx {
+    Profiler prof;
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -760,6 +793,7 @@ void graal_ctx_destroy(graal_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_level_scratch(c);
+    c->prof.destroy();
     cudaFree(c->d_ints); cudaFree(c->d_stats); cudaFree(c->d_scalars); cudaFree(c->partials);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -773,6 +807,25 @@ int graal_set_stream(graal_ctx* c, void* s) {
 }
 int graal_sync(graal_ctx* c) { if (!c) return set_err(-1, "null context"); CUDA_OK(cudaStreamSynchronize(c->stream)); return 0; }
 int64_t graal_launch_count(graal_ctx* c) { return c ? c->launches : -1; }
+
+int graal_profile_enable(graal_ctx* c, int on) {
+    if (!c) return set_err(-1, "null context");
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < PROF_KERNELS; k++) { c->prof.resolve(k); }
+    c->prof.on = on != 0;
+    return 0;
+}
+int graal_profile_read(graal_ctx* c, int kernel_id, double* total_ms, int64_t* count, int reset) {
+    if (!c || kernel_id < 0 || kernel_id >= PROF_KERNELS) return set_err(-1, "bad profile query");
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->prof.resolve(kernel_id);
+    if (total_ms) *total_ms = c->prof.total_ms[kernel_id];
+    if (count) *count = c->prof.count[kernel_id];
+    if (reset) { c->prof.total_ms[kernel_id] = 0; c->prof.count[kernel_id] = 0; }
+    return 0;
+}
 
 int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags,
                      const int32_t* sub_id, const float* sub_len_kb, const int32_t* sub_accu,
@@ -877,6 +930,7 @@ int graal_relabel_contigs(graal_ctx* c, int slot, int32_t* d_max_id) {
     const int n = c->n_new, cap = c->cap, ld = c->ld;
     int* s = slot_ptr(c, slot);
     cudaStream_t st = c->stream;
+    c->prof.begin(GRAAL_K_RELABEL, st);
     k_fill_int<<<nblk(cap, 256), 256, 0, st>>>(c->first_idx, cap, INT_MAX); CHECK_LAUNCH(c);
     k_first_index<<<nblk(n, 256), 256, 0, st>>>(s + F_ID_C * ld, n, cap, c->first_idx, c->d_ints + 2); CHECK_LAUNCH(c);
     k_relabel_keys<<<nblk(cap, 256), 256, 0, st>>>(c->first_idx, s + F_L_CONT * ld, cap, c->keys); CHECK_LAUNCH(c);
@@ -884,6 +938,7 @@ int graal_relabel_contigs(graal_ctx* c, int slot, int32_t* d_max_id) {
     CUDA_OK(cub::DeviceRadixSort::SortKeys(c->cub_tmp, tb, c->keys, c->keys_sorted, cap, 0, 64, st)); c->launches += 8;
     k_relabel_map<<<nblk(cap, 256), 256, 0, st>>>(c->keys_sorted, cap, c->map, c->d_ints + 1); CHECK_LAUNCH(c);
     k_relabel_apply<<<nblk(n, 256), 256, 0, st>>>(s + F_ID_C * ld, n, c->map, c->d_ints + 1, c->d_ints + 0, d_max_id); CHECK_LAUNCH(c);
+    c->prof.end(GRAAL_K_RELABEL, st);
     if (c->geo_base_slot == slot) c->geo_base_slot = -1;
     return 0;
 }
@@ -911,9 +966,11 @@ int graal_build_candidates(graal_ctx* c, int src_slot, int first_dst_slot, int i
     const int n = c->n_new;
     if (id_fA < 0 || id_fA >= n || id_fB < 0 || id_fB >= n) return set_err(-1, "bin id out of range");
     if (src_slot >= first_dst_slot && src_slot < first_dst_slot + GRAAL_N_CANDIDATES) return set_err(-1, "source slot inside the destination range");
+    c->prof.begin(GRAAL_K_BUILD, c->stream);
     k_build_candidates<<<nblk(n, 128), 128, 0, c->stream>>>(slot_ptr(c, src_slot), slot_ptr(c, first_dst_slot), slot_stride(c), c->ld, n,
                                                            id_fA, id_fB, c->d_ints + 0, max_id, mask & 0x1FFFu);
     CHECK_LAUNCH(c);
+    c->prof.end(GRAAL_K_BUILD, c->stream);
     if (c->geo_base_slot >= first_dst_slot && c->geo_base_slot < first_dst_slot + GRAAL_N_CANDIDATES) c->geo_base_slot = -1;
     return 0;
 }
@@ -960,12 +1017,16 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
     const double init = -(c->lf_total + g0);
     k_set_double<<<1, 1, 0, st>>>(d_out, init); CHECK_LAUNCH(c);
     if (g1 > 0) {
+        c->prof.begin(GRAAL_K_FULL_CONTACTS, st);
         k_full_contacts<<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->W, c->geo_base, p, c->partials); CHECK_LAUNCH(c);
+        c->prof.end(GRAAL_K_FULL_CONTACTS, st);
         k_reduce_partials<<<1, 256, 0, st>>>(c->partials, g1, 0, 1.0, d_out, 1); CHECK_LAUNCH(c);
     }
     const int g2 = std::min(ps, nblk(n, 8));
+    c->prof.begin(GRAAL_K_FULL_BAND, st);
     k_band<false><<<dim3(g2, 1), 256, 0, st>>>(c->order, nullptr, n, s, ld, c->lv, c->geo_base, nullptr, 0, 0, 0, 0, p,
                                               c->partials + (size_t)1 * ps, ps); CHECK_LAUNCH(c);
+    c->prof.end(GRAAL_K_FULL_BAND, st);
     k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)1 * ps, g2, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
     if (c->n_quirky > 0) {
         if (c->n_quirky > ps) return set_err(-5, "too many quirky bins (%d > %d)", c->n_quirky, ps);
@@ -1000,16 +1061,20 @@ int graal_delta_loglik(graal_ctx* c, int base_slot, int first_cand_slot, int n_c
     k_cand_order<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->sub_index, meta, piece_len, c->cand_order, n); CHECK_LAUNCH(c);
     const int gw = std::min(ps, std::max(1, nblk(n, 8)));
     // contacts: + sum over changed contacts of ob*(log ex_k - log ex_0)
+    c->prof.begin(GRAAL_K_DELTA_CONTACTS, st);
     k_delta_contacts<<<dim3(gw, n_cand), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, c->sub_index, meta, c->geo_base, c->geo_cand, (size_t)c->W,
                                                       p, c->partials, ps); CHECK_LAUNCH(c);
+    c->prof.end(GRAAL_K_DELTA_CONTACTS, st);
     k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, 1.0, d_out, 0); CHECK_LAUNCH(c);
     // band mass: - [B_U(S_k) - B_U(S_0)] over changed pairs
+    c->prof.begin(GRAAL_K_DELTA_BAND, st);
     k_band<true><<<dim3(gw, n_cand), 256, 0, st>>>(c->cand_order, meta + 4, -1, cand0, ld, c->lv, c->geo_cand, c->geo_base, (size_t)c->W, slot_stride(c), n, 1, p,
                                                   c->partials, ps); CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, -1.0, d_out, 1); CHECK_LAUNCH(c);
     k_band<true><<<dim3(gw, n_cand), 256, 0, st>>>(c->sub_index, meta + 4, -1, base, ld, c->lv, c->geo_base, c->geo_cand, (size_t)c->W, 0, 0, 0, p,
                                                   c->partials, ps); CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, 1.0, d_out, 1); CHECK_LAUNCH(c);
+    c->prof.end(GRAAL_K_DELTA_BAND, st);
     if (c->n_quirky > 0) {
         // quirk mass: - [Q_U(S_k) - Q_U(S_0)]
         k_quirk<<<dim3(c->n_quirky, n_cand), 256, 0, st>>>(c->d_quirky, c->n_quirky, cand0, ld, n, slot_stride(c), c->lv, c->sub_index, meta + 4, p,

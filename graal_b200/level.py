@@ -210,8 +210,9 @@ def yeast_shaped_pyramid(n_frags0=5000, total_bp=12_000_000, n_levels=4, **kw):
 
 
 def treesei_shaped_pyramid(n_frags0=100_000, total_bp=33_000_000, n_contigs=77, n_levels=6,
-                           seed=20141217, cis_rowsum=400.0, v_inter=0.002, **kw):
-    """BASELINE config C2: 77 contigs with log-normal lengths."""
+                           seed=20141217, cis_rowsum=400.0, v_inter=0.004, **kw):
+    """BASELINE config C2: 77 contigs with log-normal lengths; ~30 M distinct level-0 contact
+    entries (240 MB of contact lists: larger than the 126 MB L2)."""
     rs = np.random.RandomState(seed + 7)
     w = rs.lognormal(mean=0.0, sigma=1.0, size=n_contigs)
     bp = np.maximum(20_000, np.round(w / w.sum() * total_bp))

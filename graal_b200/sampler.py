@@ -36,6 +36,16 @@ MODIFICATION_STR = ['eject frag', 'flip frag',
                     'local_scramble d1', 'local_scramble d2', 'local_scramble d3', 'local_scramble d4']
 
 
+def rippe_c1(kuhn, lm, slope):
+    """c1 = float32(0.53 * (lm/kuhn)**slope * kuhn**-3) (cuda_lib_gl.py:1208) under the NumPy 1.x
+    promotion rules the reference ran with: float32 ** float32 is float32 (nuisance step, slope read
+    back from the float32 record), float32 ** float64 / python float is float64 (fit output)."""
+    kuhn, lm = F32(kuhn), F32(lm)
+    ratio = lm / kuhn
+    pw = np.power(ratio, slope) if isinstance(slope, np.float32) else np.power(np.float64(ratio), np.float64(slope))
+    return F32((0.53 * np.float64(pw)) * np.float64(np.power(kuhn, F32(-3))))
+
+
 def _torch():
     import torch
     return torch
@@ -337,7 +347,7 @@ class sampler:
         """cuda_lib_gl.py:1203-1214."""
         kuhn, lm, slope, d, fact = param
         kuhn, lm = F32(kuhn), F32(lm)
-        c1 = F32((0.53 * np.power(lm / kuhn, slope)) * np.power(kuhn, -3))
+        c1 = rippe_c1(kuhn, lm, slope)
         return np.array([(kuhn, lm, c1, F32(slope), F32(d), F32(d_max), F32(fact), self.mean_value_trans)], dtype=PARAM_DTYPE)
 
     def _set_device_params(self, p):
@@ -398,6 +408,14 @@ class sampler:
     def perform_modifications(self, id_fA, id_fB, max_id=-1, mask=0x1FFF):
         """new_perform_modificationS (cuda_lib_gl.py:1045-1048): the 13 candidates into the collector slots."""
         check(self.lib.graal_build_candidates(self.ctx, CUR, CAND0, int(id_fA), int(id_fB), int(max_id), mask))
+
+    def apply_move(self, src_slot, dst_slot, op, id_fA, id_fB=0, aux=0, max_id=0):
+        """One mutation kernel of the reference (``op`` = name in _lib.OPS) between two slots; returns
+        max(id_c) of the destination (the ga.max that follows pop_out / split, cuda_lib_gl.py:857,934)."""
+        check(self.lib.graal_apply_move(self.ctx, int(src_slot), int(dst_slot), _lib.OPS[op], int(id_fA), int(id_fB),
+                                        int(aux), int(max_id), self._ptr(self.d_max_id, 1)))
+        self.sync()
+        return int(self.d_max_id[1].item())
 
     def test_copy_struct(self, id_fA, id_f_sampled, mode, max_id):
         """cuda_lib_gl.py:1156-1183: rebuild the sampled candidate, commit it to the current slot."""
@@ -485,6 +503,19 @@ class sampler:
         self.likelihood_t = o
         return o, n_contigs, min_len, mean_len_bp, max_len, op_sampled, id_f_sampled, dist, F_t
 
+    def step_device(self, id_fA, id_neighbours, id_f_sampled, op_sampled):
+        """Device-resident replay of one step: the same kernel sequence as step_max_likelihood with the
+        proposal and the sampled candidate supplied by the caller -- nothing is copied to the host and
+        the stream is not synchronised (bench.py's resident-input timing, replay of a recorded run)."""
+        lib = self.lib
+        check(lib.graal_state_stats(self.ctx, CUR, self._ptr(self.d_out, 4)))
+        check(lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
+        if op_sampled < 0:
+            return
+        check(lib.graal_full_loglik(self.ctx, CUR, None, self._ptr(self.d_out, 0)))
+        self.score_neighbours(id_fA, id_neighbours)
+        self.test_copy_struct(id_fA, id_f_sampled, op_sampled, -1)
+
     def _sample(self, score, F_t):
         """Candidate filtering and draw (cuda_lib_gl.py:1899-1947)."""
         nt = N_TMP_STRUCT
@@ -514,7 +545,7 @@ class sampler:
         self.sigma_fact = 10 ** (np.log10(fact) - 2)
         self.sigma_slope, self.sigma_d_max, self.sigma_d_nuc = 0.05, 100, 0.5
         id_modif = self.rng.choice(4)
-        c1f = lambda sl: F32((0.53 * np.power(lm / kuhn, sl)) * np.power(kuhn, -3))
+        c1f = lambda sl: rippe_c1(kuhn, lm, sl)
         if id_modif == 0:
             new_fact = fact + self.rng.normal(loc=0.0, scale=self.sigma_fact)
             new_d_max = opti.estimate_max_dist_intra([kuhn, lm, slope, d, new_fact], d_nuc)

@@ -124,6 +124,20 @@ int graal_dist_histogram(graal_ctx* ctx, const int32_t* sub_id_c, const int32_t*
 /* instrumentation: number of kernel launches issued by this context so far */
 int64_t graal_launch_count(graal_ctx* ctx);
 
+/* per-kernel device timers: CUDA event pairs recorded on the context's stream around the kernels
+ * below (off by default).  graal_profile_read synchronises the stream and returns the accumulated
+ * device time and launch count of one kernel id. */
+enum {
+    GRAAL_K_FULL_CONTACTS = 0,   /* contact-list pass of graal_full_loglik (the HBM-bound kernel) */
+    GRAAL_K_FULL_BAND,           /* band-limited expected-mass pass of graal_full_loglik */
+    GRAAL_K_DELTA_CONTACTS,      /* contact part of graal_delta_loglik */
+    GRAAL_K_DELTA_BAND,          /* expected-mass part of graal_delta_loglik (both passes + reductions) */
+    GRAAL_K_BUILD,               /* graal_build_candidates */
+    GRAAL_K_RELABEL              /* graal_relabel_contigs */
+};
+int graal_profile_enable(graal_ctx* ctx, int on);
+int graal_profile_read(graal_ctx* ctx, int kernel_id, double* total_ms, int64_t* count, int reset);
+
 #ifdef __cplusplus
 }
 #endif

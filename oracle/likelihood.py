@@ -25,7 +25,11 @@ PARAM_FIELDS = ("kuhn", "lm", "c1", "slope", "d", "d_max", "fact", "v_inter")
 def make_params(kuhn, lm, slope, d, fact, d_max, v_inter):
     """setup_rippe_parameters (cuda_lib_gl.py:1203-1214): c1 is rounded to float32 once."""
     kuhn, lm = F32(kuhn), F32(lm)
-    c1 = F32((0.53 * np.power(lm / kuhn, slope)) * np.power(kuhn, -3))
+    # NumPy 1.x promotion, as the reference ran: float32 ** float32 stays float32 (nuisance step,
+    # slope read back from the float32 record), float32 ** float64/python float is float64 (fit)
+    ratio = lm / kuhn
+    pw = np.power(ratio, slope) if isinstance(slope, np.float32) else np.power(np.float64(ratio), np.float64(slope))
+    c1 = F32((0.53 * np.float64(pw)) * np.float64(np.power(kuhn, F32(-3))))
     return dict(kuhn=kuhn, lm=lm, c1=c1, slope=F32(slope), d=F32(d), d_max=F32(d_max),
                 fact=F32(fact), v_inter=F32(v_inter))
 

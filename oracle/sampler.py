@@ -223,6 +223,12 @@ class OracleSampler:
             max_id = I32(self.cur["id_c"].max())
             M.apply_mutation(self.ws, self.cur, i, 0, 0, max_id, self.id_contigs)
 
+    # ---- :1559-1578
+    def apply_replay_simu(self, id_fA, id_fB, op_sampled, dt=0):
+        self.modify_gl_cuda_buffer(id_fA, dt)
+        max_id = I32(self.cur["id_c"].max())
+        M.apply_mutation(self.ws, self.cur, id_fA, id_fB, op_sampled, max_id, self.id_contigs)
+
     # ---- :2392-2546
     def candidate_index_sets(self, id_fA, id_fB):
         """fill_sub_index_fA/fB (kernels3.cu:3225-3249) on the persistent sub_index, then the numpy

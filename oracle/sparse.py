@@ -156,27 +156,34 @@ def quirk_mass(slot, lv, p, bins=None):
 
 
 def band_mass(geo, lv, p, subs=None, include_same_bin=True):
-    """B(S): sum over cis sub-frag pairs (optionally restricted to ``subs``) with s < d_max of
-    ex - g(true product).  Brute force per contig (test sizes)."""
+    """B(S): sum over cis sub-frag pairs (optionally restricted to ``subs``) with 0 < s < d_max of
+    ex - g(true product).  Per contig the sub-frags are sorted by mid-point and pairs are enumerated
+    offset by offset until every distance at that offset reaches d_max (exact: pairs beyond the band
+    contribute 0)."""
     subs = np.arange(lv.W) if subs is None else np.asarray(subs)
     tot = 0.0
     idc = geo.id_c[subs]
-    for cid in np.unique(idc):
-        m = subs[idc == cid]
-        if m.size < 2:
-            continue
-        i, j = np.triu_indices(m.size, 1)
-        r, c = m[i], m[j]
-        if not include_same_bin:
-            keep = lv.sub2bin[r] != lv.sub2bin[c]
+    order = np.lexsort((geo.mid[subs], idc))
+    subs, idc = subs[order], idc[order]
+    bounds = np.r_[0, np.nonzero(idc[1:] != idc[:-1])[0] + 1, subs.size]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        m = subs[a:b]
+        mids = geo.mid[m]
+        for k in range(1, m.size):
+            s = mids[k:] - mids[:-k]
+            inb = s < p["d_max"]
+            if not inb.any():
+                break
+            r, c = m[:-k][inb], m[k:][inb]
+            keep = s[inb] > 0
+            if not include_same_bin:
+                keep &= lv.sub2bin[r] != lv.sub2bin[c]
             r, c = r[keep], c[keep]
-        s = np.abs(geo.mid[c] - geo.mid[r])
-        keep = (s > 0) & (s < p["d_max"])
-        r, c = r[keep], c[keep]
-        if r.size == 0:
-            continue
-        ex = pair_expected(geo, lv, p, r, c).astype(np.float64)
-        tot += float((ex - g_clamp(lv.accu_true[r] * lv.accu_true[c], p, lv.nfpb)).sum())
+            if r.size == 0:
+                continue
+            lo, hi = np.minimum(r, c), np.maximum(r, c)
+            ex = pair_expected(geo, lv, p, lo, hi).astype(np.float64)
+            tot += float((ex - g_clamp(lv.accu_true[lo] * lv.accu_true[hi], p, lv.nfpb)).sum())
     return tot
 
 
