@@ -6,8 +6,8 @@ in float32 through powf / expf; CUDA's and NumPy's float32 pow/exp differ by up 
 so a delta that is a small difference of large sums carries an absolute noise of a few float32 ulps
 of the summed magnitude.  The test therefore allows
         |delta_gpu - delta_oracle| <= 1e-6 * |delta_oracle| + 2**-22 * mass
-where mass = sum over touched pixels of |new| + |old| (recorded by the oracle).  Full likelihoods are
-compared at 1e-9 relative."""
+where mass = sum over touched pixels of |new| + |old| (recorded by the oracle).  Full likelihoods
+(sums of 1e5..1e7 such terms, no cancellation) are compared at 1e-7 relative."""
 import os
 
 import numpy as np
@@ -20,6 +20,9 @@ import helpers as H
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+FULL_RTOL = 1e-7
 
 
 def tol(delta, mass):
@@ -54,13 +57,13 @@ def test_full_and_delta_vs_oracle(small_pyramid, level):
     rng = np.random.RandomState(31 + level)
     n = o.n_new_frags
     fo, fg = o.eval_likelihood(), g.eval_likelihood()
-    assert abs(fo - fg) <= 1e-9 * abs(fo)                     # initial genome
+    assert abs(fo - fg) <= FULL_RTOL * abs(fo)                     # initial genome
     worst = 0.0
     for rnd in range(4):
         H.scramble(o, rng, 25, g)
         max_id = o.modify_gl_cuda_buffer(); g.modify_gl_cuda_buffer()
         fo, fg = o.eval_likelihood(), g.eval_likelihood()
-        assert abs(fo - fg) <= 1e-9 * abs(fo), (level, rnd)
+        assert abs(fo - fg) <= FULL_RTOL * abs(fo), (level, rnd)
         for it in range(3):
             fA, fB = (int(x) for x in rng.choice(n, 2, replace=False))
             M.perform_modifications(o.ws, o.cur, fA, fB, max_id)
@@ -80,7 +83,7 @@ def test_exploded_and_single_contig_states(small_pyramid):
     inp, o, g = make_pair(small_pyramid, 2)
     o.explode_genome(); g.explode_genome()
     fo, fg = o.eval_likelihood(), g.eval_likelihood()
-    assert abs(fo - fg) <= 1e-9 * abs(fo)
+    assert abs(fo - fg) <= FULL_RTOL * abs(fo)
     max_id = o.modify_gl_cuda_buffer(); g.modify_gl_cuda_buffer()
     M.perform_modifications(o.ws, o.cur, 3, 4, max_id)
     ref = oracle_deltas(o, 3, 4)
@@ -99,7 +102,7 @@ def test_ragged_level():
     H.scramble(o, rng, 30, g)
     max_id = o.modify_gl_cuda_buffer(); g.modify_gl_cuda_buffer()
     fo, fg = o.eval_likelihood(), g.eval_likelihood()
-    assert abs(fo - fg) <= 1e-9 * abs(fo)
+    assert abs(fo - fg) <= FULL_RTOL * abs(fo)
     n = o.n_new_frags
     for it in range(5):
         fA, fB = (int(x) for x in rng.choice(n, 2, replace=False))
@@ -117,7 +120,7 @@ def test_blacklisted_rows(small_pyramid):
     inp, o, g = make_pair(small_pyramid, 1, blacklist_contigs=(6,))
     assert len(inp.id_frags_blacklisted) > 0
     fo, fg = o.eval_likelihood(), g.eval_likelihood()
-    assert abs(fo - fg) <= 1e-9 * abs(fo)
+    assert abs(fo - fg) <= FULL_RTOL * abs(fo)
     g.free_gpu()
 
 
@@ -133,7 +136,7 @@ def test_test_parameters_and_v_inter_zero(small_pyramid):
         test_o = L.make_params(p[0], p[1], slope, p[3], p[4], d_max, v)
         arr = np.array([tuple(L.params_to_array(test_o))], dtype=g.param_simu.dtype)
         fo, fg = o.eval_likelihood(test_o), g.eval_likelihood(arr)
-        assert abs(fo - fg) <= 1e-9 * abs(fo), (slope, d_max, v)
+        assert abs(fo - fg) <= FULL_RTOL * abs(fo), (slope, d_max, v)
     g.free_gpu()
 
 
@@ -147,7 +150,7 @@ def test_golden_likelihood(yeast_pyramid, level):
     g._set_device_params(g.param_simu)
     g.slot_from_host(CUR, {k: z["state_" + k] for k in M.FIELDS})
     full = g.eval_likelihood()
-    assert abs(full - float(z["full"])) <= 1e-9 * abs(float(z["full"]))
+    assert abs(full - float(z["full"])) <= FULL_RTOL * abs(float(z["full"]))
     for (fA, fB), deltas, masses in zip(z["pairs"], z["deltas"], z["masses"]):
         g.perform_modifications(int(fA), int(fB), int(z["max_id"]))
         g.lib.graal_delta_loglik(g.ctx, 0, 1, 13, int(fA), int(fB), int(z["max_id"]), g._ptr(g.d_out, 16))

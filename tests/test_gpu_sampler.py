@@ -33,7 +33,7 @@ def test_live_trajectory_vs_oracle(small_pyramid):
     tr_g = start_EM(g, 3, 3, scrambled=True, max_steps=150, on_step=lambda it, tr: rows_g.append(g.slot_to_host(CUR)) if it % 50 == 0 else None)
     assert np.array_equal(tr_o.mutations(), tr_g.mutations())
     assert tr_o.n_contigs == tr_g.n_contigs
-    assert np.allclose(tr_o.likelihood, tr_g.likelihood, rtol=1e-9, atol=0)
+    assert np.allclose(tr_o.likelihood, tr_g.likelihood, rtol=1e-7, atol=0)
     assert np.allclose(tr_o.mean_len, tr_g.mean_len, rtol=1e-12) and np.allclose(tr_o.dist_from_init_genome, tr_g.dist_from_init_genome, rtol=0, atol=1e-12)
     for a, b in zip(rows_o, rows_g):
         assert H.slots_diff(a, b) == []
@@ -54,7 +54,7 @@ def test_golden_trajectory_10k_steps(yeast_pyramid, tmp_path):
     first_bad = int(np.argmin(same)) if not same.all() else -1
     margin = z["margins"][first_bad] if first_bad >= 0 else None
     assert first_bad < 0, "diverged at step %d (draw-to-boundary margin %s)" % (first_bad, margin)
-    assert np.allclose(tr.likelihood, z["likelihood"], rtol=1e-9, atol=0)
+    assert np.allclose(tr.likelihood, z["likelihood"], rtol=1e-7, atol=0)
     assert np.array_equal(np.array(tr.n_contigs), z["n_contigs"])
     final = g.slot_to_host(CUR)
     for k in M.FIELDS:
@@ -81,7 +81,7 @@ def test_golden_trajectory_with_nuisance_parameters(yeast_pyramid):
     assert np.array_equal(np.array(tr.success), z["success"])
     for k in ("fact", "slope", "d_max", "d_nuc"):
         assert np.allclose(np.array(getattr(tr, k), dtype=np.float64), z[k], rtol=1e-6), k
-    assert np.allclose(tr.likelihood, z["likelihood"], rtol=1e-9, atol=0)
+    assert np.allclose(tr.likelihood, z["likelihood"], rtol=1e-7, atol=0)
     g.free_gpu()
 
 
