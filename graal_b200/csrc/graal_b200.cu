@@ -34,18 +34,27 @@ static int set_err(int code, const char* fmt, ...) {
 // ------------------------------------------------------------------------------------------------
 // model
 // ------------------------------------------------------------------------------------------------
-struct Params { float kuhn, lm, c1, slope, d, d_max, fact, v_inter, nfpb; };
+// nd x nd tables over the distinct accu values (a_i, a_j) of the level, built on the host with the
+// same IEEE float32 operations the reference performs per pixel:
+//   t_norm[i*nd+j] = f32(f32(a_i*a_j) / nfpb)            (kernels3.cu:3065)
+//   t_g   [i*nd+j] = f32(v_inter * t_norm)               the value of every clamped / trans pixel
+//   t_logg[i*nd+j] = log((double) t_g)                   (-inf when t_g == 0: the pixel contributes 0)
+struct Params { float kuhn, lm, c1, slope, d, d_max, fact, v_inter, nfpb; int nd;
+                const float* t_norm; const float* t_g; const double* t_logg;
+                // log-space evaluation (math mode 1): ln(c1*fact), ln(v_inter), slope as double, ln(t_norm)
+                int mode; double ln_cf, ln_v, slope_d; const double* t_lnnorm;
+                const double2* t_log; const double* t_exp; };
 
 // per-sub-frag geometry record of one slot (16 B, one 128-bit load):
 //   mid  : mid-point in kb (float32, reference op order kernels3.cu:2997-3060)
 //   id_c : contig id
 //   stot : contig length in kb (float32 of l_cont_bp / 1000) -- used by circular contigs only
-//   pk   : accu_true[0:13) | accu_quirk[13:26) | local sub index[26:28) | circ[28]
+//   pk   : index of accu_true[0:8) | index of accu_quirk[8:16) (into the level's list of distinct accu
+//          values) | local sub index[26:28) | circ[28]
 struct __align__(16) Geo { float mid; int id_c; float stot; unsigned pk; };
-#define PK_ACCU_BITS 13
-#define PK_ACCU_MAX ((1 << PK_ACCU_BITS) - 1)
-__device__ __forceinline__ int pk_true(unsigned pk) { return pk & PK_ACCU_MAX; }
-__device__ __forceinline__ int pk_quirk(unsigned pk) { return (pk >> PK_ACCU_BITS) & PK_ACCU_MAX; }
+#define MAX_ACCU_VALUES 256
+__device__ __forceinline__ int pk_true(unsigned pk) { return pk & 255; }
+__device__ __forceinline__ int pk_quirk(unsigned pk) { return (pk >> 8) & 255; }
 __device__ __forceinline__ int pk_local(unsigned pk) { return (pk >> 26) & 3; }
 __device__ __forceinline__ int pk_circ(unsigned pk) { return (pk >> 28) & 1; }
 __device__ __forceinline__ bool geo_eq(const Geo& a, const Geo& b) {
@@ -63,7 +72,7 @@ __device__ __forceinline__ float rippe_contacts(float s, const Params& p) {
     float r = 0.0f;
     if (s > 0.0f && s < p.d_max) {
         float x = s * p.lm / p.kuhn;
-        r = (p.c1 * powf(s, p.slope) * expf((p.d - 2.0f) / (powf(x, 2.0f) + p.d))) * p.fact;
+        r = (p.c1 * powf(s, p.slope) * expf((p.d - 2.0f) / (x * x + p.d))) * p.fact;      // pow(x, 2) == x*x exactly
     }
     return fmaxf(r, p.v_inter);
 }
@@ -77,23 +86,103 @@ __device__ __noinline__ float rippe_contacts_circ(float s, float s_tot, const Pa
         float n = K * s * (s_tot - s) / s_tot;
         float norm_lin = rippe_contacts(s, p);
         float k3 = powf(p.kuhn, -3.0f);
-        float norm_circ = (k3 * powf(nmax, p.slope) * expf((p.d - 2.0f) / (powf(nmax, 2.0f) + p.d))) * p.fact;
-        float val = (k3 * powf(n, p.slope) * expf((p.d - 2.0f) / (powf(n, 2.0f) + p.d))) * p.fact;
+        float norm_circ = (k3 * powf(nmax, p.slope) * expf((p.d - 2.0f) / (nmax * nmax + p.d))) * p.fact;
+        float val = (k3 * powf(n, p.slope) * expf((p.d - 2.0f) / (n * n + p.d))) * p.fact;
         result = val * norm_lin / norm_circ;
     }
     return fmaxf(result, p.v_inter);
+}
+
+__device__ __forceinline__ double log_fact_term(float obf);
+
+// ---- math mode 1: log-space float64 evaluation of the in-band expected value ------------------------
+// ln(x) of a positive normal float32: 128-entry table of (1/c, ln c) on the top mantissa bits plus a
+// degree-5 log1p series in r = m/c - 1, |r| <= 2^-8 (truncation < 1e-15).
+__device__ __forceinline__ double fast_log_f32(float x, const double2* __restrict__ tab) {
+    const unsigned b = __float_as_uint(x);
+    const int e = (int)(b >> 23) - 127;
+    const int i = (b >> 16) & 127;
+    const double m = (double)__uint_as_float((b & 0x007fffffu) | 0x3f800000u);
+    const double2 t = __ldg(&tab[i]);
+    const double r = fma(m, t.x, -1.0);
+    double q = fma(r, 0.2, -0.25);
+    q = fma(q, r, 1.0 / 3.0);
+    q = fma(q, r, -0.5);
+    q = fma(q, r, 1.0);
+    return fma((double)e, 0.6931471805599453094, fma(q, r, t.y));
+}
+// exp(t), |t| < 700: k = rint(t * 32/ln2), table of 2^(j/32), degree-4 series in the remainder
+// (|r| <= ln2/64, truncation < 2e-12 relative).
+__device__ __forceinline__ double fast_exp(double t, const double* __restrict__ tab) {
+    const double kf = rint(t * 46.166241308446828384);
+    const int k = (int)kf;
+    double r = fma(kf, -0.021660849392498290, t);            // ln2/32 (hi)
+    double q = fma(r, 1.0 / 24.0, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q = fma(q, r, 1.0);
+    const double base = __ldg(&tab[k & 31]) * q;
+    const int sh = k >> 5;
+    return __longlong_as_double(__double_as_longlong(base) + ((long long)sh << 52));
+}
+// ln of rippe_contacts(s) for 0 < s < d_max on a LINEAR contig, clamp included:
+// max(ln(c1*fact) + slope*ln(s) + (d-2)/(x^2+d), ln v_inter) with x and the quotient in float32 exactly
+// as the reference computes the argument of expf (kernels3.cu:126).
+__device__ __forceinline__ double ln_rippe_inband(float s, const Params& p) {
+    const float x = s * p.lm / p.kuhn;
+    const float e = (p.d - 2.0f) / (x * x + p.d);
+    const double lr = fma(p.slope_d, fast_log_f32(s, p.t_log), p.ln_cf + (double)e);
+    return fmax(lr, p.ln_v);            // fmax drops a NaN / -inf ln_v (v_inter <= 0): max(r, v) = r
 }
 
 // expected contacts of the sub-frag pair (a, b); a belongs to the LOWER data bin (quirk Q1 side).
 __device__ __forceinline__ float expected_pair(const Geo& a, const Geo& b, const Params& p) {
     if (a.id_c == b.id_c) {
         float s = fabsf(b.mid - a.mid);
-        float norm = __int2float_rn(pk_true(a.pk) * pk_true(b.pk)) / p.nfpb;
+        float norm = __ldg(&p.t_norm[pk_true(a.pk) * p.nd + pk_true(b.pk)]);
         float r = pk_circ(a.pk) ? rippe_contacts_circ(s, a.stot, p) : rippe_contacts(s, p);
         return r * norm;
     }
-    float norm = __int2float_rn(pk_quirk(a.pk) * pk_true(b.pk)) / p.nfpb;
-    return p.v_inter * norm;
+    return __ldg(&p.t_g[pk_quirk(a.pk) * p.nd + pk_true(b.pk)]);
+}
+// ex - g of an in-band cis pair (0 < s < d_max checked by the caller), as float64
+__device__ __forceinline__ double band_excess(const Geo& a, const Geo& b, float s, const Params& p) {
+    const int idx = pk_true(a.pk) * p.nd + pk_true(b.pk);
+    const double g = (double)__ldg(&p.t_g[idx]);
+    if (p.mode == 0 || pk_circ(a.pk)) {
+        const float norm = __ldg(&p.t_norm[idx]);
+        const float r = pk_circ(a.pk) ? rippe_contacts_circ(s, a.stot, p) : rippe_contacts(s, p);
+        return (double)(r * norm) - g;
+    }
+    const double lr = ln_rippe_inband(s, p);
+    if (!(lr > p.ln_v)) return 0.0;                         // clamped: exactly the clamp value
+    return fast_exp(lr + __ldg(&p.t_lnnorm[idx]), p.t_exp) - g;
+}
+// ln(ex) of an in-band cis pair times ob (the contact term); falls back to the float32 chain for
+// circular contigs and in math mode 0
+__device__ __forceinline__ double inband_log_term(float s, float ob, float stot, int idx, int circ, const Params& p) {
+    if (p.mode == 0 || circ) {
+        const float norm = __ldg(&p.t_norm[idx]);
+        const float r = circ ? rippe_contacts_circ(s, stot, p) : rippe_contacts(s, p);
+        const float ex = r * norm;
+        return (ex != 0.0f) ? (double)ob * log((double)ex) : log_fact_term(ob);
+    }
+    const double lr = ln_rippe_inband(s, p) + __ldg(&p.t_lnnorm[idx]);
+    return (lr == lr && lr != -INFINITY) ? (double)ob * lr : ((lr != lr) ? lr : log_fact_term(ob));
+}
+// ob * ln(ex) of one stored contact between sub-frags a (row side = lower data bin) and b, or the
+// lf(ob) correction when the expected value is 0 (kernels3.cu:197: such a pixel contributes 0)
+__device__ __forceinline__ double contact_log_term(const Geo& a, const Geo& b, float ob, const Params& p) {
+    const bool cis = a.id_c == b.id_c;
+    const float s = fabsf(b.mid - a.mid);
+    if (cis && s > 0.0f && s < p.d_max)
+        return inband_log_term(s, ob, a.stot, pk_true(a.pk) * p.nd + pk_true(b.pk), pk_circ(a.pk), p);
+    const double lg = __ldg(&p.t_logg[(cis ? pk_true(a.pk) : pk_quirk(a.pk)) * p.nd + pk_true(b.pk)]);
+    return (lg != -INFINITY) ? (double)ob * lg : log_fact_term(ob);
+}
+// clamp value of the pair (true accus): what a cis pair beyond the band evaluates to
+__device__ __forceinline__ float g_pair(const Geo& a, const Geo& b, const Params& p) {
+    return __ldg(&p.t_g[pk_true(a.pk) * p.nd + pk_true(b.pk)]);
 }
 
 // the value every clamped / trans pixel takes: f32(v_inter * f32(f32(P)/nfpb))
@@ -274,15 +363,17 @@ __global__ void k_relabel_apply(int* __restrict__ id_c, int n, const int* __rest
 // ------------------------------------------------------------------------------------------------
 struct LevelView {
     const int4* sub_id; const float* sub_len; const int* sub_accu;   // [N] int4, [N*3], [N*3]
+    const unsigned char* accu_idx;                                  // [N*3] index of sub_accu in the distinct-value list
 };
 
 __device__ __forceinline__ void bin_geometry(const int* __restrict__ slot, int ld, int bin, const LevelView& lv,
-                                             Geo* __restrict__ geo) {
+                                             Geo* __restrict__ geo, unsigned short* __restrict__ cid16 = nullptr,
+                                             float* __restrict__ mid32 = nullptr) {
     const int id_d = slot[F_ID_D * ld + bin];
     const int4 sid = lv.sub_id[id_d];
     const int lim = sid.w - 1;
     const float len[3] = { lv.sub_len[id_d * 3], lv.sub_len[id_d * 3 + 1], lv.sub_len[id_d * 3 + 2] };
-    const int acc[3] = { lv.sub_accu[id_d * 3], lv.sub_accu[id_d * 3 + 1], lv.sub_accu[id_d * 3 + 2] };
+    const int acc[3] = { lv.accu_idx[id_d * 3], lv.accu_idx[id_d * 3 + 1], lv.accu_idx[id_d * 3 + 2] };
     const int ori = slot[F_ORI * ld + bin];
     const float start_kb = __int2float_rn(slot[F_START_BP * ld + bin]) / 1000.0f;
     const int id_c = slot[F_ID_C * ld + bin];
@@ -301,51 +392,207 @@ __device__ __forceinline__ void bin_geometry(const int* __restrict__ slot, int l
         const int at = (loc == 0) ? acc[0] : (loc == 1 ? acc[1] : acc[2]);
         const int aq = (ori == 1) ? at : acc_last;
         Geo g; g.mid = mid; g.id_c = id_c; g.stot = stot;
-        g.pk = (unsigned)at | ((unsigned)aq << PK_ACCU_BITS) | ((unsigned)loc << 26) | (circ << 28);
+        g.pk = (unsigned)at | ((unsigned)aq << 8) | ((unsigned)loc << 26) | (circ << 28);
         const int sub = (loc == 0) ? sid.x : (loc == 1 ? sid.y : sid.z);
         geo[sub] = g;
+        if (cid16) { cid16[sub] = (unsigned short)min(id_c < 0 ? 65535 : id_c, 65535); mid32[sub] = mid; }   // classification tables
     }
 }
 
-__global__ void k_geometry_all(const int* __restrict__ slot, int ld, int n, LevelView lv, Geo* __restrict__ geo) {
+__global__ void k_geometry_all(const int* __restrict__ slot, int ld, int n, LevelView lv, Geo* __restrict__ geo,
+                               unsigned short* __restrict__ cid16, float* __restrict__ mid32) {
     const int bin = blockIdx.x * blockDim.x + threadIdx.x;
-    if (bin < n) bin_geometry(slot, ld, bin, lv, geo);
+    if (bin < n) bin_geometry(slot, ld, bin, lv, geo, cid16, mid32);
 }
 
 // ------------------------------------------------------------------------------------------------
 // full likelihood, contact part: stream the row-segmented contact list once
 // ------------------------------------------------------------------------------------------------
 #define CHUNK 2048       // entries per warp-chunk
+#define QCAP 64          // per-warp queue of in-band entries (warp compaction)
 
-__global__ void __launch_bounds__(256)
+// One in-band cis entry waiting for the expensive evaluation (powf / expf / fp64 log).
+struct __align__(16) Pending { float s; float ob; float stot; unsigned key; };   // key = norm index | circ << 31
+
+__device__ __forceinline__ double inband_term(const Pending& q, const Params& p) {
+    return inband_log_term(q.s, q.ob, q.stot, (int)(q.key & 0x7fffffffu), (int)(q.key >> 31), p);
+}
+
+// Streams the contact list once.  Every warp owns one contiguous span of entries (one row search),
+// keeps UNROLL coalesced 256-B loads of the list plus the dependent 16-B record gathers in flight per
+// lane, and classifies each entry: trans / clamped-cis entries (the vast majority) cost one table
+// lookup (ob * log g); in-band cis entries are compacted into a per-warp shared-memory queue and
+// evaluated 32 at a time, so the expensive path (powf / expf / fp64 log) always runs with full lanes.
+#define UNROLL 4
+#define FC_MIN_BLOCKS 4
+__device__ __forceinline__ int2 ld_stream(const int2* p) {      // read-once data: evict-first
+    int2 v; asm volatile("ld.global.cs.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p)); return v;
+}
+__global__ void __launch_bounds__(256, FC_MIN_BLOCKS)
 k_full_contacts(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, long long E, int W,
-                const Geo* __restrict__ geo, Params p, double* __restrict__ partials) {
-    const int lane = threadIdx.x & 31;
+                const Geo* __restrict__ geo, const __grid_constant__ Params p, double* __restrict__ partials) {
+    __shared__ Pending queue[8][QCAP];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long n_chunks = (E + CHUNK - 1) / CHUNK;
+    // contiguous span of this warp, in units of 32 * UNROLL entries
+    const long long n_groups = (E + 32 * UNROLL - 1) / (32 * UNROLL);
+    const long long g0 = n_groups * warp / n_warps, g1 = n_groups * (warp + 1) / n_warps;
+    const long long e0 = g0 * 32 * UNROLL, e1 = min(E, g1 * 32 * UNROLL);
+    Pending* q = queue[wib];
+    int qn = 0;
     double acc = 0.0;
-    for (long long ch = warp; ch < n_chunks; ch += n_warps) {
-        const long long e0 = ch * CHUNK, e1 = min(E, e0 + (long long)CHUNK);
-        // first row whose segment ends after e0 (binary search, same result in every lane)
-        int lo = 0, hi = W;
+    if (e0 < e1) {
+        int lo = 0, hi = W;      // first row whose segment ends after e0
         while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(&rowptr[mid + 1]) > e0) hi = mid; else lo = mid + 1; }
         int row = lo;
-        long long row_end = (row < W) ? __ldg(&rowptr[row + 1]) : E;
-        Geo gr = ld_geo(&geo[min(row, W - 1)]);
-        for (long long e = e0 + lane; e < e1; e += 32) {
-            if (e >= row_end) {
-                do { row++; row_end = __ldg(&rowptr[row + 1]); } while (e >= row_end);
-                gr = ld_geo(&geo[row]);
+        long long row_end = __ldg(&rowptr[row + 1]);
+        Geo gr = ld_geo(&geo[row]);
+        for (long long eb = e0; eb < e1; eb += 32 * UNROLL) {
+            int2 ce[UNROLL]; Geo gc[UNROLL];
+            #pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const long long e = eb + u * 32 + lane;
+                ce[u] = (e < e1) ? ld_stream(&contacts[e]) : make_int2(0, 0);
             }
-            const int2 ce = __ldg(&contacts[e]);
-            const Geo gc = ld_geo(&geo[ce.x]);
-            const float ob = __int_as_float(ce.y);
-            const float ex = expected_pair(gr, gc, p);
-            if (ex != 0.0f) acc += (double)ob * log((double)ex);
-            else acc += log_fact_term(ob);          // pixel contributes 0: undo the precomputed -lf(ob)
+            #pragma unroll
+            for (int u = 0; u < UNROLL; u++) gc[u] = ld_geo(&geo[ce[u].x]);
+            #pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const long long e = eb + u * 32 + lane;
+                bool inband = false;
+                Pending mine;
+                if (e < e1) {
+                    if (e >= row_end) {
+                        do { row++; row_end = __ldg(&rowptr[row + 1]); } while (e >= row_end);
+                        gr = ld_geo(&geo[row]);
+                    }
+                    const float ob = __int_as_float(ce[u].y);
+                    const bool cis = gr.id_c == gc[u].id_c;
+                    const float s = fabsf(gc[u].mid - gr.mid);
+                    inband = cis && s > 0.0f && s < p.d_max;
+                    const int idx = (cis ? pk_true(gr.pk) : pk_quirk(gr.pk)) * p.nd + pk_true(gc[u].pk);
+                    if (inband) {
+                        mine.s = s; mine.ob = ob; mine.stot = gr.stot; mine.key = (unsigned)idx | ((unsigned)pk_circ(gr.pk) << 31);
+                    } else {
+                        const double lg = __ldg(&p.t_logg[idx]);
+                        acc += (lg != -INFINITY) ? (double)ob * lg : log_fact_term(ob);     // -inf marks g == 0
+                    }
+                }
+                const unsigned ballot = __ballot_sync(0xffffffffu, inband);
+                if (inband) q[qn + __popc(ballot & lt_mask)] = mine;
+                qn += __popc(ballot);
+                __syncwarp();
+                if (qn >= 32) {
+                    qn -= 32;
+                    acc += inband_term(q[qn + lane], p);
+                    __syncwarp();
+                }
+            }
         }
     }
+    if (lane < qn) acc += inband_term(q[lane], p);
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+// Uniform-accu variant (every sub-frag has the same accu, e.g. level 1): every trans / clamped entry
+// has the SAME log g, so their total is log g * sum(ob) with sum(ob) a level constant; the kernel only
+// CLASSIFIES entries and evaluates the in-band ones, accumulating ob * (ln ex - log g).
+//  * the list is cut into groups of 256 entries; warp w takes groups w, w + n_warps, ... so that at any
+//    time the chip streams ONE contiguous region of the list (DRAM page locality), 8 coalesced 256-B
+//    loads in flight per warp, marked evict-first;
+//  * the row of the first entry of every group is precomputed at bind time (no search);
+//  * classification reads the 2-byte contig id of the partner (a W*2-byte table that lives in L1/L2)
+//    and only cis entries -- which sit close to their row, i.e. share cache lines -- fetch the partner
+//    mid-point; all gathers of a group are issued before the first one is used.
+#define UNROLL8 8
+#define GROUP (32 * UNROLL8)
+__global__ void k_group_rows(const long long* __restrict__ rowptr, long long E, int W, int n_groups, int* __restrict__ group_row) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const long long e0 = (long long)g * GROUP;
+    int lo = 0, hi = W;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (rowptr[mid + 1] > e0) hi = mid; else lo = mid + 1; }
+    group_row[g] = lo;
+}
+
+__global__ void __launch_bounds__(256, 4)
+k_full_contacts_uniform(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, long long E, int W,
+                        const int* __restrict__ group_row, int n_groups,
+                        const Geo* __restrict__ geo, const unsigned short* __restrict__ cid16, const float* __restrict__ mid32,
+                        const __grid_constant__ Params p, double lg, double* __restrict__ partials) {
+    __shared__ Pending queue[8][QCAP];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    Pending* q = queue[wib];
+    int qn = 0;
+    double acc = 0.0;
+    for (int g = warp; g < n_groups; g += n_warps) {
+        const long long e0 = (long long)g * GROUP;
+        const int len = (int)min((long long)GROUP, E - e0);
+        int2 ce[UNROLL8];
+        #pragma unroll
+        for (int u = 0; u < UNROLL8; u++) {
+            const int r = u * 32 + lane;
+            ce[u] = (r < len) ? ld_stream(&contacts[e0 + r]) : make_int2(0, 0);
+        }
+        int row = __ldg(&group_row[g]);
+        int row_end_rel = (int)min(__ldg(&rowptr[row + 1]) - e0, (long long)INT_MAX);
+        const Geo g0 = ld_geo(&geo[row]);
+        float r_mid = g0.mid, r_stot = g0.stot; int r_idc = g0.id_c; unsigned r_circ = (unsigned)pk_circ(g0.pk) << 31;
+        unsigned cc[UNROLL8];
+        #pragma unroll
+        for (int u = 0; u < UNROLL8; u++) cc[u] = __ldg(&cid16[ce[u].x]);
+        // per-lane row of each of its 8 entries (rows are ~100s of entries long: the cursor rarely moves)
+        bool cis[UNROLL8]; float rm[UNROLL8], rs[UNROLL8]; unsigned rc[UNROLL8];
+        #pragma unroll
+        for (int u = 0; u < UNROLL8; u++) {
+            const int r = u * 32 + lane;
+            if (r < len && r >= row_end_rel) {
+                long long re;
+                do { row++; re = __ldg(&rowptr[row + 1]) - e0; } while ((long long)r >= re);
+                row_end_rel = (int)min(re, (long long)INT_MAX);
+                const Geo gg = ld_geo(&geo[row]);
+                r_mid = gg.mid; r_idc = gg.id_c; r_stot = gg.stot; r_circ = (unsigned)pk_circ(gg.pk) << 31;
+            }
+            bool c = (int)cc[u] == r_idc;
+            if (cc[u] == 65535u || (unsigned)r_idc >= 65535u) c = ld_geo(&geo[ce[u].x]).id_c == r_idc;   // ids beyond 16 bits: exact path
+            cis[u] = c && r < len;
+            rm[u] = r_mid; rs[u] = r_stot; rc[u] = r_circ;
+        }
+        float pm[UNROLL8];
+        #pragma unroll
+        for (int u = 0; u < UNROLL8; u++) pm[u] = cis[u] ? __ldg(&mid32[ce[u].x]) : 0.0f;
+        #pragma unroll
+        for (int u = 0; u < UNROLL8; u++) {
+            const float s = fabsf(pm[u] - rm[u]);
+            const bool inband = cis[u] && s > 0.0f && s < p.d_max;
+            const unsigned ballot = __ballot_sync(0xffffffffu, inband);
+            if (inband) { Pending m; m.s = s; m.ob = __int_as_float(ce[u].y); m.stot = rs[u]; m.key = rc[u]; q[qn + __popc(ballot & lt_mask)] = m; }
+            qn += __popc(ballot);
+            __syncwarp();
+            if (qn >= 32) {
+                qn -= 32;
+                const Pending m = q[qn + lane];
+                acc += inband_term(m, p) - (double)m.ob * lg;
+                __syncwarp();
+            }
+        }
+    }
+    if (lane < qn) { const Pending m = q[lane]; acc += inband_term(m, p) - (double)m.ob * lg; }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+// sum of ob over all stored contacts (level constant)
+__global__ void k_ob_total(const int2* __restrict__ contacts, long long E, double* __restrict__ partials) {
+    double acc = 0.0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x)
+        acc += (double)__int_as_float(contacts[e].y);
     acc = block_sum(acc);
     if (threadIdx.x == 0) partials[blockIdx.x] = acc;
 }
@@ -386,7 +633,7 @@ __global__ void __launch_bounds__(256)
 k_band(const int* __restrict__ order, const int* __restrict__ d_count, int count_host,
        const int* __restrict__ slot, int ld, LevelView lv, const Geo* __restrict__ geo,
        const Geo* __restrict__ geo_other, size_t cand_geo_stride, size_t cand_slot_stride, int order_stride,
-       int eval_is_cand, Params p, double* __restrict__ partials, int partial_stride) {
+       int eval_is_cand, const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
     // blockIdx.y = candidate index (delta mode); the evaluated table is either the candidate's
     // (eval_is_cand = 1, compared against the base table geo_other) or the base table (compared
     // against the candidate's)
@@ -419,8 +666,8 @@ k_band(const int* __restrict__ order, const int* __restrict__ d_count, int count
         if (!DELTA && lane == 0) {        // same-bin pairs a < b (diagonal pixel, Q4)
             #pragma unroll
             for (int a = 0; a < 3; a++) for (int b = a + 1; b < 3; b++) if (b < sx.w) {
-                const float ex = expected_pair(gx[a], gx[b], p);
-                acc += (double)ex - (double)g_clamp(pk_true(gx[a].pk) * pk_true(gx[b].pk), p.v_inter, p.nfpb);
+                const float s = fabsf(gx[b].mid - gx[a].mid);
+                if (s > 0.0f && s < p.d_max) acc += band_excess(gx[a], gx[b], s, p);
             }
         }
         for (int base = ix + 1; base < count; base += 32) {
@@ -445,8 +692,7 @@ k_band(const int* __restrict__ order, const int* __restrict__ d_count, int count
                             if (DELTA && !(chx[a] || chy)) continue;
                             const float s = fabsf(gy.mid - gx[a].mid);
                             if (!(s > 0.0f && s < p.d_max)) continue;
-                            const float ex = expected_pair(gx[a], gy, p);
-                            acc += (double)ex - (double)g_clamp(pk_true(gx[a].pk) * pk_true(gy.pk), p.v_inter, p.nfpb);
+                            acc += band_excess(gx[a], gy, s, p);
                         }
                     }
                 }
@@ -463,7 +709,7 @@ k_band(const int* __restrict__ order, const int* __restrict__ d_count, int count
 __global__ void __launch_bounds__(256)
 k_quirk(const int* __restrict__ quirky, int n_quirky, const int* __restrict__ slot, int ld, int n,
         size_t cand_slot_stride, LevelView lv, const int* __restrict__ bins_u, const int* __restrict__ d_count_u,
-        Params p, double* __restrict__ partials, int partial_stride) {
+        const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
     const int k = blockIdx.y;
     const int* sl = slot + (size_t)k * cand_slot_stride;
     const int bi = quirky[blockIdx.x];
@@ -560,7 +806,7 @@ __global__ void __launch_bounds__(256)
 k_delta_contacts(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, LevelView lv,
                  const int* __restrict__ sub_index, const int* __restrict__ meta,
                  const Geo* __restrict__ geo_base, const Geo* __restrict__ geo_cand0, size_t geo_stride,
-                 Params p, double* __restrict__ partials, int partial_stride) {
+                 const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
     const int k = blockIdx.y;
     const Geo* gK = geo_cand0 + (size_t)k * geo_stride;
     const int m = meta[4], cA = meta[0], cB = meta[1];
@@ -590,12 +836,7 @@ k_delta_contacts(const long long* __restrict__ rowptr, const int2* __restrict__ 
             const Geo rk = (a == 0) ? gkr[0] : (a == 1 ? gkr[1] : gkr[2]);
             if (geo_eq(r0, rk) && geo_eq(g0c, gkc)) continue;            // bitwise unchanged pair
             const float ob = __int_as_float(ce.y);
-            const float ex0 = expected_pair(r0, g0c, p);
-            const float exk = expected_pair(rk, gkc, p);
-            double t = 0.0;
-            if (exk != 0.0f) t += (double)ob * log((double)exk); else t += log_fact_term(ob);
-            if (ex0 != 0.0f) t -= (double)ob * log((double)ex0); else t -= log_fact_term(ob);
-            acc += t;
+            acc += contact_log_term(rk, gkc, ob, p) - contact_log_term(r0, g0c, ob, p);
         }
     }
     acc = block_sum(acc);
@@ -712,9 +953,16 @@ struct graal_ctx {
     const int* collector = nullptr; const int* dispatcher = nullptr;
     const long long* rowptr = nullptr; const int2* contacts = nullptr;
     float nfpb = 1.0f;
-    std::vector<std::pair<int, long long>> accu_hist;   // (accu value, count) over all sub-frags
+    std::vector<std::pair<int, long long>> accu_hist;   // (accu value, count) over all sub-frags; index = position
+    unsigned char* d_accu_idx = nullptr;                // [N*3]
+    float* d_tab_norm = nullptr; float* d_tab_g[2] = {nullptr, nullptr}; double* d_tab_logg[2] = {nullptr, nullptr};
+    double* d_tab_lnnorm = nullptr; double2* d_tab_log = nullptr; double* d_tab_exp = nullptr;
+    int math_mode = 1;
+    std::vector<float> h_tab_g; std::vector<double> h_tab_logg;
     int* d_quirky = nullptr; int n_quirky = 0;
-    double lf_total = 0.0;
+    double lf_total = 0.0, ob_total = 0.0;
+    unsigned short* cid16_base = nullptr; float* mid32_base = nullptr; int smem_optin = 0;
+    int* group_row = nullptr; int n_groups = 0;
     // params
     Params p{}; bool have_params = false;
     // state
@@ -751,6 +999,28 @@ static double host_g0(const graal_ctx* c, const Params& p) {
     return tot;
 }
 
+// Fill the nd x nd clamp tables of a parameter set into table slot `which` (0: current parameters,
+// 1: test parameters of the nuisance step) and point `p` at them.
+static int upload_tables(graal_ctx* c, Params& p, int which) {
+    const int nd = (int)c->accu_hist.size();
+    c->h_tab_g.resize((size_t)nd * nd); c->h_tab_logg.resize((size_t)nd * nd);
+    for (int i = 0; i < nd; i++) for (int j = 0; j < nd; j++) {
+        const float g = g_clamp(c->accu_hist[i].first * c->accu_hist[j].first, p.v_inter, p.nfpb);
+        c->h_tab_g[(size_t)i * nd + j] = g;
+        c->h_tab_logg[(size_t)i * nd + j] = (g != 0.0f) ? log((double)g) : -(double)INFINITY;   // g < 0 -> NaN, as log(ex) in the reference
+    }
+    // pageable -> device: the runtime stages the buffer before returning, so the host vectors can be reused
+    CUDA_OK(cudaMemcpyAsync(c->d_tab_g[which], c->h_tab_g.data(), (size_t)nd * nd * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->d_tab_logg[which], c->h_tab_logg.data(), (size_t)nd * nd * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    p.nd = nd; p.t_norm = c->d_tab_norm; p.t_g = c->d_tab_g[which]; p.t_logg = c->d_tab_logg[which];
+    p.mode = c->math_mode; p.t_lnnorm = c->d_tab_lnnorm; p.t_log = c->d_tab_log; p.t_exp = c->d_tab_exp;
+    const double cf = (double)p.c1 * (double)p.fact;
+    p.ln_cf = cf > 0.0 ? log(cf) : -(double)INFINITY;           // c1*fact <= 0: rippe <= 0, the clamp wins
+    p.ln_v = p.v_inter > 0.0f ? log((double)p.v_inter) : (p.v_inter == 0.0f ? -(double)INFINITY : (double)NAN);
+    p.slope_d = (double)p.slope;
+    return 0;
+}
+
 extern "C" {
 
 const char* graal_last_error(void) { return g_err; }
@@ -768,6 +1038,7 @@ int graal_ctx_create(int device, graal_ctx** out) {
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
     c->n_sm = prop.multiProcessorCount;
+    c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
     CUDA_OK(cudaMalloc(&c->d_ints, 256 * sizeof(int)));
@@ -781,9 +1052,14 @@ int graal_ctx_create(int device, graal_ctx** out) {
 }
 
 static void free_level_scratch(graal_ctx* c) {
+    cudaFree(c->cid16_base); cudaFree(c->mid32_base); cudaFree(c->group_row); c->cid16_base = nullptr; c->mid32_base = nullptr; c->group_row = nullptr;
     cudaFree(c->geo_base); cudaFree(c->geo_cand); cudaFree(c->order); cudaFree(c->cand_order); cudaFree(c->sub_index);
     cudaFree(c->cont_len); cudaFree(c->cont_off); cudaFree(c->first_idx); cudaFree(c->map); cudaFree(c->keys);
-    cudaFree(c->keys_sorted); cudaFree(c->cub_tmp); cudaFree(c->d_quirky);
+    cudaFree(c->keys_sorted); cudaFree(c->cub_tmp); cudaFree(c->d_quirky); cudaFree(c->d_accu_idx);
+    cudaFree(c->d_tab_lnnorm); cudaFree(c->d_tab_log); cudaFree(c->d_tab_exp);
+    c->d_tab_lnnorm = nullptr; c->d_tab_log = nullptr; c->d_tab_exp = nullptr;
+    cudaFree(c->d_tab_norm); cudaFree(c->d_tab_g[0]); cudaFree(c->d_tab_g[1]); cudaFree(c->d_tab_logg[0]); cudaFree(c->d_tab_logg[1]);
+    c->d_accu_idx = nullptr; c->d_tab_norm = nullptr; c->d_tab_g[0] = c->d_tab_g[1] = nullptr; c->d_tab_logg[0] = c->d_tab_logg[1] = nullptr;
     c->geo_base = c->geo_cand = nullptr; c->order = c->cand_order = c->sub_index = c->cont_len = c->cont_off = nullptr;
     c->first_idx = c->map = nullptr; c->keys = c->keys_sorted = nullptr; c->cub_tmp = nullptr; c->d_quirky = nullptr;
 }
@@ -856,7 +1132,7 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
         for (int a = 0; a < cnt; a++) {
             const int v = h_acc[(size_t)b * 3 + a];
             if (h_sid[(size_t)b * 4 + a] != (int)w_check + a) return set_err(-1, "sub-frag ids of bin %d are not consecutive", b);
-            if (v < 0 || v > PK_ACCU_MAX) return set_err(-1, "accu %d of bin %d outside 0..%d", v, b, PK_ACCU_MAX);
+            if (v < 0 || v > 46340) return set_err(-1, "accu %d of bin %d outside 0..46340", v, b);
             hist[v]++; if (v != h_acc[(size_t)b * 3 + cnt - 1]) q = true;
         }
         if (q) quirky.push_back(b);
@@ -864,6 +1140,36 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     }
     if (w_check != n_sub_frags) return set_err(-1, "sub-frag count mismatch: %lld vs %d", w_check, n_sub_frags);
     c->accu_hist.assign(hist.begin(), hist.end());
+    const int nd = (int)c->accu_hist.size();
+    if (nd > MAX_ACCU_VALUES) return set_err(-4, "%d distinct accu values (max %d)", nd, MAX_ACCU_VALUES);
+    {
+        std::map<int, int> pos; for (int i = 0; i < nd; i++) pos[c->accu_hist[i].first] = i;
+        std::vector<unsigned char> idx((size_t)n_frags * 3, 0);
+        for (int b = 0; b < n_frags; b++) for (int a = 0; a < h_sid[(size_t)b * 4 + 3]; a++) idx[(size_t)b * 3 + a] = (unsigned char)pos[h_acc[(size_t)b * 3 + a]];
+        CUDA_OK(cudaMalloc(&c->d_accu_idx, idx.size()));
+        CUDA_OK(cudaMemcpy(c->d_accu_idx, idx.data(), idx.size(), cudaMemcpyHostToDevice));
+        std::vector<float> tn((size_t)nd * nd);
+        for (int i = 0; i < nd; i++) for (int j = 0; j < nd; j++) tn[(size_t)i * nd + j] = (float)(c->accu_hist[i].first * c->accu_hist[j].first) / nfpb;
+        CUDA_OK(cudaMalloc(&c->d_tab_norm, tn.size() * sizeof(float)));
+        CUDA_OK(cudaMemcpy(c->d_tab_norm, tn.data(), tn.size() * sizeof(float), cudaMemcpyHostToDevice));
+        std::vector<double> ln(tn.size());
+        for (size_t i = 0; i < tn.size(); i++) ln[i] = tn[i] > 0.0f ? log((double)tn[i]) : -(double)INFINITY;
+        CUDA_OK(cudaMalloc(&c->d_tab_lnnorm, ln.size() * sizeof(double)));
+        CUDA_OK(cudaMemcpy(c->d_tab_lnnorm, ln.data(), ln.size() * sizeof(double), cudaMemcpyHostToDevice));
+        std::vector<double> tl(256), te(32);
+        for (int i = 0; i < 128; i++) { const double cc = 1.0 + (i + 0.5) / 128.0; tl[2 * i] = 1.0 / cc; tl[2 * i + 1] = log(cc); }
+        for (int j = 0; j < 32; j++) te[j] = exp2((double)j / 32.0);
+        CUDA_OK(cudaMalloc(&c->d_tab_log, 128 * sizeof(double2)));
+        CUDA_OK(cudaMemcpy(c->d_tab_log, tl.data(), 256 * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&c->d_tab_exp, 32 * sizeof(double)));
+        CUDA_OK(cudaMemcpy(c->d_tab_exp, te.data(), 32 * sizeof(double), cudaMemcpyHostToDevice));
+        for (int w = 0; w < 2; w++) {
+            CUDA_OK(cudaMalloc(&c->d_tab_g[w], tn.size() * sizeof(float)));
+            CUDA_OK(cudaMalloc(&c->d_tab_logg[w], tn.size() * sizeof(double)));
+        }
+        c->lv.accu_idx = c->d_accu_idx;
+    }
+    c->have_params = false;
     c->n_quirky = (int)quirky.size();
     if (c->n_quirky) {
         CUDA_OK(cudaMalloc(&c->d_quirky, quirky.size() * sizeof(int)));
@@ -872,6 +1178,9 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     const int n = n_new_frags;
     c->cap = 2 * n + 16;
     CUDA_OK(cudaMalloc(&c->geo_base, (size_t)c->W * sizeof(Geo)));
+    CUDA_OK(cudaMalloc(&c->cid16_base, ((size_t)c->W + 16) * sizeof(unsigned short)));
+    CUDA_OK(cudaMemset(c->cid16_base, 0, ((size_t)c->W + 16) * sizeof(unsigned short)));
+    CUDA_OK(cudaMalloc(&c->mid32_base, (size_t)c->W * sizeof(float)));
     CUDA_OK(cudaMalloc(&c->geo_cand, (size_t)GRAAL_N_CANDIDATES * c->W * sizeof(Geo)));
     CUDA_OK(cudaMemset(c->geo_cand, 0, (size_t)GRAAL_N_CANDIDATES * c->W * sizeof(Geo)));
     CUDA_OK(cudaMalloc(&c->order, (size_t)n * sizeof(int)));
@@ -891,6 +1200,11 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     c->cub_tmp_bytes = std::max(b1, b2);
     CUDA_OK(cudaMalloc(&c->cub_tmp, c->cub_tmp_bytes));
     c->geo_base_slot = -1;
+    c->n_groups = (int)((c->E + GROUP - 1) / GROUP);
+    if (c->n_groups > 0) {
+        CUDA_OK(cudaMalloc(&c->group_row, (size_t)c->n_groups * sizeof(int)));
+        k_group_rows<<<(c->n_groups + 255) / 256, 256, 0, c->stream>>>(c->rowptr, c->E, c->W, c->n_groups, c->group_row); CHECK_LAUNCH(c);
+    }
     // level constant: sum of lf(ob)
     c->lf_total = 0.0;
     if (c->E > 0) {
@@ -900,6 +1214,11 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
         k_reduce_partials<<<1, 256, 0, c->stream>>>(c->partials, grid, 0, 1.0, c->d_scalars + 15, 0);
         CHECK_LAUNCH(c);
         CUDA_OK(cudaMemcpyAsync(&c->lf_total, c->d_scalars + 15, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        k_ob_total<<<grid, 256, 0, c->stream>>>(c->contacts, c->E, c->partials);
+        CHECK_LAUNCH(c);
+        k_reduce_partials<<<1, 256, 0, c->stream>>>(c->partials, grid, 0, 1.0, c->d_scalars + 14, 0);
+        CHECK_LAUNCH(c);
+        CUDA_OK(cudaMemcpyAsync(&c->ob_total, c->d_scalars + 14, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(cudaStreamSynchronize(c->stream));
     }
     return 0;
@@ -909,7 +1228,16 @@ int graal_set_params(graal_ctx* c, const float q[8]) {
     if (!c || !q) return set_err(-1, "null argument");
     c->p.kuhn = q[0]; c->p.lm = q[1]; c->p.c1 = q[2]; c->p.slope = q[3]; c->p.d = q[4];
     c->p.d_max = q[5]; c->p.fact = q[6]; c->p.v_inter = q[7]; c->p.nfpb = c->nfpb;
+    if (!c->d_tab_norm) return set_err(-1, "bind the level before setting parameters");
+    CUDA_OK(cudaSetDevice(c->device));
+    int rc = upload_tables(c, c->p, 0); if (rc) return rc;
     c->have_params = true;
+    return 0;
+}
+
+int graal_set_math_mode(graal_ctx* c, int mode) {
+    if (!c || (mode != 0 && mode != 1)) return set_err(-1, "math mode must be 0 (float32 chain) or 1 (log-space float64)");
+    c->math_mode = mode; c->p.mode = mode;
     return 0;
 }
 
@@ -986,7 +1314,7 @@ int graal_commit(graal_ctx* c, int dst_slot, int src_slot) {
 
 static int ensure_base_geometry(graal_ctx* c, int slot) {
     if (c->geo_base_slot == slot) return 0;
-    k_geometry_all<<<nblk(c->n_new, 128), 128, 0, c->stream>>>(slot_ptr(c, slot), c->ld, c->n_new, c->lv, c->geo_base);
+    k_geometry_all<<<nblk(c->n_new, 128), 128, 0, c->stream>>>(slot_ptr(c, slot), c->ld, c->n_new, c->lv, c->geo_base, c->cid16_base, c->mid32_base);
     CHECK_LAUNCH(c);
     c->geo_base_slot = slot;
     return 0;
@@ -998,7 +1326,8 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
     if (!c->have_params && !p_override) return set_err(-1, "parameters not set");
     Params p = c->p;
     if (p_override) { p.kuhn = p_override[0]; p.lm = p_override[1]; p.c1 = p_override[2]; p.slope = p_override[3];
-                      p.d = p_override[4]; p.d_max = p_override[5]; p.fact = p_override[6]; p.v_inter = p_override[7]; p.nfpb = c->nfpb; }
+                      p.d = p_override[4]; p.d_max = p_override[5]; p.fact = p_override[6]; p.v_inter = p_override[7]; p.nfpb = c->nfpb;
+                      int rc0 = upload_tables(c, p, 1); if (rc0) return rc0; }
     cudaStream_t st = c->stream;
     const int n = c->n_new, ld = c->ld;
     int* s = slot_ptr(c, slot);
@@ -1011,14 +1340,33 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
     k_order_fill<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_off, c->order); CHECK_LAUNCH(c);
     const int ps = c->partial_stride;
     // contacts
-    const int g1 = c->E > 0 ? std::min<long long>(ps, (c->E + CHUNK * 8 - 1) / (CHUNK * 8)) : 0;
     const double g0 = host_g0(c, p);
-    // d_out = -(lf_total + G0)   then accumulate the three device sums
-    const double init = -(c->lf_total + g0);
+    // uniform-accu levels with a finite log g: the trans / clamped entries are a level constant
+    const int nd = (int)c->accu_hist.size();
+    double lg_uniform = 0.0;
+    bool uniform = false;
+    if (nd == 1) {
+        const float gg = g_clamp(c->accu_hist[0].first * c->accu_hist[0].first, p.v_inter, p.nfpb);
+        if (gg > 0.0f) { uniform = true; lg_uniform = log((double)gg); }
+    }
+    int g1 = 0;
+    if (c->E > 0) {
+        int fc_blocks = 0;
+        if (uniform) { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fc_blocks, k_full_contacts_uniform, 256, 0)); }
+        else { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fc_blocks, k_full_contacts, 256, 0)); }
+        g1 = (int)std::min<long long>(std::min(ps, c->n_sm * std::max(1, fc_blocks)), (c->E + 1023) / 1024);   // one resident wave
+    }
+    // d_out = -(lf_total + G0) [+ log g * sum(ob)]   then accumulate the device sums
+    const double init = -(c->lf_total + g0) + (uniform ? lg_uniform * c->ob_total : 0.0);
     k_set_double<<<1, 1, 0, st>>>(d_out, init); CHECK_LAUNCH(c);
     if (g1 > 0) {
         c->prof.begin(GRAAL_K_FULL_CONTACTS, st);
-        k_full_contacts<<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->W, c->geo_base, p, c->partials); CHECK_LAUNCH(c);
+        if (uniform)
+            k_full_contacts_uniform<<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->W, c->group_row, c->n_groups, c->geo_base,
+                                                       c->cid16_base, c->mid32_base, p, lg_uniform, c->partials);
+        else
+            k_full_contacts<<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->W, c->geo_base, p, c->partials);
+        CHECK_LAUNCH(c);
         c->prof.end(GRAAL_K_FULL_CONTACTS, st);
         k_reduce_partials<<<1, 256, 0, st>>>(c->partials, g1, 0, 1.0, d_out, 1); CHECK_LAUNCH(c);
     }

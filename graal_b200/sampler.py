@@ -354,6 +354,13 @@ class sampler:
         arr = (C.c_float * 8)(*[float(x) for x in p[0]])
         check(self.lib.graal_set_params(self.ctx, arr))
 
+    def set_math_mode(self, mode):
+        """0: the reference's float32 chain op for op; 1 (default): log-space float64 evaluation of in-band
+        pixels (see include/graal_b200.h)."""
+        check(self.lib.graal_set_math_mode(self.ctx, int(mode)))
+        if self.param_simu is not None:
+            self._set_device_params(self.param_simu)
+
     def set_parameters(self, param, d_max):
         self.param_simu = self.setup_rippe_parameters(param, d_max)
         self._set_device_params(self.param_simu)

@@ -51,9 +51,11 @@ def oracle_deltas(o, fA, fB):
     return out
 
 
-@pytest.mark.parametrize("level", [1, 2])
-def test_full_and_delta_vs_oracle(small_pyramid, level):
+@pytest.mark.parametrize("level,mode", [(1, 1), (2, 1), (1, 0), (2, 0)])
+def test_full_and_delta_vs_oracle(small_pyramid, level, mode):
+    """mode 1 = the default log-space evaluation, mode 0 = the reference's float32 chain op for op."""
     inp, o, g = make_pair(small_pyramid, level)
+    g.set_math_mode(mode)
     rng = np.random.RandomState(31 + level)
     n = o.n_new_frags
     fo, fg = o.eval_likelihood(), g.eval_likelihood()
@@ -74,7 +76,7 @@ def test_full_and_delta_vs_oracle(small_pyramid, level):
                 err = abs(got[j] - ref[j][0])
                 assert err <= tol(*ref[j]), (level, fA, fB, j, got[j], ref[j])
                 worst = max(worst, err / max(ref[j][1], 1e-30))
-    print("level %d: worst |err| / mass = %.3e" % (level, worst))
+    print("level %d math mode %d: worst |err| / mass = %.3e" % (level, mode, worst))
     g.free_gpu()
 
 
