@@ -206,7 +206,7 @@ def main():
     n = int(g.n_new_frags)
     init_state = g.slot_to_host(CUR)
     total = args.warmup + args.steps
-    sched_rng = np.random.RandomState(4242 + rank)
+    sched_rng = np.random.RandomState(4242)          # the same bins on every rank: replicas do statistically identical work
     frags = sched_rng.permutation(n)[:total]
     if frags.size < total:
         frags = np.concatenate([frags, sched_rng.randint(0, n, size=total - frags.size)])

@@ -16,6 +16,7 @@
 #include "../../include/graal_b200.h"
 #include "moves.cuh"
 
+#define GRAAL_BAND_RESYNC 256      // full recomputation of the cached band total every so many evaluations
 #define GRAAL_VERSION "graal_b200 0.1 (sm_100a)"
 
 // ------------------------------------------------------------------------------------------------
@@ -626,48 +627,54 @@ __global__ void k_order_fill(const int* __restrict__ slot, int ld, int n, int ca
 
 // B(S): sum over cis sub-frag pairs within d_max of  ex - g(true product).
 // One warp per bin x (in position order); lanes take the following bins y of the same contig.
-//   DELTA = false: all pairs, same-bin pairs included (full likelihood)
-//   DELTA = true : pairs of distinct bins whose records differ between geo and geo_other
-template <bool DELTA>
+//   BAND_FULL: all pairs of the slot; cross-bin pairs -> partials[0][.], same-bin pairs a < b (the
+//              diagonal pixels, Q4) -> partials[1][.]
+//   BAND_CAND: candidate k = blockIdx.y in ITS position order: NEW values of the pairs of distinct bins
+//              with a record that differs from the base slot (bit k of chmask) -> partials[k][.]
+//   BAND_BASE: the base slot in its own order, ONCE for all candidates: the OLD value of every pair that
+//              changed in at least one candidate is evaluated once and added to the accumulator of
+//              each candidate whose chmask bit is set -> partials[k][.], k < 13
+enum { BAND_FULL = 0, BAND_CAND = 1, BAND_BASE = 2 };
+template <int MODE>
 __global__ void __launch_bounds__(256)
 k_band(const int* __restrict__ order, const int* __restrict__ d_count, int count_host,
        const int* __restrict__ slot, int ld, LevelView lv, const Geo* __restrict__ geo,
-       const Geo* __restrict__ geo_other, size_t cand_geo_stride, size_t cand_slot_stride, int order_stride,
-       int eval_is_cand, const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
-    // blockIdx.y = candidate index (delta mode); the evaluated table is either the candidate's
-    // (eval_is_cand = 1, compared against the base table geo_other) or the base table (compared
-    // against the candidate's)
+       const unsigned* __restrict__ chmask, size_t cand_geo_stride, size_t cand_slot_stride, int order_stride,
+       unsigned skip_cands, const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
     const int k = blockIdx.y;
+    if (MODE == BAND_CAND && ((skip_cands >> k) & 1u)) return;
     const int count = (count_host >= 0) ? count_host : *d_count;
-    const Geo* gE = geo; const Geo* gO = geo_other;
+    const Geo* gE = geo;
     const int* sl = slot;
     const int* ord = order;
-    if (DELTA) {
-        if (eval_is_cand) { gE = geo + (size_t)k * cand_geo_stride; sl = slot + (size_t)k * cand_slot_stride; ord = order + (size_t)k * order_stride; }
-        else { gO = geo_other + (size_t)k * cand_geo_stride; }
-    }
+    if (MODE == BAND_CAND) { gE = geo + (size_t)k * cand_geo_stride; sl = slot + (size_t)k * cand_slot_stride; ord = order + (size_t)k * order_stride; }
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    double acc = 0.0;
+    double acc = 0.0, acc_diag = 0.0;
+    double accs[GRAAL_N_CANDIDATES];
+    if (MODE == BAND_BASE) {
+        #pragma unroll
+        for (int c = 0; c < GRAAL_N_CANDIDATES; c++) accs[c] = 0.0;
+    }
     for (int ix = warp; ix < count; ix += n_warps) {
         const int x = ord[ix];
         const int4 sx = lv.sub_id[sl[F_ID_D * ld + x]];
-        Geo gx[3]; bool chx[3];
+        Geo gx[3]; unsigned mx[3] = {0u, 0u, 0u};
         float xmax = -1e30f;
         #pragma unroll
         for (int a = 0; a < 3; a++) if (a < sx.w) {
-            const int sub = (a == 0) ? sx.x : (a == 1 ? sx.y : sx.z);
+            const int sub = sx.x + a;
             gx[a] = ld_geo(&gE[sub]);
-            if (DELTA) chx[a] = !geo_eq(gx[a], ld_geo(&gO[sub]));
+            if (MODE != BAND_FULL) mx[a] = __ldg(&chmask[sub]);
             xmax = fmaxf(xmax, gx[a].mid);
         }
         const int cx = gx[0].id_c;
-        if (!DELTA && lane == 0) {        // same-bin pairs a < b (diagonal pixel, Q4)
+        if (MODE == BAND_FULL && lane == 0) {        // same-bin pairs a < b (diagonal pixel, Q4)
             #pragma unroll
             for (int a = 0; a < 3; a++) for (int b = a + 1; b < 3; b++) if (b < sx.w) {
                 const float s = fabsf(gx[b].mid - gx[a].mid);
-                if (s > 0.0f && s < p.d_max) acc += band_excess(gx[a], gx[b], s, p);
+                if (s > 0.0f && s < p.d_max) acc_diag += band_excess(gx[a], gx[b], s, p);
             }
         }
         for (int base = ix + 1; base < count; base += 32) {
@@ -683,16 +690,24 @@ k_band(const int* __restrict__ order, const int* __restrict__ d_count, int count
                 else {
                     #pragma unroll
                     for (int b = 0; b < 3; b++) if (b < sy.w) {
-                        const int sub = (b == 0) ? sy.x : (b == 1 ? sy.y : sy.z);
+                        const int sub = sy.x + b;
+                        unsigned my = 0u;
+                        if (MODE != BAND_FULL) my = __ldg(&chmask[sub]);
+                        if (MODE == BAND_CAND && !(((mx[0] | mx[1] | mx[2] | my) >> k) & 1u)) continue;
+                        if (MODE == BAND_BASE && !(mx[0] | mx[1] | mx[2] | my)) continue;
                         const Geo gy = (b == 0) ? gy0 : ld_geo(&gE[sub]);
-                        bool chy = false;
-                        if (DELTA) chy = !geo_eq(gy, ld_geo(&gO[sub]));
                         #pragma unroll
                         for (int a = 0; a < 3; a++) if (a < sx.w) {
-                            if (DELTA && !(chx[a] || chy)) continue;
+                            const unsigned m = mx[a] | my;
+                            if (MODE == BAND_CAND && !((m >> k) & 1u)) continue;
+                            if (MODE == BAND_BASE && !m) continue;
                             const float s = fabsf(gy.mid - gx[a].mid);
                             if (!(s > 0.0f && s < p.d_max)) continue;
-                            acc += band_excess(gx[a], gy, s, p);
+                            const double v = band_excess(gx[a], gy, s, p);
+                            if (MODE == BAND_BASE) {
+                                #pragma unroll
+                                for (int c = 0; c < GRAAL_N_CANDIDATES; c++) if ((m >> c) & 1u) accs[c] += v;
+                            } else acc += v;
                         }
                     }
                 }
@@ -700,8 +715,40 @@ k_band(const int* __restrict__ order, const int* __restrict__ d_count, int count
             if (!__any_sync(0xffffffffu, live)) break;
         }
     }
+    if (MODE == BAND_BASE) {
+        #pragma unroll
+        for (int c = 0; c < GRAAL_N_CANDIDATES; c++) {
+            const double v = block_sum(accs[c]);
+            if (threadIdx.x == 0) partials[(size_t)c * partial_stride + blockIdx.x] = v;
+        }
+    } else {
+        acc = block_sum(acc);
+        if (threadIdx.x == 0) partials[(size_t)k * partial_stride + blockIdx.x] = acc;
+        if (MODE == BAND_FULL) {
+            acc_diag = block_sum(acc_diag);
+            if (threadIdx.x == 0) partials[(size_t)1 * partial_stride + blockIdx.x] = acc_diag;
+        }
+    }
+}
+
+// same-bin pairs only (the diagonal pixels): thread per bin
+__global__ void __launch_bounds__(256)
+k_band_diag(const int* __restrict__ slot, int ld, int n, LevelView lv, const Geo* __restrict__ geo,
+            const __grid_constant__ Params p, double* __restrict__ partials) {
+    double acc = 0.0;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) {
+        const int4 sx = lv.sub_id[slot[F_ID_D * ld + x]];
+        Geo gx[3];
+        #pragma unroll
+        for (int a = 0; a < 3; a++) if (a < sx.w) gx[a] = ld_geo(&geo[sx.x + a]);
+        #pragma unroll
+        for (int a = 0; a < 3; a++) for (int b = a + 1; b < 3; b++) if (b < sx.w) {
+            const float s = fabsf(gx[b].mid - gx[a].mid);
+            if (s > 0.0f && s < p.d_max) acc += band_excess(gx[a], gx[b], s, p);
+        }
+    }
     acc = block_sum(acc);
-    if (threadIdx.x == 0) partials[(size_t)k * partial_stride + blockIdx.x] = acc;
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
 }
 
 // Q(S): quirk-Q1 correction of trans pairs (bi < bj) whose lower bin is flipped and has non-uniform accu.
@@ -770,13 +817,20 @@ __device__ __forceinline__ int piece_slot(int id_c, const int* meta) {
 }
 __global__ void k_cand_geometry(const int* __restrict__ cand0, size_t slot_stride, int ld, LevelView lv,
                                 const int* __restrict__ sub_index, const int* __restrict__ meta,
-                                Geo* __restrict__ geo0, size_t geo_stride, int* __restrict__ piece_len) {
+                                Geo* __restrict__ geo0, size_t geo_stride, int* __restrict__ piece_len,
+                                const Geo* __restrict__ geo_base, unsigned* __restrict__ chmask, unsigned skip_cands) {
     const int k = blockIdx.y;
+    if ((skip_cands >> k) & 1u) return;
     const int m = meta[4];
     const int* sl = cand0 + (size_t)k * slot_stride;
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < m; u += gridDim.x * blockDim.x) {
         const int bin = sub_index[u];
         bin_geometry(sl, ld, bin, lv, geo0 + (size_t)k * geo_stride);
+        {   // bit k of chmask[sub]: the candidate's record differs from the base slot's (bitwise)
+            const int4 sid = lv.sub_id[sl[F_ID_D * ld + bin]];
+            for (int a = 0; a < sid.w; a++)
+                if (!geo_eq(geo0[(size_t)k * geo_stride + sid.x + a], geo_base[sid.x + a])) atomicOr(&chmask[sid.x + a], 1u << k);
+        }
         if (sl[F_POS * ld + bin] == 0) {
             const int ps = piece_slot(sl[F_ID_C * ld + bin], meta);
             if (ps >= 0) piece_len[k * 8 + ps] = sl[F_L_CONT * ld + bin];
@@ -785,8 +839,9 @@ __global__ void k_cand_geometry(const int* __restrict__ cand0, size_t slot_strid
 }
 __global__ void k_cand_order(const int* __restrict__ cand0, size_t slot_stride, int ld,
                              const int* __restrict__ sub_index, const int* __restrict__ meta,
-                             const int* __restrict__ piece_len, int* __restrict__ order0, int order_stride) {
+                             const int* __restrict__ piece_len, int* __restrict__ order0, int order_stride, unsigned skip_cands) {
     const int k = blockIdx.y;
+    if ((skip_cands >> k) & 1u) return;
     const int m = meta[4];
     const int* sl = cand0 + (size_t)k * slot_stride;
     int off[5]; int run = 0;
@@ -801,19 +856,31 @@ __global__ void k_cand_order(const int* __restrict__ cand0, size_t slot_stride, 
     }
 }
 
-// contact part of the delta: one warp per member bin of U, lanes stride over its (<= 3 rows of) contacts
+// contact part of the delta: one warp per member bin of U, lanes stride over its (<= 3 rows of) contacts.
+//   BASE = false: candidate k = blockIdx.y: NEW term of every contact (partner in U, other bin) with a
+//                 changed record on either side (bit k of chmask)
+//   BASE = true : once for all candidates: the OLD term of every contact changed in at least one
+//                 candidate, added to the accumulator of each flagged candidate
+template <bool BASE>
 __global__ void __launch_bounds__(256)
 k_delta_contacts(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, LevelView lv,
                  const int* __restrict__ sub_index, const int* __restrict__ meta,
                  const Geo* __restrict__ geo_base, const Geo* __restrict__ geo_cand0, size_t geo_stride,
+                 const unsigned* __restrict__ chmask, unsigned skip_cands,
                  const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
     const int k = blockIdx.y;
-    const Geo* gK = geo_cand0 + (size_t)k * geo_stride;
+    if (!BASE && ((skip_cands >> k) & 1u)) return;
+    const Geo* gK = BASE ? geo_base : geo_cand0 + (size_t)k * geo_stride;
     const int m = meta[4], cA = meta[0], cB = meta[1];
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     double acc = 0.0;
+    double accs[GRAAL_N_CANDIDATES];
+    if (BASE) {
+        #pragma unroll
+        for (int c = 0; c < GRAAL_N_CANDIDATES; c++) accs[c] = 0.0;
+    }
     for (int u = warp; u < m; u += n_warps) {
         const int bin = sub_index[u];
         const int4 sid = lv.sub_id[bin];
@@ -822,26 +889,41 @@ k_delta_contacts(const long long* __restrict__ rowptr, const int2* __restrict__ 
         const long long b1 = __ldg(&rowptr[sub0 + 1]);
         const long long b2 = (sid.w > 1) ? __ldg(&rowptr[sub0 + 2]) : b1;
         const long long e1 = (sid.w > 2) ? __ldg(&rowptr[sub0 + 3]) : b2;
-        Geo g0r[3], gkr[3];
+        Geo gr[3]; unsigned mr[3] = {0u, 0u, 0u};
         #pragma unroll
-        for (int a = 0; a < 3; a++) if (a < sid.w) { g0r[a] = ld_geo(&geo_base[sub0 + a]); gkr[a] = ld_geo(&gK[sub0 + a]); }
+        for (int a = 0; a < 3; a++) if (a < sid.w) { gr[a] = ld_geo(&gK[sub0 + a]); mr[a] = __ldg(&chmask[sub0 + a]); }
         for (long long e = e0 + lane; e < e1; e += 32) {
             const int a = (e >= b1) + (e >= b2);
             const int2 ce = __ldg(&contacts[e]);
             const Geo g0c = ld_geo(&geo_base[ce.x]);
             if (g0c.id_c != cA && g0c.id_c != cB) continue;              // partner outside U
             if (ce.x - pk_local(g0c.pk) == sub0) continue;               // same bin: diagonal pixel, not re-scored
-            const Geo gkc = ld_geo(&gK[ce.x]);
-            const Geo r0 = (a == 0) ? g0r[0] : (a == 1 ? g0r[1] : g0r[2]);
-            const Geo rk = (a == 0) ? gkr[0] : (a == 1 ? gkr[1] : gkr[2]);
-            if (geo_eq(r0, rk) && geo_eq(g0c, gkc)) continue;            // bitwise unchanged pair
-            const float ob = __int_as_float(ce.y);
-            acc += contact_log_term(rk, gkc, ob, p) - contact_log_term(r0, g0c, ob, p);
+            const unsigned mm = ((a == 0) ? mr[0] : (a == 1 ? mr[1] : mr[2])) | __ldg(&chmask[ce.x]);
+            if (BASE ? (mm == 0u) : !((mm >> k) & 1u)) continue;         // bitwise unchanged pair
+            const Geo gc = BASE ? g0c : ld_geo(&gK[ce.x]);
+            const Geo rr = (a == 0) ? gr[0] : (a == 1 ? gr[1] : gr[2]);
+            const double t = contact_log_term(rr, gc, __int_as_float(ce.y), p);
+            if (BASE) {
+                #pragma unroll
+                for (int c = 0; c < GRAAL_N_CANDIDATES; c++) if ((mm >> c) & 1u) accs[c] += t;
+            } else acc += t;
         }
     }
-    acc = block_sum(acc);
-    if (threadIdx.x == 0) partials[(size_t)k * partial_stride + blockIdx.x] = acc;
+    if (BASE) {
+        #pragma unroll
+        for (int c = 0; c < GRAAL_N_CANDIDATES; c++) {
+            const double v = block_sum(accs[c]);
+            if (threadIdx.x == 0) partials[(size_t)c * partial_stride + blockIdx.x] = v;
+        }
+    } else {
+        acc = block_sum(acc);
+        if (threadIdx.x == 0) partials[(size_t)k * partial_stride + blockIdx.x] = acc;
+    }
 }
+
+// out[dst] = out[src]   /   *total += sel[idx]   (tiny helpers of the incremental bookkeeping)
+__global__ void k_copy_double(double* p, int dst, int src) { p[dst] = p[src]; }
+__global__ void k_add_selected(double* total, const double* v, int idx) { *total += v[idx]; }
 
 // ------------------------------------------------------------------------------------------------
 // statistics and the distance histogram
@@ -963,6 +1045,9 @@ struct graal_ctx {
     double lf_total = 0.0, ob_total = 0.0;
     unsigned short* cid16_base = nullptr; float* mid32_base = nullptr; int smem_optin = 0;
     int* group_row = nullptr; int n_groups = 0;
+    unsigned* chmask = nullptr;               // [W] bit k: record differs from the base slot in candidate k
+    double* band_hist = nullptr;              // [16][13] band delta of the proposals scored since the last commit
+    int band_slot = -1; int band_age = 0;     // slot whose cross-bin band total is cached in d_scalars[40]
     // params
     Params p{}; bool have_params = false;
     // state
@@ -1052,7 +1137,7 @@ int graal_ctx_create(int device, graal_ctx** out) {
 }
 
 static void free_level_scratch(graal_ctx* c) {
-    cudaFree(c->cid16_base); cudaFree(c->mid32_base); cudaFree(c->group_row); c->cid16_base = nullptr; c->mid32_base = nullptr; c->group_row = nullptr;
+    cudaFree(c->cid16_base); cudaFree(c->mid32_base); cudaFree(c->group_row); cudaFree(c->chmask); cudaFree(c->band_hist); c->chmask = nullptr; c->band_hist = nullptr; c->cid16_base = nullptr; c->mid32_base = nullptr; c->group_row = nullptr;
     cudaFree(c->geo_base); cudaFree(c->geo_cand); cudaFree(c->order); cudaFree(c->cand_order); cudaFree(c->sub_index);
     cudaFree(c->cont_len); cudaFree(c->cont_off); cudaFree(c->first_idx); cudaFree(c->map); cudaFree(c->keys);
     cudaFree(c->keys_sorted); cudaFree(c->cub_tmp); cudaFree(c->d_quirky); cudaFree(c->d_accu_idx);
@@ -1181,6 +1266,10 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     CUDA_OK(cudaMalloc(&c->cid16_base, ((size_t)c->W + 16) * sizeof(unsigned short)));
     CUDA_OK(cudaMemset(c->cid16_base, 0, ((size_t)c->W + 16) * sizeof(unsigned short)));
     CUDA_OK(cudaMalloc(&c->mid32_base, (size_t)c->W * sizeof(float)));
+    CUDA_OK(cudaMalloc(&c->chmask, (size_t)c->W * sizeof(unsigned)));
+    CUDA_OK(cudaMalloc(&c->band_hist, 16 * GRAAL_N_CANDIDATES * sizeof(double)));
+    CUDA_OK(cudaMemset(c->band_hist, 0, 16 * GRAAL_N_CANDIDATES * sizeof(double)));
+    c->band_slot = -1;
     CUDA_OK(cudaMalloc(&c->geo_cand, (size_t)GRAAL_N_CANDIDATES * c->W * sizeof(Geo)));
     CUDA_OK(cudaMemset(c->geo_cand, 0, (size_t)GRAAL_N_CANDIDATES * c->W * sizeof(Geo)));
     CUDA_OK(cudaMalloc(&c->order, (size_t)n * sizeof(int)));
@@ -1231,13 +1320,13 @@ int graal_set_params(graal_ctx* c, const float q[8]) {
     if (!c->d_tab_norm) return set_err(-1, "bind the level before setting parameters");
     CUDA_OK(cudaSetDevice(c->device));
     int rc = upload_tables(c, c->p, 0); if (rc) return rc;
-    c->have_params = true;
+    c->have_params = true; c->band_slot = -1;
     return 0;
 }
 
 int graal_set_math_mode(graal_ctx* c, int mode) {
     if (!c || (mode != 0 && mode != 1)) return set_err(-1, "math mode must be 0 (float32 chain) or 1 (log-space float64)");
-    c->math_mode = mode; c->p.mode = mode;
+    c->math_mode = mode; c->p.mode = mode; c->band_slot = -1;
     return 0;
 }
 
@@ -1245,7 +1334,7 @@ int graal_state_bind(graal_ctx* c, int32_t* base, int ld, int n_slots) {
     if (!c || !base) return set_err(-1, "null argument");
     if (c->n_new <= 0) return set_err(-1, "bind the level first");
     if (ld < c->n_new || n_slots < 1) return set_err(-1, "bad slot geometry (ld %d < n %d)", ld, c->n_new);
-    c->slots = base; c->ld = ld; c->n_slots = n_slots; c->geo_base_slot = -1;
+    c->slots = base; c->ld = ld; c->n_slots = n_slots; c->geo_base_slot = -1; c->band_slot = -1;
     return 0;
 }
 
@@ -1286,6 +1375,7 @@ int graal_apply_move(graal_ctx* c, int src_slot, int dst_slot, int op, int id_fA
         CHECK_LAUNCH(c);
     }
     if (c->geo_base_slot == dst_slot) c->geo_base_slot = -1;
+    if (c->band_slot == dst_slot) c->band_slot = -1;
     return 0;
 }
 
@@ -1300,6 +1390,7 @@ int graal_build_candidates(graal_ctx* c, int src_slot, int first_dst_slot, int i
     CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_BUILD, c->stream);
     if (c->geo_base_slot >= first_dst_slot && c->geo_base_slot < first_dst_slot + GRAAL_N_CANDIDATES) c->geo_base_slot = -1;
+    if (c->band_slot >= first_dst_slot && c->band_slot < first_dst_slot + GRAAL_N_CANDIDATES) c->band_slot = -1;
     return 0;
 }
 
@@ -1309,6 +1400,7 @@ int graal_commit(graal_ctx* c, int dst_slot, int src_slot) {
     k_apply_move<<<nblk(c->n_new, 128), 128, 0, c->stream>>>(slot_ptr(c, src_slot), slot_ptr(c, dst_slot), c->ld, c->n_new, GRAAL_OP_COPY, 0, 0, 0, 0);
     CHECK_LAUNCH(c);
     if (c->geo_base_slot == dst_slot) c->geo_base_slot = -1;
+    if (c->band_slot == dst_slot) c->band_slot = -1;
     return 0;
 }
 
@@ -1332,12 +1424,6 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
     const int n = c->n_new, ld = c->ld;
     int* s = slot_ptr(c, slot);
     int rc = ensure_base_geometry(c, slot); if (rc) return rc;
-    // position order of the bins, contig by contig
-    CUDA_OK(cudaMemsetAsync(c->cont_len, 0, (size_t)c->cap * sizeof(int), st));
-    k_contig_lengths<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_len); CHECK_LAUNCH(c);
-    size_t tb = c->cub_tmp_bytes;
-    CUDA_OK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, tb, c->cont_len, c->cont_off, c->cap, st)); c->launches += 2;
-    k_order_fill<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_off, c->order); CHECK_LAUNCH(c);
     const int ps = c->partial_stride;
     // contacts
     const double g0 = host_g0(c, p);
@@ -1370,12 +1456,34 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
         c->prof.end(GRAAL_K_FULL_CONTACTS, st);
         k_reduce_partials<<<1, 256, 0, st>>>(c->partials, g1, 0, 1.0, d_out, 1); CHECK_LAUNCH(c);
     }
+    // band mass.  The cross-bin part of the current parameters is cached (d_scalars[40]) and kept up to
+    // date by graal_commit_scored with the committed candidate's band delta; it is recomputed from
+    // scratch every GRAAL_BAND_RESYNC evaluations.  The same-bin part is recomputed every time.
     const int g2 = std::min(ps, nblk(n, 8));
     c->prof.begin(GRAAL_K_FULL_BAND, st);
-    k_band<false><<<dim3(g2, 1), 256, 0, st>>>(c->order, nullptr, n, s, ld, c->lv, c->geo_base, nullptr, 0, 0, 0, 0, p,
-                                              c->partials + (size_t)1 * ps, ps); CHECK_LAUNCH(c);
+    const bool cached = !p_override && c->band_slot == slot && c->band_age < GRAAL_BAND_RESYNC;
+    if (cached) {
+        const int g3 = std::min(ps, nblk(n, 256));
+        k_band_diag<<<g3, 256, 0, st>>>(s, ld, n, c->lv, c->geo_base, p, c->partials + (size_t)1 * ps); CHECK_LAUNCH(c);
+        k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)1 * ps, g3, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
+        k_reduce_partials<<<1, 32, 0, st>>>(c->d_scalars + 40, 1, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
+        c->band_age++;
+    } else {
+        // position order of the bins, contig by contig
+        CUDA_OK(cudaMemsetAsync(c->cont_len, 0, (size_t)c->cap * sizeof(int), st));
+        k_contig_lengths<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_len); CHECK_LAUNCH(c);
+        size_t tb = c->cub_tmp_bytes;
+        CUDA_OK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, tb, c->cont_len, c->cont_off, c->cap, st)); c->launches += 2;
+        k_order_fill<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_off, c->order); CHECK_LAUNCH(c);
+        k_band<BAND_FULL><<<dim3(g2, 1), 256, 0, st>>>(c->order, nullptr, n, s, ld, c->lv, c->geo_base, nullptr, 0, 0, 0, 0u, p,
+                                                     c->partials, ps); CHECK_LAUNCH(c);
+        double* cross = p_override ? c->d_scalars + 41 : c->d_scalars + 40;
+        k_reduce_partials<<<1, 256, 0, st>>>(c->partials, g2, 0, 1.0, cross, 0); CHECK_LAUNCH(c);
+        k_reduce_partials<<<1, 32, 0, st>>>(cross, 1, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
+        k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)1 * ps, g2, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
+        if (!p_override) { c->band_slot = slot; c->band_age = 0; }
+    }
     c->prof.end(GRAAL_K_FULL_BAND, st);
-    k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)1 * ps, g2, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
     if (c->n_quirky > 0) {
         if (c->n_quirky > ps) return set_err(-5, "too many quirky bins (%d > %d)", c->n_quirky, ps);
         k_quirk<<<dim3(c->n_quirky, 1), 256, 0, st>>>(c->d_quirky, c->n_quirky, s, ld, n, 0, c->lv, nullptr, nullptr, p,
@@ -1385,14 +1493,9 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
     return 0;
 }
 
-int graal_delta_loglik(graal_ctx* c, int base_slot, int first_cand_slot, int n_cand, int id_fA, int id_fB, int max_id, double* d_out) {
-    NEED_STATE(c); NEED_SLOT(c, base_slot); NEED_SLOT(c, first_cand_slot);
-    if (n_cand < 1 || n_cand > GRAAL_N_CANDIDATES) return set_err(-1, "n_cand must be 1..13");
-    NEED_SLOT(c, first_cand_slot + n_cand - 1);
-    if (!d_out) return set_err(-1, "null output");
-    if (!c->have_params) return set_err(-1, "parameters not set");
+static int delta_loglik_impl(graal_ctx* c, int base_slot, int first_cand_slot, int n_cand, int id_fA, int id_fB, int max_id,
+                            unsigned skip, double* d_out, double* d_band) {
     const int n = c->n_new, ld = c->ld;
-    if (id_fA < 0 || id_fA >= n || id_fB < 0 || id_fB >= n) return set_err(-1, "bin id out of range");
     cudaStream_t st = c->stream;
     const Params p = c->p;
     int rc = ensure_base_geometry(c, base_slot); if (rc) return rc;
@@ -1404,24 +1507,32 @@ int graal_delta_loglik(graal_ctx* c, int base_slot, int first_cand_slot, int n_c
     k_delta_setup<<<1, 1, 0, st>>>(base, ld, id_fA, id_fB, c->d_ints + 0, max_id, meta); CHECK_LAUNCH(c);
     k_fill_sub_index<<<nblk(n, 256), 256, 0, st>>>(base, ld, n, meta, c->sub_index); CHECK_LAUNCH(c);
     CUDA_OK(cudaMemsetAsync(piece_len, 0, GRAAL_N_CANDIDATES * 8 * sizeof(int), st));
+    CUDA_OK(cudaMemsetAsync(c->chmask, 0, (size_t)c->W * sizeof(unsigned), st));
     const int gu = std::min(c->n_sm * 2, nblk(n, 256));
-    k_cand_geometry<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->lv, c->sub_index, meta, c->geo_cand, (size_t)c->W, piece_len); CHECK_LAUNCH(c);
-    k_cand_order<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->sub_index, meta, piece_len, c->cand_order, n); CHECK_LAUNCH(c);
+    k_cand_geometry<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->lv, c->sub_index, meta, c->geo_cand, (size_t)c->W, piece_len,
+                                                     c->geo_base, c->chmask, skip); CHECK_LAUNCH(c);
+    k_cand_order<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->sub_index, meta, piece_len, c->cand_order, n, skip); CHECK_LAUNCH(c);
     const int gw = std::min(ps, std::max(1, nblk(n, 8)));
-    // contacts: + sum over changed contacts of ob*(log ex_k - log ex_0)
+    // contacts: sum over changed contacts of ob * (ln ex_k - ln ex_0): new terms per candidate, old terms once
     c->prof.begin(GRAAL_K_DELTA_CONTACTS, st);
-    k_delta_contacts<<<dim3(gw, n_cand), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, c->sub_index, meta, c->geo_base, c->geo_cand, (size_t)c->W,
-                                                      p, c->partials, ps); CHECK_LAUNCH(c);
-    c->prof.end(GRAAL_K_DELTA_CONTACTS, st);
+    CUDA_OK(cudaMemsetAsync(c->partials, 0, (size_t)GRAAL_N_CANDIDATES * ps * sizeof(double), st));
+    k_delta_contacts<false><<<dim3(gw, n_cand), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, c->sub_index, meta, c->geo_base, c->geo_cand, (size_t)c->W,
+                                                             c->chmask, skip, p, c->partials, ps); CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, 1.0, d_out, 0); CHECK_LAUNCH(c);
-    // band mass: - [B_U(S_k) - B_U(S_0)] over changed pairs
-    c->prof.begin(GRAAL_K_DELTA_BAND, st);
-    k_band<true><<<dim3(gw, n_cand), 256, 0, st>>>(c->cand_order, meta + 4, -1, cand0, ld, c->lv, c->geo_cand, c->geo_base, (size_t)c->W, slot_stride(c), n, 1, p,
-                                                  c->partials, ps); CHECK_LAUNCH(c);
+    k_delta_contacts<true><<<dim3(gw, 1), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, c->sub_index, meta, c->geo_base, c->geo_cand, (size_t)c->W,
+                                                       c->chmask, skip, p, c->partials, ps); CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, -1.0, d_out, 1); CHECK_LAUNCH(c);
-    k_band<true><<<dim3(gw, n_cand), 256, 0, st>>>(c->sub_index, meta + 4, -1, base, ld, c->lv, c->geo_base, c->geo_cand, (size_t)c->W, 0, 0, 0, p,
-                                                  c->partials, ps); CHECK_LAUNCH(c);
-    k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, 1.0, d_out, 1); CHECK_LAUNCH(c);
+    c->prof.end(GRAAL_K_DELTA_CONTACTS, st);
+    // band mass: d_band[k] = B_U(S_k) - B_U(S_0) over changed pairs; enters the delta with a minus sign
+    c->prof.begin(GRAAL_K_DELTA_BAND, st);
+    CUDA_OK(cudaMemsetAsync(c->partials, 0, (size_t)GRAAL_N_CANDIDATES * ps * sizeof(double), st));
+    k_band<BAND_CAND><<<dim3(gw, n_cand), 256, 0, st>>>(c->cand_order, meta + 4, -1, cand0, ld, c->lv, c->geo_cand, c->chmask, (size_t)c->W, slot_stride(c), n,
+                                                       skip, p, c->partials, ps); CHECK_LAUNCH(c);
+    k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, 1.0, d_band, 0); CHECK_LAUNCH(c);
+    k_band<BAND_BASE><<<dim3(gw, 1), 256, 0, st>>>(c->sub_index, meta + 4, -1, base, ld, c->lv, c->geo_base, c->chmask, 0, 0, 0,
+                                                  skip, p, c->partials, ps); CHECK_LAUNCH(c);
+    k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, -1.0, d_band, 1); CHECK_LAUNCH(c);
+    k_reduce_partials<<<n_cand, 32, 0, st>>>(d_band, 1, 1, -1.0, d_out, 1); CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_DELTA_BAND, st);
     if (c->n_quirky > 0) {
         // quirk mass: - [Q_U(S_k) - Q_U(S_0)]
@@ -1434,6 +1545,46 @@ int graal_delta_loglik(graal_ctx* c, int base_slot, int first_cand_slot, int n_c
         for (int k = 0; k < n_cand; k++) {
             k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)13 * ps, c->n_quirky, 0, 1.0, d_out + k, 1); CHECK_LAUNCH(c);
         }
+    }
+    return 0;
+}
+
+int graal_delta_loglik(graal_ctx* c, int base_slot, int first_cand_slot, int n_cand, int id_fA, int id_fB, int max_id, double* d_out) {
+    NEED_STATE(c); NEED_SLOT(c, base_slot); NEED_SLOT(c, first_cand_slot);
+    if (n_cand < 1 || n_cand > GRAAL_N_CANDIDATES) return set_err(-1, "n_cand must be 1..13");
+    NEED_SLOT(c, first_cand_slot + n_cand - 1);
+    if (!d_out) return set_err(-1, "null output");
+    if (!c->have_params) return set_err(-1, "parameters not set");
+    if (id_fA < 0 || id_fA >= c->n_new || id_fB < 0 || id_fB >= c->n_new) return set_err(-1, "bin id out of range");
+    return delta_loglik_impl(c, base_slot, first_cand_slot, n_cand, id_fA, id_fB, max_id, 0u, d_out, c->d_scalars + 16);
+}
+
+int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int id_fA, int id_fB, int max_id, int proposal_index, double* d_out) {
+    NEED_STATE(c);
+    if (proposal_index < 0 || proposal_index >= 16) return set_err(-1, "proposal index must be 0..15");
+    if (!d_out) return set_err(-1, "null output");
+    if (!c->have_params) return set_err(-1, "parameters not set");
+    int rc = graal_build_candidates(c, base_slot, first_cand_slot, id_fA, id_fB, max_id, 0x1FFFu); if (rc) return rc;
+    // unique bins: swap_activity is the identity on the popped-out structure, candidate 8 == candidate 0 (Q7)
+    const unsigned skip = 1u << 8;
+    double* d_band = c->band_hist + (size_t)proposal_index * GRAAL_N_CANDIDATES;
+    rc = delta_loglik_impl(c, base_slot, first_cand_slot, GRAAL_N_CANDIDATES, id_fA, id_fB, max_id, skip, d_out, d_band); if (rc) return rc;
+    k_copy_double<<<1, 1, 0, c->stream>>>(d_out, 8, 0); CHECK_LAUNCH(c);
+    k_copy_double<<<1, 1, 0, c->stream>>>(d_band, 8, 0); CHECK_LAUNCH(c);
+    return 0;
+}
+
+int graal_commit_scored(graal_ctx* c, int base_slot, int first_cand_slot, int id_fA, int id_fB, int max_id, int mode, int proposal_index) {
+    NEED_STATE(c);
+    if (mode < 0 || mode >= GRAAL_N_CANDIDATES) return set_err(-1, "mode must be 0..12");
+    if (proposal_index >= 16) return set_err(-1, "proposal index must be < 16");
+    const unsigned mask = (mode < 9) ? (1u << mode) : 0x1E00u;            // test_copy_struct (cuda_lib_gl.py:1156-1183)
+    const int keep = c->band_slot;
+    int rc = graal_build_candidates(c, base_slot, first_cand_slot, id_fA, id_fB, max_id, mask); if (rc) return rc;
+    rc = graal_commit(c, base_slot, first_cand_slot + mode); if (rc) return rc;
+    if (proposal_index >= 0 && keep == base_slot) {       // keep the cached band total in step with the committed candidate
+        k_add_selected<<<1, 1, 0, c->stream>>>(c->d_scalars + 40, c->band_hist + (size_t)proposal_index * GRAAL_N_CANDIDATES, mode); CHECK_LAUNCH(c);
+        c->band_slot = base_slot;
     }
     return 0;
 }

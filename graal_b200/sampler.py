@@ -467,9 +467,8 @@ class sampler:
         """stream_likelihood (cuda_lib_gl.py:2392-2546) for every neighbour: candidates + deltas, queued
         on the stream; results land in d_out[16 + 13*x + j]."""
         for x, id_fB in enumerate(id_neighbours):
-            self.perform_modifications(id_fA, id_fB)
-            check(self.lib.graal_delta_loglik(self.ctx, CUR, CAND0, N_TMP_STRUCT, int(id_fA), int(id_fB), -1,
-                                              self._ptr(self.d_out, 16 + N_TMP_STRUCT * x)))
+            check(self.lib.graal_score_proposal(self.ctx, CUR, CAND0, int(id_fA), int(id_fB), -1, x,
+                                                self._ptr(self.d_out, 16 + N_TMP_STRUCT * x)))
 
     def step_max_likelihood(self, id_fA, delta, size_block=512, dt=0, t=0, n_step=1):
         """cuda_lib_gl.py:1793-1980.  Returns (o, n_contigs, min_len, mean_len_bp, max_len, op_sampled,
@@ -495,7 +494,8 @@ class sampler:
             sample_out = self._sample(self.score, self.temperature(t, n_step))
             id_f_sampled = id_neighbours[sample_out // N_TMP_STRUCT]
             op_sampled = sample_out % N_TMP_STRUCT
-            self.test_copy_struct(id_fA, id_f_sampled, op_sampled, -1)
+            check(lib.graal_commit_scored(self.ctx, CUR, CAND0, int(id_fA), int(id_f_sampled), -1, int(op_sampled),
+                                          int(sample_out // N_TMP_STRUCT)))
             o = self.score[sample_out]
             self.o = o
         else:
@@ -521,7 +521,8 @@ class sampler:
             return
         check(lib.graal_full_loglik(self.ctx, CUR, None, self._ptr(self.d_out, 0)))
         self.score_neighbours(id_fA, id_neighbours)
-        self.test_copy_struct(id_fA, id_f_sampled, op_sampled, -1)
+        x = id_neighbours.index(id_f_sampled) if id_f_sampled in id_neighbours else -1
+        check(lib.graal_commit_scored(self.ctx, CUR, CAND0, int(id_fA), int(id_f_sampled), -1, int(op_sampled), x))
 
     def _sample(self, score, F_t):
         """Candidate filtering and draw (cuda_lib_gl.py:1899-1947)."""

@@ -119,6 +119,20 @@ int graal_full_loglik(graal_ctx* ctx, int slot, const float* p_override, double*
 int graal_delta_loglik(graal_ctx* ctx, int base_slot, int first_cand_slot, int n_cand,
                        int id_fA, int id_fB, int max_id, double* d_out);
 
+/* stream_likelihood (cuda_lib_gl.py:2392-2546) for ONE proposal (id_fA, id_fB): the 13 candidates are
+ * built into first_cand_slot.. and scored against base_slot -> d_out[13].  proposal_index (0..15) names the
+ * proposal for a later graal_commit_scored.  Candidate 8 (swap activity) equals candidate 0 for unique
+ * bins (reference quirk Q7) and is copied, not re-evaluated. */
+int graal_score_proposal(graal_ctx* ctx, int base_slot, int first_cand_slot, int id_fA, int id_fB,
+                         int max_id, int proposal_index, double* d_out);
+
+/* test_copy_struct (cuda_lib_gl.py:1156-1183): rebuild candidate `mode` of (id_fA, id_fB) and commit it to
+ * base_slot.  proposal_index >= 0: the proposal was scored by graal_score_proposal since base_slot last
+ * changed, and the cached band total of base_slot is updated with that candidate's band delta (the next
+ * graal_full_loglik then skips the band pass); < 0: plain rebuild + commit. */
+int graal_commit_scored(graal_ctx* ctx, int base_slot, int first_cand_slot, int id_fA, int id_fB,
+                        int max_id, int mode, int proposal_index);
+
 /* per-step statistics of step_max_likelihood (cuda_lib_gl.py:1809-1816) -> d_out[4] (device doubles):
  * n_contigs, min l_cont, mean l_cont_bp over contig heads, max l_cont. */
 int graal_state_stats(graal_ctx* ctx, int slot, double* d_out);
