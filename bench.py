@@ -240,9 +240,9 @@ def main():
         barrier()
         windows.append((t_w0, time.time()))
         e2e_ms = ev0.elapsed_time(ev1)
-        # per step: D2H of the pinned output block + the state copy used by dist_inter_genome; H2D: none
+        # per step: D2H of the pinned output block, twice; H2D: none
         # (proposal ids travel as kernel arguments)
-        d2h = g.h_out.numel() * 8 + len(FRAG_FIELDS) * n * 4
+        d2h = 2 * g.h_out.numel() * 8        # two fetches of the pinned output block (scores + stats, then the distance)
         h2d = 0
     else:
         for it in range(total):

@@ -921,6 +921,70 @@ k_delta_contacts(const long long* __restrict__ rowptr, const int2* __restrict__ 
     }
 }
 
+// All candidates in ONE pass over the contacts of U: every contact is loaded once, its OLD term is
+// evaluated once, and for every candidate whose chmask bit is set on either side the NEW term is
+// evaluated from that candidate's records (row records of the 13 candidates staged in shared memory,
+// partner records gathered only where the partner changed).  acc[k] += new_k - old.
+__global__ void __launch_bounds__(256)
+k_delta_contacts_all(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, LevelView lv,
+                     const int* __restrict__ sub_index, const int* __restrict__ meta,
+                     const Geo* __restrict__ geo_base, const Geo* __restrict__ geo_cand0, size_t geo_stride,
+                     const unsigned* __restrict__ chmask, int n_cand,
+                     const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
+    __shared__ Geo rowrec[8][GRAAL_N_CANDIDATES * 3];
+    const int m = meta[4], cA = meta[0], cB = meta[1];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    double accs[GRAAL_N_CANDIDATES];
+    #pragma unroll
+    for (int c = 0; c < GRAAL_N_CANDIDATES; c++) accs[c] = 0.0;
+    for (int u = warp; u < m; u += n_warps) {
+        const int bin = sub_index[u];
+        const int4 sid = lv.sub_id[bin];
+        const int sub0 = sid.x;
+        const long long e0 = __ldg(&rowptr[sub0]);
+        const long long b1 = __ldg(&rowptr[sub0 + 1]);
+        const long long b2 = (sid.w > 1) ? __ldg(&rowptr[sub0 + 2]) : b1;
+        const long long e1 = (sid.w > 2) ? __ldg(&rowptr[sub0 + 3]) : b2;
+        Geo gr0[3]; unsigned mr[3] = {0u, 0u, 0u};
+        #pragma unroll
+        for (int a = 0; a < 3; a++) if (a < sid.w) { gr0[a] = ld_geo(&geo_base[sub0 + a]); mr[a] = __ldg(&chmask[sub0 + a]); }
+        __syncwarp();
+        for (int idx = lane; idx < n_cand * 3; idx += 32) {
+            const int k = idx / 3, a = idx - 3 * k;
+            if (a < sid.w && ((mr[0] | mr[1] | mr[2]) >> k & 1u)) rowrec[wib][idx] = ld_geo(&geo_cand0[(size_t)k * geo_stride + sub0 + a]);
+        }
+        __syncwarp();
+        for (long long e = e0 + lane; e < e1; e += 32) {
+            const int a = (e >= b1) + (e >= b2);
+            const int2 ce = __ldg(&contacts[e]);
+            const Geo g0c = ld_geo(&geo_base[ce.x]);
+            if (g0c.id_c != cA && g0c.id_c != cB) continue;              // partner outside U
+            if (ce.x - pk_local(g0c.pk) == sub0) continue;               // same bin: diagonal pixel, not re-scored
+            const unsigned mra = (a == 0) ? mr[0] : (a == 1 ? mr[1] : mr[2]);
+            const unsigned mc = __ldg(&chmask[ce.x]);
+            const unsigned mm = mra | mc;
+            if (!mm) continue;                                           // bitwise unchanged in every candidate
+            const float ob = __int_as_float(ce.y);
+            const Geo r0 = (a == 0) ? gr0[0] : (a == 1 ? gr0[1] : gr0[2]);
+            const double told = contact_log_term(r0, g0c, ob, p);
+            #pragma unroll
+            for (int k = 0; k < GRAAL_N_CANDIDATES; k++) {
+                if (!((mm >> k) & 1u)) continue;
+                const Geo rk = ((mra >> k) & 1u) ? rowrec[wib][3 * k + a] : r0;
+                const Geo gc = ((mc >> k) & 1u) ? ld_geo(&geo_cand0[(size_t)k * geo_stride + ce.x]) : g0c;
+                accs[k] += contact_log_term(rk, gc, ob, p) - told;
+            }
+        }
+    }
+    #pragma unroll
+    for (int c = 0; c < GRAAL_N_CANDIDATES; c++) {
+        const double v = block_sum(accs[c]);
+        if (threadIdx.x == 0) partials[(size_t)c * partial_stride + blockIdx.x] = v;
+    }
+}
+
 // out[dst] = out[src]   /   *total += sel[idx]   (tiny helpers of the incremental bookkeeping)
 __global__ void k_copy_double(double* p, int dst, int src) { p[dst] = p[src]; }
 __global__ void k_add_selected(double* total, const double* v, int idx) { *total += v[idx]; }
@@ -951,6 +1015,43 @@ __global__ void k_count_contigs(const int* __restrict__ first, int cap, int* __r
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(n_contigs, c);
+}
+
+// dist_inter_genome (cuda_lib_gl.py:475-541): per-bin neighbour / orientation agreement with the initial
+// genome; every term is a multiple of 0.5, so the float64 sum is exact whatever the order.
+__global__ void __launch_bounds__(256)
+k_dist_genome(const int* __restrict__ slot, int ld, int n, const int* __restrict__ init_prev, const int* __restrict__ init_next,
+              const int* __restrict__ orientable, const unsigned char* __restrict__ skip, double* __restrict__ partials) {
+    double acc = 0.0;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
+        if (skip[f]) continue;
+        const int p0 = init_prev[f], n0 = init_next[f];
+        const int tp = slot[F_PREV * ld + f], tn = slot[F_NEXT * ld + f];
+        int p1 = (tp != -1) ? slot[F_ID_D * ld + tp] : tp;
+        int n1 = (tn != -1) ? slot[F_ID_D * ld + tn] : tn;
+        double d = 3.0;
+        if ((p1 == p0 && n1 == n0) || (p1 == n0 && n1 == p0)) d -= 1.0;
+        if (orientable[f]) {
+            int swap = 1;
+            if (slot[F_ORI * ld + f] != 1) { const int t = p1; p1 = n1; n1 = t; swap = -1; }     // initial orientation is +1
+            if (p0 == p1) {
+                if (p0 == -1) d -= 1.0;
+                else if (!orientable[p1]) d -= 1.0;
+                else { d -= 0.5; if (1 == swap * slot[F_ORI * ld + p1]) d -= 0.5; }
+            }
+            if (n0 == n1) {
+                if (n0 == -1) d -= 1.0;
+                else if (!orientable[n1]) d -= 1.0;
+                else { d -= 0.5; if (1 == swap * slot[F_ORI * ld + n1]) d -= 0.5; }
+            }
+        } else {
+            if (p1 == p0 || p1 == n0) d -= 1.0;
+            if (n1 == n0 || n1 == p0) d -= 1.0;
+        }
+        acc += d;
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
 }
 
 // distance histogram of estimate_parameters (cuda_lib_gl.py:1236-1270).  The initial sub-level layout
@@ -1515,13 +1616,9 @@ static int delta_loglik_impl(graal_ctx* c, int base_slot, int first_cand_slot, i
     const int gw = std::min(ps, std::max(1, nblk(n, 8)));
     // contacts: sum over changed contacts of ob * (ln ex_k - ln ex_0): new terms per candidate, old terms once
     c->prof.begin(GRAAL_K_DELTA_CONTACTS, st);
-    CUDA_OK(cudaMemsetAsync(c->partials, 0, (size_t)GRAAL_N_CANDIDATES * ps * sizeof(double), st));
-    k_delta_contacts<false><<<dim3(gw, n_cand), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, c->sub_index, meta, c->geo_base, c->geo_cand, (size_t)c->W,
-                                                             c->chmask, skip, p, c->partials, ps); CHECK_LAUNCH(c);
+    k_delta_contacts_all<<<dim3(gw, 1), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, c->sub_index, meta, c->geo_base, c->geo_cand, (size_t)c->W,
+                                                     c->chmask, n_cand, p, c->partials, ps); CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, 1.0, d_out, 0); CHECK_LAUNCH(c);
-    k_delta_contacts<true><<<dim3(gw, 1), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, c->sub_index, meta, c->geo_base, c->geo_cand, (size_t)c->W,
-                                                       c->chmask, skip, p, c->partials, ps); CHECK_LAUNCH(c);
-    k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, -1.0, d_out, 1); CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_DELTA_CONTACTS, st);
     // band mass: d_band[k] = B_U(S_k) - B_U(S_0) over changed pairs; enters the delta with a minus sign
     c->prof.begin(GRAAL_K_DELTA_BAND, st);
@@ -1602,6 +1699,18 @@ int graal_state_stats(graal_ctx* c, int slot, double* d_out) {
     k_set_int<<<1, 1, 0, st>>>(c->d_ints + 3, 0); CHECK_LAUNCH(c);
     k_count_contigs<<<std::min(nblk(cap, 256), c->n_sm * 4), 256, 0, st>>>(c->first_idx, cap, c->d_ints + 3); CHECK_LAUNCH(c);
     k_stats_final<<<1, 1, 0, st>>>(c->d_stats, c->d_ints + 3, d_out); CHECK_LAUNCH(c);
+    return 0;
+}
+
+int graal_dist_genome(graal_ctx* c, int slot, const int32_t* init_prev, const int32_t* init_next, const int32_t* init_orientable,
+                      const uint8_t* skip, double* d_out) {
+    NEED_STATE(c); NEED_SLOT(c, slot);
+    if (!init_prev || !init_next || !init_orientable || !skip || !d_out) return set_err(-1, "null argument");
+    const int n = c->n_new;
+    const int g = std::min(c->partial_stride, std::max(1, nblk(n, 256)));
+    double* part = c->partials + (size_t)15 * c->partial_stride;
+    k_dist_genome<<<g, 256, 0, c->stream>>>(slot_ptr(c, slot), c->ld, n, init_prev, init_next, init_orientable, skip, part); CHECK_LAUNCH(c);
+    k_reduce_partials<<<1, 256, 0, c->stream>>>(part, g, 0, 1.0, d_out, 0); CHECK_LAUNCH(c);
     return 0;
 }
 

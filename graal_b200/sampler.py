@@ -280,9 +280,15 @@ class sampler:
         self.np_init_ori = np.ones(n, dtype=I32)
         self.np_init_orientable = (self.np_sub_frags_id[S_o_A_frags['id_d'], 3] > 1).astype(I32)
         self.h_id_d = np.asarray(S_o_A_frags["id_d"], dtype=I32).copy()      # never modified by any kernel
+        self.d_init_prev, self.d_init_next = t(self.np_init_prev.astype(I32)), t(self.np_init_next.astype(I32))
+        self.d_init_orientable = t(self.np_init_orientable)
         self.gpu_vect_frags = _VectFrags(self, CUR)
         self.collector_gpu_vect_frags = [_VectFrags(self, CAND0 + k) for k in range(N_TMP_STRUCT)]
         self.define_repeats()
+        skip = self.is_repeat.astype(np.uint8)
+        if self.id_frags_blacklisted:
+            skip[np.asarray(self.id_frags_blacklisted, dtype=np.int64)] = 1
+        self.d_dist_skip = t(skip)
         self.param_simu = None
         self.likelihood_t = None
         self.score = np.zeros(0)
@@ -506,9 +512,17 @@ class sampler:
             n_contigs, min_len, mean_len_bp, max_len = int(out[4]), int(out[5]), out[6], int(out[7])
             op_sampled, id_f_sampled = -1, id_fA
         F_t = self.temperature(t, n_step)
-        dist = self.dist_inter_genome(self.gpu_vect_frags)
+        dist = self.dist_inter_genome_device()
         self.likelihood_t = o
         return o, n_contigs, min_len, mean_len_bp, max_len, op_sampled, id_f_sampled, dist, F_t
+
+    def dist_inter_genome_device(self):
+        """dist_inter_genome of the current genome (cuda_lib_gl.py:475-541) reduced on the device: one
+        scalar comes back instead of the 14 state arrays."""
+        check(self.lib.graal_dist_genome(self.ctx, CUR, self._ptr(self.d_init_prev), self._ptr(self.d_init_next),
+                                         self._ptr(self.d_init_orientable), self._ptr(self.d_dist_skip), self._ptr(self.d_out, 8)))
+        norm_distance = 3.0 * (int(self.n_new_frags) - self.n_frags_4_dist)
+        return float(self._fetch()[8]) / norm_distance if norm_distance != 0 else 0.0
 
     def step_device(self, id_fA, id_neighbours, id_f_sampled, op_sampled):
         """Device-resident replay of one step: the same kernel sequence as step_max_likelihood with the

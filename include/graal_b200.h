@@ -137,6 +137,14 @@ int graal_commit_scored(graal_ctx* ctx, int base_slot, int first_cand_slot, int 
  * n_contigs, min l_cont, mean l_cont_bp over contig heads, max l_cont. */
 int graal_state_stats(graal_ctx* ctx, int slot, double* d_out);
 
+/* dist_inter_genome (cuda_lib_gl.py:475-541): d_out[0] = sum over the bins with skip[f] == 0 of their
+ * distance term (3 minus the neighbour / orientation agreements with the initial genome); the caller
+ * divides by 3 * (number of counted bins).  init_prev / init_next / init_orientable: int32[n] device
+ * arrays (np_init_prev, np_init_next, np_init_orientable, cuda_lib_gl.py:226-233); the initial orientation
+ * is +1 everywhere; skip: uint8[n], 1 for blacklisted bins and repeat copies. */
+int graal_dist_genome(graal_ctx* ctx, int slot, const int32_t* init_prev, const int32_t* init_next,
+                      const int32_t* init_orientable, const uint8_t* skip, double* d_out);
+
 /* distance histogram of estimate_parameters (cuda_lib_gl.py:1236-1270) on the INITIAL sub-level
  * layout: for cis sub-frag pairs with mid-to-mid distance d < max_dist_kb, bin int(d/bin_kb):
  * d_sum[b] += contacts (zeros included through d_cnt), d_cnt[b] += 1.
