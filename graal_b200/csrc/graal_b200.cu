@@ -379,7 +379,9 @@ __device__ __forceinline__ void bin_geometry(const int* __restrict__ slot, int l
     const float start_kb = __int2float_rn(slot[F_START_BP * ld + bin]) / 1000.0f;
     const int id_c = slot[F_ID_C * ld + bin];
     const unsigned circ = slot[F_CIRC * ld + bin] == 1 ? 1u : 0u;
-    const float stot = __int2float_rn(slot[F_L_CONT_BP * ld + bin]) / 1000.0f;
+    // contig length (kb): only rippe_contacts_circ reads it, so it is recorded for circular contigs only --
+    // a linear contig whose length changed but whose bins did not move keeps bit-identical records
+    const float stot = circ ? __int2float_rn(slot[F_L_CONT_BP * ld + bin]) / 1000.0f : 0.0f;
     const int acc_last = acc[lim];
     float accu = 0.0f;
     #pragma unroll
