@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include <vector>
 #include <map>
@@ -521,17 +522,33 @@ __global__ void k_group_rows(const long long* __restrict__ rowptr, long long E, 
     group_row[g] = lo;
 }
 
-__global__ void __launch_bounds__(256, 4)
+#define FCS_THREADS 768
+template <bool SMEM_CID>
+__global__ void __launch_bounds__(SMEM_CID ? FCS_THREADS : 256, SMEM_CID ? 1 : 4)
 k_full_contacts_uniform(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, long long E, int W,
                         const int* __restrict__ group_row, int n_groups,
                         const Geo* __restrict__ geo, const unsigned short* __restrict__ cid16, const float* __restrict__ mid32,
                         const __grid_constant__ Params p, double lg, double* __restrict__ partials) {
-    __shared__ Pending queue[8][QCAP];
+    // SMEM_CID: the W x 2-byte contig-id table is staged in shared memory (one CTA per SM): the cis test
+    // becomes a shared-memory gather (~3-way bank conflicts) instead of 32 L1 wavefronts per warp-load
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    __shared__ Pending queue_static[SMEM_CID ? 1 : 8][SMEM_CID ? 1 : QCAP];
+    Pending* queue = SMEM_CID ? reinterpret_cast<Pending*>(smem_dyn) : &queue_static[0][0];
+    const unsigned short* cid_tab = cid16;
+    if (SMEM_CID) {
+        unsigned short* cid_s = reinterpret_cast<unsigned short*>(smem_dyn + (size_t)(FCS_THREADS / 32) * QCAP * sizeof(Pending));
+        const int n16 = (W + 7) / 8;
+        const uint4* src = reinterpret_cast<const uint4*>(cid16);
+        uint4* dst = reinterpret_cast<uint4*>(cid_s);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(&src[i]);
+        __syncthreads();
+        cid_tab = cid_s;
+    }
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    Pending* q = queue[wib];
+    Pending* q = queue + wib * QCAP;
     int qn = 0;
     double acc = 0.0;
     for (int g = warp; g < n_groups; g += n_warps) {
@@ -549,7 +566,7 @@ k_full_contacts_uniform(const long long* __restrict__ rowptr, const int2* __rest
         float r_mid = g0.mid, r_stot = g0.stot; int r_idc = g0.id_c; unsigned r_circ = (unsigned)pk_circ(g0.pk) << 31;
         unsigned cc[UNROLL8];
         #pragma unroll
-        for (int u = 0; u < UNROLL8; u++) cc[u] = __ldg(&cid16[ce[u].x]);
+        for (int u = 0; u < UNROLL8; u++) cc[u] = SMEM_CID ? (unsigned)cid_tab[ce[u].x] : (unsigned)__ldg(&cid16[ce[u].x]);
         // per-lane row of each of its 8 entries (rows are ~100s of entries long: the cursor rarely moves)
         bool cis[UNROLL8]; float rm[UNROLL8], rs[UNROLL8]; unsigned rc[UNROLL8];
         #pragma unroll
@@ -1148,6 +1165,7 @@ struct graal_ctx {
     double lf_total = 0.0, ob_total = 0.0;
     unsigned short* cid16_base = nullptr; float* mid32_base = nullptr; int smem_optin = 0;
     int* group_row = nullptr; int n_groups = 0;
+    int smem_cid = 0;                         // GRAAL_SMEM_CID=1: stage the contig-id table in shared memory (measured: no faster than L1, profiles/README.md)
     unsigned* chmask = nullptr;               // [W] bit k: record differs from the base slot in candidate k
     double* band_hist = nullptr;              // [16][13] band delta of the proposals scored since the last commit
     int band_slot = -1; int band_age = 0;     // slot whose cross-bin band total is cached in d_scalars[40]
@@ -1227,6 +1245,7 @@ int graal_ctx_create(int device, graal_ctx** out) {
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
     c->n_sm = prop.multiProcessorCount;
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    { const char* e = getenv("GRAAL_SMEM_CID"); if (e && e[0] == '1') c->smem_cid = 1; }
     CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
     CUDA_OK(cudaMalloc(&c->d_ints, 256 * sizeof(int)));
@@ -1538,30 +1557,38 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
         const float gg = g_clamp(c->accu_hist[0].first * c->accu_hist[0].first, p.v_inter, p.nfpb);
         if (gg > 0.0f) { uniform = true; lg_uniform = log((double)gg); }
     }
+    // shared-memory classification needs W * 2 B + the queues in one CTA per SM
+    const size_t fcs_smem = (size_t)(FCS_THREADS / 32) * QCAP * sizeof(Pending) + (((size_t)c->W + 7) / 8) * 16;
+    const bool use_smem = uniform && c->smem_cid && fcs_smem + 1024 <= (size_t)c->smem_optin;
     int g1 = 0;
     if (c->E > 0) {
-        int fc_blocks = 0;
-        if (uniform) { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fc_blocks, k_full_contacts_uniform, 256, 0)); }
-        else { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fc_blocks, k_full_contacts, 256, 0)); }
-        g1 = (int)std::min<long long>(std::min(ps, c->n_sm * std::max(1, fc_blocks)), (c->E + 1023) / 1024);   // one resident wave
+        if (use_smem) {
+            CUDA_OK(cudaFuncSetAttribute(k_full_contacts_uniform<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fcs_smem));
+            g1 = std::min(ps, c->n_sm);
+        } else {
+            int fc_blocks = 0;
+            if (uniform) { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fc_blocks, k_full_contacts_uniform<false>, 256, 0)); }
+            else { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fc_blocks, k_full_contacts, 256, 0)); }
+            g1 = (int)std::min<long long>(std::min(ps, c->n_sm * std::max(1, fc_blocks)), (c->E + 1023) / 1024);   // one resident wave
+        }
     }
     // d_out = -(lf_total + G0) [+ log g * sum(ob)]   then accumulate the device sums
     const double init = -(c->lf_total + g0) + (uniform ? lg_uniform * c->ob_total : 0.0);
     k_set_double<<<1, 1, 0, st>>>(d_out, init); CHECK_LAUNCH(c);
     if (g1 > 0) {
         c->prof.begin(GRAAL_K_FULL_CONTACTS, st);
-        if (uniform)
-            k_full_contacts_uniform<<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->W, c->group_row, c->n_groups, c->geo_base,
-                                                       c->cid16_base, c->mid32_base, p, lg_uniform, c->partials);
+        if (use_smem)
+            k_full_contacts_uniform<true><<<g1, FCS_THREADS, fcs_smem, st>>>(c->rowptr, c->contacts, c->E, c->W, c->group_row, c->n_groups, c->geo_base,
+                                                                            c->cid16_base, c->mid32_base, p, lg_uniform, c->partials);
+        else if (uniform)
+            k_full_contacts_uniform<false><<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->W, c->group_row, c->n_groups, c->geo_base,
+                                                              c->cid16_base, c->mid32_base, p, lg_uniform, c->partials);
         else
             k_full_contacts<<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->W, c->geo_base, p, c->partials);
         CHECK_LAUNCH(c);
         c->prof.end(GRAAL_K_FULL_CONTACTS, st);
         k_reduce_partials<<<1, 256, 0, st>>>(c->partials, g1, 0, 1.0, d_out, 1); CHECK_LAUNCH(c);
     }
-    // band mass.  The cross-bin part of the current parameters is cached (d_scalars[40]) and kept up to
-    // date by graal_commit_scored with the committed candidate's band delta; it is recomputed from
-    // scratch every GRAAL_BAND_RESYNC evaluations.  The same-bin part is recomputed every time.
     const int g2 = std::min(ps, nblk(n, 8));
     c->prof.begin(GRAAL_K_FULL_BAND, st);
     const bool cached = !p_override && c->band_slot == slot && c->band_age < GRAAL_BAND_RESYNC;
