@@ -366,12 +366,22 @@ __global__ void k_relabel_apply(int* __restrict__ id_c, int n, const int* __rest
 struct LevelView {
     const int4* sub_id; const float* sub_len; const int* sub_accu;   // [N] int4, [N*3], [N*3]
     const unsigned char* accu_idx;                                  // [N*3] index of sub_accu in the distinct-value list
+    const unsigned char* dup;                                       // [N] 1: the data bin has repeat copies (nullptr: none)
+    int n_data;                                                     // N: frags >= N are repeat copies
 };
+// Bins handled by the sparse (unique x unique) kernels; every pixel touching a duplicated data bin goes
+// through the per-pixel repeat path (k_repeat_pixels).
+__device__ __forceinline__ bool eligible(const LevelView& lv, int f) {
+    return lv.dup == nullptr || (f < lv.n_data && !lv.dup[f]);
+}
+#define PK_EXCLUDED (1u << 29)
 
 __device__ __forceinline__ void bin_geometry(const int* __restrict__ slot, int ld, int bin, const LevelView& lv,
                                              Geo* __restrict__ geo, unsigned short* __restrict__ cid16 = nullptr,
                                              float* __restrict__ mid32 = nullptr) {
     const int id_d = slot[F_ID_D * ld + bin];
+    const bool elig = eligible(lv, bin);
+    if (!elig && bin >= lv.n_data) return;                   // repeat copy: its data sub-frags belong to the original
     const int4 sid = lv.sub_id[id_d];
     const int lim = sid.w - 1;
     const float len[3] = { lv.sub_len[id_d * 3], lv.sub_len[id_d * 3 + 1], lv.sub_len[id_d * 3 + 2] };
@@ -396,7 +406,7 @@ __device__ __forceinline__ void bin_geometry(const int* __restrict__ slot, int l
         const int at = (loc == 0) ? acc[0] : (loc == 1 ? acc[1] : acc[2]);
         const int aq = (ori == 1) ? at : acc_last;
         Geo g; g.mid = mid; g.id_c = id_c; g.stot = stot;
-        g.pk = (unsigned)at | ((unsigned)aq << 8) | ((unsigned)loc << 26) | (circ << 28);
+        g.pk = (unsigned)at | ((unsigned)aq << 8) | ((unsigned)loc << 26) | (circ << 28) | (elig ? 0u : PK_EXCLUDED);
         const int sub = (loc == 0) ? sid.x : (loc == 1 ? sid.y : sid.z);
         geo[sub] = g;
         if (cid16) { cid16[sub] = (unsigned short)min(id_c < 0 ? 65535 : id_c, 65535); mid32[sub] = mid; }   // classification tables
@@ -475,9 +485,11 @@ k_full_contacts(const long long* __restrict__ rowptr, const int2* __restrict__ c
                     const float ob = __int_as_float(ce[u].y);
                     const bool cis = gr.id_c == gc[u].id_c;
                     const float s = fabsf(gc[u].mid - gr.mid);
-                    inband = cis && s > 0.0f && s < p.d_max;
+                    const bool excl = ((gr.pk | gc[u].pk) & PK_EXCLUDED) != 0u;      // pixel of a duplicated bin: repeat path
+                    inband = !excl && cis && s > 0.0f && s < p.d_max;
                     const int idx = (cis ? pk_true(gr.pk) : pk_quirk(gr.pk)) * p.nd + pk_true(gc[u].pk);
-                    if (inband) {
+                    if (excl) {
+                    } else if (inband) {
                         mine.s = s; mine.ob = ob; mine.stot = gr.stot; mine.key = (unsigned)idx | ((unsigned)pk_circ(gr.pk) << 31);
                     } else {
                         const double lg = __ldg(&p.t_logg[idx]);
@@ -608,20 +620,32 @@ k_full_contacts_uniform(const long long* __restrict__ rowptr, const int2* __rest
     if (threadIdx.x == 0) partials[blockIdx.x] = acc;
 }
 
+// (entries touching a duplicated data bin are left to the repeat path: sub_dup marks their sub-frags;
+//  row_of gives the row of each 256-entry group to walk from)
+__device__ __forceinline__ bool entry_excluded(const long long* __restrict__ rowptr, int W, const unsigned char* __restrict__ sub_dup,
+                                               long long e, int col) {
+    if (!sub_dup) return false;
+    if (sub_dup[col]) return true;
+    int lo = 0, hi = W;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (rowptr[mid + 1] > e) hi = mid; else lo = mid + 1; }
+    return sub_dup[lo] != 0;
+}
 // sum of ob over all stored contacts (level constant)
-__global__ void k_ob_total(const int2* __restrict__ contacts, long long E, double* __restrict__ partials) {
+__global__ void k_ob_total(const int2* __restrict__ contacts, long long E, const long long* __restrict__ rowptr, int W,
+                           const unsigned char* __restrict__ sub_dup, double* __restrict__ partials) {
     double acc = 0.0;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x)
-        acc += (double)__int_as_float(contacts[e].y);
+        if (!entry_excluded(rowptr, W, sub_dup, e, contacts[e].x)) acc += (double)__int_as_float(contacts[e].y);
     acc = block_sum(acc);
     if (threadIdx.x == 0) partials[blockIdx.x] = acc;
 }
 
 // sum of lf(ob) over all stored contacts (level constant)
-__global__ void k_lf_total(const int2* __restrict__ contacts, long long E, double* __restrict__ partials) {
+__global__ void k_lf_total(const int2* __restrict__ contacts, long long E, const long long* __restrict__ rowptr, int W,
+                           const unsigned char* __restrict__ sub_dup, double* __restrict__ partials) {
     double acc = 0.0;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x)
-        acc += log_fact_term(__int_as_float(contacts[e].y));
+        if (!entry_excluded(rowptr, W, sub_dup, e, contacts[e].x)) acc += log_fact_term(__int_as_float(contacts[e].y));
     acc = block_sum(acc);
     if (threadIdx.x == 0) partials[blockIdx.x] = acc;
 }
@@ -678,6 +702,7 @@ k_band(const int* __restrict__ order, const int* __restrict__ d_count, int count
     }
     for (int ix = warp; ix < count; ix += n_warps) {
         const int x = ord[ix];
+        if (!eligible(lv, x)) continue;
         const int4 sx = lv.sub_id[sl[F_ID_D * ld + x]];
         Geo gx[3]; unsigned mx[3] = {0u, 0u, 0u};
         float xmax = -1e30f;
@@ -706,7 +731,7 @@ k_band(const int* __restrict__ order, const int* __restrict__ d_count, int count
                 const Geo gy0 = ld_geo(&gE[sy.x]);
                 // beyond the band (or next contig): every remaining pair evaluates to the clamp value
                 if (gy0.id_c != cx || (double)ystart - (double)xmax > (double)p.d_max * 1.00001 + 0.05) live = false;
-                else {
+                else if (eligible(lv, y)) {
                     #pragma unroll
                     for (int b = 0; b < 3; b++) if (b < sy.w) {
                         const int sub = sy.x + b;
@@ -756,6 +781,7 @@ k_band_diag(const int* __restrict__ slot, int ld, int n, LevelView lv, const Geo
             const __grid_constant__ Params p, double* __restrict__ partials) {
     double acc = 0.0;
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) {
+        if (!eligible(lv, x)) continue;
         const int4 sx = lv.sub_id[slot[F_ID_D * ld + x]];
         Geo gx[3];
         #pragma unroll
@@ -793,7 +819,7 @@ k_quirk(const int* __restrict__ quirky, int n_quirky, const int* __restrict__ sl
         if (in_u) {
             for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
                 const int bj = bins_u ? bins_u[j] : j;
-                if (bj <= bi || sl[F_ID_C * ld + bj] == ci) continue;
+                if (bj <= bi || !eligible(lv, bj) || sl[F_ID_C * ld + bj] == ci) continue;
                 const int lj = lv.sub_id[bj].w - 1;
                 for (int b = 0; b <= lj; b++) {
                     const int aj = lv.sub_accu[bj * 3 + b];
@@ -845,7 +871,7 @@ __global__ void k_cand_geometry(const int* __restrict__ cand0, size_t slot_strid
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < m; u += gridDim.x * blockDim.x) {
         const int bin = sub_index[u];
         bin_geometry(sl, ld, bin, lv, geo0 + (size_t)k * geo_stride);
-        {   // bit k of chmask[sub]: the candidate's record differs from the base slot's (bitwise)
+        if (eligible(lv, bin)) {   // bit k of chmask[sub]: the candidate's record differs from the base slot's (bitwise)
             const int4 sid = lv.sub_id[sl[F_ID_D * ld + bin]];
             for (int a = 0; a < sid.w; a++)
                 if (!geo_eq(geo0[(size_t)k * geo_stride + sid.x + a], geo_base[sid.x + a])) atomicOr(&chmask[sid.x + a], 1u << k);
@@ -960,6 +986,7 @@ k_delta_contacts_all(const long long* __restrict__ rowptr, const int2* __restric
     for (int c = 0; c < GRAAL_N_CANDIDATES; c++) accs[c] = 0.0;
     for (int u = warp; u < m; u += n_warps) {
         const int bin = sub_index[u];
+        if (!eligible(lv, bin)) continue;                     // duplicated bin: repeat path
         const int4 sid = lv.sub_id[bin];
         const int sub0 = sid.x;
         const long long e0 = __ldg(&rowptr[sub0]);
@@ -980,6 +1007,7 @@ k_delta_contacts_all(const long long* __restrict__ rowptr, const int2* __restric
             const int2 ce = __ldg(&contacts[e]);
             const Geo g0c = ld_geo(&geo_base[ce.x]);
             if (g0c.id_c != cA && g0c.id_c != cB) continue;              // partner outside U
+            if (g0c.pk & PK_EXCLUDED) continue;                          // partner is a duplicated bin: repeat path
             if (ce.x - pk_local(g0c.pk) == sub0) continue;               // same bin: diagonal pixel, not re-scored
             const unsigned mra = (a == 0) ? mr[0] : (a == 1 ? mr[1] : mr[2]);
             const unsigned mc = __ldg(&chmask[ce.x]);
@@ -1007,6 +1035,147 @@ k_delta_contacts_all(const long long* __restrict__ rowptr, const int2* __restric
 // out[dst] = out[src]   /   *total += sel[idx]   (tiny helpers of the incremental bookkeeping)
 __global__ void k_copy_double(double* p, int dst, int src) { p[dst] = p[src]; }
 __global__ void k_add_selected(double* total, const double* v, int idx) { *total += v[idx]; }
+
+// ------------------------------------------------------------------------------------------------
+// repeat path: every pixel that touches a DUPLICATED data bin, evaluated per pixel exactly like the
+// reference's pixel loop (kernels3.cu:2895-3220 == 3383-3700): float32 expected values summed over
+// the ACTIVE copy pairs in the kernel's loop order, observed counts looked up in the contact lists.
+// ------------------------------------------------------------------------------------------------
+struct FragGeom { float mid[3]; int acc[3]; int lim, id_c, pos, circ, ori; float stot; };
+
+__device__ __forceinline__ FragGeom frag_geom(const int* __restrict__ slot, int ld, int f, const LevelView& lv) {
+    FragGeom G;
+    const int id_d = slot[F_ID_D * ld + f];
+    const int4 sid = lv.sub_id[id_d];
+    G.lim = sid.w - 1;
+    const float len[3] = { lv.sub_len[id_d * 3], lv.sub_len[id_d * 3 + 1], lv.sub_len[id_d * 3 + 2] };
+    G.acc[0] = lv.sub_accu[id_d * 3]; G.acc[1] = lv.sub_accu[id_d * 3 + 1]; G.acc[2] = lv.sub_accu[id_d * 3 + 2];
+    G.ori = slot[F_ORI * ld + f];
+    G.id_c = slot[F_ID_C * ld + f]; G.pos = slot[F_POS * ld + f]; G.circ = slot[F_CIRC * ld + f];
+    G.stot = __int2float_rn(slot[F_L_CONT_BP * ld + f]) / 1000.0f;
+    const float start_kb = __int2float_rn(slot[F_START_BP * ld + f]) / 1000.0f;
+    float accu = 0.0f;
+    G.mid[0] = G.mid[1] = G.mid[2] = 0.0f;
+    #pragma unroll
+    for (int i = 0; i < 3; i++) {
+        if (i > G.lim) break;
+        const int loc = (G.ori == 1) ? i : G.lim - i;
+        const float l = (loc == 0) ? len[0] : (loc == 1 ? len[1] : len[2]);
+        float mid;
+        if (i == 0) { mid = start_kb + l / 2.0f; accu = start_kb + l; }
+        else { mid = accu + l / 2.0f; accu = accu + l; }
+        if (loc == 0) G.mid[0] = mid; else if (loc == 1) G.mid[1] = mid; else G.mid[2] = mid;
+    }
+    return G;
+}
+
+__device__ __forceinline__ float lookup_obs(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, int sa, int sb) {
+    const int r = min(sa, sb), c = max(sa, sb);
+    long long lo = rowptr[r], hi = rowptr[r + 1];
+    while (lo < hi) { const long long mid = (lo + hi) >> 1; if (contacts[mid].x < c) lo = mid + 1; else hi = mid; }
+    return (lo < rowptr[r + 1] && contacts[lo].x == c) ? __int_as_float(contacts[lo].y) : 0.0f;
+}
+
+// evaluate_likelihood_double (kernels3.cu:191-210)
+__device__ __forceinline__ double poisson_ll(float exf, float obf) {
+    const double ex = (double)exf, ob = (double)obf;
+    if (ex == 0.0) return 0.0;
+    if (ob >= 15.0) return ob * log(ex) - ex - (ob * log(ob) - ob + log(sqrt(ob * 2.0 * M_PI)));
+    if (ob > 0.0) return ob * log(ex) - ex - log((double)factorial_f32(obf));
+    if (ob == 0.0) return -ex;
+    return 0.0;
+}
+
+__device__ double repeat_pixel(const int* __restrict__ slot, int ld, const LevelView& lv, const int* __restrict__ collector,
+                               const int2* __restrict__ dispatcher, const long long* __restrict__ rowptr,
+                               const int2* __restrict__ contacts, int bi, int bj, bool diag, const Params& p) {
+    float ex[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    const int2 di = dispatcher[bi], dj = dispatcher[bj];
+    for (int ci = di.x; ci < di.y; ci++) {
+        const int fi = collector[ci];
+        if (slot[F_ACTIV * ld + fi] != 1) continue;
+        const FragGeom Gi = frag_geom(slot, ld, fi, lv);
+        for (int cj = dj.x; cj < dj.y; cj++) {
+            const int fj = collector[cj];
+            if (slot[F_ACTIV * ld + fj] != 1) continue;
+            const FragGeom Gj = frag_geom(slot, ld, fj, lv);
+            if (Gi.id_c == Gj.id_c) {
+                const bool swap = Gi.pos > Gj.pos;              // the frag closest to the contig origin decides circ / s_tot
+                const bool circ = (swap ? Gj.circ : Gi.circ) == 1;
+                const float stot = swap ? Gj.stot : Gi.stot;
+                #pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    #pragma unroll
+                    for (int b = 0; b < 3; b++) {
+                        if (a > Gi.lim || b > Gj.lim) continue;
+                        const float s = fabsf(Gj.mid[b] - Gi.mid[a]);
+                        const float norm = __int2float_rn(Gi.acc[a] * Gj.acc[b]) / p.nfpb;
+                        const float r = circ ? rippe_contacts_circ(s, stot, p) : rippe_contacts(s, p);
+                        ex[a][b] = ex[a][b] + r * norm;
+                    }
+                }
+            } else {
+                #pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    #pragma unroll
+                    for (int b = 0; b < 3; b++) {
+                        if (a > Gi.lim || b > Gj.lim) continue;
+                        const int ai = (Gi.ori == 1) ? Gi.acc[a] : ((Gi.lim == 0) ? Gi.acc[0] : (Gi.lim == 1 ? Gi.acc[1] : Gi.acc[2]));   // quirk Q1
+                        const float norm = __int2float_rn(ai * Gj.acc[b]) / p.nfpb;
+                        ex[a][b] = ex[a][b] + p.v_inter * norm;
+                    }
+                }
+            }
+        }
+    }
+    const int4 si = lv.sub_id[bi], sj = lv.sub_id[bj];
+    double ll = 0.0;
+    #pragma unroll
+    for (int a = 0; a < 3; a++) {
+        #pragma unroll
+        for (int b = 0; b < 3; b++) {
+            if (a >= si.w || b >= sj.w || (diag && b <= a)) continue;
+            ll += poisson_ll(ex[a][b], lookup_obs(rowptr, contacts, si.x + a, sj.x + b));
+        }
+    }
+    return ll;
+}
+
+// mark the duplicated data bins that have a copy inside U (sub_index_repeats of cuda_lib_gl.py:2458)
+__global__ void k_mark_rep_in_u(const int* __restrict__ base, int ld, const int* __restrict__ sub_index, const int* __restrict__ meta,
+                                LevelView lv, unsigned char* __restrict__ rep_in_u) {
+    const int m = meta[4];
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < m; u += gridDim.x * blockDim.x) {
+        const int d = base[F_ID_D * ld + sub_index[u]];
+        if (lv.dup[d]) rep_in_u[d] = 1;
+    }
+}
+
+// Pixel enumeration t in [0, n_rep * N): r = rep_bins[t / N], j = t % N.
+//   FULL : every pixel touching a duplicated bin once (j unique, j == r -> diagonal, j duplicated and j > r)
+//   DELTA: ranges 2-4 of sub_compute_likelihood (kernels3.cu:3363-3380): r must have a copy in U;
+//          r x every unique bin, r x r' for duplicated r' > r also in U, and the diagonal of r
+template <bool DELTA>
+__global__ void __launch_bounds__(128)
+k_repeat_pixels(const int* __restrict__ slot0, size_t slot_stride, int ld, LevelView lv, const int* __restrict__ collector,
+                const int2* __restrict__ dispatcher, const long long* __restrict__ rowptr, const int2* __restrict__ contacts,
+                const int* __restrict__ rep_bins, int n_rep, const unsigned char* __restrict__ rep_in_u,
+                const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
+    const int k = blockIdx.y;
+    const int* slot = slot0 + (size_t)k * slot_stride;
+    const int N = lv.n_data;
+    double acc = 0.0;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < (long long)n_rep * N; t += (long long)gridDim.x * blockDim.x) {
+        const int r = rep_bins[t / N], j = (int)(t % N);
+        if (DELTA && !rep_in_u[r]) continue;
+        const bool jdup = lv.dup[j] != 0;
+        if (jdup && j < r) continue;
+        if (DELTA && jdup && j != r && !rep_in_u[j]) continue;
+        acc += repeat_pixel(slot, ld, lv, collector, dispatcher, rowptr, contacts, min(r, j), max(r, j), j == r, p);
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[(size_t)k * partial_stride + blockIdx.x] = acc;
+}
 
 // ------------------------------------------------------------------------------------------------
 // statistics and the distance histogram
@@ -1162,6 +1331,8 @@ struct graal_ctx {
     int math_mode = 1;
     std::vector<float> h_tab_g; std::vector<double> h_tab_logg;
     int* d_quirky = nullptr; int n_quirky = 0;
+    unsigned char* d_dup = nullptr; unsigned char* d_sub_dup = nullptr; unsigned char* d_rep_in_u = nullptr;
+    int* d_rep_bins = nullptr; int n_rep = 0;
     double lf_total = 0.0, ob_total = 0.0;
     unsigned short* cid16_base = nullptr; float* mid32_base = nullptr; int smem_optin = 0;
     int* group_row = nullptr; int n_groups = 0;
@@ -1263,6 +1434,8 @@ static void free_level_scratch(graal_ctx* c) {
     cudaFree(c->geo_base); cudaFree(c->geo_cand); cudaFree(c->order); cudaFree(c->cand_order); cudaFree(c->sub_index);
     cudaFree(c->cont_len); cudaFree(c->cont_off); cudaFree(c->first_idx); cudaFree(c->map); cudaFree(c->keys);
     cudaFree(c->keys_sorted); cudaFree(c->cub_tmp); cudaFree(c->d_quirky); cudaFree(c->d_accu_idx);
+    cudaFree(c->d_dup); cudaFree(c->d_sub_dup); cudaFree(c->d_rep_in_u); cudaFree(c->d_rep_bins);
+    c->d_dup = c->d_sub_dup = c->d_rep_in_u = nullptr; c->d_rep_bins = nullptr; c->n_rep = 0;
     cudaFree(c->d_tab_lnnorm); cudaFree(c->d_tab_log); cudaFree(c->d_tab_exp);
     c->d_tab_lnnorm = nullptr; c->d_tab_log = nullptr; c->d_tab_exp = nullptr;
     cudaFree(c->d_tab_norm); cudaFree(c->d_tab_g[0]); cudaFree(c->d_tab_g[1]); cudaFree(c->d_tab_logg[0]); cudaFree(c->d_tab_logg[1]);
@@ -1317,8 +1490,7 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     if (!c) return set_err(-1, "null context");
     if (n_frags <= 0 || n_sub_frags <= 0 || n_new_frags < n_frags) return set_err(-1, "bad level sizes");
     if (!sub_id || !sub_len_kb || !sub_accu || !rowptr || (n_contacts > 0 && !contacts)) return set_err(-1, "null level pointer");
-    if (n_new_frags != n_frags)
-        return set_err(-4, "levels with repeat copies (n_new_frags %d != n_frags %d) are not supported by the device path yet", n_new_frags, n_frags);
+    if (n_new_frags != n_frags && (!collector || !dispatcher)) return set_err(-1, "repeat copies need the collector / dispatcher tables");
     CUDA_OK(cudaSetDevice(c->device));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     free_level_scratch(c);
@@ -1330,6 +1502,13 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     std::vector<int> h_sid((size_t)n_frags * 4), h_acc((size_t)n_frags * 3);
     CUDA_OK(cudaMemcpy(h_sid.data(), sub_id, h_sid.size() * sizeof(int), cudaMemcpyDeviceToHost));
     CUDA_OK(cudaMemcpy(h_acc.data(), sub_accu, h_acc.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    // duplicated data bins (dispatcher range longer than 1): handled by the repeat path
+    std::vector<unsigned char> h_dup((size_t)n_frags, 0); std::vector<int> rep_bins;
+    if (n_new_frags != n_frags) {
+        std::vector<int> h_disp((size_t)n_frags * 2);
+        CUDA_OK(cudaMemcpy(h_disp.data(), dispatcher, h_disp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int b = 0; b < n_frags; b++) if (h_disp[2 * b + 1] - h_disp[2 * b] > 1) { h_dup[b] = 1; rep_bins.push_back(b); }
+    }
     std::map<int, long long> hist; std::vector<int> quirky; long long w_check = 0;
     for (int b = 0; b < n_frags; b++) {
         const int cnt = h_sid[(size_t)b * 4 + 3];
@@ -1340,9 +1519,10 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
             const int v = h_acc[(size_t)b * 3 + a];
             if (h_sid[(size_t)b * 4 + a] != (int)w_check + a) return set_err(-1, "sub-frag ids of bin %d are not consecutive", b);
             if (v < 0 || v > 46340) return set_err(-1, "accu %d of bin %d outside 0..46340", v, b);
-            hist[v]++; if (v != h_acc[(size_t)b * 3 + cnt - 1]) q = true;
+            hist[v] += h_dup[b] ? 0 : 1;
+            if (v != h_acc[(size_t)b * 3 + cnt - 1]) q = true;
         }
-        if (q) quirky.push_back(b);
+        if (q && !h_dup[b]) quirky.push_back(b);
         w_check += cnt;
     }
     if (w_check != n_sub_frags) return set_err(-1, "sub-frag count mismatch: %lld vs %d", w_check, n_sub_frags);
@@ -1377,6 +1557,18 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
         c->lv.accu_idx = c->d_accu_idx;
     }
     c->have_params = false;
+    c->n_rep = (int)rep_bins.size();
+    c->lv.dup = nullptr; c->lv.n_data = n_frags;
+    if (c->n_rep > 0) {
+        std::vector<unsigned char> sub_dup((size_t)n_sub_frags, 0);
+        for (int b = 0; b < n_frags; b++) if (h_dup[b]) for (int a = 0; a < h_sid[(size_t)b * 4 + 3]; a++) sub_dup[h_sid[(size_t)b * 4] + a] = 1;
+        CUDA_OK(cudaMalloc(&c->d_dup, h_dup.size())); CUDA_OK(cudaMemcpy(c->d_dup, h_dup.data(), h_dup.size(), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&c->d_sub_dup, sub_dup.size())); CUDA_OK(cudaMemcpy(c->d_sub_dup, sub_dup.data(), sub_dup.size(), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&c->d_rep_in_u, h_dup.size())); CUDA_OK(cudaMemset(c->d_rep_in_u, 0, h_dup.size()));
+        CUDA_OK(cudaMalloc(&c->d_rep_bins, rep_bins.size() * sizeof(int)));
+        CUDA_OK(cudaMemcpy(c->d_rep_bins, rep_bins.data(), rep_bins.size() * sizeof(int), cudaMemcpyHostToDevice));
+        c->lv.dup = c->d_dup;
+    }
     c->n_quirky = (int)quirky.size();
     if (c->n_quirky) {
         CUDA_OK(cudaMalloc(&c->d_quirky, quirky.size() * sizeof(int)));
@@ -1420,12 +1612,12 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     c->lf_total = 0.0;
     if (c->E > 0) {
         const int grid = c->partial_stride;
-        k_lf_total<<<grid, 256, 0, c->stream>>>(c->contacts, c->E, c->partials);
+        k_lf_total<<<grid, 256, 0, c->stream>>>(c->contacts, c->E, c->rowptr, c->W, c->d_sub_dup, c->partials);
         CHECK_LAUNCH(c);
         k_reduce_partials<<<1, 256, 0, c->stream>>>(c->partials, grid, 0, 1.0, c->d_scalars + 15, 0);
         CHECK_LAUNCH(c);
         CUDA_OK(cudaMemcpyAsync(&c->lf_total, c->d_scalars + 15, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        k_ob_total<<<grid, 256, 0, c->stream>>>(c->contacts, c->E, c->partials);
+        k_ob_total<<<grid, 256, 0, c->stream>>>(c->contacts, c->E, c->rowptr, c->W, c->d_sub_dup, c->partials);
         CHECK_LAUNCH(c);
         k_reduce_partials<<<1, 256, 0, c->stream>>>(c->partials, grid, 0, 1.0, c->d_scalars + 14, 0);
         CHECK_LAUNCH(c);
@@ -1553,7 +1745,7 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
     const int nd = (int)c->accu_hist.size();
     double lg_uniform = 0.0;
     bool uniform = false;
-    if (nd == 1) {
+    if (nd == 1 && c->n_rep == 0) {
         const float gg = g_clamp(c->accu_hist[0].first * c->accu_hist[0].first, p.v_inter, p.nfpb);
         if (gg > 0.0f) { uniform = true; lg_uniform = log((double)gg); }
     }
@@ -1614,6 +1806,12 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
         if (!p_override) { c->band_slot = slot; c->band_age = 0; }
     }
     c->prof.end(GRAAL_K_FULL_BAND, st);
+    if (c->n_rep > 0) {     // every pixel touching a duplicated data bin
+        const int gr = (int)std::min<long long>(ps, ((long long)c->n_rep * c->N + 127) / 128);
+        k_repeat_pixels<false><<<dim3(gr, 1), 128, 0, st>>>(s, 0, ld, c->lv, c->collector, reinterpret_cast<const int2*>(c->dispatcher), c->rowptr, c->contacts,
+                                                           c->d_rep_bins, c->n_rep, nullptr, p, c->partials + (size_t)3 * ps, ps); CHECK_LAUNCH(c);
+        k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)3 * ps, gr, 0, 1.0, d_out, 1); CHECK_LAUNCH(c);
+    }
     if (c->n_quirky > 0) {
         if (c->n_quirky > ps) return set_err(-5, "too many quirky bins (%d > %d)", c->n_quirky, ps);
         k_quirk<<<dim3(c->n_quirky, 1), 256, 0, st>>>(c->d_quirky, c->n_quirky, s, ld, n, 0, c->lv, nullptr, nullptr, p,
@@ -1660,6 +1858,19 @@ static int delta_loglik_impl(graal_ctx* c, int base_slot, int first_cand_slot, i
     k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, -1.0, d_band, 1); CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 32, 0, st>>>(d_band, 1, 1, -1.0, d_out, 1); CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_DELTA_BAND, st);
+    if (c->n_rep > 0) {     // ranges 2-4: pixels of the duplicated bins that have a copy in U, new minus old
+        CUDA_OK(cudaMemsetAsync(c->d_rep_in_u, 0, (size_t)c->N, st));
+        k_mark_rep_in_u<<<gu, 256, 0, st>>>(base, ld, c->sub_index, meta, c->lv, c->d_rep_in_u); CHECK_LAUNCH(c);
+        const int gr = (int)std::min<long long>(ps, ((long long)c->n_rep * c->N + 127) / 128);
+        k_repeat_pixels<true><<<dim3(gr, n_cand), 128, 0, st>>>(cand0, slot_stride(c), ld, c->lv, c->collector, reinterpret_cast<const int2*>(c->dispatcher),
+                                                               c->rowptr, c->contacts, c->d_rep_bins, c->n_rep, c->d_rep_in_u, p, c->partials, ps); CHECK_LAUNCH(c);
+        k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gr, ps, 1.0, d_out, 1); CHECK_LAUNCH(c);
+        k_repeat_pixels<true><<<dim3(gr, 1), 128, 0, st>>>(base, 0, ld, c->lv, c->collector, reinterpret_cast<const int2*>(c->dispatcher),
+                                                          c->rowptr, c->contacts, c->d_rep_bins, c->n_rep, c->d_rep_in_u, p, c->partials + (size_t)13 * ps, ps); CHECK_LAUNCH(c);
+        for (int k = 0; k < n_cand; k++) {
+            k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)13 * ps, gr, 0, -1.0, d_out + k, 1); CHECK_LAUNCH(c);
+        }
+    }
     if (c->n_quirky > 0) {
         // quirk mass: - [Q_U(S_k) - Q_U(S_0)]
         k_quirk<<<dim3(c->n_quirky, n_cand), 256, 0, st>>>(c->d_quirky, c->n_quirky, cand0, ld, n, slot_stride(c), c->lv, c->sub_index, meta + 4, p,
@@ -1692,11 +1903,13 @@ int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int i
     if (!c->have_params) return set_err(-1, "parameters not set");
     int rc = graal_build_candidates(c, base_slot, first_cand_slot, id_fA, id_fB, max_id, 0x1FFFu); if (rc) return rc;
     // unique bins: swap_activity is the identity on the popped-out structure, candidate 8 == candidate 0 (Q7)
-    const unsigned skip = 1u << 8;
+    const unsigned skip = (id_fA < c->N) ? (1u << 8) : 0u;      // a repeat copy (frag >= N) really toggles its activity
     double* d_band = c->band_hist + (size_t)proposal_index * GRAAL_N_CANDIDATES;
     rc = delta_loglik_impl(c, base_slot, first_cand_slot, GRAAL_N_CANDIDATES, id_fA, id_fB, max_id, skip, d_out, d_band); if (rc) return rc;
-    k_copy_double<<<1, 1, 0, c->stream>>>(d_out, 8, 0); CHECK_LAUNCH(c);
-    k_copy_double<<<1, 1, 0, c->stream>>>(d_band, 8, 0); CHECK_LAUNCH(c);
+    if (skip) {
+        k_copy_double<<<1, 1, 0, c->stream>>>(d_out, 8, 0); CHECK_LAUNCH(c);
+        k_copy_double<<<1, 1, 0, c->stream>>>(d_band, 8, 0); CHECK_LAUNCH(c);
+    }
     return 0;
 }
 

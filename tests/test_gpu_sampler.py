@@ -99,10 +99,51 @@ def test_surface_attributes(small_pyramid):
     g.free_gpu()
 
 
-def test_repeat_levels_are_refused_loudly(small_pyramid):
-    from graal_b200.sampler import sampler, GraalError
-    inp = prepare_sampler_inputs(small_pyramid, 2, allow_repeats=True)
-    if inp.n_new_frags == inp.n_frags:
-        pytest.skip("no coverage outlier in this pyramid")
-    with pytest.raises(GraalError, match="repeat"):
-        sampler.from_inputs(inp)
+def test_repeat_levels(yeast_pyramid):
+    """H3: levels with duplicated ("repeat") bins -- the expected value of a pixel is the float32 sum
+    over ACTIVE copy pairs; unique x unique pairs stay on the sparse kernels, every pixel touching a
+    duplicated bin goes through the per-pixel repeat path.  Full likelihood, the 13 deltas (fA a
+    unique bin, an original of a duplicated bin, a repeat copy) and a live trajectory vs the oracle."""
+    from graal_b200.sampler import sampler, CUR, CAND0
+    from oracle import likelihood as L
+    inp = prepare_sampler_inputs(yeast_pyramid, 3, allow_repeats=True)
+    assert inp.n_new_frags > inp.n_frags
+    g = sampler.from_inputs(inp, rng=np.random.RandomState(5))
+    p, dm = H.default_params(yeast_pyramid)
+    g.set_parameters(p, dm)
+    o = H.make_oracle(inp, yeast_pyramid, seed=5)
+    rng = np.random.RandomState(12)
+    H.scramble(o, rng, 40, g)
+    assert H.slots_diff(o.cur, g.slot_to_host(CUR)) == []
+    max_id = o.modify_gl_cuda_buffer(); g.modify_gl_cuda_buffer()
+    fo, fg = o.eval_likelihood(), g.eval_likelihood()
+    assert abs(fo - fg) <= 1e-7 * abs(fo)
+    n, N = o.n_new_frags, o.n_frags
+    dup = int(inp.id_frag_duplicated[0])
+    copy = int(np.nonzero(np.asarray(inp.S_o_A_frags["rep"]) == 1)[0][0])
+    for fA, fB in ((3, 60), (dup, 17), (copy, 100), (50, copy), (copy, dup)):
+        M.perform_modifications(o.ws, o.cur, fA, fB, max_id)
+        no_rep, rep = o.candidate_index_sets(fA, fB)
+        bi, bj, dg, glob = L.delta_pixels(o.lv, no_rep, rep, o.uniq_frags)
+        g.score_neighbours(fA, [fB])
+        got = g._fetch()[16:29].copy()
+        for j in range(13):
+            assert H.slots_diff(o.ws.collector[j], g.slot_to_host(CAND0 + j)) == [], (fA, fB, j)
+            new = L.pixel_loglik(o.ws.collector[j], o.lv, o.param_simu, bi, bj, dg)
+            old = o.curr_likelihood[glob]
+            ref, mass = float(np.sum(new - old)), float(np.abs(new).sum() + np.abs(old).sum())
+            assert abs(got[j] - ref) <= 1e-6 * abs(ref) + 2.0 ** -22 * mass + 1e-9, (fA, fB, j, got[j], ref)
+    # de-activate a copy (mode 8) on both sides, then a live trajectory
+    M.apply_mutation(o.ws, o.cur, copy, 0, 8, max_id, o.id_contigs)
+    g.test_copy_struct(copy, 0, 8, int(max_id))
+    assert H.slots_diff(o.cur, g.slot_to_host(CUR)) == [] and g.slot_to_host(CUR)["activ"][copy] == 0
+    fo, fg = o.eval_likelihood(), g.eval_likelihood()
+    assert abs(fo - fg) <= 1e-7 * abs(fo)
+    o.rng = np.random.RandomState(3); g.rng = np.random.RandomState(3)
+    for it in range(40):
+        fA = int(np.random.RandomState(100 + it).randint(n))
+        ro, rg = o.step_max_likelihood(fA, 3), g.step_max_likelihood(fA, 3)
+        assert (ro[1], ro[5], ro[6]) == (rg[1], rg[5], rg[6]), (it, ro, rg)
+        assert abs(ro[0] - rg[0]) <= 1e-7 * abs(ro[0]) and abs(ro[7] - rg[7]) < 1e-12
+    assert H.slots_diff(o.cur, g.slot_to_host(CUR)) == []
+    g.free_gpu()
