@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=["c1", "c2", "tiny"])
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c4", "tiny"])
     ap.add_argument("--level", type=int, default=1)
     ap.add_argument("--neighbours", type=int, default=3)
     ap.add_argument("--exchange-every", type=int, default=20)
@@ -195,10 +195,22 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    pyr, inp, name = build_level(args.config, args.level)
-    g = sampler.from_inputs(inp, device=local_rank, rng=np.random.RandomState(1000 + rank))
-    p, d_max = model_params(pyr)
-    g.set_parameters(p, d_max)
+    if args.config == "c4":
+        # BASELINE config C4: 200k bins / ~200 M stored contacts, generated on the GPU (no CPU baseline: the
+        # NumPy oracle does not fit this size in the time budget)
+        from graal_b200.level import synthetic_roofline_level
+        inp, lists, tables, info = synthetic_roofline_level(device=dev)
+        name = "C4: synthetic 200k-bin / ~200M-contact level (24 contigs, offsets ~ s^-1.5 truncated at d_max = 1000 kb, 5% trans), single chain"
+        pyr = None
+        g = sampler.from_inputs(inp, device=local_rank, rng=np.random.RandomState(1000 + rank),
+                                device_contact_lists=lists, proposal_tables=tables)
+        g.set_parameters([1.0, 9.6, -1.5, 3.0, 800.0], info["d_max_kb"])
+        args.no_cpu_baseline = True
+    else:
+        pyr, inp, name = build_level(args.config, args.level)
+        g = sampler.from_inputs(inp, device=local_rank, rng=np.random.RandomState(1000 + rank))
+        p, d_max = model_params(pyr)
+        g.set_parameters(p, d_max)
     rex = None
     if world > 1:
         rex = R.ReplicaExchange(1, R.temperature_ladder(world), exchange_every=args.exchange_every, seed=20141217, device=dev)

@@ -339,3 +339,113 @@ def prepare_sampler_inputs(pyr, level, allow_repeats=False, blacklist_contigs=()
         np_sub_frags_accu=sub_accu, mean_squared_frags_per_bin=msfpb, norm_vect_accu=norm_vect,
         S_o_A_sub_frags=sub.S_o_A_frags, level_coo=(lv.rows, lv.cols, lv.vals),
         sub_coo=(sub.rows, sub.cols, sub.vals), mean_value_trans=float(sub.mean_value_trans))
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE config C4 / C5: one large level generated on the GPU
+# ----------------------------------------------------------------------------------------------
+def synthetic_roofline_level(n_bins=200_000, n_contigs=24, n_draws=240_000_000, d_max_kb=1000.0, trans_frac=0.05,
+                             seed=20141217, device="cuda"):
+    """One level of ``n_bins`` bins (3 sub-frags each, uniform accu) in ``n_contigs`` contigs with roughly
+    ``n_draws`` stored contacts: the row is uniform, a cis partner sits at a sub-frag offset drawn from
+    p(k) ~ k^-1.5 truncated at the band (d_max), 5 % of the draws are uniform trans pairs, counts are
+    1 + Poisson(0.5), duplicate pairs are summed.  Everything is generated with torch on ``device``.
+    Returns (SamplerInputs with sub_coo = None, (rowptr, contacts) device tensors, (xk, pk) proposal tables)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    rs = np.random.RandomState(seed)
+    w = rs.lognormal(0.0, 0.6, size=n_contigs)
+    sizes = np.maximum(3, np.round(w / w.sum() * n_bins).astype(np.int64))
+    sizes[np.argmax(sizes)] += n_bins - sizes.sum()
+    cid = np.repeat(np.arange(1, n_contigs + 1), sizes).astype(I32)
+    N, W = n_bins, 3 * n_bins
+    sub_len_bp = rs.randint(500, 1500, size=W).astype(np.int64)
+    len_bp = sub_len_bp.reshape(N, 3).sum(axis=1)
+    first = np.r_[True, cid[1:] != cid[:-1]]
+    starts = np.nonzero(first)[0]
+    seg = np.cumsum(first) - 1
+    csum = np.cumsum(len_bp) - len_bp
+    start_bp = csum - csum[starts][seg]
+    ids = np.arange(N)
+    last = np.r_[cid[1:] != cid[:-1], True]
+    soa = {"pos": ids - starts[seg], "id_c": cid, "start_bp": start_bp, "len_bp": len_bp, "circ": np.zeros(N),
+           "id": ids, "prev": np.where(first, -1, ids - 1), "next": np.where(last, -1, ids + 1),
+           "l_cont": np.bincount(seg)[seg], "l_cont_bp": np.bincount(seg, weights=len_bp).astype(np.int64)[seg],
+           "n_accu": np.full(N, 3), "ori": np.ones(N), "rep": np.zeros(N), "activ": np.ones(N), "id_d": ids}
+    soa = {k: np.asarray(v, dtype=I32) for k, v in soa.items()}
+    sub_id = np.zeros((N, 4), dtype=I32)
+    sub_id[:, 0] = 3 * ids; sub_id[:, 1] = 3 * ids + 1; sub_id[:, 2] = 3 * ids + 2; sub_id[:, 3] = 3
+    sub_len = (sub_len_bp.astype(F32) / F32(1000.0)).reshape(N, 3)
+    sub_accu = np.ones((N, 3), dtype=I32)
+    # sub-level SoA (initial layout) for the distance histogram
+    sub_cid = np.repeat(cid, 3)
+    sfirst = np.r_[True, sub_cid[1:] != sub_cid[:-1]]
+    sstarts = np.nonzero(sfirst)[0]
+    sseg = np.cumsum(sfirst) - 1
+    scs = np.cumsum(sub_len_bp) - sub_len_bp
+    sub_soa = {"id_c": sub_cid.astype(I32), "start_bp": (scs - scs[sstarts][sseg]).astype(I32),
+               "len_bp": sub_len_bp.astype(I32), "pos": (np.arange(W) - sstarts[sseg]).astype(I32)}
+    # ---- contacts on the device: per row, offset k is present with probability min(1, lam * k^-1.5)
+    # (a thinned power law: the near diagonal is full, the tail sparse); lam is set so that the expected
+    # number of cis entries per row is (1 - trans_frac) * n_draws / W
+    t_cid = torch.from_numpy(sub_cid.astype(np.int64)).to(device)
+    mean_sub_kb = float(sub_len_bp.mean()) / 1000.0
+    kmax = max(2, int(d_max_kb / mean_sub_kb))
+    target = (1.0 - trans_frac) * n_draws / W
+    kk = np.arange(1, kmax + 1, dtype=np.float64)
+    lo_l, hi_l = 1e-3, 1e9
+    for _ in range(200):
+        lam = np.sqrt(lo_l * hi_l)
+        if np.minimum(1.0, lam * kk ** -1.5).sum() < target:
+            lo_l = lam
+        else:
+            hi_l = lam
+    pk_dev = torch.from_numpy(np.minimum(1.0, lam * kk ** -1.5).astype(np.float32)).to(device)
+    keys = []
+    rows_per_chunk = max(1, 40_000_000 // kmax)
+    for r0 in range(0, W, rows_per_chunk):
+        r1 = min(W, r0 + rows_per_chunk)
+        hit = torch.rand((r1 - r0, kmax), device=device, generator=g) < pk_dev[None, :]
+        rr, ko = torch.nonzero(hit, as_tuple=True)
+        rr = rr + r0
+        cc = rr + ko + 1
+        ok = cc < W
+        rr, cc = rr[ok], cc[ok]
+        ok = t_cid[rr] == t_cid[cc]
+        keys.append(rr[ok] * W + cc[ok])
+        del hit, rr, ko, cc, ok
+    n_trans_draws = int(trans_frac * n_draws)
+    r = torch.randint(0, W, (n_trans_draws,), device=device, generator=g)
+    c = torch.randint(0, W, (n_trans_draws,), device=device, generator=g)
+    ok = t_cid[r] != t_cid[c]
+    r, c = r[ok], c[ok]
+    keys.append(torch.minimum(r, c) * W + torch.maximum(r, c))
+    del r, c, ok
+    keys = torch.cat(keys)
+    keys, _ = torch.sort(keys)
+    uk, cnt = torch.unique_consecutive(keys, return_counts=True)
+    del keys
+    extra = torch.poisson(torch.full((uk.numel(),), 0.5, device=device), generator=g)
+    vals = (cnt.to(torch.float32) + extra)
+    rows = torch.div(uk, W, rounding_mode="floor")
+    cols = (uk - rows * W).to(torch.int32)
+    rowptr = torch.zeros(W + 1, dtype=torch.int64, device=device)
+    rowptr[1:] = torch.cumsum(torch.bincount(rows, minlength=W), 0)
+    contacts = torch.stack([cols, vals.view(torch.int32)], dim=1).contiguous()
+    n_trans = int((t_cid[rows] != t_cid[cols.to(torch.int64)]).sum().item())
+    sizes_f = sizes.astype(np.float64) * 3
+    mvt = float(vals[t_cid[rows] != t_cid[cols.to(torch.int64)]].sum().item()) / float((sizes_f * W - sizes_f * sizes_f).sum())
+    del rows, cols, vals, uk, cnt, extra
+    # proposal tables: the ten nearest bins in the initial layout, uniform weights
+    offs = np.array([1, -1, 2, -2, 3, -3, 4, -4, 5, -5])
+    xk = np.clip(ids[:, None] + offs[None, :], 0, N - 1).astype(I32)
+    pk = np.full((N, 10), F32(0.1), dtype=F32)
+    inp = SamplerInputs(
+        S_o_A_frags=soa, collector_id_repeats=np.arange(N, dtype=I32),
+        frag_dispatcher=np.stack([ids, ids + 1], axis=1).astype(I32), id_frag_duplicated=np.zeros(0, dtype=I32),
+        id_frags_blacklisted=[], n_frags=N, n_new_frags=N, init_n_sub_frags=W, n_new_sub_frags=W,
+        np_rep_sub_frags_id=sub_id.copy(), np_sub_frags_len_bp=sub_len, np_sub_frags_id=sub_id, np_sub_frags_accu=sub_accu,
+        mean_squared_frags_per_bin=F32(1.0), norm_vect_accu=sub_accu.sum(axis=1), S_o_A_sub_frags=sub_soa,
+        level_coo=None, sub_coo=None, mean_value_trans=mvt)
+    return inp, (rowptr, contacts), (xk, pk), dict(kmax=kmax, n_trans_entries=n_trans, d_max_kb=d_max_kb)

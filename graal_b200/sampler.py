@@ -195,11 +195,13 @@ class sampler:
                  mean_squared_frags_per_bin, norm_vect_accu,
                  S_o_A_sub_frags,
                  hic_matrix, mean_value_trans, n_iterations=0, is_simu=False,
-                 device=0, rng=None, sub_sample_factor=0):
+                 device=0, rng=None, sub_sample_factor=0, device_contact_lists=None, proposal_tables=None):
         """Arguments as in cuda_lib_gl.py:33-42 without the GL objects.  ``hic_matrix_sub_sampled``
         (current level) and ``hic_matrix`` (sub level) are upper-triangle COO triples
         (rows, cols, counts) instead of dense arrays.  ``rng``: np.random.RandomState (default: the
-        global np.random module, as the reference)."""
+        global np.random module, as the reference).  ``device_contact_lists`` = (rowptr int64[W+1],
+        contacts int32[E, 2]) torch tensors already on the device and ``proposal_tables`` = (xk, pk) replace
+        the host-side preparation of the two matrices (levels generated on the GPU)."""
         if not use_rippe:
             raise GraalError("only the Rippe model exists (kernels4.cu is not part of the reference tree)")
         torch = _torch()
@@ -237,16 +239,21 @@ class sampler:
         for f in self.id_frags_blacklisted:
             da = self.np_sub_frags_id[S_o_A_frags["id_d"][f]]
             black_subs.extend(int(da[k]) for k in range(da[3]))
-        rowptr, contacts = build_contact_lists(hic_matrix, int(init_n_sub_frags), black_subs, mean_value_trans)
+        if device_contact_lists is None:
+            rowptr, contacts = build_contact_lists(hic_matrix, int(init_n_sub_frags), black_subs, mean_value_trans)
+        else:
+            rowptr, contacts = device_contact_lists
         self.n_contacts = int(contacts.shape[0])
-        self.max_obs = float(contacts[:, 1].view(F32).max()) if self.n_contacts else 0.0
         # ---- proposal tables (cuda_lib_gl.py:444-445)
         self.n_neighbors = 10
         black_bins = [int(S_o_A_frags["id_d"][f]) for f in self.id_frags_blacklisted]
-        self.distri_xk, self.distri_pk = neighbour_tables(hic_matrix_sub_sampled, int(n_frags), black_bins, self.n_neighbors)
+        if proposal_tables is None:
+            self.distri_xk, self.distri_pk = neighbour_tables(hic_matrix_sub_sampled, int(n_frags), black_bins, self.n_neighbors)
+        else:
+            self.distri_xk, self.distri_pk = proposal_tables
         # ---- device buffers (torch owns them)
         dev = self.device
-        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        t = lambda a: a.to(dev) if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         self.d_sub_id, self.d_sub_len, self.d_sub_accu = t(self.np_sub_frags_id), t(self.np_sub_frags_len_bp), t(self.np_sub_frags_accu)
         self.d_collector, self.d_dispatcher = t(self.collector_id_repeats), t(self.frag_dispatcher)
         self.d_rowptr, self.d_contacts = t(rowptr), t(contacts)
@@ -296,13 +303,14 @@ class sampler:
         self.gpu_launches_at_start = self.lib.graal_launch_count(self.ctx)
 
     @classmethod
-    def from_inputs(cls, inp, device=0, rng=None):
+    def from_inputs(cls, inp, device=0, rng=None, device_contact_lists=None, proposal_tables=None):
         """Build from ``graal_b200.level.SamplerInputs`` (what simulation.__init__ assembles)."""
         return cls(True, inp.S_o_A_frags, inp.collector_id_repeats, inp.frag_dispatcher, inp.id_frag_duplicated,
                    inp.id_frags_blacklisted, inp.n_frags, inp.n_new_frags, inp.init_n_sub_frags, inp.n_new_sub_frags,
                    inp.np_rep_sub_frags_id, inp.level_coo, inp.np_sub_frags_len_bp, inp.np_sub_frags_id,
                    inp.np_sub_frags_accu, inp.mean_squared_frags_per_bin, inp.norm_vect_accu, inp.S_o_A_sub_frags,
-                   inp.sub_coo, inp.mean_value_trans, device=device, rng=rng)
+                   inp.sub_coo, inp.mean_value_trans, device=device, rng=rng,
+                   device_contact_lists=device_contact_lists, proposal_tables=proposal_tables)
 
     # ------------------------------------------------------------------ plumbing
     def sync(self):

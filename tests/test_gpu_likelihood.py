@@ -204,3 +204,42 @@ def test_size_independent_properties_at_c2_scale():
         assert abs((like + d[mode]) - full) <= 1e-7 * abs(full), mode
         g.slot_from_host(CUR, backup)
     g.free_gpu()
+
+
+def test_size_independent_properties_at_c4_scale():
+    """BASELINE config C4 at FULL size (200,000 bins, 600,000 sub-frags, ~200 M stored contact entries,
+    1.6 GB of contact lists -- 40x beyond the reference's N < 4,609 limit), generated on
+    the GPU.  No dense oracle exists at this size; size-independent properties instead:
+    (a) reproducible full likelihood, (b) the proposal that rebuilds the same genome scores exactly 0,
+    (c) candidate 8 == candidate 0 (Q7), (d) likelihood_t + delta == full(candidate) up to the
+    never-re-scored diagonal pixels, (e) flip o flip returns the likelihood bit for bit."""
+    import torch
+    from graal_b200.level import synthetic_roofline_level
+    from graal_b200.sampler import sampler, CUR, CAND0
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs ~40 GB of free device memory")
+    inp, lists, tables, info = synthetic_roofline_level(device="cuda")
+    assert inp.n_frags == 200_000 and lists[1].shape[0] > 150_000_000
+    g = sampler.from_inputs(inp, rng=np.random.RandomState(5), device_contact_lists=lists, proposal_tables=tables)
+    g.set_parameters([1.0, 9.6, -1.5, 3.0, 800.0], info["d_max_kb"])
+    g.modify_gl_cuda_buffer()
+    like = g.eval_likelihood()
+    assert np.isfinite(like) and like == g.eval_likelihood()
+    s = inp.S_o_A_frags
+    fA = int(np.nonzero((s["pos"] > 100) & (s["next"] >= 0))[0][12345])
+    left = int(s["prev"][fA])
+    g.score_neighbours(fA, [left])
+    d = g._fetch()[16:29].copy()
+    assert d[6] == 0.0 and d[0] == d[8] and np.all(np.isfinite(d))
+    for mode in (1, 0, 4, 10):
+        g.perform_modifications(fA, left)
+        g.lib.graal_commit(g.ctx, CUR, CAND0 + mode)
+        full = g.eval_likelihood()
+        assert abs((like + d[mode]) - full) <= 1e-7 * abs(full), (mode, like + d[mode], full)
+        # undo through the reciprocal move where it exists, else restore the initial genome
+        g.slot_from_host(CUR, {k: s[k] for k in M.FIELDS})
+        g.modify_gl_cuda_buffer()
+    g.test_copy_struct(fA, left, 1, -1); g.test_copy_struct(fA, left, 1, -1)
+    assert g.eval_likelihood() == like
+    g.free_gpu()
