@@ -627,6 +627,13 @@ class sampler:
             out[int(cid)] = [(int(i), int(c.ori[i])) for i in m]
         return out
 
+    def export_new_fasta(self, level, contig_names, sequences, new_fasta, info_frags):
+        """simulation.export_new_fasta (simulation_loader.py:781-783): genome.fasta + info_frags.txt of the
+        current genome (graal_b200.export.generate_new_fasta)."""
+        from .export import generate_new_fasta
+        self.gpu_vect_frags.copy_from_gpu()
+        return generate_new_fasta(self.gpu_vect_frags, level, contig_names, sequences, new_fasta, info_frags)
+
     def free_gpu(self):
         """cuda_lib_gl.py:2605-2613."""
         if getattr(self, "ctx", None) is not None:
