@@ -45,7 +45,15 @@ struct Params { float kuhn, lm, c1, slope, d, d_max, fact, v_inter, nfpb; int nd
                 const float* t_norm; const float* t_g; const double* t_logg;
                 // log-space evaluation (math mode 1): ln(c1*fact), ln(v_inter), slope as double, ln(t_norm)
                 int mode; double ln_cf, ln_v, slope_d; const double* t_lnnorm;
-                const double2* t_log; const double* t_exp; };
+                const double2* t_log; const double* t_exp;
+                // tabulated law (math mode 2): cubic-Hermite nodes {value, d/ds} of ln f(s) and of f(s), one node
+                // per float bit pattern with LAW_M mantissa bits, s in [2^LAW_EMIN, 2^LAW_EMAX) kb;
+                // v_clamp = v_inter as double (the clamp of f), t_normd = t_norm as double
+                const double2* t_lnf; const double2* t_f; double v_clamp; const double* t_normd; };
+#define LAW_M 7
+#define LAW_EMIN (-12)
+#define LAW_EMAX 11
+#define LAW_NODES (((LAW_EMAX) - (LAW_EMIN)) << LAW_M)
 
 // per-sub-frag geometry record of one slot (16 B, one 128-bit load):
 //   mid  : mid-point in kb (float32, reference op order kernels3.cu:2997-3060)
@@ -127,6 +135,29 @@ __device__ __forceinline__ double fast_exp(double t, const double* __restrict__ 
     const int sh = k >> 5;
     return __longlong_as_double(__double_as_longlong(base) + ((long long)sh << 52));
 }
+// Cubic-Hermite interpolation of a tabulated function of s (math mode 2).  The node index and the local
+// abscissa come straight from the float bit pattern: node = exponent | top LAW_M mantissa bits, t = the
+// remaining mantissa bits / 2^(23-LAW_M) (exact), interval length 2^(e-LAW_M).  Relative error of the
+// interpolant for the Rippe law: < 1e-9 (profiles/README.md), far below one float32 ulp.
+__device__ __forceinline__ bool law_in_table(float s) {
+    const int e = (int)(__float_as_uint(s) >> 23) - 127;
+    return e >= LAW_EMIN && e < LAW_EMAX;
+}
+__device__ __forceinline__ double law_interp(float s, const double2* __restrict__ tab) {
+    const unsigned b = __float_as_uint(s);
+    const int e = (int)(b >> 23) - 127;
+    const int node = (int)(b >> (23 - LAW_M)) - ((127 + LAW_EMIN) << LAW_M);
+    const double t = (double)(b & ((1u << (23 - LAW_M)) - 1u)) * (1.0 / (double)(1u << (23 - LAW_M)));
+    const double dl = __longlong_as_double((long long)(1023 + e - LAW_M) << 52);        // 2^(e - LAW_M)
+    const double2 n0 = __ldg(&tab[node]), n1 = __ldg(&tab[node + 1]);
+    const double m0 = n0.y * dl, m1 = n1.y * dl;
+    // Hermite: h = n0.x + t*(m0 + t*(c2 + t*c3)),  c2 = 3d - 2 m0 - m1, c3 = m0 + m1 - 2d, d = n1.x - n0.x
+    const double d = n1.x - n0.x;
+    const double c3 = m0 + m1 - 2.0 * d;
+    const double c2 = 3.0 * d - 2.0 * m0 - m1;
+    return fma(t, fma(t, fma(t, c3, c2), m0), n0.x);
+}
+
 // ln of rippe_contacts(s) for 0 < s < d_max on a LINEAR contig, clamp included:
 // max(ln(c1*fact) + slope*ln(s) + (d-2)/(x^2+d), ln v_inter) with x and the quotient in float32 exactly
 // as the reference computes the argument of expf (kernels3.cu:126).
@@ -156,6 +187,11 @@ __device__ __forceinline__ double band_excess(const Geo& a, const Geo& b, float 
         const float r = pk_circ(a.pk) ? rippe_contacts_circ(s, a.stot, p) : rippe_contacts(s, p);
         return (double)(r * norm) - g;
     }
+    if (p.mode == 2 && law_in_table(s)) {
+        const double f = law_interp(s, p.t_f);
+        if (!(f > p.v_clamp)) return 0.0;                   // clamped: exactly the clamp value
+        return f * __ldg(&p.t_normd[idx]) - g;
+    }
     const double lr = ln_rippe_inband(s, p);
     if (!(lr > p.ln_v)) return 0.0;                         // clamped: exactly the clamp value
     return fast_exp(lr + __ldg(&p.t_lnnorm[idx]), p.t_exp) - g;
@@ -169,7 +205,8 @@ __device__ __forceinline__ double inband_log_term(float s, float ob, float stot,
         const float ex = r * norm;
         return (ex != 0.0f) ? (double)ob * log((double)ex) : log_fact_term(ob);
     }
-    const double lr = ln_rippe_inband(s, p) + __ldg(&p.t_lnnorm[idx]);
+    const double lr = ((p.mode == 2 && law_in_table(s)) ? fmax(law_interp(s, p.t_lnf), p.ln_v) : ln_rippe_inband(s, p))
+                      + __ldg(&p.t_lnnorm[idx]);
     return (lr == lr && lr != -INFINITY) ? (double)ob * lr : ((lr != lr) ? lr : log_fact_term(ob));
 }
 // ob * ln(ex) of one stored contact between sub-frags a (row side = lower data bin) and b, or the
@@ -882,9 +919,14 @@ __global__ void k_cand_geometry(const int* __restrict__ cand0, size_t slot_strid
         }
     }
 }
+// Position order of U in every candidate + one 16-byte record per order position:
+//   x = first sub-frag | n_sub << 28,  y = start of the bin in kb (float bits),
+//   z = 1 if any record of the bin differs from the base slot in this candidate,  w = contig id
+// and the first / last order index of a changed bin (rng[2k], rng[2k+1]).
 __global__ void k_cand_order(const int* __restrict__ cand0, size_t slot_stride, int ld,
                              const int* __restrict__ sub_index, const int* __restrict__ meta,
-                             const int* __restrict__ piece_len, int* __restrict__ order0, int order_stride, unsigned skip_cands) {
+                             const int* __restrict__ piece_len, int* __restrict__ order0, int order_stride, unsigned skip_cands,
+                             LevelView lv, const unsigned* __restrict__ chmask, int4* __restrict__ ordrec0, int* __restrict__ rng) {
     const int k = blockIdx.y;
     if ((skip_cands >> k) & 1u) return;
     const int m = meta[4];
@@ -892,12 +934,132 @@ __global__ void k_cand_order(const int* __restrict__ cand0, size_t slot_stride, 
     int off[5]; int run = 0;
     #pragma unroll
     for (int s = 0; s < 5; s++) { off[s] = run; run += piece_len[k * 8 + s]; }
+    int lo = INT_MAX, hi = -1;
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < m; u += gridDim.x * blockDim.x) {
         const int bin = sub_index[u];
         const int ps = piece_slot(sl[F_ID_C * ld + bin], meta);
         if (ps < 0) continue;
         const int idx = off[ps] + sl[F_POS * ld + bin];
-        if (idx >= 0 && idx < m) order0[(size_t)k * order_stride + idx] = bin;
+        if (idx < 0 || idx >= m) continue;
+        order0[(size_t)k * order_stride + idx] = bin;
+        const int4 sid = lv.sub_id[sl[F_ID_D * ld + bin]];
+        unsigned chg = 0u;
+        if (eligible(lv, bin)) for (int a = 0; a < sid.w; a++) chg |= (chmask[sid.x + a] >> k) & 1u;
+        const float start_kb = __int2float_rn(sl[F_START_BP * ld + bin]) / 1000.0f;
+        ordrec0[(size_t)k * order_stride + idx] = make_int4(sid.x | ((eligible(lv, bin) ? sid.w : 0) << 28), __float_as_int(start_kb), (int)chg, sl[F_ID_C * ld + bin]);
+        if (chg) { lo = min(lo, idx); hi = max(hi, idx); }
+    }
+    if (hi >= 0) { atomicMin(&rng[2 * k], lo); atomicMax(&rng[2 * k + 1], hi); }
+}
+// the same records for the base slot in ITS order (sub_index); z = OR of the chmask words of the bin
+__global__ void k_base_order(const int* __restrict__ base, int ld, const int* __restrict__ sub_index, const int* __restrict__ meta,
+                             LevelView lv, const unsigned* __restrict__ chmask, int4* __restrict__ ordrec, int* __restrict__ rng) {
+    const int m = meta[4];
+    int lo = INT_MAX, hi = -1;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < m; u += gridDim.x * blockDim.x) {
+        const int bin = sub_index[u];
+        const int4 sid = lv.sub_id[base[F_ID_D * ld + bin]];
+        unsigned chg = 0u;
+        const bool el = eligible(lv, bin);
+        if (el) for (int a = 0; a < sid.w; a++) chg |= chmask[sid.x + a];
+        const float start_kb = __int2float_rn(base[F_START_BP * ld + bin]) / 1000.0f;
+        ordrec[u] = make_int4(sid.x | ((el ? sid.w : 0) << 28), __float_as_int(start_kb), (int)chg, base[F_ID_C * ld + bin]);
+        if (chg) { lo = min(lo, u); hi = max(hi, u); }
+    }
+    if (hi >= 0) { atomicMin(&rng[0], lo); atomicMax(&rng[1], hi); }
+}
+__global__ void k_init_ranges(int* rng, int n) { const int i = threadIdx.x; if (i < n) rng[i] = (i & 1) ? -1 : INT_MAX; }
+
+// Band mass of the delta from the ordered records: warp per bin x, lanes over the following bins.
+//   BASE = false: candidate k = blockIdx.y, NEW values of pairs with a changed record (bit k)
+//   BASE = true : base slot, OLD values once, credited to every candidate whose bit is set
+// Only windows that can contain a changed pair are scanned: x beyond the last changed bin is skipped, an
+// unchanged x starts its scan at the first changed bin and stops at the last one.
+template <bool BASE>
+__global__ void __launch_bounds__(256)
+k_band_delta(const int4* __restrict__ ordrec0, int order_stride, const int* __restrict__ d_count, const int* __restrict__ rng0,
+             const Geo* __restrict__ geo0, size_t cand_geo_stride, const unsigned* __restrict__ chmask, unsigned skip_cands,
+             const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
+    const int k = blockIdx.y;
+    const int count = *d_count;
+    const int4* ordrec = BASE ? ordrec0 : ordrec0 + (size_t)k * order_stride;
+    const Geo* gE = BASE ? geo0 : geo0 + (size_t)k * cand_geo_stride;
+    const int* rng = BASE ? rng0 : rng0 + 2 * k;
+    const int lo = rng[0], hi = rng[1];
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    double acc = 0.0;
+    double accs[GRAAL_N_CANDIDATES];
+    if (BASE) {
+        #pragma unroll
+        for (int c = 0; c < GRAAL_N_CANDIDATES; c++) accs[c] = 0.0;
+    }
+    const bool idle = (!BASE && ((skip_cands >> k) & 1u)) || hi < 0;
+    if (!idle) for (int ix = warp; ix <= hi && ix < count; ix += n_warps) {
+        const int4 rx = ordrec[ix];
+        const int nx = (rx.x >> 28) & 7, sx0 = rx.x & 0x0fffffff;
+        if (nx == 0) continue;                                   // duplicated bin: repeat path
+        const unsigned xm = (unsigned)rx.z;
+        const bool xchg = BASE ? (xm != 0u) : (xm != 0u);
+        int y0 = ix + 1, y1 = count;
+        if (!xchg) { y0 = max(y0, lo); y1 = min(y1, hi + 1); }
+        if (y0 >= y1) continue;
+        Geo gx[3]; unsigned mx[3] = {0u, 0u, 0u};
+        float xmax = -1e30f;
+        #pragma unroll
+        for (int a = 0; a < 3; a++) if (a < nx) {
+            gx[a] = ld_geo(&gE[sx0 + a]);
+            mx[a] = __ldg(&chmask[sx0 + a]);
+            xmax = fmaxf(xmax, gx[a].mid);
+        }
+        const int cx = rx.w;
+        for (int basei = y0; basei < y1; basei += 32) {
+            const int iy = basei + lane;
+            bool live = iy < y1;
+            if (live) {
+                const int4 ry = ordrec[iy];
+                // beyond the band (or next contig): every remaining pair evaluates to the clamp value
+                if (ry.w != cx || (double)__int_as_float(ry.y) - (double)xmax > (double)p.d_max * 1.00001 + 0.05) live = false;
+                else {
+                    const int ny = (ry.x >> 28) & 7, sy0 = ry.x & 0x0fffffff;
+                    const unsigned ym = (unsigned)ry.z;
+                    const bool rel = BASE ? ((xm | ym) != 0u) : (xchg || ym != 0u);
+                    if (rel) {
+                        #pragma unroll
+                        for (int b = 0; b < 3; b++) if (b < ny) {
+                            const int sub = sy0 + b;
+                            const unsigned my = __ldg(&chmask[sub]);
+                            if (BASE ? !(mx[0] | mx[1] | mx[2] | my) : !(((mx[0] | mx[1] | mx[2] | my) >> k) & 1u)) continue;
+                            const Geo gy = ld_geo(&gE[sub]);
+                            #pragma unroll
+                            for (int a = 0; a < 3; a++) if (a < nx) {
+                                const unsigned mm = mx[a] | my;
+                                if (BASE ? !mm : !((mm >> k) & 1u)) continue;
+                                const float s = fabsf(gy.mid - gx[a].mid);
+                                if (!(s > 0.0f && s < p.d_max)) continue;
+                                const double v = band_excess(gx[a], gy, s, p);
+                                if (BASE) {
+                                    #pragma unroll
+                                    for (int c = 0; c < GRAAL_N_CANDIDATES; c++) if ((mm >> c) & 1u) accs[c] += v;
+                                } else acc += v;
+                            }
+                        }
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, live)) break;
+        }
+    }
+    if (BASE) {
+        #pragma unroll
+        for (int c = 0; c < GRAAL_N_CANDIDATES; c++) {
+            const double v = block_sum(accs[c]);
+            if (threadIdx.x == 0) partials[(size_t)c * partial_stride + blockIdx.x] = v;
+        }
+    } else {
+        acc = block_sum(acc);
+        if (threadIdx.x == 0) partials[(size_t)k * partial_stride + blockIdx.x] = acc;
     }
 }
 
@@ -1328,7 +1490,9 @@ struct graal_ctx {
     unsigned char* d_accu_idx = nullptr;                // [N*3]
     float* d_tab_norm = nullptr; float* d_tab_g[2] = {nullptr, nullptr}; double* d_tab_logg[2] = {nullptr, nullptr};
     double* d_tab_lnnorm = nullptr; double2* d_tab_log = nullptr; double* d_tab_exp = nullptr;
-    int math_mode = 1;
+    double2* d_tab_lnf[2] = {nullptr, nullptr}; double2* d_tab_f[2] = {nullptr, nullptr}; double* d_tab_normd = nullptr;
+    std::vector<double> h_law;
+    int math_mode = 2;
     std::vector<float> h_tab_g; std::vector<double> h_tab_logg;
     int* d_quirky = nullptr; int n_quirky = 0;
     unsigned char* d_dup = nullptr; unsigned char* d_sub_dup = nullptr; unsigned char* d_rep_in_u = nullptr;
@@ -1338,6 +1502,7 @@ struct graal_ctx {
     int* group_row = nullptr; int n_groups = 0;
     int smem_cid = 0;                         // GRAAL_SMEM_CID=1: stage the contig-id table in shared memory (measured: no faster than L1, profiles/README.md)
     unsigned* chmask = nullptr;               // [W] bit k: record differs from the base slot in candidate k
+    int4* cand_ordrec = nullptr; int4* base_ordrec = nullptr;   // [13][n] / [n] position-ordered bin records of U
     double* band_hist = nullptr;              // [16][13] band delta of the proposals scored since the last commit
     int band_slot = -1; int band_age = 0;     // slot whose cross-bin band total is cached in d_scalars[40]
     // params
@@ -1395,6 +1560,29 @@ static int upload_tables(graal_ctx* c, Params& p, int which) {
     p.ln_cf = cf > 0.0 ? log(cf) : -(double)INFINITY;           // c1*fact <= 0: rippe <= 0, the clamp wins
     p.ln_v = p.v_inter > 0.0f ? log((double)p.v_inter) : (p.v_inter == 0.0f ? -(double)INFINITY : (double)NAN);
     p.slope_d = (double)p.slope;
+    // tabulated law: f(s) = c1*fact * s^slope * exp((d-2)/(x^2+d)), x = s*lm/kuhn, and ln f, with d/ds, float64
+    p.t_lnf = c->d_tab_lnf[which]; p.t_f = c->d_tab_f[which]; p.t_normd = c->d_tab_normd; p.v_clamp = (double)p.v_inter;
+    if (p.mode == 2) {
+        if (!(cf > 0.0) || !(p.kuhn > 0.0f) || !(p.lm > 0.0f)) p.mode = 1;      // degenerate parameters: analytic path
+        else {
+            c->h_law.resize((size_t)(LAW_NODES + 2) * 4);
+            const double K = (double)p.d - 2.0, dd = (double)p.d, q = (double)p.lm / (double)p.kuhn, sl = (double)p.slope;
+            for (int i = 0; i < LAW_NODES + 2; i++) {
+                const int e = LAW_EMIN + (i >> LAW_M);
+                const double sv = ldexp(1.0 + (double)(i & ((1 << LAW_M) - 1)) / (double)(1 << LAW_M), e);
+                const double x = sv * q, den = x * x + dd;
+                const double lnf = p.ln_cf + sl * log(sv) + K / den;
+                const double dlnf = sl / sv - K * 2.0 * x * q / (den * den);
+                const double f = exp(lnf);
+                c->h_law[(size_t)i * 2] = lnf; c->h_law[(size_t)i * 2 + 1] = dlnf;
+                c->h_law[(size_t)(LAW_NODES + 2) * 2 + (size_t)i * 2] = f;
+                c->h_law[(size_t)(LAW_NODES + 2) * 2 + (size_t)i * 2 + 1] = f * dlnf;
+            }
+            CUDA_OK(cudaMemcpyAsync(c->d_tab_lnf[which], c->h_law.data(), (size_t)(LAW_NODES + 2) * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+            CUDA_OK(cudaMemcpyAsync(c->d_tab_f[which], c->h_law.data() + (size_t)(LAW_NODES + 2) * 2, (size_t)(LAW_NODES + 2) * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+            CUDA_OK(cudaStreamSynchronize(c->stream));      // h_law is reused by the next call
+        }
+    }
     return 0;
 }
 
@@ -1430,13 +1618,15 @@ int graal_ctx_create(int device, graal_ctx** out) {
 }
 
 static void free_level_scratch(graal_ctx* c) {
-    cudaFree(c->cid16_base); cudaFree(c->mid32_base); cudaFree(c->group_row); cudaFree(c->chmask); cudaFree(c->band_hist); c->chmask = nullptr; c->band_hist = nullptr; c->cid16_base = nullptr; c->mid32_base = nullptr; c->group_row = nullptr;
+    cudaFree(c->cid16_base); cudaFree(c->mid32_base); cudaFree(c->group_row); cudaFree(c->cand_ordrec); cudaFree(c->base_ordrec); c->cand_ordrec = c->base_ordrec = nullptr; cudaFree(c->chmask); cudaFree(c->band_hist); c->chmask = nullptr; c->band_hist = nullptr; c->cid16_base = nullptr; c->mid32_base = nullptr; c->group_row = nullptr;
     cudaFree(c->geo_base); cudaFree(c->geo_cand); cudaFree(c->order); cudaFree(c->cand_order); cudaFree(c->sub_index);
     cudaFree(c->cont_len); cudaFree(c->cont_off); cudaFree(c->first_idx); cudaFree(c->map); cudaFree(c->keys);
     cudaFree(c->keys_sorted); cudaFree(c->cub_tmp); cudaFree(c->d_quirky); cudaFree(c->d_accu_idx);
     cudaFree(c->d_dup); cudaFree(c->d_sub_dup); cudaFree(c->d_rep_in_u); cudaFree(c->d_rep_bins);
     c->d_dup = c->d_sub_dup = c->d_rep_in_u = nullptr; c->d_rep_bins = nullptr; c->n_rep = 0;
-    cudaFree(c->d_tab_lnnorm); cudaFree(c->d_tab_log); cudaFree(c->d_tab_exp);
+    cudaFree(c->d_tab_lnnorm); cudaFree(c->d_tab_log); cudaFree(c->d_tab_exp); cudaFree(c->d_tab_normd);
+    for (int w = 0; w < 2; w++) { cudaFree(c->d_tab_lnf[w]); cudaFree(c->d_tab_f[w]); c->d_tab_lnf[w] = nullptr; c->d_tab_f[w] = nullptr; }
+    c->d_tab_normd = nullptr;
     c->d_tab_lnnorm = nullptr; c->d_tab_log = nullptr; c->d_tab_exp = nullptr;
     cudaFree(c->d_tab_norm); cudaFree(c->d_tab_g[0]); cudaFree(c->d_tab_g[1]); cudaFree(c->d_tab_logg[0]); cudaFree(c->d_tab_logg[1]);
     c->d_accu_idx = nullptr; c->d_tab_norm = nullptr; c->d_tab_g[0] = c->d_tab_g[1] = nullptr; c->d_tab_logg[0] = c->d_tab_logg[1] = nullptr;
@@ -1550,6 +1740,13 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
         CUDA_OK(cudaMemcpy(c->d_tab_log, tl.data(), 256 * sizeof(double), cudaMemcpyHostToDevice));
         CUDA_OK(cudaMalloc(&c->d_tab_exp, 32 * sizeof(double)));
         CUDA_OK(cudaMemcpy(c->d_tab_exp, te.data(), 32 * sizeof(double), cudaMemcpyHostToDevice));
+        std::vector<double> tnd(tn.begin(), tn.end());
+        CUDA_OK(cudaMalloc(&c->d_tab_normd, tnd.size() * sizeof(double)));
+        CUDA_OK(cudaMemcpy(c->d_tab_normd, tnd.data(), tnd.size() * sizeof(double), cudaMemcpyHostToDevice));
+        for (int w = 0; w < 2; w++) {
+            CUDA_OK(cudaMalloc(&c->d_tab_lnf[w], (size_t)(LAW_NODES + 2) * sizeof(double2)));
+            CUDA_OK(cudaMalloc(&c->d_tab_f[w], (size_t)(LAW_NODES + 2) * sizeof(double2)));
+        }
         for (int w = 0; w < 2; w++) {
             CUDA_OK(cudaMalloc(&c->d_tab_g[w], tn.size() * sizeof(float)));
             CUDA_OK(cudaMalloc(&c->d_tab_logg[w], tn.size() * sizeof(double)));
@@ -1581,6 +1778,10 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     CUDA_OK(cudaMemset(c->cid16_base, 0, ((size_t)c->W + 16) * sizeof(unsigned short)));
     CUDA_OK(cudaMalloc(&c->mid32_base, (size_t)c->W * sizeof(float)));
     CUDA_OK(cudaMalloc(&c->chmask, (size_t)c->W * sizeof(unsigned)));
+    CUDA_OK(cudaMalloc(&c->cand_ordrec, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int4)));
+    CUDA_OK(cudaMalloc(&c->base_ordrec, (size_t)n * sizeof(int4)));
+    CUDA_OK(cudaMemset(c->cand_ordrec, 0, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int4)));
+    CUDA_OK(cudaMemset(c->base_ordrec, 0, (size_t)n * sizeof(int4)));
     CUDA_OK(cudaMalloc(&c->band_hist, 16 * GRAAL_N_CANDIDATES * sizeof(double)));
     CUDA_OK(cudaMemset(c->band_hist, 0, 16 * GRAAL_N_CANDIDATES * sizeof(double)));
     c->band_slot = -1;
@@ -1639,7 +1840,7 @@ int graal_set_params(graal_ctx* c, const float q[8]) {
 }
 
 int graal_set_math_mode(graal_ctx* c, int mode) {
-    if (!c || (mode != 0 && mode != 1)) return set_err(-1, "math mode must be 0 (float32 chain) or 1 (log-space float64)");
+    if (!c || mode < 0 || mode > 2) return set_err(-1, "math mode must be 0 (float32 chain), 1 (log-space float64) or 2 (tabulated law)");
     c->math_mode = mode; c->p.mode = mode; c->band_slot = -1;
     return 0;
 }
@@ -1839,7 +2040,11 @@ static int delta_loglik_impl(graal_ctx* c, int base_slot, int first_cand_slot, i
     const int gu = std::min(c->n_sm * 2, nblk(n, 256));
     k_cand_geometry<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->lv, c->sub_index, meta, c->geo_cand, (size_t)c->W, piece_len,
                                                      c->geo_base, c->chmask, skip); CHECK_LAUNCH(c);
-    k_cand_order<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->sub_index, meta, piece_len, c->cand_order, n, skip); CHECK_LAUNCH(c);
+    int* rng = c->d_ints + 160;                       // [0,1] base range, [2 + 2k, 3 + 2k] candidate k
+    k_init_ranges<<<1, 32, 0, st>>>(rng, 2 + 2 * GRAAL_N_CANDIDATES); CHECK_LAUNCH(c);
+    k_cand_order<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->sub_index, meta, piece_len, c->cand_order, n, skip,
+                                                  c->lv, c->chmask, c->cand_ordrec, rng + 2); CHECK_LAUNCH(c);
+    k_base_order<<<gu, 256, 0, st>>>(base, ld, c->sub_index, meta, c->lv, c->chmask, c->base_ordrec, rng); CHECK_LAUNCH(c);
     const int gw = std::min(ps, std::max(1, nblk(n, 8)));
     // contacts: sum over changed contacts of ob * (ln ex_k - ln ex_0): new terms per candidate, old terms once
     c->prof.begin(GRAAL_K_DELTA_CONTACTS, st);
@@ -1849,12 +2054,11 @@ static int delta_loglik_impl(graal_ctx* c, int base_slot, int first_cand_slot, i
     c->prof.end(GRAAL_K_DELTA_CONTACTS, st);
     // band mass: d_band[k] = B_U(S_k) - B_U(S_0) over changed pairs; enters the delta with a minus sign
     c->prof.begin(GRAAL_K_DELTA_BAND, st);
-    CUDA_OK(cudaMemsetAsync(c->partials, 0, (size_t)GRAAL_N_CANDIDATES * ps * sizeof(double), st));
-    k_band<BAND_CAND><<<dim3(gw, n_cand), 256, 0, st>>>(c->cand_order, meta + 4, -1, cand0, ld, c->lv, c->geo_cand, c->chmask, (size_t)c->W, slot_stride(c), n,
-                                                       skip, p, c->partials, ps); CHECK_LAUNCH(c);
+    k_band_delta<false><<<dim3(gw, n_cand), 256, 0, st>>>(c->cand_ordrec, n, meta + 4, rng + 2, c->geo_cand, (size_t)c->W, c->chmask, skip, p,
+                                                         c->partials, ps); CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, 1.0, d_band, 0); CHECK_LAUNCH(c);
-    k_band<BAND_BASE><<<dim3(gw, 1), 256, 0, st>>>(c->sub_index, meta + 4, -1, base, ld, c->lv, c->geo_base, c->chmask, 0, 0, 0,
-                                                  skip, p, c->partials, ps); CHECK_LAUNCH(c);
+    k_band_delta<true><<<dim3(gw, 1), 256, 0, st>>>(c->base_ordrec, n, meta + 4, rng, c->geo_base, 0, c->chmask, skip, p,
+                                                   c->partials, ps); CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, -1.0, d_band, 1); CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 32, 0, st>>>(d_band, 1, 1, -1.0, d_out, 1); CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_DELTA_BAND, st);

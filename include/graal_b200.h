@@ -78,10 +78,13 @@ int graal_set_params(graal_ctx* ctx, const float p[8]);
 /* How the expected value of an IN-BAND cis pixel (0 < s < d_max) is evaluated:
  *   0  the reference's float32 chain op for op: c1 * powf(s, slope) * expf((d-2)/(x*x+d)) * fact, max with
  *      v_inter, times norm, then log() of the float (kernels3.cu:120-133, 191-210)
- *   1  (default) the same quantity in log space, float64: max(ln(c1*fact) + slope*ln(s) + (d-2)/(x*x+d),
+ *   1  the same quantity in log space, float64: max(ln(c1*fact) + slope*ln(s) + (d-2)/(x*x+d),
  *      ln v_inter) + ln norm, from the same float32 distance s.  Differs from mode 0 by the float32
  *      roundings of the chain (<= ~1.5e-7 relative per pixel, zero mean), the order of the difference
- *      between two float32 libm implementations; ~2.5x fewer instructions per pixel.
+ *      between two float32 libm implementations.
+ *   2  (default) mode 1 with the law tabulated: f(s) and ln f(s) as float64 cubic-Hermite tables with 128
+ *      nodes per octave of s (rebuilt on the host for every parameter set), indexed by the float bit
+ *      pattern of s; interpolation error < 1e-9 relative.  No log / exp / division per pixel.
  * Circular contigs always use the float32 chain (rippe_contacts_circ, kernels3.cu:135-166). */
 int graal_set_math_mode(graal_ctx* ctx, int mode);
 

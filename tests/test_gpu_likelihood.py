@@ -51,9 +51,9 @@ def oracle_deltas(o, fA, fB):
     return out
 
 
-@pytest.mark.parametrize("level,mode", [(1, 1), (2, 1), (1, 0), (2, 0)])
+@pytest.mark.parametrize("level,mode", [(1, 2), (2, 2), (1, 1), (2, 1), (1, 0), (2, 0)])
 def test_full_and_delta_vs_oracle(small_pyramid, level, mode):
-    """mode 1 = the default log-space evaluation, mode 0 = the reference's float32 chain op for op."""
+    """mode 2 = the default tabulated law, mode 1 = log-space float64, mode 0 = the reference's float32 chain."""
     inp, o, g = make_pair(small_pyramid, level)
     g.set_math_mode(mode)
     rng = np.random.RandomState(31 + level)
