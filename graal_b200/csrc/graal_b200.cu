@@ -46,7 +46,7 @@ struct Params { float kuhn, lm, c1, slope, d, d_max, fact, v_inter, nfpb; int nd
                 // log-space evaluation (math mode 1): ln(c1*fact), ln(v_inter), slope as double, ln(t_norm)
                 int mode; double ln_cf, ln_v, slope_d; const double* t_lnnorm;
                 const double2* t_log; const double* t_exp;
-                // tabulated law (math mode 2): cubic-Hermite nodes {value, d/ds} of ln f(s) and of f(s), one node
+                // tabulated law (math mode 2): piecewise cubics (a0,a1),(a2,a3) of ln f(s) and of f(s), one interval
                 // per float bit pattern with LAW_M mantissa bits, s in [2^LAW_EMIN, 2^LAW_EMAX) kb;
                 // v_clamp = v_inter as double (the clamp of f), t_normd = t_norm as double
                 const double2* t_lnf; const double2* t_f; double v_clamp; const double* t_normd; };
@@ -135,27 +135,22 @@ __device__ __forceinline__ double fast_exp(double t, const double* __restrict__ 
     const int sh = k >> 5;
     return __longlong_as_double(__double_as_longlong(base) + ((long long)sh << 52));
 }
-// Cubic-Hermite interpolation of a tabulated function of s (math mode 2).  The node index and the local
-// abscissa come straight from the float bit pattern: node = exponent | top LAW_M mantissa bits, t = the
-// remaining mantissa bits / 2^(23-LAW_M) (exact), interval length 2^(e-LAW_M).  Relative error of the
-// interpolant for the Rippe law: < 1e-9 (profiles/README.md), far below one float32 ulp.
+// Piecewise-cubic (Hermite) tabulated function of s (math mode 2).  The interval index and the local
+// abscissa come straight from the float bit pattern: interval = exponent | top LAW_M mantissa bits, and the
+// remaining 23-LAW_M mantissa bits, placed at the top of a float64 mantissa with exponent 0, ARE the
+// abscissa u = 1 + t in [1, 2) -- no int->double conversion.  Each interval stores the cubic re-expanded
+// in u: (a0, a1), (a2, a3).  Relative error of the interpolant for the Rippe law: < 1e-9
+// (profiles/README.md), far below one float32 ulp.
 __device__ __forceinline__ bool law_in_table(float s) {
     const int e = (int)(__float_as_uint(s) >> 23) - 127;
     return e >= LAW_EMIN && e < LAW_EMAX;
 }
 __device__ __forceinline__ double law_interp(float s, const double2* __restrict__ tab) {
     const unsigned b = __float_as_uint(s);
-    const int e = (int)(b >> 23) - 127;
-    const int node = (int)(b >> (23 - LAW_M)) - ((127 + LAW_EMIN) << LAW_M);
-    const double t = (double)(b & ((1u << (23 - LAW_M)) - 1u)) * (1.0 / (double)(1u << (23 - LAW_M)));
-    const double dl = __longlong_as_double((long long)(1023 + e - LAW_M) << 52);        // 2^(e - LAW_M)
-    const double2 n0 = __ldg(&tab[node]), n1 = __ldg(&tab[node + 1]);
-    const double m0 = n0.y * dl, m1 = n1.y * dl;
-    // Hermite: h = n0.x + t*(m0 + t*(c2 + t*c3)),  c2 = 3d - 2 m0 - m1, c3 = m0 + m1 - 2d, d = n1.x - n0.x
-    const double d = n1.x - n0.x;
-    const double c3 = m0 + m1 - 2.0 * d;
-    const double c2 = 3.0 * d - 2.0 * m0 - m1;
-    return fma(t, fma(t, fma(t, c3, c2), m0), n0.x);
+    const int iv = (int)(b >> (23 - LAW_M)) - ((127 + LAW_EMIN) << LAW_M);
+    const double u = __hiloint2double((int)(0x3ff00000u | ((b & ((1u << (23 - LAW_M)) - 1u)) << (LAW_M - 3))), 0);
+    const double2 c01 = __ldg(&tab[2 * iv]), c23 = __ldg(&tab[2 * iv + 1]);
+    return fma(u, fma(u, fma(u, c23.y, c23.x), c01.y), c01.x);
 }
 
 // ln of rippe_contacts(s) for 0 < s < d_max on a LINEAR contig, clamp included:
@@ -975,7 +970,7 @@ __global__ void k_init_ranges(int* rng, int n) { const int i = threadIdx.x; if (
 //   BASE = true : base slot, OLD values once, credited to every candidate whose bit is set
 // Only windows that can contain a changed pair are scanned: x beyond the last changed bin is skipped, an
 // unchanged x starts its scan at the first changed bin and stops at the last one.
-template <bool BASE>
+template <bool BASE, int PARTS>
 __global__ void __launch_bounds__(256)
 k_band_delta(const int4* __restrict__ ordrec0, int order_stride, const int* __restrict__ d_count, const int* __restrict__ rng0,
              const Geo* __restrict__ geo0, size_t cand_geo_stride, const unsigned* __restrict__ chmask, unsigned skip_cands,
@@ -996,7 +991,9 @@ k_band_delta(const int4* __restrict__ ordrec0, int order_stride, const int* __re
         for (int c = 0; c < GRAAL_N_CANDIDATES; c++) accs[c] = 0.0;
     }
     const bool idle = (!BASE && ((skip_cands >> k) & 1u)) || hi < 0;
-    if (!idle) for (int ix = warp; ix <= hi && ix < count; ix += n_warps) {
+    // PARTS warps share one x: warp part takes the 32-bin chunks part, part + PARTS, ... of the window
+    if (!idle) for (int wx = warp; wx / PARTS <= hi && wx / PARTS < count; wx += n_warps) {
+        const int ix = wx / PARTS, part = wx % PARTS;
         const int4 rx = ordrec[ix];
         const int nx = (rx.x >> 28) & 7, sx0 = rx.x & 0x0fffffff;
         if (nx == 0) continue;                                   // duplicated bin: repeat path
@@ -1014,7 +1011,7 @@ k_band_delta(const int4* __restrict__ ordrec0, int order_stride, const int* __re
             xmax = fmaxf(xmax, gx[a].mid);
         }
         const int cx = rx.w;
-        for (int basei = y0; basei < y1; basei += 32) {
+        for (int basei = y0 + 32 * part; basei < y1; basei += 32 * PARTS) {
             const int iy = basei + lane;
             bool live = iy < y1;
             if (live) {
@@ -1063,127 +1060,62 @@ k_band_delta(const int4* __restrict__ ordrec0, int order_stride, const int* __re
     }
 }
 
-// contact part of the delta: one warp per member bin of U, lanes stride over its (<= 3 rows of) contacts.
-//   BASE = false: candidate k = blockIdx.y: NEW term of every contact (partner in U, other bin) with a
-//                 changed record on either side (bit k of chmask)
-//   BASE = true : once for all candidates: the OLD term of every contact changed in at least one
-//                 candidate, added to the accumulator of each flagged candidate
-template <bool BASE>
+// Contact part of the delta, all candidates in ONE pass over the rows of U: one warp per sub-frag row of a
+// member bin, four 32-entry slices of the row in flight per trip (the loads of a slice do not depend on
+// the previous one).  For every stored contact whose partner is in U, in another bin, with a changed
+// record on either side (chmask), the OLD term is evaluated once and the NEW term once per flagged
+// candidate:  accs[k] += ob * (ln ex_k - ln ex_0).
+#define DC_UNROLL 4
 __global__ void __launch_bounds__(256)
-k_delta_contacts(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, LevelView lv,
-                 const int* __restrict__ sub_index, const int* __restrict__ meta,
-                 const Geo* __restrict__ geo_base, const Geo* __restrict__ geo_cand0, size_t geo_stride,
-                 const unsigned* __restrict__ chmask, unsigned skip_cands,
-                 const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
-    const int k = blockIdx.y;
-    if (!BASE && ((skip_cands >> k) & 1u)) return;
-    const Geo* gK = BASE ? geo_base : geo_cand0 + (size_t)k * geo_stride;
+k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, LevelView lv,
+                      const int* __restrict__ sub_index, const int* __restrict__ meta,
+                      const Geo* __restrict__ geo_base, const Geo* __restrict__ geo_cand0, size_t geo_stride,
+                      const unsigned* __restrict__ chmask,
+                      const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
     const int m = meta[4], cA = meta[0], cB = meta[1];
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    double acc = 0.0;
-    double accs[GRAAL_N_CANDIDATES];
-    if (BASE) {
-        #pragma unroll
-        for (int c = 0; c < GRAAL_N_CANDIDATES; c++) accs[c] = 0.0;
-    }
-    for (int u = warp; u < m; u += n_warps) {
-        const int bin = sub_index[u];
-        const int4 sid = lv.sub_id[bin];
-        const int sub0 = sid.x;
-        const long long e0 = __ldg(&rowptr[sub0]);
-        const long long b1 = __ldg(&rowptr[sub0 + 1]);
-        const long long b2 = (sid.w > 1) ? __ldg(&rowptr[sub0 + 2]) : b1;
-        const long long e1 = (sid.w > 2) ? __ldg(&rowptr[sub0 + 3]) : b2;
-        Geo gr[3]; unsigned mr[3] = {0u, 0u, 0u};
-        #pragma unroll
-        for (int a = 0; a < 3; a++) if (a < sid.w) { gr[a] = ld_geo(&gK[sub0 + a]); mr[a] = __ldg(&chmask[sub0 + a]); }
-        for (long long e = e0 + lane; e < e1; e += 32) {
-            const int a = (e >= b1) + (e >= b2);
-            const int2 ce = __ldg(&contacts[e]);
-            const Geo g0c = ld_geo(&geo_base[ce.x]);
-            if (g0c.id_c != cA && g0c.id_c != cB) continue;              // partner outside U
-            if (ce.x - pk_local(g0c.pk) == sub0) continue;               // same bin: diagonal pixel, not re-scored
-            const unsigned mm = ((a == 0) ? mr[0] : (a == 1 ? mr[1] : mr[2])) | __ldg(&chmask[ce.x]);
-            if (BASE ? (mm == 0u) : !((mm >> k) & 1u)) continue;         // bitwise unchanged pair
-            const Geo gc = BASE ? g0c : ld_geo(&gK[ce.x]);
-            const Geo rr = (a == 0) ? gr[0] : (a == 1 ? gr[1] : gr[2]);
-            const double t = contact_log_term(rr, gc, __int_as_float(ce.y), p);
-            if (BASE) {
-                #pragma unroll
-                for (int c = 0; c < GRAAL_N_CANDIDATES; c++) if ((mm >> c) & 1u) accs[c] += t;
-            } else acc += t;
-        }
-    }
-    if (BASE) {
-        #pragma unroll
-        for (int c = 0; c < GRAAL_N_CANDIDATES; c++) {
-            const double v = block_sum(accs[c]);
-            if (threadIdx.x == 0) partials[(size_t)c * partial_stride + blockIdx.x] = v;
-        }
-    } else {
-        acc = block_sum(acc);
-        if (threadIdx.x == 0) partials[(size_t)k * partial_stride + blockIdx.x] = acc;
-    }
-}
-
-// All candidates in ONE pass over the contacts of U: every contact is loaded once, its OLD term is
-// evaluated once, and for every candidate whose chmask bit is set on either side the NEW term is
-// evaluated from that candidate's records (row records of the 13 candidates staged in shared memory,
-// partner records gathered only where the partner changed).  acc[k] += new_k - old.
-__global__ void __launch_bounds__(256)
-k_delta_contacts_all(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, LevelView lv,
-                     const int* __restrict__ sub_index, const int* __restrict__ meta,
-                     const Geo* __restrict__ geo_base, const Geo* __restrict__ geo_cand0, size_t geo_stride,
-                     const unsigned* __restrict__ chmask, int n_cand,
-                     const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
-    __shared__ Geo rowrec[8][GRAAL_N_CANDIDATES * 3];
-    const int m = meta[4], cA = meta[0], cB = meta[1];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     double accs[GRAAL_N_CANDIDATES];
     #pragma unroll
     for (int c = 0; c < GRAAL_N_CANDIDATES; c++) accs[c] = 0.0;
-    for (int u = warp; u < m; u += n_warps) {
+    for (int w = warp; w < 3 * m; w += n_warps) {
+        const int u = w / 3, a = w - 3 * u;
         const int bin = sub_index[u];
         if (!eligible(lv, bin)) continue;                     // duplicated bin: repeat path
         const int4 sid = lv.sub_id[bin];
-        const int sub0 = sid.x;
-        const long long e0 = __ldg(&rowptr[sub0]);
-        const long long b1 = __ldg(&rowptr[sub0 + 1]);
-        const long long b2 = (sid.w > 1) ? __ldg(&rowptr[sub0 + 2]) : b1;
-        const long long e1 = (sid.w > 2) ? __ldg(&rowptr[sub0 + 3]) : b2;
-        Geo gr0[3]; unsigned mr[3] = {0u, 0u, 0u};
-        #pragma unroll
-        for (int a = 0; a < 3; a++) if (a < sid.w) { gr0[a] = ld_geo(&geo_base[sub0 + a]); mr[a] = __ldg(&chmask[sub0 + a]); }
-        __syncwarp();
-        for (int idx = lane; idx < n_cand * 3; idx += 32) {
-            const int k = idx / 3, a = idx - 3 * k;
-            if (a < sid.w && ((mr[0] | mr[1] | mr[2]) >> k & 1u)) rowrec[wib][idx] = ld_geo(&geo_cand0[(size_t)k * geo_stride + sub0 + a]);
-        }
-        __syncwarp();
-        for (long long e = e0 + lane; e < e1; e += 32) {
-            const int a = (e >= b1) + (e >= b2);
-            const int2 ce = __ldg(&contacts[e]);
-            const Geo g0c = ld_geo(&geo_base[ce.x]);
-            if (g0c.id_c != cA && g0c.id_c != cB) continue;              // partner outside U
-            if (g0c.pk & PK_EXCLUDED) continue;                          // partner is a duplicated bin: repeat path
-            if (ce.x - pk_local(g0c.pk) == sub0) continue;               // same bin: diagonal pixel, not re-scored
-            const unsigned mra = (a == 0) ? mr[0] : (a == 1 ? mr[1] : mr[2]);
-            const unsigned mc = __ldg(&chmask[ce.x]);
-            const unsigned mm = mra | mc;
-            if (!mm) continue;                                           // bitwise unchanged in every candidate
-            const float ob = __int_as_float(ce.y);
-            const Geo r0 = (a == 0) ? gr0[0] : (a == 1 ? gr0[1] : gr0[2]);
-            const double told = contact_log_term(r0, g0c, ob, p);
+        if (a >= sid.w) continue;
+        const int sub0 = sid.x, rowsub = sid.x + a;
+        const long long e0 = __ldg(&rowptr[rowsub]), e1 = __ldg(&rowptr[rowsub + 1]);
+        const Geo r0 = ld_geo(&geo_base[rowsub]);
+        const unsigned mra = __ldg(&chmask[rowsub]);
+        for (long long eb = e0 + lane; eb < e1; eb += 32 * DC_UNROLL) {
+            int2 ce[DC_UNROLL]; Geo g0[DC_UNROLL]; unsigned mc[DC_UNROLL]; bool ok[DC_UNROLL];
             #pragma unroll
-            for (int k = 0; k < GRAAL_N_CANDIDATES; k++) {
-                if (!((mm >> k) & 1u)) continue;
-                const Geo rk = ((mra >> k) & 1u) ? rowrec[wib][3 * k + a] : r0;
-                const Geo gc = ((mc >> k) & 1u) ? ld_geo(&geo_cand0[(size_t)k * geo_stride + ce.x]) : g0c;
-                accs[k] += contact_log_term(rk, gc, ob, p) - told;
+            for (int j = 0; j < DC_UNROLL; j++) {
+                ok[j] = eb + 32 * j < e1;
+                ce[j] = ok[j] ? __ldg(&contacts[eb + 32 * j]) : make_int2(0, 0);   // rows of U recur in the next proposals: keep them in L2
+            }
+            #pragma unroll
+            for (int j = 0; j < DC_UNROLL; j++) if (ok[j]) { g0[j] = ld_geo(&geo_base[ce[j].x]); mc[j] = __ldg(&chmask[ce[j].x]); }
+            #pragma unroll
+            for (int j = 0; j < DC_UNROLL; j++) {
+                if (!ok[j]) continue;
+                const Geo g0c = g0[j];
+                if (g0c.id_c != cA && g0c.id_c != cB) continue;              // partner outside U
+                if (g0c.pk & PK_EXCLUDED) continue;                          // partner is a duplicated bin: repeat path
+                if (ce[j].x - pk_local(g0c.pk) == sub0) continue;            // same bin: diagonal pixel, not re-scored
+                const unsigned mm = mra | mc[j];
+                if (!mm) continue;                                           // bitwise unchanged in every candidate
+                const float ob = __int_as_float(ce[j].y);
+                const double told = contact_log_term(r0, g0c, ob, p);
+                #pragma unroll
+                for (int k = 0; k < GRAAL_N_CANDIDATES; k++) {
+                    if (!((mm >> k) & 1u)) continue;
+                    const Geo rk = ((mra >> k) & 1u) ? ld_geo(&geo_cand0[(size_t)k * geo_stride + rowsub]) : r0;
+                    const Geo gc = ((mc[j] >> k) & 1u) ? ld_geo(&geo_cand0[(size_t)k * geo_stride + ce[j].x]) : g0c;
+                    accs[k] += contact_log_term(rk, gc, ob, p) - told;
+                }
             }
         }
     }
@@ -1565,21 +1497,34 @@ static int upload_tables(graal_ctx* c, Params& p, int which) {
     if (p.mode == 2) {
         if (!(cf > 0.0) || !(p.kuhn > 0.0f) || !(p.lm > 0.0f)) p.mode = 1;      // degenerate parameters: analytic path
         else {
-            c->h_law.resize((size_t)(LAW_NODES + 2) * 4);
+            const size_t half = (size_t)(LAW_NODES + 2) * 4;          // doubles per table: 4 coefficients per interval
+            c->h_law.resize(half * 2);
             const double K = (double)p.d - 2.0, dd = (double)p.d, q = (double)p.lm / (double)p.kuhn, sl = (double)p.slope;
-            for (int i = 0; i < LAW_NODES + 2; i++) {
+            auto node = [&](int i, double& lnf, double& dlnf) {
                 const int e = LAW_EMIN + (i >> LAW_M);
                 const double sv = ldexp(1.0 + (double)(i & ((1 << LAW_M) - 1)) / (double)(1 << LAW_M), e);
                 const double x = sv * q, den = x * x + dd;
-                const double lnf = p.ln_cf + sl * log(sv) + K / den;
-                const double dlnf = sl / sv - K * 2.0 * x * q / (den * den);
-                const double f = exp(lnf);
-                c->h_law[(size_t)i * 2] = lnf; c->h_law[(size_t)i * 2 + 1] = dlnf;
-                c->h_law[(size_t)(LAW_NODES + 2) * 2 + (size_t)i * 2] = f;
-                c->h_law[(size_t)(LAW_NODES + 2) * 2 + (size_t)i * 2 + 1] = f * dlnf;
+                lnf = p.ln_cf + sl * log(sv) + K / den;
+                dlnf = sl / sv - K * 2.0 * x * q / (den * den);
+            };
+            auto cubic = [](double f0, double d0, double f1, double d1, double dl, double* a) {
+                // Hermite in t on [0,1]: c0 + c1 t + c2 t^2 + c3 t^3, then t = u - 1
+                const double m0 = d0 * dl, m1 = d1 * dl, d = f1 - f0;
+                const double c0 = f0, c1 = m0, c2 = 3.0 * d - 2.0 * m0 - m1, c3 = m0 + m1 - 2.0 * d;
+                a[0] = c0 - c1 + c2 - c3; a[1] = c1 - 2.0 * c2 + 3.0 * c3; a[2] = c2 - 3.0 * c3; a[3] = c3;
+            };
+            double l0, g0; node(0, l0, g0);
+            for (int i = 0; i < LAW_NODES + 1; i++) {
+                double l1, g1; node(i + 1, l1, g1);
+                const double dl = ldexp(1.0, LAW_EMIN + (i >> LAW_M) - LAW_M);
+                cubic(l0, g0, l1, g1, dl, &c->h_law[(size_t)i * 4]);
+                const double f0 = exp(l0), f1 = exp(l1);
+                cubic(f0, f0 * g0, f1, f1 * g1, dl, &c->h_law[half + (size_t)i * 4]);
+                l0 = l1; g0 = g1;
             }
-            CUDA_OK(cudaMemcpyAsync(c->d_tab_lnf[which], c->h_law.data(), (size_t)(LAW_NODES + 2) * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
-            CUDA_OK(cudaMemcpyAsync(c->d_tab_f[which], c->h_law.data() + (size_t)(LAW_NODES + 2) * 2, (size_t)(LAW_NODES + 2) * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+            for (int k = 0; k < 4; k++) { c->h_law[(size_t)(LAW_NODES + 1) * 4 + k] = 0.0; c->h_law[half + (size_t)(LAW_NODES + 1) * 4 + k] = 0.0; }
+            CUDA_OK(cudaMemcpyAsync(c->d_tab_lnf[which], c->h_law.data(), half * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            CUDA_OK(cudaMemcpyAsync(c->d_tab_f[which], c->h_law.data() + half, half * sizeof(double), cudaMemcpyHostToDevice, c->stream));
             CUDA_OK(cudaStreamSynchronize(c->stream));      // h_law is reused by the next call
         }
     }
@@ -1744,8 +1689,8 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
         CUDA_OK(cudaMalloc(&c->d_tab_normd, tnd.size() * sizeof(double)));
         CUDA_OK(cudaMemcpy(c->d_tab_normd, tnd.data(), tnd.size() * sizeof(double), cudaMemcpyHostToDevice));
         for (int w = 0; w < 2; w++) {
-            CUDA_OK(cudaMalloc(&c->d_tab_lnf[w], (size_t)(LAW_NODES + 2) * sizeof(double2)));
-            CUDA_OK(cudaMalloc(&c->d_tab_f[w], (size_t)(LAW_NODES + 2) * sizeof(double2)));
+            CUDA_OK(cudaMalloc(&c->d_tab_lnf[w], (size_t)(LAW_NODES + 2) * 2 * sizeof(double2)));
+            CUDA_OK(cudaMalloc(&c->d_tab_f[w], (size_t)(LAW_NODES + 2) * 2 * sizeof(double2)));
         }
         for (int w = 0; w < 2; w++) {
             CUDA_OK(cudaMalloc(&c->d_tab_g[w], tn.size() * sizeof(float)));
@@ -2045,21 +1990,23 @@ static int delta_loglik_impl(graal_ctx* c, int base_slot, int first_cand_slot, i
     k_cand_order<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->sub_index, meta, piece_len, c->cand_order, n, skip,
                                                   c->lv, c->chmask, c->cand_ordrec, rng + 2); CHECK_LAUNCH(c);
     k_base_order<<<gu, 256, 0, st>>>(base, ld, c->sub_index, meta, c->lv, c->chmask, c->base_ordrec, rng); CHECK_LAUNCH(c);
-    const int gw = std::min(ps, std::max(1, nblk(n, 8)));
+    // grid-stride kernels over the (device-side) size of U: a few CTAs per SM, not one warp per bin of the level
+    const int gw = std::min(ps, std::max(1, std::min(nblk(n, 1), c->n_sm * 8)));
+    const int gb = std::min(ps, std::max(1, std::min(nblk(n, 4), c->n_sm * 4)));
     // contacts: sum over changed contacts of ob * (ln ex_k - ln ex_0): new terms per candidate, old terms once
     c->prof.begin(GRAAL_K_DELTA_CONTACTS, st);
-    k_delta_contacts_all<<<dim3(gw, 1), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, c->sub_index, meta, c->geo_base, c->geo_cand, (size_t)c->W,
-                                                     c->chmask, n_cand, p, c->partials, ps); CHECK_LAUNCH(c);
+    k_delta_contacts_rows<<<dim3(gw, 1), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, c->sub_index, meta, c->geo_base, c->geo_cand, (size_t)c->W,
+                                                      c->chmask, p, c->partials, ps); CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, 1.0, d_out, 0); CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_DELTA_CONTACTS, st);
     // band mass: d_band[k] = B_U(S_k) - B_U(S_0) over changed pairs; enters the delta with a minus sign
     c->prof.begin(GRAAL_K_DELTA_BAND, st);
-    k_band_delta<false><<<dim3(gw, n_cand), 256, 0, st>>>(c->cand_ordrec, n, meta + 4, rng + 2, c->geo_cand, (size_t)c->W, c->chmask, skip, p,
+    k_band_delta<false, 2><<<dim3(gb, n_cand), 256, 0, st>>>(c->cand_ordrec, n, meta + 4, rng + 2, c->geo_cand, (size_t)c->W, c->chmask, skip, p,
                                                          c->partials, ps); CHECK_LAUNCH(c);
-    k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, 1.0, d_band, 0); CHECK_LAUNCH(c);
-    k_band_delta<true><<<dim3(gw, 1), 256, 0, st>>>(c->base_ordrec, n, meta + 4, rng, c->geo_base, 0, c->chmask, skip, p,
+    k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gb, ps, 1.0, d_band, 0); CHECK_LAUNCH(c);
+    k_band_delta<true, 8><<<dim3(gb, 1), 256, 0, st>>>(c->base_ordrec, n, meta + 4, rng, c->geo_base, 0, c->chmask, skip, p,
                                                    c->partials, ps); CHECK_LAUNCH(c);
-    k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, -1.0, d_band, 1); CHECK_LAUNCH(c);
+    k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gb, ps, -1.0, d_band, 1); CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 32, 0, st>>>(d_band, 1, 1, -1.0, d_out, 1); CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_DELTA_BAND, st);
     if (c->n_rep > 0) {     // ranges 2-4: pixels of the duplicated bins that have a copy in U, new minus old
