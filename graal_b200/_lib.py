@@ -53,6 +53,7 @@ _SIGS = {
     "graal_last_error": (C.c_char_p, []),
     "graal_set_stream": (_I, [_P, _P]),
     "graal_sync": (_I, [_P]),
+    "graal_join": (_I, [_P]),
     "graal_version": (C.c_char_p, []),
     "graal_level_bind": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _LL, _F]),
     "graal_set_params": (_I, [_P, C.POINTER(_F)]),

@@ -1404,8 +1404,26 @@ struct Profiler {
     void destroy() { for (int k = 0; k < PROF_KERNELS; k++) { for (auto& e : ev[k]) cudaEventDestroy(e); ev[k].clear(); } }
 };
 
+// Scratch of one proposal being scored.  Proposals of one step are independent given the base slot, so
+// graal_score_proposal runs each on its own lane (stream + buffers) and their kernels overlap on the GPU;
+// every other entry point joins the lanes back into the context stream first.
+#define GRAAL_MAX_LANES 4
+struct Lane {
+    cudaStream_t st = nullptr; cudaEvent_t done = nullptr; bool pending = false;
+    int cand_first = -1;                     // candidate slots [cand_first, cand_first + 13) in use while pending
+    int* ints = nullptr;                     // [256]: [8..16) delta meta, [16..120) piece_len, [160..188) changed ranges
+    int* sub_index = nullptr;                // [n]
+    unsigned* chmask = nullptr;              // [W] bit k: record differs from the base slot in candidate k
+    Geo* geo_cand = nullptr;                 // [13][W]
+    int* cand_order = nullptr;               // [13][n]
+    int4* cand_ordrec = nullptr; int4* base_ordrec = nullptr;   // [13][n] / [n] position-ordered bin records of U
+    double* partials = nullptr;              // [16][partial_stride]
+    unsigned char* rep_in_u = nullptr;       // [N]
+};
+
 struct graal_ctx {
     Profiler prof;
+    Lane lanes[GRAAL_MAX_LANES]; int n_lanes = 3; cudaEvent_t ev_fork = nullptr;
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -1427,14 +1445,12 @@ struct graal_ctx {
     int math_mode = 2;
     std::vector<float> h_tab_g; std::vector<double> h_tab_logg;
     int* d_quirky = nullptr; int n_quirky = 0;
-    unsigned char* d_dup = nullptr; unsigned char* d_sub_dup = nullptr; unsigned char* d_rep_in_u = nullptr;
+    unsigned char* d_dup = nullptr; unsigned char* d_sub_dup = nullptr;
     int* d_rep_bins = nullptr; int n_rep = 0;
     double lf_total = 0.0, ob_total = 0.0;
     unsigned short* cid16_base = nullptr; float* mid32_base = nullptr; int smem_optin = 0;
     int* group_row = nullptr; int n_groups = 0;
     int smem_cid = 0;                         // GRAAL_SMEM_CID=1: stage the contig-id table in shared memory (measured: no faster than L1, profiles/README.md)
-    unsigned* chmask = nullptr;               // [W] bit k: record differs from the base slot in candidate k
-    int4* cand_ordrec = nullptr; int4* base_ordrec = nullptr;   // [13][n] / [n] position-ordered bin records of U
     double* band_hist = nullptr;              // [16][13] band delta of the proposals scored since the last commit
     int band_slot = -1; int band_age = 0;     // slot whose cross-bin band total is cached in d_scalars[40]
     // params
@@ -1443,10 +1459,7 @@ struct graal_ctx {
     int* slots = nullptr; int ld = 0, n_slots = 0;
     // scratch
     Geo* geo_base = nullptr; int geo_base_slot = -1;
-    Geo* geo_cand = nullptr;                 // [13][W]
     int* order = nullptr;                    // [n]
-    int* cand_order = nullptr;               // [13][n]
-    int* sub_index = nullptr;                // [n]
     int* cont_len = nullptr; int* cont_off = nullptr; int cap = 0;   // [cap]
     int* first_idx = nullptr; int* map = nullptr;
     unsigned long long* keys = nullptr; unsigned long long* keys_sorted = nullptr;
@@ -1531,6 +1544,17 @@ static int upload_tables(graal_ctx* c, Params& p, int which) {
     return 0;
 }
 
+// make the context stream wait for every proposal still running on a lane
+static int join_lanes(graal_ctx* c) {
+    for (int l = 0; l < c->n_lanes; l++) {
+        Lane& L = c->lanes[l];
+        if (!L.pending) continue;
+        CUDA_OK(cudaStreamWaitEvent(c->stream, L.done, 0));
+        L.pending = false; L.cand_first = -1;
+    }
+    return 0;
+}
+
 extern "C" {
 
 const char* graal_last_error(void) { return g_err; }
@@ -1558,32 +1582,55 @@ int graal_ctx_create(int device, graal_ctx** out) {
     CUDA_OK(cudaMalloc(&c->d_scalars, 64 * sizeof(double)));
     c->partial_stride = c->n_sm * 8;
     CUDA_OK(cudaMalloc(&c->partials, (size_t)16 * c->partial_stride * sizeof(double)));
+    { const char* e = getenv("GRAAL_LANES"); if (e && e[0] >= '1' && e[0] <= '0' + GRAAL_MAX_LANES) c->n_lanes = e[0] - '0'; }
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (int l = 0; l < c->n_lanes; l++) {
+        Lane& L = c->lanes[l];
+        CUDA_OK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+        CUDA_OK(cudaMalloc(&L.ints, 256 * sizeof(int)));
+        CUDA_OK(cudaMemset(L.ints, 0, 256 * sizeof(int)));
+        CUDA_OK(cudaMalloc(&L.partials, (size_t)16 * c->partial_stride * sizeof(double)));
+    }
     *out = c;
     return 0;
 }
 
 static void free_level_scratch(graal_ctx* c) {
-    cudaFree(c->cid16_base); cudaFree(c->mid32_base); cudaFree(c->group_row); cudaFree(c->cand_ordrec); cudaFree(c->base_ordrec); c->cand_ordrec = c->base_ordrec = nullptr; cudaFree(c->chmask); cudaFree(c->band_hist); c->chmask = nullptr; c->band_hist = nullptr; c->cid16_base = nullptr; c->mid32_base = nullptr; c->group_row = nullptr;
-    cudaFree(c->geo_base); cudaFree(c->geo_cand); cudaFree(c->order); cudaFree(c->cand_order); cudaFree(c->sub_index);
+    cudaFree(c->cid16_base); cudaFree(c->mid32_base); cudaFree(c->group_row); cudaFree(c->band_hist); c->band_hist = nullptr; c->cid16_base = nullptr; c->mid32_base = nullptr; c->group_row = nullptr;
+    for (int l = 0; l < GRAAL_MAX_LANES; l++) {
+        Lane& L = c->lanes[l];
+        cudaFree(L.sub_index); cudaFree(L.chmask); cudaFree(L.geo_cand); cudaFree(L.cand_order); cudaFree(L.cand_ordrec); cudaFree(L.base_ordrec); cudaFree(L.rep_in_u);
+        L.sub_index = nullptr; L.chmask = nullptr; L.geo_cand = nullptr; L.cand_order = nullptr; L.cand_ordrec = L.base_ordrec = nullptr; L.rep_in_u = nullptr;
+    }
+    cudaFree(c->geo_base); cudaFree(c->order);
     cudaFree(c->cont_len); cudaFree(c->cont_off); cudaFree(c->first_idx); cudaFree(c->map); cudaFree(c->keys);
     cudaFree(c->keys_sorted); cudaFree(c->cub_tmp); cudaFree(c->d_quirky); cudaFree(c->d_accu_idx);
-    cudaFree(c->d_dup); cudaFree(c->d_sub_dup); cudaFree(c->d_rep_in_u); cudaFree(c->d_rep_bins);
-    c->d_dup = c->d_sub_dup = c->d_rep_in_u = nullptr; c->d_rep_bins = nullptr; c->n_rep = 0;
+    cudaFree(c->d_dup); cudaFree(c->d_sub_dup); cudaFree(c->d_rep_bins);
+    c->d_dup = c->d_sub_dup = nullptr; c->d_rep_bins = nullptr; c->n_rep = 0;
     cudaFree(c->d_tab_lnnorm); cudaFree(c->d_tab_log); cudaFree(c->d_tab_exp); cudaFree(c->d_tab_normd);
     for (int w = 0; w < 2; w++) { cudaFree(c->d_tab_lnf[w]); cudaFree(c->d_tab_f[w]); c->d_tab_lnf[w] = nullptr; c->d_tab_f[w] = nullptr; }
     c->d_tab_normd = nullptr;
     c->d_tab_lnnorm = nullptr; c->d_tab_log = nullptr; c->d_tab_exp = nullptr;
     cudaFree(c->d_tab_norm); cudaFree(c->d_tab_g[0]); cudaFree(c->d_tab_g[1]); cudaFree(c->d_tab_logg[0]); cudaFree(c->d_tab_logg[1]);
     c->d_accu_idx = nullptr; c->d_tab_norm = nullptr; c->d_tab_g[0] = c->d_tab_g[1] = nullptr; c->d_tab_logg[0] = c->d_tab_logg[1] = nullptr;
-    c->geo_base = c->geo_cand = nullptr; c->order = c->cand_order = c->sub_index = c->cont_len = c->cont_off = nullptr;
+    c->geo_base = nullptr; c->order = c->cont_len = c->cont_off = nullptr;
     c->first_idx = c->map = nullptr; c->keys = c->keys_sorted = nullptr; c->cub_tmp = nullptr; c->d_quirky = nullptr;
 }
 
 void graal_ctx_destroy(graal_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    for (int l = 0; l < GRAAL_MAX_LANES; l++) if (c->lanes[l].st) cudaStreamSynchronize(c->lanes[l].st);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_level_scratch(c);
+    for (int l = 0; l < GRAAL_MAX_LANES; l++) {
+        Lane& L = c->lanes[l];
+        cudaFree(L.ints); cudaFree(L.partials);
+        if (L.done) cudaEventDestroy(L.done);
+        if (L.st) cudaStreamDestroy(L.st);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     c->prof.destroy();
     cudaFree(c->d_ints); cudaFree(c->d_stats); cudaFree(c->d_scalars); cudaFree(c->partials);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -1592,11 +1639,18 @@ void graal_ctx_destroy(graal_ctx* c) {
 
 int graal_set_stream(graal_ctx* c, void* s) {
     if (!c) return set_err(-1, "null context");
+    { int rc = join_lanes(c); if (rc) return rc; }
     if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     c->stream = (cudaStream_t)s; c->own_stream = false;
     return 0;
 }
-int graal_sync(graal_ctx* c) { if (!c) return set_err(-1, "null context"); CUDA_OK(cudaStreamSynchronize(c->stream)); return 0; }
+int graal_sync(graal_ctx* c) {
+    if (!c) return set_err(-1, "null context");
+    int rc = join_lanes(c); if (rc) return rc;
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int graal_join(graal_ctx* c) { if (!c) return set_err(-1, "null context"); return join_lanes(c); }
 int64_t graal_launch_count(graal_ctx* c) { return c ? c->launches : -1; }
 
 int graal_profile_enable(graal_ctx* c, int on) {
@@ -1627,6 +1681,7 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     if (!sub_id || !sub_len_kb || !sub_accu || !rowptr || (n_contacts > 0 && !contacts)) return set_err(-1, "null level pointer");
     if (n_new_frags != n_frags && (!collector || !dispatcher)) return set_err(-1, "repeat copies need the collector / dispatcher tables");
     CUDA_OK(cudaSetDevice(c->device));
+    { int rcj = join_lanes(c); if (rcj) return rcj; }
     CUDA_OK(cudaStreamSynchronize(c->stream));
     free_level_scratch(c);
     c->N = n_frags; c->n_new = n_new_frags; c->W = n_sub_frags; c->E = n_contacts; c->nfpb = nfpb;
@@ -1706,7 +1761,7 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
         for (int b = 0; b < n_frags; b++) if (h_dup[b]) for (int a = 0; a < h_sid[(size_t)b * 4 + 3]; a++) sub_dup[h_sid[(size_t)b * 4] + a] = 1;
         CUDA_OK(cudaMalloc(&c->d_dup, h_dup.size())); CUDA_OK(cudaMemcpy(c->d_dup, h_dup.data(), h_dup.size(), cudaMemcpyHostToDevice));
         CUDA_OK(cudaMalloc(&c->d_sub_dup, sub_dup.size())); CUDA_OK(cudaMemcpy(c->d_sub_dup, sub_dup.data(), sub_dup.size(), cudaMemcpyHostToDevice));
-        CUDA_OK(cudaMalloc(&c->d_rep_in_u, h_dup.size())); CUDA_OK(cudaMemset(c->d_rep_in_u, 0, h_dup.size()));
+        for (int l = 0; l < c->n_lanes; l++) { CUDA_OK(cudaMalloc(&c->lanes[l].rep_in_u, h_dup.size())); CUDA_OK(cudaMemset(c->lanes[l].rep_in_u, 0, h_dup.size())); }
         CUDA_OK(cudaMalloc(&c->d_rep_bins, rep_bins.size() * sizeof(int)));
         CUDA_OK(cudaMemcpy(c->d_rep_bins, rep_bins.data(), rep_bins.size() * sizeof(int), cudaMemcpyHostToDevice));
         c->lv.dup = c->d_dup;
@@ -1722,21 +1777,25 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     CUDA_OK(cudaMalloc(&c->cid16_base, ((size_t)c->W + 16) * sizeof(unsigned short)));
     CUDA_OK(cudaMemset(c->cid16_base, 0, ((size_t)c->W + 16) * sizeof(unsigned short)));
     CUDA_OK(cudaMalloc(&c->mid32_base, (size_t)c->W * sizeof(float)));
-    CUDA_OK(cudaMalloc(&c->chmask, (size_t)c->W * sizeof(unsigned)));
-    CUDA_OK(cudaMalloc(&c->cand_ordrec, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int4)));
-    CUDA_OK(cudaMalloc(&c->base_ordrec, (size_t)n * sizeof(int4)));
-    CUDA_OK(cudaMemset(c->cand_ordrec, 0, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int4)));
-    CUDA_OK(cudaMemset(c->base_ordrec, 0, (size_t)n * sizeof(int4)));
+    for (int l = 0; l < c->n_lanes; l++) {
+        Lane& L = c->lanes[l];
+        CUDA_OK(cudaMalloc(&L.chmask, (size_t)c->W * sizeof(unsigned)));
+        CUDA_OK(cudaMalloc(&L.cand_ordrec, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int4)));
+        CUDA_OK(cudaMalloc(&L.base_ordrec, (size_t)n * sizeof(int4)));
+        CUDA_OK(cudaMemset(L.cand_ordrec, 0, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int4)));
+        CUDA_OK(cudaMemset(L.base_ordrec, 0, (size_t)n * sizeof(int4)));
+        CUDA_OK(cudaMalloc(&L.geo_cand, (size_t)GRAAL_N_CANDIDATES * c->W * sizeof(Geo)));
+        CUDA_OK(cudaMemset(L.geo_cand, 0, (size_t)GRAAL_N_CANDIDATES * c->W * sizeof(Geo)));
+        CUDA_OK(cudaMalloc(&L.cand_order, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int)));
+        CUDA_OK(cudaMalloc(&L.sub_index, (size_t)n * sizeof(int)));
+        CUDA_OK(cudaMemset(L.sub_index, 0, (size_t)n * sizeof(int)));
+        CUDA_OK(cudaMemset(L.cand_order, 0, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int)));
+        L.pending = false; L.cand_first = -1;
+    }
     CUDA_OK(cudaMalloc(&c->band_hist, 16 * GRAAL_N_CANDIDATES * sizeof(double)));
     CUDA_OK(cudaMemset(c->band_hist, 0, 16 * GRAAL_N_CANDIDATES * sizeof(double)));
     c->band_slot = -1;
-    CUDA_OK(cudaMalloc(&c->geo_cand, (size_t)GRAAL_N_CANDIDATES * c->W * sizeof(Geo)));
-    CUDA_OK(cudaMemset(c->geo_cand, 0, (size_t)GRAAL_N_CANDIDATES * c->W * sizeof(Geo)));
     CUDA_OK(cudaMalloc(&c->order, (size_t)n * sizeof(int)));
-    CUDA_OK(cudaMalloc(&c->cand_order, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int)));
-    CUDA_OK(cudaMalloc(&c->sub_index, (size_t)n * sizeof(int)));
-    CUDA_OK(cudaMemset(c->sub_index, 0, (size_t)n * sizeof(int)));
-    CUDA_OK(cudaMemset(c->cand_order, 0, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int)));
     CUDA_OK(cudaMalloc(&c->cont_len, (size_t)c->cap * sizeof(int)));
     CUDA_OK(cudaMalloc(&c->cont_off, (size_t)c->cap * sizeof(int)));
     CUDA_OK(cudaMalloc(&c->first_idx, (size_t)c->cap * sizeof(int)));
@@ -1779,7 +1838,8 @@ int graal_set_params(graal_ctx* c, const float q[8]) {
     c->p.d_max = q[5]; c->p.fact = q[6]; c->p.v_inter = q[7]; c->p.nfpb = c->nfpb;
     if (!c->d_tab_norm) return set_err(-1, "bind the level before setting parameters");
     CUDA_OK(cudaSetDevice(c->device));
-    int rc = upload_tables(c, c->p, 0); if (rc) return rc;
+    int rc = join_lanes(c); if (rc) return rc;          // pending proposals still read the tables being replaced
+    rc = upload_tables(c, c->p, 0); if (rc) return rc;
     c->have_params = true; c->band_slot = -1;
     return 0;
 }
@@ -1794,11 +1854,13 @@ int graal_state_bind(graal_ctx* c, int32_t* base, int ld, int n_slots) {
     if (!c || !base) return set_err(-1, "null argument");
     if (c->n_new <= 0) return set_err(-1, "bind the level first");
     if (ld < c->n_new || n_slots < 1) return set_err(-1, "bad slot geometry (ld %d < n %d)", ld, c->n_new);
+    { int rcj = join_lanes(c); if (rcj) return rcj; }
     c->slots = base; c->ld = ld; c->n_slots = n_slots; c->geo_base_slot = -1; c->band_slot = -1;
     return 0;
 }
 
-#define NEED_STATE(c) do { if (!(c) || !(c)->slots) return set_err(-1, "state not bound"); CUDA_OK(cudaSetDevice((c)->device)); } while (0)
+#define NEED_STATE(c) do { if (!(c) || !(c)->slots) return set_err(-1, "state not bound"); CUDA_OK(cudaSetDevice((c)->device)); \
+                           { int rcj_ = join_lanes(c); if (rcj_) return rcj_; } } while (0)
 #define NEED_SLOT(c, s) do { if ((s) < 0 || (s) >= (c)->n_slots) return set_err(-1, "slot %d out of range", (s)); } while (0)
 static inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
 
@@ -1873,7 +1935,16 @@ static int ensure_base_geometry(graal_ctx* c, int slot) {
 }
 
 int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d_out) {
-    NEED_STATE(c); NEED_SLOT(c, slot);
+    if (!c || !c->slots) return set_err(-1, "state not bound");
+    CUDA_OK(cudaSetDevice(c->device));
+    NEED_SLOT(c, slot);
+    {   // The full likelihood only reads the slot and the base geometry: it may run beside pending proposals
+        // when they were scored against this very slot (geometry current) and it is not one of their candidates.
+        bool join = c->geo_base_slot != slot || p_override != nullptr || c->prof.on;
+        for (int l = 0; l < c->n_lanes; l++)
+            if (c->lanes[l].pending && slot >= c->lanes[l].cand_first && slot < c->lanes[l].cand_first + GRAAL_N_CANDIDATES) join = true;
+        if (join) { int rcj = join_lanes(c); if (rcj) return rcj; }
+    }
     if (!d_out) return set_err(-1, "null output");
     if (!c->have_params && !p_override) return set_err(-1, "parameters not set");
     Params p = c->p;
@@ -1967,71 +2038,70 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
     return 0;
 }
 
-static int delta_loglik_impl(graal_ctx* c, int base_slot, int first_cand_slot, int n_cand, int id_fA, int id_fB, int max_id,
+// the base slot's geometry must be current (ensure_base_geometry on the context stream) before this runs on `st`
+static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_slot, int first_cand_slot, int n_cand, int id_fA, int id_fB, int max_id,
                             unsigned skip, double* d_out, double* d_band) {
     const int n = c->n_new, ld = c->ld;
-    cudaStream_t st = c->stream;
     const Params p = c->p;
-    int rc = ensure_base_geometry(c, base_slot); if (rc) return rc;
     int* base = slot_ptr(c, base_slot);
     int* cand0 = slot_ptr(c, first_cand_slot);
-    int* meta = c->d_ints + 8;
-    int* piece_len = c->d_ints + 16;
+    int* meta = L.ints + 8;
+    int* piece_len = L.ints + 16;
     const int ps = c->partial_stride;
     k_delta_setup<<<1, 1, 0, st>>>(base, ld, id_fA, id_fB, c->d_ints + 0, max_id, meta); CHECK_LAUNCH(c);
-    k_fill_sub_index<<<nblk(n, 256), 256, 0, st>>>(base, ld, n, meta, c->sub_index); CHECK_LAUNCH(c);
+    k_fill_sub_index<<<nblk(n, 256), 256, 0, st>>>(base, ld, n, meta, L.sub_index); CHECK_LAUNCH(c);
     CUDA_OK(cudaMemsetAsync(piece_len, 0, GRAAL_N_CANDIDATES * 8 * sizeof(int), st));
-    CUDA_OK(cudaMemsetAsync(c->chmask, 0, (size_t)c->W * sizeof(unsigned), st));
+    CUDA_OK(cudaMemsetAsync(L.chmask, 0, (size_t)c->W * sizeof(unsigned), st));
     const int gu = std::min(c->n_sm * 2, nblk(n, 256));
-    k_cand_geometry<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->lv, c->sub_index, meta, c->geo_cand, (size_t)c->W, piece_len,
-                                                     c->geo_base, c->chmask, skip); CHECK_LAUNCH(c);
-    int* rng = c->d_ints + 160;                       // [0,1] base range, [2 + 2k, 3 + 2k] candidate k
+    k_cand_geometry<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->lv, L.sub_index, meta, L.geo_cand, (size_t)c->W, piece_len,
+                                                     c->geo_base, L.chmask, skip); CHECK_LAUNCH(c);
+    int* rng = L.ints + 160;                       // [0,1] base range, [2 + 2k, 3 + 2k] candidate k
     k_init_ranges<<<1, 32, 0, st>>>(rng, 2 + 2 * GRAAL_N_CANDIDATES); CHECK_LAUNCH(c);
-    k_cand_order<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->sub_index, meta, piece_len, c->cand_order, n, skip,
-                                                  c->lv, c->chmask, c->cand_ordrec, rng + 2); CHECK_LAUNCH(c);
-    k_base_order<<<gu, 256, 0, st>>>(base, ld, c->sub_index, meta, c->lv, c->chmask, c->base_ordrec, rng); CHECK_LAUNCH(c);
+    k_cand_order<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, L.sub_index, meta, piece_len, L.cand_order, n, skip,
+                                                  c->lv, L.chmask, L.cand_ordrec, rng + 2); CHECK_LAUNCH(c);
+    k_base_order<<<gu, 256, 0, st>>>(base, ld, L.sub_index, meta, c->lv, L.chmask, L.base_ordrec, rng); CHECK_LAUNCH(c);
     // grid-stride kernels over the (device-side) size of U: a few CTAs per SM, not one warp per bin of the level
     const int gw = std::min(ps, std::max(1, std::min(nblk(n, 1), c->n_sm * 8)));
     const int gb = std::min(ps, std::max(1, std::min(nblk(n, 4), c->n_sm * 4)));
     // contacts: sum over changed contacts of ob * (ln ex_k - ln ex_0): new terms per candidate, old terms once
     c->prof.begin(GRAAL_K_DELTA_CONTACTS, st);
-    k_delta_contacts_rows<<<dim3(gw, 1), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, c->sub_index, meta, c->geo_base, c->geo_cand, (size_t)c->W,
-                                                      c->chmask, p, c->partials, ps); CHECK_LAUNCH(c);
-    k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gw, ps, 1.0, d_out, 0); CHECK_LAUNCH(c);
+    k_delta_contacts_rows<<<dim3(gw, 1), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, L.sub_index, meta, c->geo_base, L.geo_cand, (size_t)c->W,
+                                                      L.chmask, p, L.partials, ps); CHECK_LAUNCH(c);
+    k_reduce_partials<<<n_cand, 256, 0, st>>>(L.partials, gw, ps, 1.0, d_out, 0); CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_DELTA_CONTACTS, st);
     // band mass: d_band[k] = B_U(S_k) - B_U(S_0) over changed pairs; enters the delta with a minus sign
     c->prof.begin(GRAAL_K_DELTA_BAND, st);
-    k_band_delta<false, 2><<<dim3(gb, n_cand), 256, 0, st>>>(c->cand_ordrec, n, meta + 4, rng + 2, c->geo_cand, (size_t)c->W, c->chmask, skip, p,
-                                                         c->partials, ps); CHECK_LAUNCH(c);
-    k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gb, ps, 1.0, d_band, 0); CHECK_LAUNCH(c);
-    k_band_delta<true, 8><<<dim3(gb, 1), 256, 0, st>>>(c->base_ordrec, n, meta + 4, rng, c->geo_base, 0, c->chmask, skip, p,
-                                                   c->partials, ps); CHECK_LAUNCH(c);
-    k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gb, ps, -1.0, d_band, 1); CHECK_LAUNCH(c);
+    k_band_delta<false, 2><<<dim3(gb, n_cand), 256, 0, st>>>(L.cand_ordrec, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, L.chmask, skip, p,
+                                                         L.partials, ps); CHECK_LAUNCH(c);
+    k_reduce_partials<<<n_cand, 256, 0, st>>>(L.partials, gb, ps, 1.0, d_band, 0); CHECK_LAUNCH(c);
+    k_band_delta<true, 8><<<dim3(gb, 1), 256, 0, st>>>(L.base_ordrec, n, meta + 4, rng, c->geo_base, 0, L.chmask, skip, p,
+                                                   L.partials, ps); CHECK_LAUNCH(c);
+    k_reduce_partials<<<n_cand, 256, 0, st>>>(L.partials, gb, ps, -1.0, d_band, 1); CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 32, 0, st>>>(d_band, 1, 1, -1.0, d_out, 1); CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_DELTA_BAND, st);
     if (c->n_rep > 0) {     // ranges 2-4: pixels of the duplicated bins that have a copy in U, new minus old
-        CUDA_OK(cudaMemsetAsync(c->d_rep_in_u, 0, (size_t)c->N, st));
-        k_mark_rep_in_u<<<gu, 256, 0, st>>>(base, ld, c->sub_index, meta, c->lv, c->d_rep_in_u); CHECK_LAUNCH(c);
+        CUDA_OK(cudaMemsetAsync(L.rep_in_u, 0, (size_t)c->N, st));
+        k_mark_rep_in_u<<<gu, 256, 0, st>>>(base, ld, L.sub_index, meta, c->lv, L.rep_in_u); CHECK_LAUNCH(c);
         const int gr = (int)std::min<long long>(ps, ((long long)c->n_rep * c->N + 127) / 128);
         k_repeat_pixels<true><<<dim3(gr, n_cand), 128, 0, st>>>(cand0, slot_stride(c), ld, c->lv, c->collector, reinterpret_cast<const int2*>(c->dispatcher),
-                                                               c->rowptr, c->contacts, c->d_rep_bins, c->n_rep, c->d_rep_in_u, p, c->partials, ps); CHECK_LAUNCH(c);
-        k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, gr, ps, 1.0, d_out, 1); CHECK_LAUNCH(c);
+                                                               c->rowptr, c->contacts, c->d_rep_bins, c->n_rep, L.rep_in_u, p, L.partials, ps); CHECK_LAUNCH(c);
+        k_reduce_partials<<<n_cand, 256, 0, st>>>(L.partials, gr, ps, 1.0, d_out, 1); CHECK_LAUNCH(c);
         k_repeat_pixels<true><<<dim3(gr, 1), 128, 0, st>>>(base, 0, ld, c->lv, c->collector, reinterpret_cast<const int2*>(c->dispatcher),
-                                                          c->rowptr, c->contacts, c->d_rep_bins, c->n_rep, c->d_rep_in_u, p, c->partials + (size_t)13 * ps, ps); CHECK_LAUNCH(c);
+                                                          c->rowptr, c->contacts, c->d_rep_bins, c->n_rep, L.rep_in_u, p, L.partials + (size_t)13 * ps, ps); CHECK_LAUNCH(c);
         for (int k = 0; k < n_cand; k++) {
-            k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)13 * ps, gr, 0, -1.0, d_out + k, 1); CHECK_LAUNCH(c);
+            k_reduce_partials<<<1, 256, 0, st>>>(L.partials + (size_t)13 * ps, gr, 0, -1.0, d_out + k, 1); CHECK_LAUNCH(c);
         }
     }
     if (c->n_quirky > 0) {
         // quirk mass: - [Q_U(S_k) - Q_U(S_0)]
-        k_quirk<<<dim3(c->n_quirky, n_cand), 256, 0, st>>>(c->d_quirky, c->n_quirky, cand0, ld, n, slot_stride(c), c->lv, c->sub_index, meta + 4, p,
-                                                          c->partials, ps); CHECK_LAUNCH(c);
-        k_reduce_partials<<<n_cand, 256, 0, st>>>(c->partials, c->n_quirky, ps, -1.0, d_out, 1); CHECK_LAUNCH(c);
+        k_quirk<<<dim3(c->n_quirky, n_cand), 256, 0, st>>>(c->d_quirky, c->n_quirky, cand0, ld, n, slot_stride(c), c->lv, L.sub_index, meta + 4, p,
+                                                          L.partials, ps); CHECK_LAUNCH(c);
+        k_reduce_partials<<<n_cand, 256, 0, st>>>(L.partials, c->n_quirky, ps, -1.0, d_out, 1); CHECK_LAUNCH(c);
         // the base slot's term is the same for every candidate: computed once, added to all
-        k_quirk<<<dim3(c->n_quirky, 1), 256, 0, st>>>(c->d_quirky, c->n_quirky, base, ld, n, 0, c->lv, c->sub_index, meta + 4, p,
-                                                     c->partials + (size_t)13 * ps, ps); CHECK_LAUNCH(c);
+        k_quirk<<<dim3(c->n_quirky, 1), 256, 0, st>>>(c->d_quirky, c->n_quirky, base, ld, n, 0, c->lv, L.sub_index, meta + 4, p,
+                                                     L.partials + (size_t)13 * ps, ps); CHECK_LAUNCH(c);
         for (int k = 0; k < n_cand; k++) {
-            k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)13 * ps, c->n_quirky, 0, 1.0, d_out + k, 1); CHECK_LAUNCH(c);
+            k_reduce_partials<<<1, 256, 0, st>>>(L.partials + (size_t)13 * ps, c->n_quirky, 0, 1.0, d_out + k, 1); CHECK_LAUNCH(c);
         }
     }
     return 0;
@@ -2044,22 +2114,58 @@ int graal_delta_loglik(graal_ctx* c, int base_slot, int first_cand_slot, int n_c
     if (!d_out) return set_err(-1, "null output");
     if (!c->have_params) return set_err(-1, "parameters not set");
     if (id_fA < 0 || id_fA >= c->n_new || id_fB < 0 || id_fB >= c->n_new) return set_err(-1, "bin id out of range");
-    return delta_loglik_impl(c, base_slot, first_cand_slot, n_cand, id_fA, id_fB, max_id, 0u, d_out, c->d_scalars + 16);
+    int rc = ensure_base_geometry(c, base_slot); if (rc) return rc;
+    return delta_loglik_impl(c, c->lanes[0], c->stream, base_slot, first_cand_slot, n_cand, id_fA, id_fB, max_id, 0u, d_out, c->d_scalars + 16);
 }
 
 int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int id_fA, int id_fB, int max_id, int proposal_index, double* d_out) {
-    NEED_STATE(c);
+    if (!c || !c->slots) return set_err(-1, "state not bound");
+    CUDA_OK(cudaSetDevice(c->device));
     if (proposal_index < 0 || proposal_index >= 16) return set_err(-1, "proposal index must be 0..15");
     if (!d_out) return set_err(-1, "null output");
     if (!c->have_params) return set_err(-1, "parameters not set");
-    int rc = graal_build_candidates(c, base_slot, first_cand_slot, id_fA, id_fB, max_id, 0x1FFFu); if (rc) return rc;
+    NEED_SLOT(c, base_slot); NEED_SLOT(c, first_cand_slot); NEED_SLOT(c, first_cand_slot + GRAAL_N_CANDIDATES - 1);
+    const int n = c->n_new;
+    if (id_fA < 0 || id_fA >= n || id_fB < 0 || id_fB >= n) return set_err(-1, "bin id out of range");
+    if (base_slot >= first_cand_slot && base_slot < first_cand_slot + GRAAL_N_CANDIDATES) return set_err(-1, "source slot inside the destination range");
+    // Lane of this proposal.  It runs concurrently with the proposals pending on the other lanes unless its
+    // candidate slots overlap theirs (a caller with a single set of 13 candidate slots scores serially) or the
+    // per-kernel profiler is on (its brackets assume one stream).
+    Lane& L = c->lanes[proposal_index % c->n_lanes];
+    bool serial = c->prof.on || c->n_lanes == 1;
+    for (int l = 0; l < c->n_lanes && !serial; l++) {
+        const Lane& o = c->lanes[l];
+        if (&o != &L && o.pending && first_cand_slot < o.cand_first + GRAAL_N_CANDIDATES && o.cand_first < first_cand_slot + GRAAL_N_CANDIDATES) serial = true;
+    }
+    int rc;
+    if (serial) { rc = join_lanes(c); if (rc) return rc; }
+    rc = ensure_base_geometry(c, base_slot); if (rc) return rc;
+    cudaStream_t st = c->stream;
+    if (!serial) {
+        CUDA_OK(cudaEventRecord(c->ev_fork, c->stream));
+        CUDA_OK(cudaStreamWaitEvent(L.st, c->ev_fork, 0));
+        st = L.st;
+    }
+    c->prof.begin(GRAAL_K_BUILD, st);
+    k_build_candidates<<<nblk(n, 128), 128, 0, st>>>(slot_ptr(c, base_slot), slot_ptr(c, first_cand_slot), slot_stride(c), c->ld, n,
+                                                    id_fA, id_fB, c->d_ints + 0, max_id, 0x1FFFu);
+    CHECK_LAUNCH(c);
+    c->prof.end(GRAAL_K_BUILD, st);
+    for (int k = 0; k < GRAAL_N_CANDIDATES; k++) {
+        if (c->geo_base_slot == first_cand_slot + k) c->geo_base_slot = -1;
+        if (c->band_slot == first_cand_slot + k) c->band_slot = -1;
+    }
     // unique bins: swap_activity is the identity on the popped-out structure, candidate 8 == candidate 0 (Q7)
     const unsigned skip = (id_fA < c->N) ? (1u << 8) : 0u;      // a repeat copy (frag >= N) really toggles its activity
     double* d_band = c->band_hist + (size_t)proposal_index * GRAAL_N_CANDIDATES;
-    rc = delta_loglik_impl(c, base_slot, first_cand_slot, GRAAL_N_CANDIDATES, id_fA, id_fB, max_id, skip, d_out, d_band); if (rc) return rc;
+    rc = delta_loglik_impl(c, L, st, base_slot, first_cand_slot, GRAAL_N_CANDIDATES, id_fA, id_fB, max_id, skip, d_out, d_band); if (rc) return rc;
     if (skip) {
-        k_copy_double<<<1, 1, 0, c->stream>>>(d_out, 8, 0); CHECK_LAUNCH(c);
-        k_copy_double<<<1, 1, 0, c->stream>>>(d_band, 8, 0); CHECK_LAUNCH(c);
+        k_copy_double<<<1, 1, 0, st>>>(d_out, 8, 0); CHECK_LAUNCH(c);
+        k_copy_double<<<1, 1, 0, st>>>(d_band, 8, 0); CHECK_LAUNCH(c);
+    }
+    if (!serial) {
+        CUDA_OK(cudaEventRecord(L.done, L.st));
+        L.pending = true; L.cand_first = first_cand_slot;
     }
     return 0;
 }

@@ -25,6 +25,7 @@ F32, I32 = np.float32, np.int32
 N_TMP_STRUCT = 13
 CUR = 0            # slot of the current genome (reference: gpu_vect_frags)
 CAND0 = 1          # first of the 13 collector slots (reference: collector_gpu_vect_frags)
+N_LANES = 3        # proposals of one step scored concurrently: lane q owns candidate slots CAND0 + 13*q .. +13
 PARAM_FIELDS = ("kuhn", "lm", "c1", "slope", "d", "d_max", "fact", "v_inter")
 PARAM_DTYPE = np.dtype([(k if k != "d_max" else "l_max", F32) for k in PARAM_FIELDS], align=True)
 
@@ -258,7 +259,7 @@ class sampler:
         self.d_collector, self.d_dispatcher = t(self.collector_id_repeats), t(self.frag_dispatcher)
         self.d_rowptr, self.d_contacts = t(rowptr), t(contacts)
         self.ld = (n + 31) // 32 * 32
-        self.n_slots = 1 + N_TMP_STRUCT
+        self.n_slots = 1 + N_TMP_STRUCT * N_LANES
         host = np.zeros((self.n_slots, len(FRAG_FIELDS), self.ld), dtype=I32)
         for fi, k in enumerate(FRAG_FIELDS):
             host[CUR, fi, :n] = np.ones(n, dtype=I32) if k == "ori" else np.asarray(S_o_A_frags[k], dtype=I32)   # Q5
@@ -321,6 +322,7 @@ class sampler:
 
     def _fetch(self):
         """One D2H of the whole output block (pinned), after the stream has drained."""
+        check(self.lib.graal_join(self.ctx))          # proposals still on their lanes -> ordered before the copy
         with self.torch.cuda.stream(self.stream):
             self.h_out.copy_(self.d_out, non_blocking=True)
         self.stream.synchronize()
@@ -481,7 +483,7 @@ class sampler:
         """stream_likelihood (cuda_lib_gl.py:2392-2546) for every neighbour: candidates + deltas, queued
         on the stream; results land in d_out[16 + 13*x + j]."""
         for x, id_fB in enumerate(id_neighbours):
-            check(self.lib.graal_score_proposal(self.ctx, CUR, CAND0, int(id_fA), int(id_fB), -1, x,
+            check(self.lib.graal_score_proposal(self.ctx, CUR, CAND0 + N_TMP_STRUCT * (x % N_LANES), int(id_fA), int(id_fB), -1, x,
                                                 self._ptr(self.d_out, 16 + N_TMP_STRUCT * x)))
 
     def step_max_likelihood(self, id_fA, delta, size_block=512, dt=0, t=0, n_step=1):
@@ -491,14 +493,16 @@ class sampler:
         if id_fA not in self.id_frags_blacklisted:
             check(lib.graal_state_stats(self.ctx, CUR, self._ptr(self.d_out, 4)))
             check(lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
-            check(lib.graal_full_loglik(self.ctx, CUR, None, self._ptr(self.d_out, 0)))
             id_neighbours = self.return_neighbours(id_fA, delta)
             n_neighbours = len(id_neighbours)
             if n_neighbours > 16:
                 raise GraalError("more than 16 neighbours in one step")
             id_neighbours.sort()
             self.id_neighbours = id_neighbours
+            # the proposals go to their lanes first; the full likelihood of the current state does not depend
+            # on them and runs on the context stream next to them
             self.score_neighbours(id_fA, id_neighbours)
+            check(lib.graal_full_loglik(self.ctx, CUR, None, self._ptr(self.d_out, 0)))
             out = self._fetch()
             likelihood_t = np.float64(out[0])
             self.likelihood_t = likelihood_t
@@ -541,8 +545,8 @@ class sampler:
         check(lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
         if op_sampled < 0:
             return
-        check(lib.graal_full_loglik(self.ctx, CUR, None, self._ptr(self.d_out, 0)))
         self.score_neighbours(id_fA, id_neighbours)
+        check(lib.graal_full_loglik(self.ctx, CUR, None, self._ptr(self.d_out, 0)))
         x = id_neighbours.index(id_f_sampled) if id_f_sampled in id_neighbours else -1
         check(lib.graal_commit_scored(self.ctx, CUR, CAND0, int(id_fA), int(id_f_sampled), -1, int(op_sampled), x))
 

@@ -57,7 +57,12 @@ int  graal_ctx_create(int device, graal_ctx** out);
 void graal_ctx_destroy(graal_ctx* ctx);
 const char* graal_last_error(void);
 int  graal_set_stream(graal_ctx* ctx, void* cuda_stream);       /* cudaStream_t; default: own stream */
-int  graal_sync(graal_ctx* ctx);
+int  graal_sync(graal_ctx* ctx);                                 /* graal_join + wait for the context stream */
+/* Proposals scored by graal_score_proposal run on internal lanes (streams) beside the context stream, the
+ * way the reference scores its candidates on 13 streams (cuda_lib_gl.py:2441-2538).  graal_join makes the
+ * context stream wait for them WITHOUT blocking the host: call it before enqueueing your own work (e.g. the
+ * D2H copy of d_out) on the context stream.  Every other entry point that touches the state joins by itself. */
+int  graal_join(graal_ctx* ctx);
 const char* graal_version(void);
 
 /* ---- level (read-only inputs of the likelihood kernels) ---------------------------------------
@@ -125,7 +130,10 @@ int graal_delta_loglik(graal_ctx* ctx, int base_slot, int first_cand_slot, int n
 /* stream_likelihood (cuda_lib_gl.py:2392-2546) for ONE proposal (id_fA, id_fB): the 13 candidates are
  * built into first_cand_slot.. and scored against base_slot -> d_out[13].  proposal_index (0..15) names the
  * proposal for a later graal_commit_scored.  Candidate 8 (swap activity) equals candidate 0 for unique
- * bins (reference quirk Q7) and is copied, not re-evaluated. */
+ * bins (reference quirk Q7) and is copied, not re-evaluated.
+ * Concurrency: proposal_index selects a lane; proposals given DISJOINT candidate slot ranges overlap on the
+ * GPU, proposals sharing one range are serialised (GRAAL_LANES=1 in the environment forces one lane).
+ * d_out is valid after graal_join / graal_sync. */
 int graal_score_proposal(graal_ctx* ctx, int base_slot, int first_cand_slot, int id_fA, int id_fB,
                          int max_id, int proposal_index, double* d_out);
 
