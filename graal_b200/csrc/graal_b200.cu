@@ -368,21 +368,24 @@ __global__ void k_first_index(const int* __restrict__ id_c, int n, int cap, int*
     if (c < 0 || c >= cap) { atomicExch(err, 1); return; }
     atomicMin(&first[c], i);
 }
-__global__ void k_relabel_keys(const int* __restrict__ first, const int* __restrict__ l_cont, int cap,
-                               unsigned long long* __restrict__ keys) {
+// sort key of contig c = its length (sentinel: id not in use), value = c.  The radix sort is stable and the
+// input is in id order, so the result is ordered by (length, old id) -- the reference's
+// np.unique + argsort(kind='mergesort') order (cuda_lib_gl.py:1695-1749) -- with log2(n) key bits only.
+__global__ void k_relabel_keys(const int* __restrict__ first, const int* __restrict__ l_cont, int cap, unsigned sentinel,
+                               unsigned* __restrict__ keys, unsigned* __restrict__ vals) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cap) return;
     const int f = first[c];
-    keys[c] = (f == INT_MAX) ? ~0ull : (((unsigned long long)(unsigned)l_cont[f]) << 32) | (unsigned)c;
+    keys[c] = (f == INT_MAX) ? sentinel : min((unsigned)l_cont[f], sentinel - 1u);
+    vals[c] = (unsigned)c;
 }
-__global__ void k_relabel_map(const unsigned long long* __restrict__ sorted, int cap, int* __restrict__ map,
-                              int* __restrict__ n_contigs) {
+__global__ void k_relabel_map(const unsigned* __restrict__ keys, const unsigned* __restrict__ vals, int cap, unsigned sentinel,
+                              int* __restrict__ map, int* __restrict__ n_contigs) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= cap) return;
-    const unsigned long long k = sorted[r];
-    if (k == ~0ull) return;
-    map[(int)(k & 0xffffffffull)] = r;
-    if (r + 1 == cap || sorted[r + 1] == ~0ull) *n_contigs = r + 1;
+    if (keys[r] == sentinel) return;
+    map[vals[r]] = r;
+    if (r + 1 == cap || keys[r + 1] == sentinel) *n_contigs = r + 1;
 }
 __global__ void k_relabel_apply(int* __restrict__ id_c, int n, const int* __restrict__ map,
                                 const int* __restrict__ n_contigs, int* __restrict__ max_id_a, int* __restrict__ max_id_b) {
@@ -1459,11 +1462,12 @@ struct graal_ctx {
     int* slots = nullptr; int ld = 0, n_slots = 0;
     // scratch
     Geo* geo_base = nullptr; int geo_base_slot = -1;
+    int first_idx_slot = -1;                 // slot whose first-bin-of-contig table (first_idx) is current
     int* order = nullptr;                    // [n]
     int* cont_len = nullptr; int* cont_off = nullptr; int cap = 0;   // [cap]
     int* first_idx = nullptr; int* map = nullptr;
     unsigned long long* keys = nullptr; unsigned long long* keys_sorted = nullptr;
-    void* cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
+    void* cub_tmp = nullptr; size_t cub_tmp_bytes = 0; int key_bits = 32;
     int* d_ints = nullptr;                   // [0]=max_id [1]=n_contigs [2]=err [3]=tmp max  [8..16)=delta meta  [16..16+13*8)=piece_len
     unsigned long long* d_stats = nullptr;   // [4]
     double* partials = nullptr; int partial_stride = 0;   // [14][partial_stride]
@@ -1803,11 +1807,13 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     CUDA_OK(cudaMalloc(&c->keys, (size_t)c->cap * sizeof(unsigned long long)));
     CUDA_OK(cudaMalloc(&c->keys_sorted, (size_t)c->cap * sizeof(unsigned long long)));
     size_t b1 = 0, b2 = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, b1, c->keys, c->keys_sorted, c->cap);
+    c->key_bits = 1; while ((1ll << c->key_bits) < (long long)n + 2) c->key_bits++;      // lengths 0..n and the sentinel
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, reinterpret_cast<unsigned*>(c->keys), reinterpret_cast<unsigned*>(c->keys_sorted),
+                                    reinterpret_cast<unsigned*>(c->keys), reinterpret_cast<unsigned*>(c->keys_sorted), c->cap, 0, c->key_bits);
     cub::DeviceScan::ExclusiveSum(nullptr, b2, c->cont_len, c->cont_off, c->cap);
     c->cub_tmp_bytes = std::max(b1, b2);
     CUDA_OK(cudaMalloc(&c->cub_tmp, c->cub_tmp_bytes));
-    c->geo_base_slot = -1;
+    c->geo_base_slot = -1; c->first_idx_slot = -1;
     c->n_groups = (int)((c->E + GROUP - 1) / GROUP);
     if (c->n_groups > 0) {
         CUDA_OK(cudaMalloc(&c->group_row, (size_t)c->n_groups * sizeof(int)));
@@ -1855,7 +1861,7 @@ int graal_state_bind(graal_ctx* c, int32_t* base, int ld, int n_slots) {
     if (c->n_new <= 0) return set_err(-1, "bind the level first");
     if (ld < c->n_new || n_slots < 1) return set_err(-1, "bad slot geometry (ld %d < n %d)", ld, c->n_new);
     { int rcj = join_lanes(c); if (rcj) return rcj; }
-    c->slots = base; c->ld = ld; c->n_slots = n_slots; c->geo_base_slot = -1; c->band_slot = -1;
+    c->slots = base; c->ld = ld; c->n_slots = n_slots; c->geo_base_slot = -1; c->band_slot = -1; c->first_idx_slot = -1;
     return 0;
 }
 
@@ -1870,15 +1876,21 @@ int graal_relabel_contigs(graal_ctx* c, int slot, int32_t* d_max_id) {
     int* s = slot_ptr(c, slot);
     cudaStream_t st = c->stream;
     c->prof.begin(GRAAL_K_RELABEL, st);
-    k_fill_int<<<nblk(cap, 256), 256, 0, st>>>(c->first_idx, cap, INT_MAX); CHECK_LAUNCH(c);
-    k_first_index<<<nblk(n, 256), 256, 0, st>>>(s + F_ID_C * ld, n, cap, c->first_idx, c->d_ints + 2); CHECK_LAUNCH(c);
-    k_relabel_keys<<<nblk(cap, 256), 256, 0, st>>>(c->first_idx, s + F_L_CONT * ld, cap, c->keys); CHECK_LAUNCH(c);
+    if (c->first_idx_slot != slot) {          // graal_state_stats of the same state leaves the table behind
+        k_fill_int<<<nblk(cap, 256), 256, 0, st>>>(c->first_idx, cap, INT_MAX); CHECK_LAUNCH(c);
+        k_first_index<<<nblk(n, 256), 256, 0, st>>>(s + F_ID_C * ld, n, cap, c->first_idx, c->d_ints + 2); CHECK_LAUNCH(c);
+    }
+    unsigned* k_in = reinterpret_cast<unsigned*>(c->keys); unsigned* v_in = k_in + cap;
+    unsigned* k_out = reinterpret_cast<unsigned*>(c->keys_sorted); unsigned* v_out = k_out + cap;
+    const unsigned sentinel = (1u << c->key_bits) - 1u;
+    k_relabel_keys<<<nblk(cap, 256), 256, 0, st>>>(c->first_idx, s + F_L_CONT * ld, cap, sentinel, k_in, v_in); CHECK_LAUNCH(c);
     size_t tb = c->cub_tmp_bytes;
-    CUDA_OK(cub::DeviceRadixSort::SortKeys(c->cub_tmp, tb, c->keys, c->keys_sorted, cap, 0, 64, st)); c->launches += 8;
-    k_relabel_map<<<nblk(cap, 256), 256, 0, st>>>(c->keys_sorted, cap, c->map, c->d_ints + 1); CHECK_LAUNCH(c);
+    CUDA_OK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tb, k_in, k_out, v_in, v_out, cap, 0, c->key_bits, st)); c->launches += 2 + (c->key_bits + 7) / 8;
+    k_relabel_map<<<nblk(cap, 256), 256, 0, st>>>(k_out, v_out, cap, sentinel, c->map, c->d_ints + 1); CHECK_LAUNCH(c);
     k_relabel_apply<<<nblk(n, 256), 256, 0, st>>>(s + F_ID_C * ld, n, c->map, c->d_ints + 1, c->d_ints + 0, d_max_id); CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_RELABEL, st);
     if (c->geo_base_slot == slot) c->geo_base_slot = -1;
+    c->first_idx_slot = -1;                  // indexed by the OLD contig ids
     return 0;
 }
 
@@ -1897,6 +1909,7 @@ int graal_apply_move(graal_ctx* c, int src_slot, int dst_slot, int op, int id_fA
         CHECK_LAUNCH(c);
     }
     if (c->geo_base_slot == dst_slot) c->geo_base_slot = -1;
+    if (c->first_idx_slot == dst_slot) c->first_idx_slot = -1;
     if (c->band_slot == dst_slot) c->band_slot = -1;
     return 0;
 }
@@ -1912,6 +1925,7 @@ int graal_build_candidates(graal_ctx* c, int src_slot, int first_dst_slot, int i
     CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_BUILD, c->stream);
     if (c->geo_base_slot >= first_dst_slot && c->geo_base_slot < first_dst_slot + GRAAL_N_CANDIDATES) c->geo_base_slot = -1;
+    if (c->first_idx_slot >= first_dst_slot && c->first_idx_slot < first_dst_slot + GRAAL_N_CANDIDATES) c->first_idx_slot = -1;
     if (c->band_slot >= first_dst_slot && c->band_slot < first_dst_slot + GRAAL_N_CANDIDATES) c->band_slot = -1;
     return 0;
 }
@@ -1922,6 +1936,7 @@ int graal_commit(graal_ctx* c, int dst_slot, int src_slot) {
     k_apply_move<<<nblk(c->n_new, 128), 128, 0, c->stream>>>(slot_ptr(c, src_slot), slot_ptr(c, dst_slot), c->ld, c->n_new, GRAAL_OP_COPY, 0, 0, 0, 0);
     CHECK_LAUNCH(c);
     if (c->geo_base_slot == dst_slot) c->geo_base_slot = -1;
+    if (c->first_idx_slot == dst_slot) c->first_idx_slot = -1;
     if (c->band_slot == dst_slot) c->band_slot = -1;
     return 0;
 }
@@ -2153,6 +2168,7 @@ int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int i
     c->prof.end(GRAAL_K_BUILD, st);
     for (int k = 0; k < GRAAL_N_CANDIDATES; k++) {
         if (c->geo_base_slot == first_cand_slot + k) c->geo_base_slot = -1;
+        if (c->first_idx_slot == first_cand_slot + k) c->first_idx_slot = -1;
         if (c->band_slot == first_cand_slot + k) c->band_slot = -1;
     }
     // unique bins: swap_activity is the identity on the popped-out structure, candidate 8 == candidate 0 (Q7)
@@ -2198,6 +2214,7 @@ int graal_state_stats(graal_ctx* c, int slot, double* d_out) {
     k_set_int<<<1, 1, 0, st>>>(c->d_ints + 3, 0); CHECK_LAUNCH(c);
     k_count_contigs<<<std::min(nblk(cap, 256), c->n_sm * 4), 256, 0, st>>>(c->first_idx, cap, c->d_ints + 3); CHECK_LAUNCH(c);
     k_stats_final<<<1, 1, 0, st>>>(c->d_stats, c->d_ints + 3, d_out); CHECK_LAUNCH(c);
+    c->first_idx_slot = slot;
     return 0;
 }
 
