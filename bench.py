@@ -254,7 +254,7 @@ def main():
         e2e_ms = ev0.elapsed_time(ev1)
         # per step: D2H of the pinned output block, twice; H2D: none
         # (proposal ids travel as kernel arguments)
-        d2h = 2 * g.h_out.numel() * 8        # two fetches of the pinned output block (scores + stats, then the distance)
+        d2h = g.h_out.numel() * 8            # one fetch of the pinned output block per step: scores, stats, candidate distances
         h2d = 0
     else:
         for it in range(total):

@@ -1305,8 +1305,9 @@ __global__ void k_count_contigs(const int* __restrict__ first, int cap, int* __r
 // dist_inter_genome (cuda_lib_gl.py:475-541): per-bin neighbour / orientation agreement with the initial
 // genome; every term is a multiple of 0.5, so the float64 sum is exact whatever the order.
 __global__ void __launch_bounds__(256)
-k_dist_genome(const int* __restrict__ slot, int ld, int n, const int* __restrict__ init_prev, const int* __restrict__ init_next,
-              const int* __restrict__ orientable, const unsigned char* __restrict__ skip, double* __restrict__ partials) {
+k_dist_genome(const int* __restrict__ slot0, size_t slot_stride, int ld, int n, const int* __restrict__ init_prev, const int* __restrict__ init_next,
+              const int* __restrict__ orientable, const unsigned char* __restrict__ skip, double* __restrict__ partials, int partial_stride) {
+    const int* slot = slot0 + (size_t)blockIdx.y * slot_stride;          // blockIdx.y: one of several consecutive slots
     double acc = 0.0;
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
         if (skip[f]) continue;
@@ -1336,7 +1337,7 @@ k_dist_genome(const int* __restrict__ slot, int ld, int n, const int* __restrict
         acc += d;
     }
     acc = block_sum(acc);
-    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+    if (threadIdx.x == 0) partials[(size_t)blockIdx.y * partial_stride + blockIdx.x] = acc;
 }
 
 // distance histogram of estimate_parameters (cuda_lib_gl.py:1236-1270).  The initial sub-level layout
@@ -2225,8 +2226,29 @@ int graal_dist_genome(graal_ctx* c, int slot, const int32_t* init_prev, const in
     const int n = c->n_new;
     const int g = std::min(c->partial_stride, std::max(1, nblk(n, 256)));
     double* part = c->partials + (size_t)15 * c->partial_stride;
-    k_dist_genome<<<g, 256, 0, c->stream>>>(slot_ptr(c, slot), c->ld, n, init_prev, init_next, init_orientable, skip, part); CHECK_LAUNCH(c);
+    k_dist_genome<<<g, 256, 0, c->stream>>>(slot_ptr(c, slot), 0, c->ld, n, init_prev, init_next, init_orientable, skip, part, 0); CHECK_LAUNCH(c);
     k_reduce_partials<<<1, 256, 0, c->stream>>>(part, g, 0, 1.0, d_out, 0); CHECK_LAUNCH(c);
+    return 0;
+}
+
+int graal_dist_candidates(graal_ctx* c, int first_cand_slot, int n_cand, int proposal_index, const int32_t* init_prev, const int32_t* init_next,
+                          const int32_t* init_orientable, const uint8_t* skip, double* d_out) {
+    if (!c || !c->slots) return set_err(-1, "state not bound");
+    CUDA_OK(cudaSetDevice(c->device));
+    if (n_cand < 1 || n_cand > GRAAL_N_CANDIDATES) return set_err(-1, "n_cand must be 1..13");
+    NEED_SLOT(c, first_cand_slot); NEED_SLOT(c, first_cand_slot + n_cand - 1);
+    if (!init_prev || !init_next || !init_orientable || !skip || !d_out) return set_err(-1, "null argument");
+    if (proposal_index >= 16) return set_err(-1, "proposal index must be < 16");
+    // on the lane that is scoring these candidates, right behind its kernels; otherwise on the context stream
+    Lane* L = (proposal_index >= 0) ? &c->lanes[proposal_index % c->n_lanes] : nullptr;
+    cudaStream_t st = c->stream; double* part = c->partials; 
+    if (L && L->pending && L->cand_first == first_cand_slot) { st = L->st; part = L->partials; }
+    else { int rc = join_lanes(c); if (rc) return rc; }
+    const int n = c->n_new, ps = c->partial_stride;
+    const int g = std::min(ps, std::max(1, nblk(n, 256)));
+    k_dist_genome<<<dim3(g, n_cand), 256, 0, st>>>(slot_ptr(c, first_cand_slot), slot_stride(c), c->ld, n, init_prev, init_next, init_orientable, skip, part, ps); CHECK_LAUNCH(c);
+    k_reduce_partials<<<n_cand, 256, 0, st>>>(part, g, ps, 1.0, d_out, 0); CHECK_LAUNCH(c);
+    if (st != c->stream) CUDA_OK(cudaEventRecord(L->done, L->st));      // the join must cover this work too
     return 0;
 }
 

@@ -25,6 +25,7 @@ F32, I32 = np.float32, np.int32
 N_TMP_STRUCT = 13
 CUR = 0            # slot of the current genome (reference: gpu_vect_frags)
 CAND0 = 1          # first of the 13 collector slots (reference: collector_gpu_vect_frags)
+OFF_DIST = 16 + 16 * 13   # offset of the candidates' genome distances in the output block
 N_LANES = 3        # proposals of one step scored concurrently: lane q owns candidate slots CAND0 + 13*q .. +13
 PARAM_FIELDS = ("kuhn", "lm", "c1", "slope", "d", "d_max", "fact", "v_inter")
 PARAM_DTYPE = np.dtype([(k if k != "d_max" else "l_max", F32) for k in PARAM_FIELDS], align=True)
@@ -266,7 +267,8 @@ class sampler:
         host[CAND0:, FRAG_FIELDS.index("ori"), :] = 1           # collector initial content (cuda_lib_gl.py:269-287)
         host[CAND0:, FRAG_FIELDS.index("activ"), :] = 1
         self.d_slots = t(host)
-        self.d_out = torch.zeros(64 + 16 * N_TMP_STRUCT, dtype=torch.float64, device=dev)   # [0] full, [1] test, [4:8] stats, [16:] deltas
+        # [0] full, [1] test, [4:8] stats, [8] dist, [16:224] deltas of <= 16 proposals, [224:432] their genome distances
+        self.d_out = torch.zeros(64 + 2 * 16 * N_TMP_STRUCT, dtype=torch.float64, device=dev)
         self.d_max_id = torch.zeros(4, dtype=torch.int32, device=dev)
         self.h_out = torch.zeros_like(self.d_out, device="cpu").pin_memory()
         # ---- context
@@ -479,12 +481,17 @@ class sampler:
     def temperature(self, t, n_step):
         return 1.0
 
-    def score_neighbours(self, id_fA, id_neighbours):
+    def score_neighbours(self, id_fA, id_neighbours, with_dist=False):
         """stream_likelihood (cuda_lib_gl.py:2392-2546) for every neighbour: candidates + deltas, queued
         on the stream; results land in d_out[16 + 13*x + j]."""
         for x, id_fB in enumerate(id_neighbours):
-            check(self.lib.graal_score_proposal(self.ctx, CUR, CAND0 + N_TMP_STRUCT * (x % N_LANES), int(id_fA), int(id_fB), -1, x,
+            first = CAND0 + N_TMP_STRUCT * (x % N_LANES)
+            check(self.lib.graal_score_proposal(self.ctx, CUR, first, int(id_fA), int(id_fB), -1, x,
                                                 self._ptr(self.d_out, 16 + N_TMP_STRUCT * x)))
+            if with_dist:       # genome distance of every candidate, fetched with the scores (no second round trip)
+                check(self.lib.graal_dist_candidates(self.ctx, first, N_TMP_STRUCT, x, self._ptr(self.d_init_prev), self._ptr(self.d_init_next),
+                                                     self._ptr(self.d_init_orientable), self._ptr(self.d_dist_skip),
+                                                     self._ptr(self.d_out, OFF_DIST + N_TMP_STRUCT * x)))
 
     def step_max_likelihood(self, id_fA, delta, size_block=512, dt=0, t=0, n_step=1):
         """cuda_lib_gl.py:1793-1980.  Returns (o, n_contigs, min_len, mean_len_bp, max_len, op_sampled,
@@ -501,7 +508,7 @@ class sampler:
             self.id_neighbours = id_neighbours
             # the proposals go to their lanes first; the full likelihood of the current state does not depend
             # on them and runs on the context stream next to them
-            self.score_neighbours(id_fA, id_neighbours)
+            self.score_neighbours(id_fA, id_neighbours, with_dist=True)
             check(lib.graal_full_loglik(self.ctx, CUR, None, self._ptr(self.d_out, 0)))
             out = self._fetch()
             likelihood_t = np.float64(out[0])
@@ -516,6 +523,9 @@ class sampler:
                                           int(sample_out // N_TMP_STRUCT)))
             o = self.score[sample_out]
             self.o = o
+            # dist_inter_genome of the committed candidate (cuda_lib_gl.py:1962) came back with the scores
+            norm_distance = 3.0 * (int(self.n_new_frags) - self.n_frags_4_dist)
+            dist = float(out[OFF_DIST + sample_out]) / norm_distance if norm_distance != 0 else 0.0
         else:
             o = self.o
             check(lib.graal_state_stats(self.ctx, CUR, self._ptr(self.d_out, 4)))
@@ -523,8 +533,8 @@ class sampler:
             out = self._fetch()
             n_contigs, min_len, mean_len_bp, max_len = int(out[4]), int(out[5]), out[6], int(out[7])
             op_sampled, id_f_sampled = -1, id_fA
+            dist = self.dist_inter_genome_device()
         F_t = self.temperature(t, n_step)
-        dist = self.dist_inter_genome_device()
         self.likelihood_t = o
         return o, n_contigs, min_len, mean_len_bp, max_len, op_sampled, id_f_sampled, dist, F_t
 
@@ -545,7 +555,7 @@ class sampler:
         check(lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
         if op_sampled < 0:
             return
-        self.score_neighbours(id_fA, id_neighbours)
+        self.score_neighbours(id_fA, id_neighbours, with_dist=True)
         check(lib.graal_full_loglik(self.ctx, CUR, None, self._ptr(self.d_out, 0)))
         x = id_neighbours.index(id_f_sampled) if id_f_sampled in id_neighbours else -1
         check(lib.graal_commit_scored(self.ctx, CUR, CAND0, int(id_fA), int(id_f_sampled), -1, int(op_sampled), x))

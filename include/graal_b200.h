@@ -156,6 +156,14 @@ int graal_state_stats(graal_ctx* ctx, int slot, double* d_out);
 int graal_dist_genome(graal_ctx* ctx, int slot, const int32_t* init_prev, const int32_t* init_next,
                       const int32_t* init_orientable, const uint8_t* skip, double* d_out);
 
+/* The same sum for the n_cand consecutive candidate slots first_cand_slot.. -> d_out[n_cand]: the distance
+ * the genome WOULD have after committing each candidate, so that step_max_likelihood (cuda_lib_gl.py:1962)
+ * needs no second device round trip after the draw.  proposal_index >= 0: the candidates are those of that
+ * graal_score_proposal call and the work is queued on its lane; < 0: on the context stream. */
+int graal_dist_candidates(graal_ctx* ctx, int first_cand_slot, int n_cand, int proposal_index,
+                          const int32_t* init_prev, const int32_t* init_next,
+                          const int32_t* init_orientable, const uint8_t* skip, double* d_out);
+
 /* distance histogram of estimate_parameters (cuda_lib_gl.py:1236-1270) on the INITIAL sub-level
  * layout: for cis sub-frag pairs with mid-to-mid distance d < max_dist_kb, bin int(d/bin_kb):
  * d_sum[b] += contacts (zeros included through d_cnt), d_cnt[b] += 1.
