@@ -46,11 +46,11 @@ struct Params { float kuhn, lm, c1, slope, d, d_max, fact, v_inter, nfpb; int nd
                 // log-space evaluation (math mode 1): ln(c1*fact), ln(v_inter), slope as double, ln(t_norm)
                 int mode; double ln_cf, ln_v, slope_d; const double* t_lnnorm;
                 const double2* t_log; const double* t_exp;
-                // tabulated law (math mode 2): piecewise cubics (a0,a1),(a2,a3) of ln f(s) and of f(s), one interval
-                // per float bit pattern with LAW_M mantissa bits, s in [2^LAW_EMIN, 2^LAW_EMAX) kb;
+                // tabulated law (math mode 2): piecewise quadratics {double a0; float a1, a2} of ln f(s) and of f(s),
+                // one interval per float bit pattern with LAW_M mantissa bits, s in [2^LAW_EMIN, 2^LAW_EMAX) kb;
                 // v_clamp = v_inter as double (the clamp of f), t_normd = t_norm as double
-                const double2* t_lnf; const double2* t_f; double v_clamp; const double* t_normd; };
-#define LAW_M 7
+                const int4* t_lnf; const int4* t_f; double v_clamp; const double* t_normd; };
+#define LAW_M 9
 #define LAW_EMIN (-12)
 #define LAW_EMAX 11
 #define LAW_NODES (((LAW_EMAX) - (LAW_EMIN)) << LAW_M)
@@ -135,22 +135,23 @@ __device__ __forceinline__ double fast_exp(double t, const double* __restrict__ 
     const int sh = k >> 5;
     return __longlong_as_double(__double_as_longlong(base) + ((long long)sh << 52));
 }
-// Piecewise-cubic (Hermite) tabulated function of s (math mode 2).  The interval index and the local
-// abscissa come straight from the float bit pattern: interval = exponent | top LAW_M mantissa bits, and the
-// remaining 23-LAW_M mantissa bits, placed at the top of a float64 mantissa with exponent 0, ARE the
-// abscissa u = 1 + t in [1, 2) -- no int->double conversion.  Each interval stores the cubic re-expanded
-// in u: (a0, a1), (a2, a3).  Relative error of the interpolant for the Rippe law: < 1e-9
-// (profiles/README.md), far below one float32 ulp.
+// Piecewise-quadratic tabulated function of s (math mode 2).  The interval index and the local abscissa come
+// straight from the float bit pattern: interval = exponent | top LAW_M mantissa bits, and the remaining
+// 23-LAW_M mantissa bits, moved to the top of a float32 mantissa with exponent 0, ARE the abscissa
+// u = 1 + t in [1, 2) -- no conversion, no division.  One 16-byte entry per interval {double a0; float a1, a2}:
+// value = a0 + u * (a1 + u * a2), the quadratic through the three Chebyshev nodes of the interval; the
+// u-dependent part is below 1 % of a0, so float32 is enough for it.  One gather per evaluation.
+// Relative error for the Rippe law: < 2e-9 (measured, profiles/README.md), far below one float32 ulp.
 __device__ __forceinline__ bool law_in_table(float s) {
     const int e = (int)(__float_as_uint(s) >> 23) - 127;
     return e >= LAW_EMIN && e < LAW_EMAX;
 }
-__device__ __forceinline__ double law_interp(float s, const double2* __restrict__ tab) {
+__device__ __forceinline__ double law_interp(float s, const int4* __restrict__ tab) {
     const unsigned b = __float_as_uint(s);
     const int iv = (int)(b >> (23 - LAW_M)) - ((127 + LAW_EMIN) << LAW_M);
-    const double u = __hiloint2double((int)(0x3ff00000u | ((b & ((1u << (23 - LAW_M)) - 1u)) << (LAW_M - 3))), 0);
-    const double2 c01 = __ldg(&tab[2 * iv]), c23 = __ldg(&tab[2 * iv + 1]);
-    return fma(u, fma(u, fma(u, c23.y, c23.x), c01.y), c01.x);
+    const float u = __uint_as_float(0x3f800000u | ((b & ((1u << (23 - LAW_M)) - 1u)) << LAW_M));
+    const int4 e = __ldg(&tab[iv]);
+    return __hiloint2double(e.y, e.x) + (double)(u * fmaf(u, __int_as_float(e.w), __int_as_float(e.z)));
 }
 
 // ln of rippe_contacts(s) for 0 < s < d_max on a LINEAR contig, clamp included:
@@ -917,14 +918,28 @@ __global__ void k_cand_geometry(const int* __restrict__ cand0, size_t slot_strid
         }
     }
 }
-// Position order of U in every candidate + one 16-byte record per order position:
-//   x = first sub-frag | n_sub << 28,  y = start of the bin in kb (float bits),
-//   z = 1 if any record of the bin differs from the base slot in this candidate,  w = contig id
+// Position order of U in every candidate + 16-byte records per order position (what the band pass reads,
+// coalesced, instead of chasing order -> slot -> sub_id -> geometry per neighbour):
+//   A: x = first sub-frag | n_sub << 28 (n_sub = 0: duplicated bin, not scored here), y = start of the bin in kb
+//      (float bits), z = bit a set if the record of sub-frag a differs from the base slot in this candidate,
+//      w = contig id
+//   B: x, y, z = mid-points of the sub-frags (float bits), w = accu index a | b << 8 | c << 16 | circular << 24
 // and the first / last order index of a changed bin (rng[2k], rng[2k+1]).
+__device__ __forceinline__ int4 band_record_b(const Geo* __restrict__ g, int sub0, int n_sub) {
+    int mid[3] = {0, 0, 0}; unsigned info = 0u;
+    for (int a = 0; a < n_sub; a++) {
+        const Geo r = g[sub0 + a];
+        mid[a] = __float_as_int(r.mid);
+        info |= (unsigned)pk_true(r.pk) << (8 * a);
+        if (a == 0) info |= (unsigned)pk_circ(r.pk) << 24;
+    }
+    return make_int4(mid[0], mid[1], mid[2], (int)info);
+}
 __global__ void k_cand_order(const int* __restrict__ cand0, size_t slot_stride, int ld,
                              const int* __restrict__ sub_index, const int* __restrict__ meta,
                              const int* __restrict__ piece_len, int* __restrict__ order0, int order_stride, unsigned skip_cands,
-                             LevelView lv, const unsigned* __restrict__ chmask, int4* __restrict__ ordrec0, int* __restrict__ rng) {
+                             LevelView lv, const unsigned* __restrict__ chmask, const Geo* __restrict__ geo0, size_t geo_stride,
+                             int4* __restrict__ rec_a0, int4* __restrict__ rec_b0, int* __restrict__ rng) {
     const int k = blockIdx.y;
     if ((skip_cands >> k) & 1u) return;
     const int m = meta[4];
@@ -941,52 +956,73 @@ __global__ void k_cand_order(const int* __restrict__ cand0, size_t slot_stride, 
         if (idx < 0 || idx >= m) continue;
         order0[(size_t)k * order_stride + idx] = bin;
         const int4 sid = lv.sub_id[sl[F_ID_D * ld + bin]];
+        const int n_sub = eligible(lv, bin) ? sid.w : 0;
         unsigned chg = 0u;
-        if (eligible(lv, bin)) for (int a = 0; a < sid.w; a++) chg |= (chmask[sid.x + a] >> k) & 1u;
+        for (int a = 0; a < n_sub; a++) chg |= ((chmask[sid.x + a] >> k) & 1u) << a;
         const float start_kb = __int2float_rn(sl[F_START_BP * ld + bin]) / 1000.0f;
-        ordrec0[(size_t)k * order_stride + idx] = make_int4(sid.x | ((eligible(lv, bin) ? sid.w : 0) << 28), __float_as_int(start_kb), (int)chg, sl[F_ID_C * ld + bin]);
+        rec_a0[(size_t)k * order_stride + idx] = make_int4(sid.x | (n_sub << 28), __float_as_int(start_kb), (int)chg, sl[F_ID_C * ld + bin]);
+        rec_b0[(size_t)k * order_stride + idx] = band_record_b(geo0 + (size_t)k * geo_stride, sid.x, n_sub);
         if (chg) { lo = min(lo, idx); hi = max(hi, idx); }
     }
     if (hi >= 0) { atomicMin(&rng[2 * k], lo); atomicMax(&rng[2 * k + 1], hi); }
 }
-// the same records for the base slot in ITS order (sub_index); z = OR of the chmask words of the bin
+// the same records for the base slot in ITS order (sub_index); A.z = OR of the chmask words of the bin, and
+//   C: x, y, z = chmask words of the sub-frags (bit k: differs from the base slot in candidate k)
 __global__ void k_base_order(const int* __restrict__ base, int ld, const int* __restrict__ sub_index, const int* __restrict__ meta,
-                             LevelView lv, const unsigned* __restrict__ chmask, int4* __restrict__ ordrec, int* __restrict__ rng) {
+                             LevelView lv, const unsigned* __restrict__ chmask, const Geo* __restrict__ geo_base,
+                             int4* __restrict__ rec_a, int4* __restrict__ rec_b, int4* __restrict__ rec_c, int* __restrict__ rng) {
     const int m = meta[4];
     int lo = INT_MAX, hi = -1;
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < m; u += gridDim.x * blockDim.x) {
         const int bin = sub_index[u];
         const int4 sid = lv.sub_id[base[F_ID_D * ld + bin]];
-        unsigned chg = 0u;
-        const bool el = eligible(lv, bin);
-        if (el) for (int a = 0; a < sid.w; a++) chg |= chmask[sid.x + a];
+        const int n_sub = eligible(lv, bin) ? sid.w : 0;
+        unsigned ms[3] = {0u, 0u, 0u};
+        for (int a = 0; a < n_sub; a++) ms[a] = chmask[sid.x + a];
+        const unsigned chg = ms[0] | ms[1] | ms[2];
         const float start_kb = __int2float_rn(base[F_START_BP * ld + bin]) / 1000.0f;
-        ordrec[u] = make_int4(sid.x | ((el ? sid.w : 0) << 28), __float_as_int(start_kb), (int)chg, base[F_ID_C * ld + bin]);
+        rec_a[u] = make_int4(sid.x | (n_sub << 28), __float_as_int(start_kb), (int)chg, base[F_ID_C * ld + bin]);
+        rec_b[u] = band_record_b(geo_base, sid.x, n_sub);
+        rec_c[u] = make_int4((int)ms[0], (int)ms[1], (int)ms[2], 0);
         if (chg) { lo = min(lo, u); hi = max(hi, u); }
     }
     if (hi >= 0) { atomicMin(&rng[0], lo); atomicMax(&rng[1], hi); }
 }
 __global__ void k_init_ranges(int* rng, int n) { const int i = threadIdx.x; if (i < n) rng[i] = (i & 1) ? -1 : INT_MAX; }
 
+// ex - g of an in-band cis pair from its distance, accu table index and (circular contigs) contig length
+__device__ __forceinline__ double band_excess_general(float s, int idx, int circ, float stot, const Params& p) {
+    Geo a; a.mid = 0.0f; a.id_c = 0; a.stot = stot; a.pk = (unsigned)(idx / p.nd) | ((unsigned)circ << 28);
+    Geo b = a; b.pk = (unsigned)(idx % p.nd);
+    return band_excess(a, b, s, p);
+}
+
 // Band mass of the delta from the ordered records: warp per bin x, lanes over the following bins.
 //   BASE = false: candidate k = blockIdx.y, NEW values of pairs with a changed record (bit k)
 //   BASE = true : base slot, OLD values once, credited to every candidate whose bit is set
 // Only windows that can contain a changed pair are scanned: x beyond the last changed bin is skipped, an
-// unchanged x starts its scan at the first changed bin and stops at the last one.
+// unchanged x starts its scan at the first changed bin and stops at the last one.  Per neighbour bin a lane
+// reads two (three) coalesced records; the nine sub-frag pairs are evaluated branch-free on the tabulated
+// law (one table gather each, nine independent chains); pairs outside the table, circular contigs and math
+// modes 0 / 1 take the general path.
 template <bool BASE, int PARTS>
 __global__ void __launch_bounds__(256)
-k_band_delta(const int4* __restrict__ ordrec0, int order_stride, const int* __restrict__ d_count, const int* __restrict__ rng0,
-             const Geo* __restrict__ geo0, size_t cand_geo_stride, const unsigned* __restrict__ chmask, unsigned skip_cands,
+k_band_delta(const int4* __restrict__ rec_a0, const int4* __restrict__ rec_b0, const int4* __restrict__ rec_c, int order_stride,
+             const int* __restrict__ d_count, const int* __restrict__ rng0,
+             const Geo* __restrict__ geo0, size_t cand_geo_stride, unsigned skip_cands,
              const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
     const int k = blockIdx.y;
     const int count = *d_count;
-    const int4* ordrec = BASE ? ordrec0 : ordrec0 + (size_t)k * order_stride;
+    const int4* rec_a = BASE ? rec_a0 : rec_a0 + (size_t)k * order_stride;
+    const int4* rec_b = BASE ? rec_b0 : rec_b0 + (size_t)k * order_stride;
     const Geo* gE = BASE ? geo0 : geo0 + (size_t)k * cand_geo_stride;
     const int* rng = BASE ? rng0 : rng0 + 2 * k;
     const int lo = rng[0], hi = rng[1];
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const bool uni = p.nd == 1;                                  // one accu value in the level: the pair tables are scalars
+    const double normd0 = __ldg(&p.t_normd[0]), g00 = (double)__ldg(&p.t_g[0]);
     double acc = 0.0;
     double accs[GRAAL_N_CANDIDATES];
     if (BASE) {
@@ -997,51 +1033,64 @@ k_band_delta(const int4* __restrict__ ordrec0, int order_stride, const int* __re
     // PARTS warps share one x: warp part takes the 32-bin chunks part, part + PARTS, ... of the window
     if (!idle) for (int wx = warp; wx / PARTS <= hi && wx / PARTS < count; wx += n_warps) {
         const int ix = wx / PARTS, part = wx % PARTS;
-        const int4 rx = ordrec[ix];
-        const int nx = (rx.x >> 28) & 7, sx0 = rx.x & 0x0fffffff;
+        const int4 rx = rec_a[ix];
+        const int nx = (rx.x >> 28) & 7;
         if (nx == 0) continue;                                   // duplicated bin: repeat path
         const unsigned xm = (unsigned)rx.z;
-        const bool xchg = BASE ? (xm != 0u) : (xm != 0u);
+        const bool xchg = xm != 0u;
         int y0 = ix + 1, y1 = count;
         if (!xchg) { y0 = max(y0, lo); y1 = min(y1, hi + 1); }
         if (y0 >= y1) continue;
-        Geo gx[3]; unsigned mx[3] = {0u, 0u, 0u};
-        float xmax = -1e30f;
-        #pragma unroll
-        for (int a = 0; a < 3; a++) if (a < nx) {
-            gx[a] = ld_geo(&gE[sx0 + a]);
-            mx[a] = __ldg(&chmask[sx0 + a]);
-            xmax = fmaxf(xmax, gx[a].mid);
-        }
+        const int4 xb = rec_b[ix];
+        const float xmid[3] = {__int_as_float(xb.x), __int_as_float(xb.y), __int_as_float(xb.z)};
+        unsigned mx[3];
+        if (BASE) { const int4 xc = rec_c[ix]; mx[0] = (unsigned)xc.x; mx[1] = (unsigned)xc.y; mx[2] = (unsigned)xc.z; }
+        else { mx[0] = xm & 1u; mx[1] = (xm >> 1) & 1u; mx[2] = (xm >> 2) & 1u; }
+        float xmax = xmid[0];
+        if (nx > 1) xmax = fmaxf(xmax, xmid[1]);
+        if (nx > 2) xmax = fmaxf(xmax, xmid[2]);
         const int cx = rx.w;
+        const int circ = (xb.w >> 24) & 1;
+        const float stot = circ ? gE[rx.x & 0x0fffffff].stot : 0.0f;
+        const bool fast_ok = p.mode == 2 && !circ;
+        double tot[3] = {0.0, 0.0, 0.0};                         // BASE: old values of the pairs of sub a of x
         for (int basei = y0 + 32 * part; basei < y1; basei += 32 * PARTS) {
             const int iy = basei + lane;
             bool live = iy < y1;
             if (live) {
-                const int4 ry = ordrec[iy];
+                const int4 ry = rec_a[iy];
                 // beyond the band (or next contig): every remaining pair evaluates to the clamp value
                 if (ry.w != cx || (double)__int_as_float(ry.y) - (double)xmax > (double)p.d_max * 1.00001 + 0.05) live = false;
                 else {
-                    const int ny = (ry.x >> 28) & 7, sy0 = ry.x & 0x0fffffff;
+                    const int ny = (ry.x >> 28) & 7;
                     const unsigned ym = (unsigned)ry.z;
-                    const bool rel = BASE ? ((xm | ym) != 0u) : (xchg || ym != 0u);
-                    if (rel) {
+                    if (ny > 0 && (xchg || ym != 0u)) {
+                        const int4 yb = rec_b[iy];
+                        const float ymid[3] = {__int_as_float(yb.x), __int_as_float(yb.y), __int_as_float(yb.z)};
+                        unsigned my[3];
+                        if (BASE) { const int4 yc = rec_c[iy]; my[0] = (unsigned)yc.x; my[1] = (unsigned)yc.y; my[2] = (unsigned)yc.z; }
+                        else { my[0] = ym & 1u; my[1] = (ym >> 1) & 1u; my[2] = (ym >> 2) & 1u; }
                         #pragma unroll
-                        for (int b = 0; b < 3; b++) if (b < ny) {
-                            const int sub = sy0 + b;
-                            const unsigned my = __ldg(&chmask[sub]);
-                            if (BASE ? !(mx[0] | mx[1] | mx[2] | my) : !(((mx[0] | mx[1] | mx[2] | my) >> k) & 1u)) continue;
-                            const Geo gy = ld_geo(&gE[sub]);
+                        for (int b = 0; b < 3; b++) {
                             #pragma unroll
-                            for (int a = 0; a < 3; a++) if (a < nx) {
-                                const unsigned mm = mx[a] | my;
-                                if (BASE ? !mm : !((mm >> k) & 1u)) continue;
-                                const float s = fabsf(gy.mid - gx[a].mid);
-                                if (!(s > 0.0f && s < p.d_max)) continue;
-                                const double v = band_excess(gx[a], gy, s, p);
+                            for (int a = 0; a < 3; a++) {
+                                const unsigned mm = mx[a] | my[b];
+                                const float s = fabsf(ymid[b] - xmid[a]);
+                                const bool on = a < nx && b < ny && mm != 0u && s > 0.0f && s < p.d_max;
+                                const bool fast = on && fast_ok && law_in_table(s);
+                                const int idx = uni ? 0 : (int)((xb.w >> (8 * a)) & 255) * p.nd + (int)((yb.w >> (8 * b)) & 255);
+                                double v = 0.0;
+                                if (on && !fast) v = band_excess_general(s, idx, circ, stot, p);
+                                const double f = law_interp(fast ? s : 1.0f, p.t_f);
+                                const double vf = uni ? f * normd0 - g00 : f * __ldg(&p.t_normd[idx]) - (double)__ldg(&p.t_g[idx]);
+                                if (fast && f > p.v_clamp) v = vf;
                                 if (BASE) {
-                                    #pragma unroll
-                                    for (int c = 0; c < GRAAL_N_CANDIDATES; c++) if ((mm >> c) & 1u) accs[c] += v;
+                                    tot[a] += v;                              // credited below to every candidate of mx[a]
+                                    const unsigned extra = on ? (my[b] & ~mx[a]) : 0u;
+                                    if (extra) {
+                                        #pragma unroll
+                                        for (int c = 0; c < GRAAL_N_CANDIDATES; c++) if ((extra >> c) & 1u) accs[c] += v;
+                                    }
                                 } else acc += v;
                             }
                         }
@@ -1049,6 +1098,14 @@ k_band_delta(const int4* __restrict__ ordrec0, int order_stride, const int* __re
                 }
             }
             if (!__any_sync(0xffffffffu, live)) break;
+        }
+        if (BASE) {
+            #pragma unroll
+            for (int a = 0; a < 3; a++) {
+                if (a >= nx || mx[a] == 0u) continue;
+                #pragma unroll
+                for (int c = 0; c < GRAAL_N_CANDIDATES; c++) if ((mx[a] >> c) & 1u) accs[c] += tot[a];
+            }
         }
     }
     if (BASE) {
@@ -1420,7 +1477,8 @@ struct Lane {
     unsigned* chmask = nullptr;              // [W] bit k: record differs from the base slot in candidate k
     Geo* geo_cand = nullptr;                 // [13][W]
     int* cand_order = nullptr;               // [13][n]
-    int4* cand_ordrec = nullptr; int4* base_ordrec = nullptr;   // [13][n] / [n] position-ordered bin records of U
+    int4* cand_ordrec = nullptr; int4* base_ordrec = nullptr;   // [13][n] / [n] position-ordered bin records A of U
+    int4* cand_ordb = nullptr; int4* base_ordb = nullptr; int4* base_ordc = nullptr;   // records B (mid-points) and C (masks)
     double* partials = nullptr;              // [16][partial_stride]
     unsigned char* rep_in_u = nullptr;       // [N]
 };
@@ -1444,7 +1502,7 @@ struct graal_ctx {
     unsigned char* d_accu_idx = nullptr;                // [N*3]
     float* d_tab_norm = nullptr; float* d_tab_g[2] = {nullptr, nullptr}; double* d_tab_logg[2] = {nullptr, nullptr};
     double* d_tab_lnnorm = nullptr; double2* d_tab_log = nullptr; double* d_tab_exp = nullptr;
-    double2* d_tab_lnf[2] = {nullptr, nullptr}; double2* d_tab_f[2] = {nullptr, nullptr}; double* d_tab_normd = nullptr;
+    int4* d_tab_lnf[2] = {nullptr, nullptr}; int4* d_tab_f[2] = {nullptr, nullptr}; double* d_tab_normd = nullptr;
     std::vector<double> h_law;
     int math_mode = 2;
     std::vector<float> h_tab_g; std::vector<double> h_tab_logg;
@@ -1515,32 +1573,32 @@ static int upload_tables(graal_ctx* c, Params& p, int which) {
     if (p.mode == 2) {
         if (!(cf > 0.0) || !(p.kuhn > 0.0f) || !(p.lm > 0.0f)) p.mode = 1;      // degenerate parameters: analytic path
         else {
-            const size_t half = (size_t)(LAW_NODES + 2) * 4;          // doubles per table: 4 coefficients per interval
-            c->h_law.resize(half * 2);
+            struct Entry { double a0; float a1, a2; };
+            static_assert(sizeof(Entry) == 16, "law table entry");
+            const size_t half = (size_t)(LAW_NODES + 2) * 2;          // doubles per table (16 bytes per interval)
+            c->h_law.assign(half * 2, 0.0);
+            Entry* e_ln = reinterpret_cast<Entry*>(c->h_law.data());
+            Entry* e_f = reinterpret_cast<Entry*>(c->h_law.data() + half);
             const double K = (double)p.d - 2.0, dd = (double)p.d, q = (double)p.lm / (double)p.kuhn, sl = (double)p.slope;
-            auto node = [&](int i, double& lnf, double& dlnf) {
-                const int e = LAW_EMIN + (i >> LAW_M);
-                const double sv = ldexp(1.0 + (double)(i & ((1 << LAW_M) - 1)) / (double)(1 << LAW_M), e);
-                const double x = sv * q, den = x * x + dd;
-                lnf = p.ln_cf + sl * log(sv) + K / den;
-                dlnf = sl / sv - K * 2.0 * x * q / (den * den);
-            };
-            auto cubic = [](double f0, double d0, double f1, double d1, double dl, double* a) {
-                // Hermite in t on [0,1]: c0 + c1 t + c2 t^2 + c3 t^3, then t = u - 1
-                const double m0 = d0 * dl, m1 = d1 * dl, d = f1 - f0;
-                const double c0 = f0, c1 = m0, c2 = 3.0 * d - 2.0 * m0 - m1, c3 = m0 + m1 - 2.0 * d;
-                a[0] = c0 - c1 + c2 - c3; a[1] = c1 - 2.0 * c2 + 3.0 * c3; a[2] = c2 - 3.0 * c3; a[3] = c3;
-            };
-            double l0, g0; node(0, l0, g0);
-            for (int i = 0; i < LAW_NODES + 1; i++) {
-                double l1, g1; node(i + 1, l1, g1);
-                const double dl = ldexp(1.0, LAW_EMIN + (i >> LAW_M) - LAW_M);
-                cubic(l0, g0, l1, g1, dl, &c->h_law[(size_t)i * 4]);
-                const double f0 = exp(l0), f1 = exp(l1);
-                cubic(f0, f0 * g0, f1, f1 * g1, dl, &c->h_law[half + (size_t)i * 4]);
-                l0 = l1; g0 = g1;
+            auto lnf = [&](double sv) { const double x = sv * q; return p.ln_cf + sl * log(sv) + K / (x * x + dd); };
+            // quadratic in u = 1 + t through the Chebyshev nodes t_j = 1/2 + cos((2j+1) pi/6)/2 of the interval
+            double un[3], w[3][3];
+            for (int j = 0; j < 3; j++) un[j] = 1.5 + 0.5 * cos((2 * j + 1) * 3.14159265358979323846 / 6.0);
+            for (int j = 0; j < 3; j++) {         // Lagrange basis of node j expanded in powers of u
+                const double u1 = un[(j + 1) % 3], u2 = un[(j + 2) % 3], den = (un[j] - u1) * (un[j] - u2);
+                w[j][0] = u1 * u2 / den; w[j][1] = -(u1 + u2) / den; w[j][2] = 1.0 / den;
             }
-            for (int k = 0; k < 4; k++) { c->h_law[(size_t)(LAW_NODES + 1) * 4 + k] = 0.0; c->h_law[half + (size_t)(LAW_NODES + 1) * 4 + k] = 0.0; }
+            for (int i = 0; i < LAW_NODES; i++) {
+                const int e = LAW_EMIN + (i >> LAW_M);
+                const double lo = ldexp(1.0 + (double)(i & ((1 << LAW_M) - 1)) / (double)(1 << LAW_M), e), h = ldexp(1.0, e - LAW_M);
+                double al[3] = {0, 0, 0}, af[3] = {0, 0, 0};
+                for (int j = 0; j < 3; j++) {
+                    const double v = lnf(lo + h * (un[j] - 1.0)), f = exp(v);
+                    for (int k = 0; k < 3; k++) { al[k] += v * w[j][k]; af[k] += f * w[j][k]; }
+                }
+                e_ln[i].a0 = al[0]; e_ln[i].a1 = (float)al[1]; e_ln[i].a2 = (float)al[2];
+                e_f[i].a0 = af[0]; e_f[i].a1 = (float)af[1]; e_f[i].a2 = (float)af[2];
+            }
             CUDA_OK(cudaMemcpyAsync(c->d_tab_lnf[which], c->h_law.data(), half * sizeof(double), cudaMemcpyHostToDevice, c->stream));
             CUDA_OK(cudaMemcpyAsync(c->d_tab_f[which], c->h_law.data() + half, half * sizeof(double), cudaMemcpyHostToDevice, c->stream));
             CUDA_OK(cudaStreamSynchronize(c->stream));      // h_law is reused by the next call
@@ -1605,8 +1663,8 @@ static void free_level_scratch(graal_ctx* c) {
     cudaFree(c->cid16_base); cudaFree(c->mid32_base); cudaFree(c->group_row); cudaFree(c->band_hist); c->band_hist = nullptr; c->cid16_base = nullptr; c->mid32_base = nullptr; c->group_row = nullptr;
     for (int l = 0; l < GRAAL_MAX_LANES; l++) {
         Lane& L = c->lanes[l];
-        cudaFree(L.sub_index); cudaFree(L.chmask); cudaFree(L.geo_cand); cudaFree(L.cand_order); cudaFree(L.cand_ordrec); cudaFree(L.base_ordrec); cudaFree(L.rep_in_u);
-        L.sub_index = nullptr; L.chmask = nullptr; L.geo_cand = nullptr; L.cand_order = nullptr; L.cand_ordrec = L.base_ordrec = nullptr; L.rep_in_u = nullptr;
+        cudaFree(L.sub_index); cudaFree(L.chmask); cudaFree(L.geo_cand); cudaFree(L.cand_order); cudaFree(L.cand_ordrec); cudaFree(L.base_ordrec); cudaFree(L.cand_ordb); cudaFree(L.base_ordb); cudaFree(L.base_ordc); cudaFree(L.rep_in_u);
+        L.sub_index = nullptr; L.chmask = nullptr; L.geo_cand = nullptr; L.cand_order = nullptr; L.cand_ordrec = L.base_ordrec = L.cand_ordb = L.base_ordb = L.base_ordc = nullptr; L.rep_in_u = nullptr;
     }
     cudaFree(c->geo_base); cudaFree(c->order);
     cudaFree(c->cont_len); cudaFree(c->cont_off); cudaFree(c->first_idx); cudaFree(c->map); cudaFree(c->keys);
@@ -1749,8 +1807,8 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
         CUDA_OK(cudaMalloc(&c->d_tab_normd, tnd.size() * sizeof(double)));
         CUDA_OK(cudaMemcpy(c->d_tab_normd, tnd.data(), tnd.size() * sizeof(double), cudaMemcpyHostToDevice));
         for (int w = 0; w < 2; w++) {
-            CUDA_OK(cudaMalloc(&c->d_tab_lnf[w], (size_t)(LAW_NODES + 2) * 2 * sizeof(double2)));
-            CUDA_OK(cudaMalloc(&c->d_tab_f[w], (size_t)(LAW_NODES + 2) * 2 * sizeof(double2)));
+            CUDA_OK(cudaMalloc(&c->d_tab_lnf[w], (size_t)(LAW_NODES + 2) * sizeof(int4)));
+            CUDA_OK(cudaMalloc(&c->d_tab_f[w], (size_t)(LAW_NODES + 2) * sizeof(int4)));
         }
         for (int w = 0; w < 2; w++) {
             CUDA_OK(cudaMalloc(&c->d_tab_g[w], tn.size() * sizeof(float)));
@@ -1789,6 +1847,12 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
         CUDA_OK(cudaMalloc(&L.base_ordrec, (size_t)n * sizeof(int4)));
         CUDA_OK(cudaMemset(L.cand_ordrec, 0, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int4)));
         CUDA_OK(cudaMemset(L.base_ordrec, 0, (size_t)n * sizeof(int4)));
+        CUDA_OK(cudaMalloc(&L.cand_ordb, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int4)));
+        CUDA_OK(cudaMalloc(&L.base_ordb, (size_t)n * sizeof(int4)));
+        CUDA_OK(cudaMalloc(&L.base_ordc, (size_t)n * sizeof(int4)));
+        CUDA_OK(cudaMemset(L.cand_ordb, 0, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int4)));
+        CUDA_OK(cudaMemset(L.base_ordb, 0, (size_t)n * sizeof(int4)));
+        CUDA_OK(cudaMemset(L.base_ordc, 0, (size_t)n * sizeof(int4)));
         CUDA_OK(cudaMalloc(&L.geo_cand, (size_t)GRAAL_N_CANDIDATES * c->W * sizeof(Geo)));
         CUDA_OK(cudaMemset(L.geo_cand, 0, (size_t)GRAAL_N_CANDIDATES * c->W * sizeof(Geo)));
         CUDA_OK(cudaMalloc(&L.cand_order, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int)));
@@ -2074,8 +2138,8 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
     int* rng = L.ints + 160;                       // [0,1] base range, [2 + 2k, 3 + 2k] candidate k
     k_init_ranges<<<1, 32, 0, st>>>(rng, 2 + 2 * GRAAL_N_CANDIDATES); CHECK_LAUNCH(c);
     k_cand_order<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, L.sub_index, meta, piece_len, L.cand_order, n, skip,
-                                                  c->lv, L.chmask, L.cand_ordrec, rng + 2); CHECK_LAUNCH(c);
-    k_base_order<<<gu, 256, 0, st>>>(base, ld, L.sub_index, meta, c->lv, L.chmask, L.base_ordrec, rng); CHECK_LAUNCH(c);
+                                                  c->lv, L.chmask, L.geo_cand, (size_t)c->W, L.cand_ordrec, L.cand_ordb, rng + 2); CHECK_LAUNCH(c);
+    k_base_order<<<gu, 256, 0, st>>>(base, ld, L.sub_index, meta, c->lv, L.chmask, c->geo_base, L.base_ordrec, L.base_ordb, L.base_ordc, rng); CHECK_LAUNCH(c);
     // grid-stride kernels over the (device-side) size of U: a few CTAs per SM, not one warp per bin of the level
     const int gw = std::min(ps, std::max(1, std::min(nblk(n, 1), c->n_sm * 8)));
     const int gb = std::min(ps, std::max(1, std::min(nblk(n, 4), c->n_sm * 4)));
@@ -2087,10 +2151,10 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
     c->prof.end(GRAAL_K_DELTA_CONTACTS, st);
     // band mass: d_band[k] = B_U(S_k) - B_U(S_0) over changed pairs; enters the delta with a minus sign
     c->prof.begin(GRAAL_K_DELTA_BAND, st);
-    k_band_delta<false, 2><<<dim3(gb, n_cand), 256, 0, st>>>(L.cand_ordrec, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, L.chmask, skip, p,
+    k_band_delta<false, 2><<<dim3(gb, n_cand), 256, 0, st>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
                                                          L.partials, ps); CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 256, 0, st>>>(L.partials, gb, ps, 1.0, d_band, 0); CHECK_LAUNCH(c);
-    k_band_delta<true, 8><<<dim3(gb, 1), 256, 0, st>>>(L.base_ordrec, n, meta + 4, rng, c->geo_base, 0, L.chmask, skip, p,
+    k_band_delta<true, 8><<<dim3(gb, 1), 256, 0, st>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
                                                    L.partials, ps); CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 256, 0, st>>>(L.partials, gb, ps, -1.0, d_band, 1); CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 32, 0, st>>>(d_band, 1, 1, -1.0, d_out, 1); CHECK_LAUNCH(c);
