@@ -207,13 +207,30 @@ __device__ __forceinline__ double inband_log_term(float s, float ob, float stot,
 }
 // ob * ln(ex) of one stored contact between sub-frags a (row side = lower data bin) and b, or the
 // lf(ob) correction when the expected value is 0 (kernels3.cu:197: such a pixel contributes 0)
-__device__ __forceinline__ double contact_log_term(const Geo& a, const Geo& b, float ob, const Params& p) {
+__device__ __noinline__ double contact_log_term_general(const Geo& a, const Geo& b, float ob, const Params& p) {
     const bool cis = a.id_c == b.id_c;
     const float s = fabsf(b.mid - a.mid);
     if (cis && s > 0.0f && s < p.d_max)
         return inband_log_term(s, ob, a.stot, pk_true(a.pk) * p.nd + pk_true(b.pk), pk_circ(a.pk), p);
     const double lg = __ldg(&p.t_logg[(cis ? pk_true(a.pk) : pk_quirk(a.pk)) * p.nd + pk_true(b.pk)]);
     return (lg != -INFINITY) ? (double)ob * lg : log_fact_term(ob);
+}
+// The same value with the common cases inline (tabulated law on a linear contig, finite clamp tables) and
+// everything else behind ONE call: the 14 evaluations per contact of the delta pass stay small enough for
+// the instruction cache.
+__device__ __forceinline__ double contact_log_term(const Geo& a, const Geo& b, float ob, const Params& p) {
+    const bool cis = a.id_c == b.id_c;
+    const float s = fabsf(b.mid - a.mid);
+    if (cis && s > 0.0f && s < p.d_max) {
+        if (p.mode == 2 && !pk_circ(a.pk) && law_in_table(s)) {
+            const double lr = fmax(law_interp(s, p.t_lnf), p.ln_v) + __ldg(&p.t_lnnorm[pk_true(a.pk) * p.nd + pk_true(b.pk)]);
+            if (lr - lr == 0.0) return (double)ob * lr;                     // finite
+        }
+    } else {
+        const double lg = __ldg(&p.t_logg[(cis ? pk_true(a.pk) : pk_quirk(a.pk)) * p.nd + pk_true(b.pk)]);
+        if (lg - lg == 0.0) return (double)ob * lg;
+    }
+    return contact_log_term_general(a, b, ob, p);
 }
 // clamp value of the pair (true accus): what a cis pair beyond the band evaluates to
 __device__ __forceinline__ float g_pair(const Geo& a, const Geo& b, const Params& p) {
