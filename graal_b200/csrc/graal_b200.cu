@@ -1008,7 +1008,7 @@ __global__ void k_base_order(const int* __restrict__ base, int ld, const int* __
 __global__ void k_init_ranges(int* rng, int n) { const int i = threadIdx.x; if (i < n) rng[i] = (i & 1) ? -1 : INT_MAX; }
 
 // ex - g of an in-band cis pair from its distance, accu table index and (circular contigs) contig length
-__device__ __forceinline__ double band_excess_general(float s, int idx, int circ, float stot, const Params& p) {
+__device__ __noinline__ double band_excess_general(float s, int idx, int circ, float stot, const Params& p) {
     Geo a; a.mid = 0.0f; a.id_c = 0; a.stot = stot; a.pk = (unsigned)(idx / p.nd) | ((unsigned)circ << 28);
     Geo b = a; b.pk = (unsigned)(idx % p.nd);
     return band_excess(a, b, s, p);
@@ -1022,7 +1022,7 @@ __device__ __forceinline__ double band_excess_general(float s, int idx, int circ
 // reads two (three) coalesced records; the nine sub-frag pairs are evaluated branch-free on the tabulated
 // law (one table gather each, nine independent chains); pairs outside the table, circular contigs and math
 // modes 0 / 1 take the general path.
-template <bool BASE, int PARTS>
+template <bool BASE, int PARTS, bool UNI>
 __global__ void __launch_bounds__(256)
 k_band_delta(const int4* __restrict__ rec_a0, const int4* __restrict__ rec_b0, const int4* __restrict__ rec_c, int order_stride,
              const int* __restrict__ d_count, const int* __restrict__ rng0,
@@ -1038,8 +1038,11 @@ k_band_delta(const int4* __restrict__ rec_a0, const int4* __restrict__ rec_b0, c
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    const bool uni = p.nd == 1;                                  // one accu value in the level: the pair tables are scalars
-    const double normd0 = __ldg(&p.t_normd[0]), g00 = (double)__ldg(&p.t_g[0]);
+    // UNI: one accu value in the level (p.nd == 1), the pair tables are scalars
+    const double normd0 = __ldg(&p.t_normd[0]), neg_g00 = -(double)__ldg(&p.t_g[0]);
+    const int4* __restrict__ t_f = p.t_f;
+    const double v_clamp = p.v_clamp;
+    const float d_max = p.d_max;
     double acc = 0.0;
     double accs[GRAAL_N_CANDIDATES];
     if (BASE) {
@@ -1087,28 +1090,45 @@ k_band_delta(const int4* __restrict__ rec_a0, const int4* __restrict__ rec_b0, c
                         unsigned my[3];
                         if (BASE) { const int4 yc = rec_c[iy]; my[0] = (unsigned)yc.x; my[1] = (unsigned)yc.y; my[2] = (unsigned)yc.z; }
                         else { my[0] = ym & 1u; my[1] = (ym >> 1) & 1u; my[2] = (ym >> 2) & 1u; }
+                        unsigned slow = 0u;                        // pairs left to the general path (rare): after the fast ones
                         #pragma unroll
                         for (int b = 0; b < 3; b++) {
                             #pragma unroll
                             for (int a = 0; a < 3; a++) {
                                 const unsigned mm = mx[a] | my[b];
                                 const float s = fabsf(ymid[b] - xmid[a]);
-                                const bool on = a < nx && b < ny && mm != 0u && s > 0.0f && s < p.d_max;
+                                const bool on = a < nx && b < ny && mm != 0u && s > 0.0f && s < d_max;
                                 const bool fast = on && fast_ok && law_in_table(s);
-                                const int idx = uni ? 0 : (int)((xb.w >> (8 * a)) & 255) * p.nd + (int)((yb.w >> (8 * b)) & 255);
-                                double v = 0.0;
-                                if (on && !fast) v = band_excess_general(s, idx, circ, stot, p);
-                                const double f = law_interp(fast ? s : 1.0f, p.t_f);
-                                const double vf = uni ? f * normd0 - g00 : f * __ldg(&p.t_normd[idx]) - (double)__ldg(&p.t_g[idx]);
-                                if (fast && f > p.v_clamp) v = vf;
+                                if (on && !fast) slow |= 1u << (3 * b + a);
+                                const int idx = UNI ? 0 : (int)((xb.w >> (8 * a)) & 255) * p.nd + (int)((yb.w >> (8 * b)) & 255);
+                                const double f = law_interp(fast ? s : 1.0f, t_f);
+                                const double vf = UNI ? fma(f, normd0, neg_g00) : fma(f, __ldg(&p.t_normd[idx]), -(double)__ldg(&p.t_g[idx]));
+                                const double v = (fast && f > v_clamp) ? vf : 0.0;
                                 if (BASE) {
                                     tot[a] += v;                              // credited below to every candidate of mx[a]
-                                    const unsigned extra = on ? (my[b] & ~mx[a]) : 0u;
+                                    const unsigned extra = fast ? (my[b] & ~mx[a]) : 0u;
                                     if (extra) {
                                         #pragma unroll
                                         for (int c = 0; c < GRAAL_N_CANDIDATES; c++) if ((extra >> c) & 1u) accs[c] += v;
                                     }
                                 } else acc += v;
+                            }
+                        }
+                        if (slow) {
+                            #pragma unroll
+                            for (int b = 0; b < 3; b++) {
+                                #pragma unroll
+                                for (int a = 0; a < 3; a++) {
+                                    if (!((slow >> (3 * b + a)) & 1u)) continue;
+                                    const int idx = UNI ? 0 : (int)((xb.w >> (8 * a)) & 255) * p.nd + (int)((yb.w >> (8 * b)) & 255);
+                                    const double v = band_excess_general(fabsf(ymid[b] - xmid[a]), idx, circ, stot, p);
+                                    if (BASE) {
+                                        tot[a] += v;
+                                        const unsigned extra = my[b] & ~mx[a];
+                                        #pragma unroll
+                                        for (int c = 0; c < GRAAL_N_CANDIDATES; c++) if ((extra >> c) & 1u) accs[c] += v;
+                                    } else acc += v;
+                                }
                             }
                         }
                     }
@@ -2168,11 +2188,17 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
     c->prof.end(GRAAL_K_DELTA_CONTACTS, st);
     // band mass: d_band[k] = B_U(S_k) - B_U(S_0) over changed pairs; enters the delta with a minus sign
     c->prof.begin(GRAAL_K_DELTA_BAND, st);
-    k_band_delta<false, 2><<<dim3(gb, n_cand), 256, 0, st>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
-                                                         L.partials, ps); CHECK_LAUNCH(c);
+    if (p.nd == 1) k_band_delta<false, 2, true><<<dim3(gb, n_cand), 256, 0, st>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
+                                                                              L.partials, ps);
+    else k_band_delta<false, 2, false><<<dim3(gb, n_cand), 256, 0, st>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
+                                                                     L.partials, ps);
+    CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 256, 0, st>>>(L.partials, gb, ps, 1.0, d_band, 0); CHECK_LAUNCH(c);
-    k_band_delta<true, 8><<<dim3(gb, 1), 256, 0, st>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
-                                                   L.partials, ps); CHECK_LAUNCH(c);
+    if (p.nd == 1) k_band_delta<true, 8, true><<<dim3(gb, 1), 256, 0, st>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
+                                                                        L.partials, ps);
+    else k_band_delta<true, 8, false><<<dim3(gb, 1), 256, 0, st>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
+                                                               L.partials, ps);
+    CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 256, 0, st>>>(L.partials, gb, ps, -1.0, d_band, 1); CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 32, 0, st>>>(d_band, 1, 1, -1.0, d_out, 1); CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_DELTA_BAND, st);
