@@ -467,9 +467,12 @@ __device__ __forceinline__ void bin_geometry(const int* __restrict__ slot, int l
 }
 
 __global__ void k_geometry_all(const int* __restrict__ slot, int ld, int n, LevelView lv, Geo* __restrict__ geo,
-                               unsigned short* __restrict__ cid16, float* __restrict__ mid32) {
+                               unsigned short* __restrict__ cid16, float* __restrict__ mid32, int* __restrict__ wide_ids) {
     const int bin = blockIdx.x * blockDim.x + threadIdx.x;
-    if (bin < n) bin_geometry(slot, ld, bin, lv, geo, cid16, mid32);
+    if (bin >= n) return;
+    bin_geometry(slot, ld, bin, lv, geo, cid16, mid32);
+    const int id_c = slot[F_ID_C * ld + bin];
+    if (id_c < 0 || id_c >= 65535) *wide_ids = 1;          // some contig id does not fit the 2-byte table: exact compare needed
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -669,6 +672,90 @@ k_full_contacts_uniform(const long long* __restrict__ rowptr, const int2* __rest
         }
     }
     if (lane < qn) { const Pending m = q[lane]; acc += inband_term(m, p) - (double)m.ob * lg; }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+// Math mode 2 on a uniform-accu level: the in-band term is one table gather and a dozen instructions, cheaper
+// than compacting the in-band lanes through shared memory -- every lane evaluates its own entries,
+// branch-free; circular contigs and distances outside the table take the general path (rare).
+//   acc += ob * (max(ln f(s), ln v) + ln norm - log g)   for in-band cis entries
+__global__ void __launch_bounds__(256, 3)
+k_full_contacts_direct(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, long long E,
+                       const int* __restrict__ group_row, int n_groups,
+                       const Geo* __restrict__ geo, const unsigned short* __restrict__ cid16, const float* __restrict__ mid32,
+                       const int* __restrict__ wide_ids,
+                       const __grid_constant__ Params p, double lg, double* __restrict__ partials) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const bool wide = __ldg(wide_ids) != 0;
+    const double lnnorm0 = __ldg(&p.t_lnnorm[0]);
+    const double cst = lnnorm0 - lg;
+    const bool fast_ok = cst - cst == 0.0;                      // finite
+    const double ln_v = p.ln_v;
+    const float d_max = p.d_max;
+    const int4* __restrict__ t_lnf = p.t_lnf;
+    double acc = 0.0;
+    for (int g = warp; g < n_groups; g += n_warps) {
+        const long long e0 = (long long)g * GROUP;
+        const int len = (int)min((long long)GROUP, E - e0);
+        int2 ce[UNROLL8];
+        #pragma unroll
+        for (int u = 0; u < UNROLL8; u++) {
+            const int r = u * 32 + lane;
+            ce[u] = (r < len) ? ld_stream(&contacts[e0 + r]) : make_int2(0, 0);
+        }
+        int row = __ldg(&group_row[g]);
+        int row_end_rel = (int)min(__ldg(&rowptr[row + 1]) - e0, (long long)INT_MAX);
+        const Geo g0 = ld_geo(&geo[row]);
+        float r_mid = g0.mid, r_stot = g0.stot; int r_idc = g0.id_c; int r_circ = pk_circ(g0.pk);
+        unsigned cc[UNROLL8];
+        #pragma unroll
+        for (int u = 0; u < UNROLL8; u++) cc[u] = (unsigned)__ldg(&cid16[ce[u].x]);
+        bool cis[UNROLL8]; float rm[UNROLL8]; bool slowrow[UNROLL8];
+        #pragma unroll
+        for (int u = 0; u < UNROLL8; u++) {
+            const int r = u * 32 + lane;
+            if (r < len && r >= row_end_rel) {                      // rows are ~100s of entries long: the cursor rarely moves
+                long long re;
+                do { row++; re = __ldg(&rowptr[row + 1]) - e0; } while ((long long)r >= re);
+                row_end_rel = (int)min(re, (long long)INT_MAX);
+                const Geo gg = ld_geo(&geo[row]);
+                r_mid = gg.mid; r_idc = gg.id_c; r_stot = gg.stot; r_circ = pk_circ(gg.pk);
+            }
+            bool c = (int)cc[u] == r_idc;
+            if (wide && (cc[u] == 65535u || (unsigned)r_idc >= 65535u)) c = ld_geo(&geo[ce[u].x]).id_c == r_idc;   // ids beyond 16 bits: exact path
+            cis[u] = c && r < len;
+            rm[u] = r_mid; slowrow[u] = r_circ != 0;
+        }
+        float pm[UNROLL8];
+        #pragma unroll
+        for (int u = 0; u < UNROLL8; u++) pm[u] = cis[u] ? __ldg(&mid32[ce[u].x]) : 0.0f;
+        unsigned slow = 0u;
+        #pragma unroll
+        for (int u = 0; u < UNROLL8; u++) {
+            const float s = fabsf(pm[u] - rm[u]);
+            const bool inband = cis[u] && s > 0.0f && s < d_max;
+            const bool fast = inband && fast_ok && !slowrow[u] && law_in_table(s);
+            if (inband && !fast) slow |= 1u << u;
+            const double lr = fmax(law_interp(fast ? s : 1.0f, t_lnf), ln_v) + cst;
+            acc += fast ? (double)__int_as_float(ce[u].y) * lr : 0.0;
+        }
+        if (slow) {                                                 // circular contig / outside the table / non-finite tables
+            #pragma unroll
+            for (int u = 0; u < UNROLL8; u++) {
+                if (!((slow >> u) & 1u)) continue;
+                // the row of entry u is not kept per entry: find it again
+                const long long e = e0 + u * 32 + lane;
+                int lo = __ldg(&group_row[g]);
+                while (__ldg(&rowptr[lo + 1]) <= e) lo++;
+                const Geo gr = ld_geo(&geo[lo]);
+                const float ob = __int_as_float(ce[u].y);
+                acc += inband_log_term(fabsf(pm[u] - gr.mid), ob, gr.stot, 0, pk_circ(gr.pk), p) - (double)ob * lg;
+            }
+        }
+    }
     acc = block_sum(acc);
     if (threadIdx.x == 0) partials[blockIdx.x] = acc;
 }
@@ -2045,7 +2132,8 @@ int graal_commit(graal_ctx* c, int dst_slot, int src_slot) {
 
 static int ensure_base_geometry(graal_ctx* c, int slot) {
     if (c->geo_base_slot == slot) return 0;
-    k_geometry_all<<<nblk(c->n_new, 128), 128, 0, c->stream>>>(slot_ptr(c, slot), c->ld, c->n_new, c->lv, c->geo_base, c->cid16_base, c->mid32_base);
+    k_set_int<<<1, 1, 0, c->stream>>>(c->d_ints + 4, 0); CHECK_LAUNCH(c);
+    k_geometry_all<<<nblk(c->n_new, 128), 128, 0, c->stream>>>(slot_ptr(c, slot), c->ld, c->n_new, c->lv, c->geo_base, c->cid16_base, c->mid32_base, c->d_ints + 4);
     CHECK_LAUNCH(c);
     c->geo_base_slot = slot;
     return 0;
@@ -2093,7 +2181,8 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
             g1 = std::min(ps, c->n_sm);
         } else {
             int fc_blocks = 0;
-            if (uniform) { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fc_blocks, k_full_contacts_uniform<false>, 256, 0)); }
+            if (uniform && p.mode == 2) { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fc_blocks, k_full_contacts_direct, 256, 0)); }
+            else if (uniform) { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fc_blocks, k_full_contacts_uniform<false>, 256, 0)); }
             else { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fc_blocks, k_full_contacts, 256, 0)); }
             g1 = (int)std::min<long long>(std::min(ps, c->n_sm * std::max(1, fc_blocks)), (c->E + 1023) / 1024);   // one resident wave
         }
@@ -2106,6 +2195,9 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
         if (use_smem)
             k_full_contacts_uniform<true><<<g1, FCS_THREADS, fcs_smem, st>>>(c->rowptr, c->contacts, c->E, c->W, c->group_row, c->n_groups, c->geo_base,
                                                                             c->cid16_base, c->mid32_base, p, lg_uniform, c->partials);
+        else if (uniform && p.mode == 2)
+            k_full_contacts_direct<<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->group_row, c->n_groups, c->geo_base,
+                                                      c->cid16_base, c->mid32_base, c->d_ints + 4, p, lg_uniform, c->partials);
         else if (uniform)
             k_full_contacts_uniform<false><<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->W, c->group_row, c->n_groups, c->geo_base,
                                                               c->cid16_base, c->mid32_base, p, lg_uniform, c->partials);
