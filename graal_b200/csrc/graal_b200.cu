@@ -232,6 +232,9 @@ __device__ __forceinline__ double contact_log_term(const Geo& a, const Geo& b, f
     }
     return contact_log_term_general(a, b, ob, p);
 }
+__device__ __noinline__ double inband_log_term_general(float s, float ob, float stot, int idx, int circ, const Params& p) {
+    return inband_log_term(s, ob, stot, idx, circ, p);
+}
 // clamp value of the pair (true accus): what a cis pair beyond the band evaluates to
 __device__ __forceinline__ float g_pair(const Geo& a, const Geo& b, const Params& p) {
     return __ldg(&p.t_g[pk_true(a.pk) * p.nd + pk_true(b.pk)]);
@@ -431,7 +434,7 @@ __device__ __forceinline__ bool eligible(const LevelView& lv, int f) {
 
 __device__ __forceinline__ void bin_geometry(const int* __restrict__ slot, int ld, int bin, const LevelView& lv,
                                              Geo* __restrict__ geo, unsigned short* __restrict__ cid16 = nullptr,
-                                             float* __restrict__ mid32 = nullptr) {
+                                             float* __restrict__ mid32 = nullptr, int2* __restrict__ cm = nullptr) {
     const int id_d = slot[F_ID_D * ld + bin];
     const bool elig = eligible(lv, bin);
     if (!elig && bin >= lv.n_data) return;                   // repeat copy: its data sub-frags belong to the original
@@ -463,16 +466,14 @@ __device__ __forceinline__ void bin_geometry(const int* __restrict__ slot, int l
         const int sub = (loc == 0) ? sid.x : (loc == 1 ? sid.y : sid.z);
         geo[sub] = g;
         if (cid16) { cid16[sub] = (unsigned short)min(id_c < 0 ? 65535 : id_c, 65535); mid32[sub] = mid; }   // classification tables
+        if (cm) cm[sub] = make_int2(id_c, __float_as_int(mid));                                                // {contig id, mid-point}: one 8-byte gather
     }
 }
 
 __global__ void k_geometry_all(const int* __restrict__ slot, int ld, int n, LevelView lv, Geo* __restrict__ geo,
-                               unsigned short* __restrict__ cid16, float* __restrict__ mid32, int* __restrict__ wide_ids) {
+                               unsigned short* __restrict__ cid16, float* __restrict__ mid32, int2* __restrict__ cm) {
     const int bin = blockIdx.x * blockDim.x + threadIdx.x;
-    if (bin >= n) return;
-    bin_geometry(slot, ld, bin, lv, geo, cid16, mid32);
-    const int id_c = slot[F_ID_C * ld + bin];
-    if (id_c < 0 || id_c >= 65535) *wide_ids = 1;          // some contig id does not fit the 2-byte table: exact compare needed
+    if (bin < n) bin_geometry(slot, ld, bin, lv, geo, cid16, mid32, cm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -680,18 +681,21 @@ k_full_contacts_uniform(const long long* __restrict__ rowptr, const int2* __rest
 // than compacting the in-band lanes through shared memory -- every lane evaluates its own entries,
 // branch-free; circular contigs and distances outside the table take the general path (rare).
 //   acc += ob * (max(ln f(s), ln v) + ln norm - log g)   for in-band cis entries
+// Per entry: the streamed 8-byte contact, ONE 8-byte gather {contig id, mid-point} of the partner, one 16-byte
+// table gather.  Entries past the end of the list are loaded as (col 0, ob 0) and contribute exactly 0.
+// The eight 256-byte stream loads of a group are staged in registers.  Measured slower on B200 (profiles/README.md):
+// per-warp rings in shared memory filled by 2 KB cp.async.bulk copies + mbarrier (0.212 ms per pass: the per-SM
+// bulk-copy rate is the limit) or by 16-byte cp.async four groups ahead (0.145 ms) against 0.123 ms here --
+// the pass waits on its gathers and on instruction issue, not on the stream.
 __global__ void __launch_bounds__(256, 3)
 k_full_contacts_direct(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, long long E,
                        const int* __restrict__ group_row, int n_groups,
-                       const Geo* __restrict__ geo, const unsigned short* __restrict__ cid16, const float* __restrict__ mid32,
-                       const int* __restrict__ wide_ids,
+                       const Geo* __restrict__ geo, const int2* __restrict__ cm,
                        const __grid_constant__ Params p, double lg, double* __restrict__ partials) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    const bool wide = __ldg(wide_ids) != 0;
-    const double lnnorm0 = __ldg(&p.t_lnnorm[0]);
-    const double cst = lnnorm0 - lg;
+    const double cst = __ldg(&p.t_lnnorm[0]) - lg;
     const bool fast_ok = cst - cst == 0.0;                      // finite
     const double ln_v = p.ln_v;
     const float d_max = p.d_max;
@@ -700,59 +704,48 @@ k_full_contacts_direct(const long long* __restrict__ rowptr, const int2* __restr
     for (int g = warp; g < n_groups; g += n_warps) {
         const long long e0 = (long long)g * GROUP;
         const int len = (int)min((long long)GROUP, E - e0);
+        const int2* __restrict__ cg = contacts + e0;
         int2 ce[UNROLL8];
         #pragma unroll
         for (int u = 0; u < UNROLL8; u++) {
             const int r = u * 32 + lane;
-            ce[u] = (r < len) ? ld_stream(&contacts[e0 + r]) : make_int2(0, 0);
+            ce[u] = (r < len) ? ld_stream(&cg[r]) : make_int2(0, 0);
         }
         int row = __ldg(&group_row[g]);
-        int row_end_rel = (int)min(__ldg(&rowptr[row + 1]) - e0, (long long)INT_MAX);
-        const Geo g0 = ld_geo(&geo[row]);
-        float r_mid = g0.mid, r_stot = g0.stot; int r_idc = g0.id_c; int r_circ = pk_circ(g0.pk);
-        unsigned cc[UNROLL8];
+        int row_end_rel = (int)min(__ldg(&rowptr[row + 1]) - e0, (long long)GROUP);
+        int2 rr = __ldg(&cm[row]);                                  // {contig id, mid-point} of the row
+        int r_slow = pk_circ(__ldg(&geo[row].pk));
+        int2 pc[UNROLL8];
         #pragma unroll
-        for (int u = 0; u < UNROLL8; u++) cc[u] = (unsigned)__ldg(&cid16[ce[u].x]);
-        bool cis[UNROLL8]; float rm[UNROLL8]; bool slowrow[UNROLL8];
-        #pragma unroll
-        for (int u = 0; u < UNROLL8; u++) {
-            const int r = u * 32 + lane;
-            if (r < len && r >= row_end_rel) {                      // rows are ~100s of entries long: the cursor rarely moves
-                long long re;
-                do { row++; re = __ldg(&rowptr[row + 1]) - e0; } while ((long long)r >= re);
-                row_end_rel = (int)min(re, (long long)INT_MAX);
-                const Geo gg = ld_geo(&geo[row]);
-                r_mid = gg.mid; r_idc = gg.id_c; r_stot = gg.stot; r_circ = pk_circ(gg.pk);
-            }
-            bool c = (int)cc[u] == r_idc;
-            if (wide && (cc[u] == 65535u || (unsigned)r_idc >= 65535u)) c = ld_geo(&geo[ce[u].x]).id_c == r_idc;   // ids beyond 16 bits: exact path
-            cis[u] = c && r < len;
-            rm[u] = r_mid; slowrow[u] = r_circ != 0;
-        }
-        float pm[UNROLL8];
-        #pragma unroll
-        for (int u = 0; u < UNROLL8; u++) pm[u] = cis[u] ? __ldg(&mid32[ce[u].x]) : 0.0f;
+        for (int u = 0; u < UNROLL8; u++) pc[u] = __ldg(&cm[ce[u].x]);
         unsigned slow = 0u;
         #pragma unroll
         for (int u = 0; u < UNROLL8; u++) {
-            const float s = fabsf(pm[u] - rm[u]);
-            const bool inband = cis[u] && s > 0.0f && s < d_max;
-            const bool fast = inband && fast_ok && !slowrow[u] && law_in_table(s);
+            const int r = u * 32 + lane;
+            if (r >= row_end_rel && r < len) {                      // rows are ~100s of entries long: the cursor rarely moves
+                long long re;
+                do { row++; re = __ldg(&rowptr[row + 1]) - e0; } while ((long long)r >= re);
+                row_end_rel = (int)min(re, (long long)GROUP);
+                rr = __ldg(&cm[row]);
+                r_slow = pk_circ(__ldg(&geo[row].pk));
+            }
+            const float s = fabsf(__int_as_float(pc[u].y) - __int_as_float(rr.y));
+            const bool inband = pc[u].x == rr.x && s > 0.0f && s < d_max;
+            const bool fast = inband && fast_ok && !r_slow && law_in_table(s);
             if (inband && !fast) slow |= 1u << u;
             const double lr = fmax(law_interp(fast ? s : 1.0f, t_lnf), ln_v) + cst;
-            acc += fast ? (double)__int_as_float(ce[u].y) * lr : 0.0;
+            acc = fma((double)(fast ? __int_as_float(ce[u].y) : 0.0f), lr, acc);
         }
         if (slow) {                                                 // circular contig / outside the table / non-finite tables
             #pragma unroll
             for (int u = 0; u < UNROLL8; u++) {
-                if (!((slow >> u) & 1u)) continue;
-                // the row of entry u is not kept per entry: find it again
-                const long long e = e0 + u * 32 + lane;
+                if (!((slow >> u) & 1u) || u * 32 + lane >= len) continue;
+                const long long e = e0 + u * 32 + lane;             // the row of entry u is not kept per entry: find it again
                 int lo = __ldg(&group_row[g]);
                 while (__ldg(&rowptr[lo + 1]) <= e) lo++;
                 const Geo gr = ld_geo(&geo[lo]);
                 const float ob = __int_as_float(ce[u].y);
-                acc += inband_log_term(fabsf(pm[u] - gr.mid), ob, gr.stot, 0, pk_circ(gr.pk), p) - (double)ob * lg;
+                acc += inband_log_term_general(fabsf(__int_as_float(pc[u].y) - gr.mid), ob, gr.stot, 0, pk_circ(gr.pk), p) - (double)ob * lg;
             }
         }
     }
@@ -1634,7 +1627,7 @@ struct graal_ctx {
     unsigned char* d_dup = nullptr; unsigned char* d_sub_dup = nullptr;
     int* d_rep_bins = nullptr; int n_rep = 0;
     double lf_total = 0.0, ob_total = 0.0;
-    unsigned short* cid16_base = nullptr; float* mid32_base = nullptr; int smem_optin = 0;
+    unsigned short* cid16_base = nullptr; float* mid32_base = nullptr; int2* cm_base = nullptr; int smem_optin = 0;
     int* group_row = nullptr; int n_groups = 0;
     int smem_cid = 0;                         // GRAAL_SMEM_CID=1: stage the contig-id table in shared memory (measured: no faster than L1, profiles/README.md)
     double* band_hist = nullptr;              // [16][13] band delta of the proposals scored since the last commit
@@ -1784,7 +1777,7 @@ int graal_ctx_create(int device, graal_ctx** out) {
 }
 
 static void free_level_scratch(graal_ctx* c) {
-    cudaFree(c->cid16_base); cudaFree(c->mid32_base); cudaFree(c->group_row); cudaFree(c->band_hist); c->band_hist = nullptr; c->cid16_base = nullptr; c->mid32_base = nullptr; c->group_row = nullptr;
+    cudaFree(c->cid16_base); cudaFree(c->mid32_base); cudaFree(c->cm_base); c->cm_base = nullptr; cudaFree(c->group_row); cudaFree(c->band_hist); c->band_hist = nullptr; c->cid16_base = nullptr; c->mid32_base = nullptr; c->group_row = nullptr;
     for (int l = 0; l < GRAAL_MAX_LANES; l++) {
         Lane& L = c->lanes[l];
         cudaFree(L.sub_index); cudaFree(L.chmask); cudaFree(L.geo_cand); cudaFree(L.cand_order); cudaFree(L.cand_ordrec); cudaFree(L.base_ordrec); cudaFree(L.cand_ordb); cudaFree(L.base_ordb); cudaFree(L.base_ordc); cudaFree(L.rep_in_u);
@@ -1963,6 +1956,8 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     CUDA_OK(cudaMalloc(&c->geo_base, (size_t)c->W * sizeof(Geo)));
     CUDA_OK(cudaMalloc(&c->cid16_base, ((size_t)c->W + 16) * sizeof(unsigned short)));
     CUDA_OK(cudaMemset(c->cid16_base, 0, ((size_t)c->W + 16) * sizeof(unsigned short)));
+    CUDA_OK(cudaMalloc(&c->cm_base, (size_t)c->W * sizeof(int2)));
+    CUDA_OK(cudaMemset(c->cm_base, 0, (size_t)c->W * sizeof(int2)));
     CUDA_OK(cudaMalloc(&c->mid32_base, (size_t)c->W * sizeof(float)));
     for (int l = 0; l < c->n_lanes; l++) {
         Lane& L = c->lanes[l];
@@ -2132,8 +2127,7 @@ int graal_commit(graal_ctx* c, int dst_slot, int src_slot) {
 
 static int ensure_base_geometry(graal_ctx* c, int slot) {
     if (c->geo_base_slot == slot) return 0;
-    k_set_int<<<1, 1, 0, c->stream>>>(c->d_ints + 4, 0); CHECK_LAUNCH(c);
-    k_geometry_all<<<nblk(c->n_new, 128), 128, 0, c->stream>>>(slot_ptr(c, slot), c->ld, c->n_new, c->lv, c->geo_base, c->cid16_base, c->mid32_base, c->d_ints + 4);
+    k_geometry_all<<<nblk(c->n_new, 128), 128, 0, c->stream>>>(slot_ptr(c, slot), c->ld, c->n_new, c->lv, c->geo_base, c->cid16_base, c->mid32_base, c->cm_base);
     CHECK_LAUNCH(c);
     c->geo_base_slot = slot;
     return 0;
@@ -2197,7 +2191,7 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
                                                                             c->cid16_base, c->mid32_base, p, lg_uniform, c->partials);
         else if (uniform && p.mode == 2)
             k_full_contacts_direct<<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->group_row, c->n_groups, c->geo_base,
-                                                      c->cid16_base, c->mid32_base, c->d_ints + 4, p, lg_uniform, c->partials);
+                                                      c->cm_base, p, lg_uniform, c->partials);
         else if (uniform)
             k_full_contacts_uniform<false><<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->W, c->group_row, c->n_groups, c->geo_base,
                                                               c->cid16_base, c->mid32_base, p, lg_uniform, c->partials);
