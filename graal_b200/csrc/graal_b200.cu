@@ -387,7 +387,9 @@ __global__ void k_first_index(const int* __restrict__ id_c, int n, int cap, int*
     if (i >= n) return;
     const int c = id_c[i];
     if (c < 0 || c >= cap) { atomicExch(err, 1); return; }
-    atomicMin(&first[c], i);
+    // neighbouring bins mostly share their contig: one atomic per distinct id in the warp (its lowest lane = lowest bin)
+    const unsigned peers = __match_any_sync(__activemask(), c);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicMin(&first[c], i);
 }
 // sort key of contig c = its length (sentinel: id not in use), value = c.  The radix sort is stable and the
 // input is in id order, so the result is ordered by (length, old id) -- the reference's
@@ -1304,6 +1306,7 @@ k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restri
 }
 
 // out[dst] = out[src]   /   *total += sel[idx]   (tiny helpers of the incremental bookkeeping)
+__global__ void k_copy_double2(double* p, double* q, int dst, int src) { p[dst] = p[src]; q[dst] = q[src]; }
 __global__ void k_copy_double(double* p, int dst, int src) { p[dst] = p[src]; }
 __global__ void k_add_selected(double* total, const double* v, int idx) { *total += v[idx]; }
 
@@ -1459,8 +1462,15 @@ __global__ void k_stats(const int* __restrict__ slot, int ld, int n, unsigned lo
         mn = min(mn, lc); mx = max(mx, lc);
         if (slot[F_START_BP * ld + i] == 0) { heads++; sum += (unsigned long long)(long long)slot[F_L_CONT_BP * ld + i]; }
     }
-    atomicAdd(&acc[0], heads); atomicAdd(&acc[1], sum);
-    atomicMin((int*)&acc[2], mn); atomicMax((int*)&acc[3], mx);
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {                      // one set of atomics per warp, not per thread
+        heads += __shfl_down_sync(0xffffffffu, heads, o); sum += __shfl_down_sync(0xffffffffu, sum, o);
+        mn = min(mn, __shfl_down_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (heads) { atomicAdd(&acc[0], heads); atomicAdd(&acc[1], sum); }
+        atomicMin((int*)&acc[2], mn); atomicMax((int*)&acc[3], mx);
+    }
 }
 __global__ void k_stats_final(const unsigned long long* __restrict__ acc, const int* __restrict__ n_contigs, double* __restrict__ out) {
     out[0] = (double)*n_contigs;
@@ -2369,10 +2379,7 @@ int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int i
     const unsigned skip = (id_fA < c->N) ? (1u << 8) : 0u;      // a repeat copy (frag >= N) really toggles its activity
     double* d_band = c->band_hist + (size_t)proposal_index * GRAAL_N_CANDIDATES;
     rc = delta_loglik_impl(c, L, st, base_slot, first_cand_slot, GRAAL_N_CANDIDATES, id_fA, id_fB, max_id, skip, d_out, d_band); if (rc) return rc;
-    if (skip) {
-        k_copy_double<<<1, 1, 0, st>>>(d_out, 8, 0); CHECK_LAUNCH(c);
-        k_copy_double<<<1, 1, 0, st>>>(d_band, 8, 0); CHECK_LAUNCH(c);
-    }
+    if (skip) { k_copy_double2<<<1, 1, 0, st>>>(d_out, d_band, 8, 0); CHECK_LAUNCH(c); }
     if (!serial) {
         CUDA_OK(cudaEventRecord(L.done, L.st));
         L.pending = true; L.cand_first = first_cand_slot;
