@@ -220,8 +220,11 @@ class sampler:
         self.n_iterations = n_iterations
         self.is_simu = is_simu
         self.id_frags_blacklisted = list(id_frags_blacklisted)
+        self._black_set = set(int(f) for f in self.id_frags_blacklisted)          # O(1) membership on the step path
         self.id_frag_duplicated = id_frag_duplicated
         self.np_id_frag_duplicated = np.asarray(id_frag_duplicated, dtype=I32)
+        self._dup_set = set(int(f) for f in self.np_id_frag_duplicated)
+        self._n_cand_cache = {}
         self.n_frags, self.n_new_frags = I32(n_frags), I32(n_new_frags)
         self.init_n_sub_frags, self.n_new_sub_frags = I32(init_n_sub_frags), I32(n_new_sub_frags)
         self.uniq_frags = np.setdiff1d(np.arange(n_frags, dtype=I32), self.np_id_frag_duplicated).astype(I32)
@@ -467,16 +470,19 @@ class sampler:
         ori_id = int(self.h_id_d[id_fA])
         delta = min(self.n_neighbors, delta0)
         distri = self.distri_pk[ori_id]
-        n_max_candidates = min(delta, np.nonzero(distri != 0)[0].shape[0])
+        n_nonzero = self._n_cand_cache.get(ori_id)
+        if n_nonzero is None:
+            n_nonzero = self._n_cand_cache[ori_id] = int(np.count_nonzero(distri))
+        n_max_candidates = min(delta, n_nonzero)
         init_id = self.rng.choice(self.distri_xk[ori_id], n_max_candidates, p=distri, replace=False)
         out = []
-        if ori_id in self.np_id_frag_duplicated:
+        if ori_id in self._dup_set:
             d = self.frag_dispatcher[ori_id]
             out.extend(np.setdiff1d(self.collector_id_repeats[d[0]:d[1]], id_fA))
         for id_fB in init_id:
             d = self.frag_dispatcher[id_fB]
             out.extend(self.collector_id_repeats[d[0]:d[1]])
-        return [int(e) for e in out if e not in self.id_frags_blacklisted]
+        return [int(e) for e in out if int(e) not in self._black_set]
 
     def temperature(self, t, n_step):
         return 1.0
@@ -497,7 +503,7 @@ class sampler:
         """cuda_lib_gl.py:1793-1980.  Returns (o, n_contigs, min_len, mean_len_bp, max_len, op_sampled,
         id_f_sampled, dist, F_t)."""
         lib = self.lib
-        if id_fA not in self.id_frags_blacklisted:
+        if id_fA not in self._black_set:
             check(lib.graal_state_stats(self.ctx, CUR, self._ptr(self.d_out, 4)))
             check(lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
             id_neighbours = self.return_neighbours(id_fA, delta)
