@@ -1610,9 +1610,26 @@ struct Lane {
     unsigned char* rep_in_u = nullptr;       // [N]
 };
 
+// The ~20 launches that score one proposal, captured once per proposal index and replayed with the two
+// kernels that take (id_fA, id_fB, max_id) by value re-parameterised: one graph launch instead of twenty
+// kernel launches on the host's critical path between two draws.
+struct ProposalGraph {
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t n_build = nullptr, n_setup = nullptr;
+    cudaKernelNodeParams kp_build{}, kp_setup{};
+    int base_slot = -1, first_cand = -1; double* d_out = nullptr; unsigned skip = 0u; long long version = -1; cudaStream_t st = nullptr;
+    int n_launches = 0;
+    void reset() {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        exec = nullptr; graph = nullptr; n_build = n_setup = nullptr; version = -1;
+    }
+};
+
 struct graal_ctx {
     Profiler prof;
     Lane lanes[GRAAL_MAX_LANES]; int n_lanes = 3; cudaEvent_t ev_fork = nullptr;
+    ProposalGraph graphs[16]; long long version = 0; int use_graphs = 1;      // version: bumped whenever captured arguments go stale
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -1772,6 +1789,7 @@ int graal_ctx_create(int device, graal_ctx** out) {
     CUDA_OK(cudaMalloc(&c->d_scalars, 64 * sizeof(double)));
     c->partial_stride = c->n_sm * 8;
     CUDA_OK(cudaMalloc(&c->partials, (size_t)16 * c->partial_stride * sizeof(double)));
+    { const char* e = getenv("GRAAL_GRAPHS"); if (e && e[0] == '0') c->use_graphs = 0; }
     { const char* e = getenv("GRAAL_LANES"); if (e && e[0] >= '1' && e[0] <= '0' + GRAAL_MAX_LANES) c->n_lanes = e[0] - '0'; }
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     for (int l = 0; l < c->n_lanes; l++) {
@@ -1821,6 +1839,7 @@ void graal_ctx_destroy(graal_ctx* c) {
         if (L.st) cudaStreamDestroy(L.st);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int i = 0; i < 16; i++) c->graphs[i].reset();
     c->prof.destroy();
     cudaFree(c->d_ints); cudaFree(c->d_stats); cudaFree(c->d_scalars); cudaFree(c->partials);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -1830,6 +1849,7 @@ void graal_ctx_destroy(graal_ctx* c) {
 int graal_set_stream(graal_ctx* c, void* s) {
     if (!c) return set_err(-1, "null context");
     { int rc = join_lanes(c); if (rc) return rc; }
+    c->version++;
     if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     c->stream = (cudaStream_t)s; c->own_stream = false;
     return 0;
@@ -1873,6 +1893,8 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     CUDA_OK(cudaSetDevice(c->device));
     { int rcj = join_lanes(c); if (rcj) return rcj; }
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->version++;
+    for (int i = 0; i < 16; i++) c->graphs[i].reset();
     free_level_scratch(c);
     c->N = n_frags; c->n_new = n_new_frags; c->W = n_sub_frags; c->E = n_contacts; c->nfpb = nfpb;
     c->lv.sub_id = reinterpret_cast<const int4*>(sub_id); c->lv.sub_len = sub_len_kb; c->lv.sub_accu = sub_accu;
@@ -2040,13 +2062,13 @@ int graal_set_params(graal_ctx* c, const float q[8]) {
     CUDA_OK(cudaSetDevice(c->device));
     int rc = join_lanes(c); if (rc) return rc;          // pending proposals still read the tables being replaced
     rc = upload_tables(c, c->p, 0); if (rc) return rc;
-    c->have_params = true; c->band_slot = -1;
+    c->have_params = true; c->band_slot = -1; c->version++;
     return 0;
 }
 
 int graal_set_math_mode(graal_ctx* c, int mode) {
     if (!c || mode < 0 || mode > 2) return set_err(-1, "math mode must be 0 (float32 chain), 1 (log-space float64) or 2 (tabulated law)");
-    c->math_mode = mode; c->p.mode = mode; c->band_slot = -1;
+    c->math_mode = mode; c->p.mode = mode; c->band_slot = -1; c->version++;
     return 0;
 }
 
@@ -2055,6 +2077,7 @@ int graal_state_bind(graal_ctx* c, int32_t* base, int ld, int n_slots) {
     if (c->n_new <= 0) return set_err(-1, "bind the level first");
     if (ld < c->n_new || n_slots < 1) return set_err(-1, "bad slot geometry (ld %d < n %d)", ld, c->n_new);
     { int rcj = join_lanes(c); if (rcj) return rcj; }
+    c->version++;
     c->slots = base; c->ld = ld; c->n_slots = n_slots; c->geo_base_slot = -1; c->band_slot = -1; c->first_idx_slot = -1;
     return 0;
 }
@@ -2365,11 +2388,6 @@ int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int i
         CUDA_OK(cudaStreamWaitEvent(L.st, c->ev_fork, 0));
         st = L.st;
     }
-    c->prof.begin(GRAAL_K_BUILD, st);
-    k_build_candidates<<<nblk(n, 128), 128, 0, st>>>(slot_ptr(c, base_slot), slot_ptr(c, first_cand_slot), slot_stride(c), c->ld, n,
-                                                    id_fA, id_fB, c->d_ints + 0, max_id, 0x1FFFu);
-    CHECK_LAUNCH(c);
-    c->prof.end(GRAAL_K_BUILD, st);
     for (int k = 0; k < GRAAL_N_CANDIDATES; k++) {
         if (c->geo_base_slot == first_cand_slot + k) c->geo_base_slot = -1;
         if (c->first_idx_slot == first_cand_slot + k) c->first_idx_slot = -1;
@@ -2378,8 +2396,62 @@ int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int i
     // unique bins: swap_activity is the identity on the popped-out structure, candidate 8 == candidate 0 (Q7)
     const unsigned skip = (id_fA < c->N) ? (1u << 8) : 0u;      // a repeat copy (frag >= N) really toggles its activity
     double* d_band = c->band_hist + (size_t)proposal_index * GRAAL_N_CANDIDATES;
-    rc = delta_loglik_impl(c, L, st, base_slot, first_cand_slot, GRAAL_N_CANDIDATES, id_fA, id_fB, max_id, skip, d_out, d_band); if (rc) return rc;
-    if (skip) { k_copy_double2<<<1, 1, 0, st>>>(d_out, d_band, 8, 0); CHECK_LAUNCH(c); }
+    // the launch sequence of one proposal (candidates, deltas, copy of candidate 8)
+    auto enqueue = [&]() -> int {
+        c->prof.begin(GRAAL_K_BUILD, st);
+        k_build_candidates<<<nblk(n, 128), 128, 0, st>>>(slot_ptr(c, base_slot), slot_ptr(c, first_cand_slot), slot_stride(c), c->ld, n,
+                                                        id_fA, id_fB, c->d_ints + 0, max_id, 0x1FFFu);
+        CHECK_LAUNCH(c);
+        c->prof.end(GRAAL_K_BUILD, st);
+        int r = delta_loglik_impl(c, L, st, base_slot, first_cand_slot, GRAAL_N_CANDIDATES, id_fA, id_fB, max_id, skip, d_out, d_band); if (r) return r;
+        if (skip) { k_copy_double2<<<1, 1, 0, st>>>(d_out, d_band, 8, 0); CHECK_LAUNCH(c); }
+        return 0;
+    };
+    ProposalGraph& G = c->graphs[proposal_index];
+    if (!c->use_graphs || c->prof.on) { rc = enqueue(); if (rc) return rc; }
+    else {
+        const bool hit = G.exec && G.version == c->version && G.base_slot == base_slot && G.first_cand == first_cand_slot &&
+                         G.d_out == d_out && G.skip == skip && G.st == st;
+        if (!hit) {                                             // capture the sequence for this proposal index
+            G.reset();
+            const int64_t before = c->launches;
+            CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue();
+            cudaGraph_t graph = nullptr;
+            const cudaError_t e_end = cudaStreamEndCapture(st, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e_end != cudaSuccess) return set_err(-2, "stream capture of a proposal failed: %s", cudaGetErrorString(e_end));
+            G.graph = graph; G.n_launches = (int)(c->launches - before); c->launches = before;
+            size_t nn = 0;
+            CUDA_OK(cudaGraphGetNodes(graph, nullptr, &nn));
+            std::vector<cudaGraphNode_t> nodes(nn);
+            CUDA_OK(cudaGraphGetNodes(graph, nodes.data(), &nn));
+            for (size_t i = 0; i < nn; i++) {
+                cudaGraphNodeType t;
+                CUDA_OK(cudaGraphNodeGetType(nodes[i], &t));
+                if (t != cudaGraphNodeTypeKernel) continue;
+                cudaKernelNodeParams kp;
+                CUDA_OK(cudaGraphKernelNodeGetParams(nodes[i], &kp));
+                if (kp.func == (void*)k_build_candidates) { G.n_build = nodes[i]; G.kp_build = kp; }
+                else if (kp.func == (void*)k_delta_setup) { G.n_setup = nodes[i]; G.kp_setup = kp; }
+            }
+            if (!G.n_build || !G.n_setup) { G.reset(); return set_err(-2, "proposal graph: parameter nodes not found"); }
+            CUDA_OK(cudaGraphInstantiate(&G.exec, graph, 0));
+            G.version = c->version; G.base_slot = base_slot; G.first_cand = first_cand_slot; G.d_out = d_out; G.skip = skip; G.st = st;
+        } else {                                                // same sequence, new (id_fA, id_fB, max_id)
+            const int* a_src = slot_ptr(c, base_slot); int* a_dst = slot_ptr(c, first_cand_slot); size_t a_stride = slot_stride(c);
+            int a_ld = c->ld, a_n = n, a_fA = id_fA, a_fB = id_fB, a_max = max_id; const int* a_dmax = c->d_ints + 0; unsigned a_mask = 0x1FFFu;
+            void* args_build[] = {&a_src, &a_dst, &a_stride, &a_ld, &a_n, &a_fA, &a_fB, &a_dmax, &a_max, &a_mask};
+            cudaKernelNodeParams kp = G.kp_build; kp.kernelParams = args_build; kp.extra = nullptr;
+            CUDA_OK(cudaGraphExecKernelNodeSetParams(G.exec, G.n_build, &kp));
+            int* a_meta = L.ints + 8;
+            void* args_setup[] = {&a_src, &a_ld, &a_fA, &a_fB, &a_dmax, &a_max, &a_meta};
+            kp = G.kp_setup; kp.kernelParams = args_setup; kp.extra = nullptr;
+            CUDA_OK(cudaGraphExecKernelNodeSetParams(G.exec, G.n_setup, &kp));
+        }
+        CUDA_OK(cudaGraphLaunch(G.exec, st));
+        c->launches += G.n_launches;
+    }
     if (!serial) {
         CUDA_OK(cudaEventRecord(L.done, L.st));
         L.pending = true; L.cand_first = first_cand_slot;
