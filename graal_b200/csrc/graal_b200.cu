@@ -207,12 +207,15 @@ __device__ __forceinline__ double inband_log_term(float s, float ob, float stot,
 }
 // ob * ln(ex) of one stored contact between sub-frags a (row side = lower data bin) and b, or the
 // lf(ob) correction when the expected value is 0 (kernels3.cu:197: such a pixel contributes 0)
-__device__ __noinline__ double contact_log_term_general(const Geo& a, const Geo& b, float ob, const Params& p) {
-    const bool cis = a.id_c == b.id_c;
-    const float s = fabsf(b.mid - a.mid);
+// (scalar arguments: records passed by reference to an out-of-line function would be spilled to the stack on
+//  the hot path of every caller)
+__device__ __noinline__ double contact_log_term_general(float a_mid, int a_idc, float a_stot, unsigned a_pk,
+                                                        float b_mid, int b_idc, unsigned b_pk, float ob, const Params& p) {
+    const bool cis = a_idc == b_idc;
+    const float s = fabsf(b_mid - a_mid);
     if (cis && s > 0.0f && s < p.d_max)
-        return inband_log_term(s, ob, a.stot, pk_true(a.pk) * p.nd + pk_true(b.pk), pk_circ(a.pk), p);
-    const double lg = __ldg(&p.t_logg[(cis ? pk_true(a.pk) : pk_quirk(a.pk)) * p.nd + pk_true(b.pk)]);
+        return inband_log_term(s, ob, a_stot, pk_true(a_pk) * p.nd + pk_true(b_pk), pk_circ(a_pk), p);
+    const double lg = __ldg(&p.t_logg[(cis ? pk_true(a_pk) : pk_quirk(a_pk)) * p.nd + pk_true(b_pk)]);
     return (lg != -INFINITY) ? (double)ob * lg : log_fact_term(ob);
 }
 // The same value with the common cases inline (tabulated law on a linear contig, finite clamp tables) and
@@ -230,7 +233,7 @@ __device__ __forceinline__ double contact_log_term(const Geo& a, const Geo& b, f
         const double lg = __ldg(&p.t_logg[(cis ? pk_true(a.pk) : pk_quirk(a.pk)) * p.nd + pk_true(b.pk)]);
         if (lg - lg == 0.0) return (double)ob * lg;
     }
-    return contact_log_term_general(a, b, ob, p);
+    return contact_log_term_general(a.mid, a.id_c, a.stot, a.pk, b.mid, b.id_c, b.pk, ob, p);
 }
 __device__ __noinline__ double inband_log_term_general(float s, float ob, float stot, int idx, int circ, const Params& p) {
     return inband_log_term(s, ob, stot, idx, circ, p);
