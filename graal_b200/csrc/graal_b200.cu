@@ -1629,8 +1629,21 @@ struct ProposalGraph {
     }
 };
 
+// A launch sequence whose arguments do not change from call to call (state statistics, relabel): captured
+// once per argument set, replayed with one graph launch.
+struct FixedGraph {
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    long long version = -1, k0 = 0, k1 = 0, k2 = 0; int n_launches = 0;
+    void reset() {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        exec = nullptr; graph = nullptr; version = -1;
+    }
+};
+
 struct graal_ctx {
     Profiler prof;
+    FixedGraph g_stats, g_relabel;
     Lane lanes[GRAAL_MAX_LANES]; int n_lanes = 3; cudaEvent_t ev_fork = nullptr;
     ProposalGraph graphs[16]; long long version = 0; int use_graphs = 1;      // version: bumped whenever captured arguments go stale
     int device = 0;
@@ -1765,6 +1778,27 @@ static int join_lanes(graal_ctx* c) {
     return 0;
 }
 
+template <class F>
+static int run_graphed(graal_ctx* c, FixedGraph& G, long long k0, long long k1, long long k2, F&& enqueue) {
+    if (!c->use_graphs || c->prof.on) return enqueue();
+    if (!(G.exec && G.version == c->version && G.k0 == k0 && G.k1 == k1 && G.k2 == k2)) {
+        G.reset();
+        const int64_t before = c->launches;
+        CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue();
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e_end = cudaStreamEndCapture(c->stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e_end != cudaSuccess) return set_err(-2, "stream capture failed: %s", cudaGetErrorString(e_end));
+        G.graph = graph; G.n_launches = (int)(c->launches - before); c->launches = before;
+        CUDA_OK(cudaGraphInstantiate(&G.exec, graph, 0));
+        G.version = c->version; G.k0 = k0; G.k1 = k1; G.k2 = k2;
+    }
+    CUDA_OK(cudaGraphLaunch(G.exec, c->stream));
+    c->launches += G.n_launches;
+    return 0;
+}
+
 extern "C" {
 
 const char* graal_last_error(void) { return g_err; }
@@ -1843,6 +1877,7 @@ void graal_ctx_destroy(graal_ctx* c) {
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (int i = 0; i < 16; i++) c->graphs[i].reset();
+    c->g_stats.reset(); c->g_relabel.reset();
     c->prof.destroy();
     cudaFree(c->d_ints); cudaFree(c->d_stats); cudaFree(c->d_scalars); cudaFree(c->partials);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -1898,6 +1933,7 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     CUDA_OK(cudaStreamSynchronize(c->stream));
     c->version++;
     for (int i = 0; i < 16; i++) c->graphs[i].reset();
+    c->g_stats.reset(); c->g_relabel.reset();
     free_level_scratch(c);
     c->N = n_frags; c->n_new = n_new_frags; c->W = n_sub_frags; c->E = n_contacts; c->nfpb = nfpb;
     c->lv.sub_id = reinterpret_cast<const int4*>(sub_id); c->lv.sub_len = sub_len_kb; c->lv.sub_accu = sub_accu;
@@ -2095,20 +2131,25 @@ int graal_relabel_contigs(graal_ctx* c, int slot, int32_t* d_max_id) {
     const int n = c->n_new, cap = c->cap, ld = c->ld;
     int* s = slot_ptr(c, slot);
     cudaStream_t st = c->stream;
-    c->prof.begin(GRAAL_K_RELABEL, st);
-    if (c->first_idx_slot != slot) {          // graal_state_stats of the same state leaves the table behind
-        k_fill_int<<<nblk(cap, 256), 256, 0, st>>>(c->first_idx, cap, INT_MAX); CHECK_LAUNCH(c);
-        k_first_index<<<nblk(n, 256), 256, 0, st>>>(s + F_ID_C * ld, n, cap, c->first_idx, c->d_ints + 2); CHECK_LAUNCH(c);
-    }
-    unsigned* k_in = reinterpret_cast<unsigned*>(c->keys); unsigned* v_in = k_in + cap;
-    unsigned* k_out = reinterpret_cast<unsigned*>(c->keys_sorted); unsigned* v_out = k_out + cap;
-    const unsigned sentinel = (1u << c->key_bits) - 1u;
-    k_relabel_keys<<<nblk(cap, 256), 256, 0, st>>>(c->first_idx, s + F_L_CONT * ld, cap, sentinel, k_in, v_in); CHECK_LAUNCH(c);
-    size_t tb = c->cub_tmp_bytes;
-    CUDA_OK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tb, k_in, k_out, v_in, v_out, cap, 0, c->key_bits, st)); c->launches += 2 + (c->key_bits + 7) / 8;
-    k_relabel_map<<<nblk(cap, 256), 256, 0, st>>>(k_out, v_out, cap, sentinel, c->map, c->d_ints + 1); CHECK_LAUNCH(c);
-    k_relabel_apply<<<nblk(n, 256), 256, 0, st>>>(s + F_ID_C * ld, n, c->map, c->d_ints + 1, c->d_ints + 0, d_max_id); CHECK_LAUNCH(c);
-    c->prof.end(GRAAL_K_RELABEL, st);
+    const bool have_first = c->first_idx_slot == slot;      // graal_state_stats of the same state leaves the table behind
+    auto enqueue = [&]() -> int {
+        c->prof.begin(GRAAL_K_RELABEL, st);
+        if (!have_first) {
+            k_fill_int<<<nblk(cap, 256), 256, 0, st>>>(c->first_idx, cap, INT_MAX); CHECK_LAUNCH(c);
+            k_first_index<<<nblk(n, 256), 256, 0, st>>>(s + F_ID_C * ld, n, cap, c->first_idx, c->d_ints + 2); CHECK_LAUNCH(c);
+        }
+        unsigned* k_in = reinterpret_cast<unsigned*>(c->keys); unsigned* v_in = k_in + cap;
+        unsigned* k_out = reinterpret_cast<unsigned*>(c->keys_sorted); unsigned* v_out = k_out + cap;
+        const unsigned sentinel = (1u << c->key_bits) - 1u;
+        k_relabel_keys<<<nblk(cap, 256), 256, 0, st>>>(c->first_idx, s + F_L_CONT * ld, cap, sentinel, k_in, v_in); CHECK_LAUNCH(c);
+        size_t tb = c->cub_tmp_bytes;
+        CUDA_OK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tb, k_in, k_out, v_in, v_out, cap, 0, c->key_bits, st)); c->launches += 2 + (c->key_bits + 7) / 8;
+        k_relabel_map<<<nblk(cap, 256), 256, 0, st>>>(k_out, v_out, cap, sentinel, c->map, c->d_ints + 1); CHECK_LAUNCH(c);
+        k_relabel_apply<<<nblk(n, 256), 256, 0, st>>>(s + F_ID_C * ld, n, c->map, c->d_ints + 1, c->d_ints + 0, d_max_id); CHECK_LAUNCH(c);
+        c->prof.end(GRAAL_K_RELABEL, st);
+        return 0;
+    };
+    { const int rc = run_graphed(c, c->g_relabel, slot, (long long)(uintptr_t)d_max_id, have_first ? 1 : 0, enqueue); if (rc) return rc; }
     if (c->geo_base_slot == slot) c->geo_base_slot = -1;
     c->first_idx_slot = -1;                  // indexed by the OLD contig ids
     return 0;
@@ -2483,13 +2524,17 @@ int graal_state_stats(graal_ctx* c, int slot, double* d_out) {
     const int n = c->n_new, ld = c->ld, cap = c->cap;
     int* s = slot_ptr(c, slot);
     cudaStream_t st = c->stream;
-    k_init_stats<<<1, 1, 0, st>>>(c->d_stats); CHECK_LAUNCH(c);
-    k_stats<<<std::min(nblk(n, 256), c->n_sm * 4), 256, 0, st>>>(s, ld, n, c->d_stats); CHECK_LAUNCH(c);
-    k_fill_int<<<nblk(cap, 256), 256, 0, st>>>(c->first_idx, cap, INT_MAX); CHECK_LAUNCH(c);
-    k_first_index<<<nblk(n, 256), 256, 0, st>>>(s + F_ID_C * ld, n, cap, c->first_idx, c->d_ints + 2); CHECK_LAUNCH(c);
-    k_set_int<<<1, 1, 0, st>>>(c->d_ints + 3, 0); CHECK_LAUNCH(c);
-    k_count_contigs<<<std::min(nblk(cap, 256), c->n_sm * 4), 256, 0, st>>>(c->first_idx, cap, c->d_ints + 3); CHECK_LAUNCH(c);
-    k_stats_final<<<1, 1, 0, st>>>(c->d_stats, c->d_ints + 3, d_out); CHECK_LAUNCH(c);
+    auto enqueue = [&]() -> int {
+        k_init_stats<<<1, 1, 0, st>>>(c->d_stats); CHECK_LAUNCH(c);
+        k_stats<<<std::min(nblk(n, 256), c->n_sm * 4), 256, 0, st>>>(s, ld, n, c->d_stats); CHECK_LAUNCH(c);
+        k_fill_int<<<nblk(cap, 256), 256, 0, st>>>(c->first_idx, cap, INT_MAX); CHECK_LAUNCH(c);
+        k_first_index<<<nblk(n, 256), 256, 0, st>>>(s + F_ID_C * ld, n, cap, c->first_idx, c->d_ints + 2); CHECK_LAUNCH(c);
+        k_set_int<<<1, 1, 0, st>>>(c->d_ints + 3, 0); CHECK_LAUNCH(c);
+        k_count_contigs<<<std::min(nblk(cap, 256), c->n_sm * 4), 256, 0, st>>>(c->first_idx, cap, c->d_ints + 3); CHECK_LAUNCH(c);
+        k_stats_final<<<1, 1, 0, st>>>(c->d_stats, c->d_ints + 3, d_out); CHECK_LAUNCH(c);
+        return 0;
+    };
+    { const int rc = run_graphed(c, c->g_stats, slot, (long long)(uintptr_t)d_out, 0, enqueue); if (rc) return rc; }
     c->first_idx_slot = slot;
     return 0;
 }
