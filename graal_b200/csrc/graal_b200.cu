@@ -1643,7 +1643,7 @@ struct FixedGraph {
 
 struct graal_ctx {
     Profiler prof;
-    FixedGraph g_stats, g_relabel;
+    FixedGraph g_stats, g_relabel, g_full, g_full_cached;
     Lane lanes[GRAAL_MAX_LANES]; int n_lanes = 3; cudaEvent_t ev_fork = nullptr;
     ProposalGraph graphs[16]; long long version = 0; int use_graphs = 1;      // version: bumped whenever captured arguments go stale
     int device = 0;
@@ -1877,7 +1877,7 @@ void graal_ctx_destroy(graal_ctx* c) {
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (int i = 0; i < 16; i++) c->graphs[i].reset();
-    c->g_stats.reset(); c->g_relabel.reset();
+    c->g_stats.reset(); c->g_relabel.reset(); c->g_full.reset(); c->g_full_cached.reset();
     c->prof.destroy();
     cudaFree(c->d_ints); cudaFree(c->d_stats); cudaFree(c->d_scalars); cudaFree(c->partials);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -1933,7 +1933,7 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     CUDA_OK(cudaStreamSynchronize(c->stream));
     c->version++;
     for (int i = 0; i < 16; i++) c->graphs[i].reset();
-    c->g_stats.reset(); c->g_relabel.reset();
+    c->g_stats.reset(); c->g_relabel.reset(); c->g_full.reset(); c->g_full_cached.reset();
     free_level_scratch(c);
     c->N = n_frags; c->n_new = n_new_frags; c->W = n_sub_frags; c->E = n_contacts; c->nfpb = nfpb;
     c->lv.sub_id = reinterpret_cast<const int4*>(sub_id); c->lv.sub_len = sub_len_kb; c->lv.sub_accu = sub_accu;
@@ -2258,63 +2258,70 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
             g1 = (int)std::min<long long>(std::min(ps, c->n_sm * std::max(1, fc_blocks)), (c->E + 1023) / 1024);   // one resident wave
         }
     }
-    // d_out = -(lf_total + G0) [+ log g * sum(ob)]   then accumulate the device sums
-    const double init = -(c->lf_total + g0) + (uniform ? lg_uniform * c->ob_total : 0.0);
-    k_set_double<<<1, 1, 0, st>>>(d_out, init); CHECK_LAUNCH(c);
-    if (g1 > 0) {
-        c->prof.begin(GRAAL_K_FULL_CONTACTS, st);
-        if (use_smem)
-            k_full_contacts_uniform<true><<<g1, FCS_THREADS, fcs_smem, st>>>(c->rowptr, c->contacts, c->E, c->W, c->group_row, c->n_groups, c->geo_base,
-                                                                            c->cid16_base, c->mid32_base, p, lg_uniform, c->partials);
-        else if (uniform && p.mode == 2)
-            k_full_contacts_direct<<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->group_row, c->n_groups, c->geo_base,
-                                                      c->cm_base, p, lg_uniform, c->partials);
-        else if (uniform)
-            k_full_contacts_uniform<false><<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->W, c->group_row, c->n_groups, c->geo_base,
-                                                              c->cid16_base, c->mid32_base, p, lg_uniform, c->partials);
-        else
-            k_full_contacts<<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->W, c->geo_base, p, c->partials);
-        CHECK_LAUNCH(c);
-        c->prof.end(GRAAL_K_FULL_CONTACTS, st);
-        k_reduce_partials<<<1, 256, 0, st>>>(c->partials, g1, 0, 1.0, d_out, 1); CHECK_LAUNCH(c);
-    }
-    const int g2 = std::min(ps, nblk(n, 8));
-    c->prof.begin(GRAAL_K_FULL_BAND, st);
+    if (c->n_quirky > ps) return set_err(-5, "too many quirky bins (%d > %d)", c->n_quirky, ps);
     const bool cached = !p_override && c->band_slot == slot && c->band_age < GRAAL_BAND_RESYNC;
-    if (cached) {
-        const int g3 = std::min(ps, nblk(n, 256));
-        k_band_diag<<<g3, 256, 0, st>>>(s, ld, n, c->lv, c->geo_base, p, c->partials + (size_t)1 * ps); CHECK_LAUNCH(c);
-        k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)1 * ps, g3, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
-        k_reduce_partials<<<1, 32, 0, st>>>(c->d_scalars + 40, 1, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
-        c->band_age++;
-    } else {
-        // position order of the bins, contig by contig
-        CUDA_OK(cudaMemsetAsync(c->cont_len, 0, (size_t)c->cap * sizeof(int), st));
-        k_contig_lengths<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_len); CHECK_LAUNCH(c);
-        size_t tb = c->cub_tmp_bytes;
-        CUDA_OK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, tb, c->cont_len, c->cont_off, c->cap, st)); c->launches += 2;
-        k_order_fill<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_off, c->order); CHECK_LAUNCH(c);
-        k_band<BAND_FULL><<<dim3(g2, 1), 256, 0, st>>>(c->order, nullptr, n, s, ld, c->lv, c->geo_base, nullptr, 0, 0, 0, 0u, p,
-                                                     c->partials, ps); CHECK_LAUNCH(c);
-        double* cross = p_override ? c->d_scalars + 41 : c->d_scalars + 40;
-        k_reduce_partials<<<1, 256, 0, st>>>(c->partials, g2, 0, 1.0, cross, 0); CHECK_LAUNCH(c);
-        k_reduce_partials<<<1, 32, 0, st>>>(cross, 1, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
-        k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)1 * ps, g2, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
-        if (!p_override) { c->band_slot = slot; c->band_age = 0; }
-    }
-    c->prof.end(GRAAL_K_FULL_BAND, st);
-    if (c->n_rep > 0) {     // every pixel touching a duplicated data bin
-        const int gr = (int)std::min<long long>(ps, ((long long)c->n_rep * c->N + 127) / 128);
-        k_repeat_pixels<false><<<dim3(gr, 1), 128, 0, st>>>(s, 0, ld, c->lv, c->collector, reinterpret_cast<const int2*>(c->dispatcher), c->rowptr, c->contacts,
-                                                           c->d_rep_bins, c->n_rep, nullptr, p, c->partials + (size_t)3 * ps, ps); CHECK_LAUNCH(c);
-        k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)3 * ps, gr, 0, 1.0, d_out, 1); CHECK_LAUNCH(c);
-    }
-    if (c->n_quirky > 0) {
-        if (c->n_quirky > ps) return set_err(-5, "too many quirky bins (%d > %d)", c->n_quirky, ps);
-        k_quirk<<<dim3(c->n_quirky, 1), 256, 0, st>>>(c->d_quirky, c->n_quirky, s, ld, n, 0, c->lv, nullptr, nullptr, p,
-                                                      c->partials + (size_t)2 * ps, ps); CHECK_LAUNCH(c);
-        k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)2 * ps, c->n_quirky, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
-    }
+    auto enqueue = [&]() -> int {
+        // d_out = -(lf_total + G0) [+ log g * sum(ob)]   then accumulate the device sums
+        const double init = -(c->lf_total + g0) + (uniform ? lg_uniform * c->ob_total : 0.0);
+        k_set_double<<<1, 1, 0, st>>>(d_out, init); CHECK_LAUNCH(c);
+        if (g1 > 0) {
+            c->prof.begin(GRAAL_K_FULL_CONTACTS, st);
+            if (use_smem)
+                k_full_contacts_uniform<true><<<g1, FCS_THREADS, fcs_smem, st>>>(c->rowptr, c->contacts, c->E, c->W, c->group_row, c->n_groups, c->geo_base,
+                                                                                c->cid16_base, c->mid32_base, p, lg_uniform, c->partials);
+            else if (uniform && p.mode == 2)
+                k_full_contacts_direct<<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->group_row, c->n_groups, c->geo_base,
+                                                          c->cm_base, p, lg_uniform, c->partials);
+            else if (uniform)
+                k_full_contacts_uniform<false><<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->W, c->group_row, c->n_groups, c->geo_base,
+                                                                  c->cid16_base, c->mid32_base, p, lg_uniform, c->partials);
+            else
+                k_full_contacts<<<g1, 256, 0, st>>>(c->rowptr, c->contacts, c->E, c->W, c->geo_base, p, c->partials);
+            CHECK_LAUNCH(c);
+            c->prof.end(GRAAL_K_FULL_CONTACTS, st);
+            k_reduce_partials<<<1, 256, 0, st>>>(c->partials, g1, 0, 1.0, d_out, 1); CHECK_LAUNCH(c);
+        }
+        const int g2 = std::min(ps, nblk(n, 8));
+        c->prof.begin(GRAAL_K_FULL_BAND, st);
+        if (cached) {
+            const int g3 = std::min(ps, nblk(n, 256));
+            k_band_diag<<<g3, 256, 0, st>>>(s, ld, n, c->lv, c->geo_base, p, c->partials + (size_t)1 * ps); CHECK_LAUNCH(c);
+            k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)1 * ps, g3, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
+            k_reduce_partials<<<1, 32, 0, st>>>(c->d_scalars + 40, 1, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
+        } else {
+            // position order of the bins, contig by contig
+            CUDA_OK(cudaMemsetAsync(c->cont_len, 0, (size_t)c->cap * sizeof(int), st));
+            k_contig_lengths<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_len); CHECK_LAUNCH(c);
+            size_t tb = c->cub_tmp_bytes;
+            CUDA_OK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, tb, c->cont_len, c->cont_off, c->cap, st)); c->launches += 2;
+            k_order_fill<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_off, c->order); CHECK_LAUNCH(c);
+            k_band<BAND_FULL><<<dim3(g2, 1), 256, 0, st>>>(c->order, nullptr, n, s, ld, c->lv, c->geo_base, nullptr, 0, 0, 0, 0u, p,
+                                                         c->partials, ps); CHECK_LAUNCH(c);
+            double* cross = p_override ? c->d_scalars + 41 : c->d_scalars + 40;
+            k_reduce_partials<<<1, 256, 0, st>>>(c->partials, g2, 0, 1.0, cross, 0); CHECK_LAUNCH(c);
+            k_reduce_partials<<<1, 32, 0, st>>>(cross, 1, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
+            k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)1 * ps, g2, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
+        }
+        c->prof.end(GRAAL_K_FULL_BAND, st);
+        if (c->n_rep > 0) {     // every pixel touching a duplicated data bin
+            const int gr = (int)std::min<long long>(ps, ((long long)c->n_rep * c->N + 127) / 128);
+            k_repeat_pixels<false><<<dim3(gr, 1), 128, 0, st>>>(s, 0, ld, c->lv, c->collector, reinterpret_cast<const int2*>(c->dispatcher), c->rowptr, c->contacts,
+                                                               c->d_rep_bins, c->n_rep, nullptr, p, c->partials + (size_t)3 * ps, ps); CHECK_LAUNCH(c);
+            k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)3 * ps, gr, 0, 1.0, d_out, 1); CHECK_LAUNCH(c);
+        }
+        if (c->n_quirky > 0) {
+            k_quirk<<<dim3(c->n_quirky, 1), 256, 0, st>>>(c->d_quirky, c->n_quirky, s, ld, n, 0, c->lv, nullptr, nullptr, p,
+                                                          c->partials + (size_t)2 * ps, ps); CHECK_LAUNCH(c);
+            k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)2 * ps, c->n_quirky, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
+        }
+        return 0;
+    };
+    // current parameters: the sequence only depends on (slot, output, cached band total) -> one graph launch
+    if (p_override) rc = enqueue();
+    else rc = run_graphed(c, cached ? c->g_full_cached : c->g_full, slot, (long long)(uintptr_t)d_out, 0, enqueue);
+    if (rc) return rc;
+    if (cached) c->band_age++;
+    else if (!p_override) { c->band_slot = slot; c->band_age = 0; }
     return 0;
 }
 
