@@ -147,3 +147,37 @@ def test_repeat_levels(yeast_pyramid):
         assert abs(ro[0] - rg[0]) <= 1e-7 * abs(ro[0]) and abs(ro[7] - rg[7]) < 1e-12
     assert H.slots_diff(o.cur, g.slot_to_host(CUR)) == []
     g.free_gpu()
+
+
+def test_lanes_and_graphs_match_the_plain_abi(small_pyramid):
+    """graal_score_proposal (lanes, captured graphs, replayed with new bins) against the unfused serial calls
+    graal_build_candidates + graal_delta_loglik on the same state: the 13 deltas are the same doubles, and
+    graal_dist_candidates equals graal_dist_genome of each candidate slot."""
+    import ctypes as C
+    from graal_b200.sampler import CUR, CAND0, N_LANES, OFF_DIST, N_TMP_STRUCT
+    from graal_b200._lib import check
+    inp, g = gpu_sampler(small_pyramid, 2, 5)
+    rng = np.random.RandomState(9)
+    n = int(g.n_new_frags)
+    lib, ctx = g.lib, g.ctx
+    for rnd in range(4):                                    # rounds 1.. replay the graphs captured in round 0
+        g.modify_gl_cuda_buffer()
+        fA = int(rng.randint(n))
+        fBs = [int(x) for x in rng.choice(np.setdiff1d(np.arange(n), [fA]), 3, replace=False)]
+        g.score_neighbours(fA, fBs, with_dist=True)
+        fast = g._fetch().copy()
+        for x, fB in enumerate(fBs):
+            check(lib.graal_build_candidates(ctx, CUR, CAND0, fA, fB, -1, 0x1FFF))
+            check(lib.graal_delta_loglik(ctx, CUR, CAND0, N_TMP_STRUCT, fA, fB, -1, g._ptr(g.d_out, 32)))
+            ref = g._fetch()[32:32 + N_TMP_STRUCT].copy()
+            got = fast[16 + N_TMP_STRUCT * x: 16 + N_TMP_STRUCT * (x + 1)]
+            keep = np.arange(N_TMP_STRUCT) != 8             # candidate 8 is a copy of candidate 0 in the fused path
+            assert np.array_equal(got[keep], ref[keep]), (rnd, x, got, ref)
+            assert got[8] == got[0]
+            for k in (0, 5, 12):
+                check(lib.graal_dist_genome(ctx, CAND0 + k, g._ptr(g.d_init_prev), g._ptr(g.d_init_next),
+                                            g._ptr(g.d_init_orientable), g._ptr(g.d_dist_skip), g._ptr(g.d_out, 60)))
+                assert g._fetch()[60] == fast[OFF_DIST + N_TMP_STRUCT * x + k]
+        # move on: commit something so that the next round sees another state
+        check(lib.graal_commit_scored(ctx, CUR, CAND0, fA, fBs[1], -1, int(rng.randint(13)), 1))
+    g.free_gpu()
