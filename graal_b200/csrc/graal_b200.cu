@@ -295,6 +295,23 @@ __global__ void k_reduce_partials(const double* __restrict__ partials, int n, in
     if (threadIdx.x == 0) out[k] = (accumulate ? out[k] : 0.0) + scale * v;
 }
 
+// End of a proposal's delta, one launch for the 13 candidates: second stage of the three reductions and
+//   band[k] = sum(cand band) - sum(base band);   out[k] = sum(contacts) - band[k];   candidate `copy_to` = candidate 0
+__global__ void k_finish_delta(const double* __restrict__ p_contacts, int n_contacts, const double* __restrict__ p_cand, const double* __restrict__ p_base,
+                               int n_band, int stride, double* __restrict__ out, double* __restrict__ band, int copy_to) {
+    const int k = blockIdx.x;
+    const int src = (copy_to > 0 && k == copy_to) ? 0 : k;         // the copied candidate sums candidate 0's partials itself
+    double vc = 0.0, vn = 0.0, vb = 0.0;
+    for (int j = threadIdx.x; j < n_contacts; j += blockDim.x) vc += p_contacts[(size_t)src * stride + j];
+    for (int j = threadIdx.x; j < n_band; j += blockDim.x) { vn += p_cand[(size_t)src * stride + j]; vb += p_base[(size_t)src * stride + j]; }
+    vc = block_sum(vc); vn = block_sum(vn); vb = block_sum(vb);
+    if (threadIdx.x == 0) {
+        double b = 0.0 + 1.0 * vn; b = b + (-1.0) * vb;
+        double o = 0.0 + 1.0 * vc; o = o + (-1.0) * b;
+        band[k] = b; out[k] = o;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // structure mutations
 // ------------------------------------------------------------------------------------------------
@@ -975,21 +992,25 @@ k_quirk(const int* __restrict__ quirky, int n_quirky, const int* __restrict__ sl
 // delta likelihood of candidate slots against the base slot (sub_compute_likelihood, range 1)
 // ------------------------------------------------------------------------------------------------
 // meta[0]=contig A, [1]=contig B, [2]=len A, [3]=len B (0 if same contig), [4]=m = |U|, [5]=max_id
+// Start of a proposal's delta, one launch: the touched contigs (meta), U in the base slot's position order
+// (fill_sub_index_fA / fB, kernels3.cu:3225-3249), and the per-proposal scratch cleared (chmask, piece lengths,
+// changed ranges).  Every thread derives the contigs itself; thread 0 publishes them for the later kernels.
+//   meta: [0] contig of fA, [1] contig of fB, [2] |A|, [3] |B| (0 if the same contig), [4] |U|, [5] max contig id
 __global__ void k_delta_setup(const int* __restrict__ base, int ld, int fA, int fB, const int* __restrict__ d_max_id,
-                              int max_id_host, int* __restrict__ meta) {
+                              int max_id_host, int* __restrict__ meta, int n, int W, int* __restrict__ sub_index,
+                              unsigned* __restrict__ chmask, int* __restrict__ piece_len, int* __restrict__ rng) {
     const int cA = base[F_ID_C * ld + fA], cB = base[F_ID_C * ld + fB];
     const int lA = base[F_L_CONT * ld + fA], lB = (cB != cA) ? base[F_L_CONT * ld + fB] : 0;
-    meta[0] = cA; meta[1] = cB; meta[2] = lA; meta[3] = lB; meta[4] = lA + lB; meta[5] = (max_id_host >= 0) ? max_id_host : *d_max_id;
-}
-// fill_sub_index_fA / fB (kernels3.cu:3225-3249): U in the base slot's position order
-__global__ void k_fill_sub_index(const int* __restrict__ base, int ld, int n, const int* __restrict__ meta,
-                                 int* __restrict__ sub_index) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { meta[0] = cA; meta[1] = cB; meta[2] = lA; meta[3] = lB; meta[4] = lA + lB; meta[5] = (max_id_host >= 0) ? max_id_host : *d_max_id; }
+    if (i < GRAAL_N_CANDIDATES * 8) piece_len[i] = 0;
+    if (i < 2 + 2 * GRAAL_N_CANDIDATES) rng[i] = (i & 1) ? -1 : INT_MAX;
+    for (int j = i; j < W; j += gridDim.x * blockDim.x) chmask[j] = 0u;
     if (i >= n) return;
     const int c = base[F_ID_C * ld + i];
     const int pos = base[F_POS * ld + i];
-    if (c == meta[0]) { if (pos >= 0 && pos < n) sub_index[pos] = i; }
-    else if (c == meta[1]) { const int k = meta[2] + pos; if (k >= 0 && k < n) sub_index[k] = i; }
+    if (c == cA) { if (pos >= 0 && pos < n) sub_index[pos] = i; }
+    else if (c == cB) { const int k = lA + pos; if (k >= 0 && k < n) sub_index[k] = i; }
 }
 // candidate geometry (members of U only) + contig lengths of the candidate's pieces of U
 __device__ __forceinline__ int piece_slot(int id_c, const int* meta) {
@@ -1037,12 +1058,37 @@ __device__ __forceinline__ int4 band_record_b(const Geo* __restrict__ g, int sub
     }
     return make_int4(mid[0], mid[1], mid[2], (int)info);
 }
+// the same records for the base slot in ITS order (sub_index); A.z = OR of the chmask words of the bin, and
+//   C: x, y, z = chmask words of the sub-frags (bit k: differs from the base slot in candidate k)
+__device__ __forceinline__ void base_order(const int* __restrict__ base, int ld, const int* __restrict__ sub_index, const int* __restrict__ meta,
+                             LevelView lv, const unsigned* __restrict__ chmask, const Geo* __restrict__ geo_base,
+                             int4* __restrict__ rec_a, int4* __restrict__ rec_b, int4* __restrict__ rec_c, int* __restrict__ rng) {
+    const int m = meta[4];
+    int lo = INT_MAX, hi = -1;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < m; u += gridDim.x * blockDim.x) {
+        const int bin = sub_index[u];
+        const int4 sid = lv.sub_id[base[F_ID_D * ld + bin]];
+        const int n_sub = eligible(lv, bin) ? sid.w : 0;
+        unsigned ms[3] = {0u, 0u, 0u};
+        for (int a = 0; a < n_sub; a++) ms[a] = chmask[sid.x + a];
+        const unsigned chg = ms[0] | ms[1] | ms[2];
+        const float start_kb = __int2float_rn(base[F_START_BP * ld + bin]) / 1000.0f;
+        rec_a[u] = make_int4(sid.x | (n_sub << 28), __float_as_int(start_kb), (int)chg, base[F_ID_C * ld + bin]);
+        rec_b[u] = band_record_b(geo_base, sid.x, n_sub);
+        rec_c[u] = make_int4((int)ms[0], (int)ms[1], (int)ms[2], 0);
+        if (chg) { lo = min(lo, u); hi = max(hi, u); }
+    }
+    if (hi >= 0) { atomicMin(&rng[0], lo); atomicMax(&rng[1], hi); }
+}
 __global__ void k_cand_order(const int* __restrict__ cand0, size_t slot_stride, int ld,
                              const int* __restrict__ sub_index, const int* __restrict__ meta,
                              const int* __restrict__ piece_len, int* __restrict__ order0, int order_stride, unsigned skip_cands,
                              LevelView lv, const unsigned* __restrict__ chmask, const Geo* __restrict__ geo0, size_t geo_stride,
-                             int4* __restrict__ rec_a0, int4* __restrict__ rec_b0, int* __restrict__ rng) {
+                             int4* __restrict__ rec_a0, int4* __restrict__ rec_b0, int* __restrict__ rng,
+                             int n_cand, const int* __restrict__ base, const Geo* __restrict__ geo_base,
+                             int4* __restrict__ base_a, int4* __restrict__ base_b, int4* __restrict__ base_c, int* __restrict__ base_rng) {
     const int k = blockIdx.y;
+    if (k == n_cand) { base_order(base, ld, sub_index, meta, lv, chmask, geo_base, base_a, base_b, base_c, base_rng); return; }   // last grid row: the base slot
     if ((skip_cands >> k) & 1u) return;
     const int m = meta[4];
     const int* sl = cand0 + (size_t)k * slot_stride;
@@ -1068,29 +1114,6 @@ __global__ void k_cand_order(const int* __restrict__ cand0, size_t slot_stride, 
     }
     if (hi >= 0) { atomicMin(&rng[2 * k], lo); atomicMax(&rng[2 * k + 1], hi); }
 }
-// the same records for the base slot in ITS order (sub_index); A.z = OR of the chmask words of the bin, and
-//   C: x, y, z = chmask words of the sub-frags (bit k: differs from the base slot in candidate k)
-__global__ void k_base_order(const int* __restrict__ base, int ld, const int* __restrict__ sub_index, const int* __restrict__ meta,
-                             LevelView lv, const unsigned* __restrict__ chmask, const Geo* __restrict__ geo_base,
-                             int4* __restrict__ rec_a, int4* __restrict__ rec_b, int4* __restrict__ rec_c, int* __restrict__ rng) {
-    const int m = meta[4];
-    int lo = INT_MAX, hi = -1;
-    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < m; u += gridDim.x * blockDim.x) {
-        const int bin = sub_index[u];
-        const int4 sid = lv.sub_id[base[F_ID_D * ld + bin]];
-        const int n_sub = eligible(lv, bin) ? sid.w : 0;
-        unsigned ms[3] = {0u, 0u, 0u};
-        for (int a = 0; a < n_sub; a++) ms[a] = chmask[sid.x + a];
-        const unsigned chg = ms[0] | ms[1] | ms[2];
-        const float start_kb = __int2float_rn(base[F_START_BP * ld + bin]) / 1000.0f;
-        rec_a[u] = make_int4(sid.x | (n_sub << 28), __float_as_int(start_kb), (int)chg, base[F_ID_C * ld + bin]);
-        rec_b[u] = band_record_b(geo_base, sid.x, n_sub);
-        rec_c[u] = make_int4((int)ms[0], (int)ms[1], (int)ms[2], 0);
-        if (chg) { lo = min(lo, u); hi = max(hi, u); }
-    }
-    if (hi >= 0) { atomicMin(&rng[0], lo); atomicMax(&rng[1], hi); }
-}
-__global__ void k_init_ranges(int* rng, int n) { const int i = threadIdx.x; if (i < n) rng[i] = (i & 1) ? -1 : INT_MAX; }
 
 // ex - g of an in-band cis pair from its distance, accu table index and (circular contigs) contig length
 __device__ __noinline__ double band_excess_general(float s, int idx, int circ, float stot, const Params& p) {
@@ -1609,7 +1632,7 @@ struct Lane {
     int* cand_order = nullptr;               // [13][n]
     int4* cand_ordrec = nullptr; int4* base_ordrec = nullptr;   // [13][n] / [n] position-ordered bin records A of U
     int4* cand_ordb = nullptr; int4* base_ordb = nullptr; int4* base_ordc = nullptr;   // records B (mid-points) and C (masks)
-    double* partials = nullptr;              // [16][partial_stride]
+    double* partials = nullptr;              // [48][partial_stride]: contacts rows 0..12, candidate band 16..28, base band 32..44
     unsigned char* rep_in_u = nullptr;       // [N]
 };
 
@@ -1835,7 +1858,7 @@ int graal_ctx_create(int device, graal_ctx** out) {
         CUDA_OK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
         CUDA_OK(cudaMalloc(&L.ints, 256 * sizeof(int)));
         CUDA_OK(cudaMemset(L.ints, 0, 256 * sizeof(int)));
-        CUDA_OK(cudaMalloc(&L.partials, (size_t)16 * c->partial_stride * sizeof(double)));
+        CUDA_OK(cudaMalloc(&L.partials, (size_t)48 * c->partial_stride * sizeof(double)));
     }
     *out = c;
     return 0;
@@ -2327,7 +2350,7 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
 
 // the base slot's geometry must be current (ensure_base_geometry on the context stream) before this runs on `st`
 static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_slot, int first_cand_slot, int n_cand, int id_fA, int id_fB, int max_id,
-                            unsigned skip, double* d_out, double* d_band) {
+                            unsigned skip, double* d_out, double* d_band, int copy_to = 0) {
     const int n = c->n_new, ld = c->ld;
     const Params p = c->p;
     int* base = slot_ptr(c, base_slot);
@@ -2335,43 +2358,38 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
     int* meta = L.ints + 8;
     int* piece_len = L.ints + 16;
     const int ps = c->partial_stride;
-    k_delta_setup<<<1, 1, 0, st>>>(base, ld, id_fA, id_fB, c->d_ints + 0, max_id, meta); CHECK_LAUNCH(c);
-    k_fill_sub_index<<<nblk(n, 256), 256, 0, st>>>(base, ld, n, meta, L.sub_index); CHECK_LAUNCH(c);
-    CUDA_OK(cudaMemsetAsync(piece_len, 0, GRAAL_N_CANDIDATES * 8 * sizeof(int), st));
-    CUDA_OK(cudaMemsetAsync(L.chmask, 0, (size_t)c->W * sizeof(unsigned), st));
+    int* rng = L.ints + 160;                       // [0,1] base range, [2 + 2k, 3 + 2k] candidate k
+    k_delta_setup<<<nblk(n, 256), 256, 0, st>>>(base, ld, id_fA, id_fB, c->d_ints + 0, max_id, meta, n, c->W, L.sub_index, L.chmask, piece_len, rng); CHECK_LAUNCH(c);
     const int gu = std::min(c->n_sm * 2, nblk(n, 256));
     k_cand_geometry<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->lv, L.sub_index, meta, L.geo_cand, (size_t)c->W, piece_len,
                                                      c->geo_base, L.chmask, skip); CHECK_LAUNCH(c);
-    int* rng = L.ints + 160;                       // [0,1] base range, [2 + 2k, 3 + 2k] candidate k
-    k_init_ranges<<<1, 32, 0, st>>>(rng, 2 + 2 * GRAAL_N_CANDIDATES); CHECK_LAUNCH(c);
-    k_cand_order<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, L.sub_index, meta, piece_len, L.cand_order, n, skip,
-                                                  c->lv, L.chmask, L.geo_cand, (size_t)c->W, L.cand_ordrec, L.cand_ordb, rng + 2); CHECK_LAUNCH(c);
-    k_base_order<<<gu, 256, 0, st>>>(base, ld, L.sub_index, meta, c->lv, L.chmask, c->geo_base, L.base_ordrec, L.base_ordb, L.base_ordc, rng); CHECK_LAUNCH(c);
+    k_cand_order<<<dim3(gu, n_cand + 1), 256, 0, st>>>(cand0, slot_stride(c), ld, L.sub_index, meta, piece_len, L.cand_order, n, skip,
+                                                      c->lv, L.chmask, L.geo_cand, (size_t)c->W, L.cand_ordrec, L.cand_ordb, rng + 2,
+                                                      n_cand, base, c->geo_base, L.base_ordrec, L.base_ordb, L.base_ordc, rng); CHECK_LAUNCH(c);
     // grid-stride kernels over the (device-side) size of U: a few CTAs per SM, not one warp per bin of the level
     const int gw = std::min(ps, std::max(1, std::min(nblk(n, 1), c->n_sm * 8)));
     const int gb = std::min(ps, std::max(1, std::min(nblk(n, 4), c->n_sm * 4)));
+    double* p_contacts = L.partials, *p_cand = L.partials + (size_t)16 * ps, *p_base = L.partials + (size_t)32 * ps;
     // contacts: sum over changed contacts of ob * (ln ex_k - ln ex_0): new terms per candidate, old terms once
     c->prof.begin(GRAAL_K_DELTA_CONTACTS, st);
     k_delta_contacts_rows<<<dim3(gw, 1), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, L.sub_index, meta, c->geo_base, L.geo_cand, (size_t)c->W,
-                                                      L.chmask, p, L.partials, ps); CHECK_LAUNCH(c);
-    k_reduce_partials<<<n_cand, 256, 0, st>>>(L.partials, gw, ps, 1.0, d_out, 0); CHECK_LAUNCH(c);
+                                                      L.chmask, p, p_contacts, ps); CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_DELTA_CONTACTS, st);
     // band mass: d_band[k] = B_U(S_k) - B_U(S_0) over changed pairs; enters the delta with a minus sign
     c->prof.begin(GRAAL_K_DELTA_BAND, st);
     if (p.nd == 1) k_band_delta<false, 2, true><<<dim3(gb, n_cand), 256, 0, st>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
-                                                                              L.partials, ps);
+                                                                              p_cand, ps);
     else k_band_delta<false, 2, false><<<dim3(gb, n_cand), 256, 0, st>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
-                                                                     L.partials, ps);
+                                                                     p_cand, ps);
     CHECK_LAUNCH(c);
-    k_reduce_partials<<<n_cand, 256, 0, st>>>(L.partials, gb, ps, 1.0, d_band, 0); CHECK_LAUNCH(c);
     if (p.nd == 1) k_band_delta<true, 8, true><<<dim3(gb, 1), 256, 0, st>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
-                                                                        L.partials, ps);
+                                                                        p_base, ps);
     else k_band_delta<true, 8, false><<<dim3(gb, 1), 256, 0, st>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
-                                                               L.partials, ps);
+                                                               p_base, ps);
     CHECK_LAUNCH(c);
-    k_reduce_partials<<<n_cand, 256, 0, st>>>(L.partials, gb, ps, -1.0, d_band, 1); CHECK_LAUNCH(c);
-    k_reduce_partials<<<n_cand, 32, 0, st>>>(d_band, 1, 1, -1.0, d_out, 1); CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_DELTA_BAND, st);
+    // second stage of the three reductions, out = contacts - (cand band - base band); candidate 8 (skipped) copies candidate 0
+    k_finish_delta<<<n_cand, 256, 0, st>>>(p_contacts, gw, p_cand, p_base, gb, ps, d_out, d_band, copy_to); CHECK_LAUNCH(c);
     if (c->n_rep > 0) {     // ranges 2-4: pixels of the duplicated bins that have a copy in U, new minus old
         CUDA_OK(cudaMemsetAsync(L.rep_in_u, 0, (size_t)c->N, st));
         k_mark_rep_in_u<<<gu, 256, 0, st>>>(base, ld, L.sub_index, meta, c->lv, L.rep_in_u); CHECK_LAUNCH(c);
@@ -2454,9 +2472,7 @@ int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int i
                                                         id_fA, id_fB, c->d_ints + 0, max_id, 0x1FFFu);
         CHECK_LAUNCH(c);
         c->prof.end(GRAAL_K_BUILD, st);
-        int r = delta_loglik_impl(c, L, st, base_slot, first_cand_slot, GRAAL_N_CANDIDATES, id_fA, id_fB, max_id, skip, d_out, d_band); if (r) return r;
-        if (skip) { k_copy_double2<<<1, 1, 0, st>>>(d_out, d_band, 8, 0); CHECK_LAUNCH(c); }
-        return 0;
+        return delta_loglik_impl(c, L, st, base_slot, first_cand_slot, GRAAL_N_CANDIDATES, id_fA, id_fB, max_id, skip, d_out, d_band, skip ? 8 : 0);
     };
     ProposalGraph& G = c->graphs[proposal_index];
     if (!c->use_graphs || c->prof.on) { rc = enqueue(); if (rc) return rc; }
@@ -2495,8 +2511,8 @@ int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int i
             void* args_build[] = {&a_src, &a_dst, &a_stride, &a_ld, &a_n, &a_fA, &a_fB, &a_dmax, &a_max, &a_mask};
             cudaKernelNodeParams kp = G.kp_build; kp.kernelParams = args_build; kp.extra = nullptr;
             CUDA_OK(cudaGraphExecKernelNodeSetParams(G.exec, G.n_build, &kp));
-            int* a_meta = L.ints + 8;
-            void* args_setup[] = {&a_src, &a_ld, &a_fA, &a_fB, &a_dmax, &a_max, &a_meta};
+            int* a_meta = L.ints + 8; int a_W = c->W; int* a_sub = L.sub_index; unsigned* a_chm = L.chmask; int* a_pl = L.ints + 16; int* a_rng = L.ints + 160;
+            void* args_setup[] = {&a_src, &a_ld, &a_fA, &a_fB, &a_dmax, &a_max, &a_meta, &a_n, &a_W, &a_sub, &a_chm, &a_pl, &a_rng};
             kp = G.kp_setup; kp.kernelParams = args_setup; kp.extra = nullptr;
             CUDA_OK(cudaGraphExecKernelNodeSetParams(G.exec, G.n_setup, &kp));
         }
