@@ -823,53 +823,27 @@ __global__ void k_order_fill(const int* __restrict__ slot, int ld, int n, int ca
     if (k >= 0 && k < n) order[k] = i;
 }
 
-// B(S): sum over cis sub-frag pairs within d_max of  ex - g(true product).
-// One warp per bin x (in position order); lanes take the following bins y of the same contig.
-//   BAND_FULL: all pairs of the slot; cross-bin pairs -> partials[0][.], same-bin pairs a < b (the
-//              diagonal pixels, Q4) -> partials[1][.]
-//   BAND_CAND: candidate k = blockIdx.y in ITS position order: NEW values of the pairs of distinct bins
-//              with a record that differs from the base slot (bit k of chmask) -> partials[k][.]
-//   BAND_BASE: the base slot in its own order, ONCE for all candidates: the OLD value of every pair that
-//              changed in at least one candidate is evaluated once and added to the accumulator of
-//              each candidate whose chmask bit is set -> partials[k][.], k < 13
-enum { BAND_FULL = 0, BAND_CAND = 1, BAND_BASE = 2 };
-template <int MODE>
+// B(S) of a whole slot: sum over cis sub-frag pairs within d_max of  ex - g(true product).
+// One warp per bin x (in position order); lanes take the following bins y of the same contig.  Cross-bin pairs
+// -> partials[0][.], same-bin pairs a < b (the diagonal pixels, Q4) -> partials[1][.].  Runs when the cached
+// band total is (re)synchronised; the step path updates the total from the committed candidate's band delta.
 __global__ void __launch_bounds__(256)
-k_band(const int* __restrict__ order, const int* __restrict__ d_count, int count_host,
-       const int* __restrict__ slot, int ld, LevelView lv, const Geo* __restrict__ geo,
-       const unsigned* __restrict__ chmask, size_t cand_geo_stride, size_t cand_slot_stride, int order_stride,
-       unsigned skip_cands, const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
-    const int k = blockIdx.y;
-    if (MODE == BAND_CAND && ((skip_cands >> k) & 1u)) return;
-    const int count = (count_host >= 0) ? count_host : *d_count;
-    const Geo* gE = geo;
-    const int* sl = slot;
-    const int* ord = order;
-    if (MODE == BAND_CAND) { gE = geo + (size_t)k * cand_geo_stride; sl = slot + (size_t)k * cand_slot_stride; ord = order + (size_t)k * order_stride; }
+k_band(const int* __restrict__ order, int count, const int* __restrict__ slot, int ld, LevelView lv, const Geo* __restrict__ geo,
+       const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     double acc = 0.0, acc_diag = 0.0;
-    double accs[GRAAL_N_CANDIDATES];
-    if (MODE == BAND_BASE) {
-        #pragma unroll
-        for (int c = 0; c < GRAAL_N_CANDIDATES; c++) accs[c] = 0.0;
-    }
     for (int ix = warp; ix < count; ix += n_warps) {
-        const int x = ord[ix];
+        const int x = order[ix];
         if (!eligible(lv, x)) continue;
-        const int4 sx = lv.sub_id[sl[F_ID_D * ld + x]];
-        Geo gx[3]; unsigned mx[3] = {0u, 0u, 0u};
+        const int4 sx = lv.sub_id[slot[F_ID_D * ld + x]];
+        Geo gx[3];
         float xmax = -1e30f;
         #pragma unroll
-        for (int a = 0; a < 3; a++) if (a < sx.w) {
-            const int sub = sx.x + a;
-            gx[a] = ld_geo(&gE[sub]);
-            if (MODE != BAND_FULL) mx[a] = __ldg(&chmask[sub]);
-            xmax = fmaxf(xmax, gx[a].mid);
-        }
+        for (int a = 0; a < 3; a++) if (a < sx.w) { gx[a] = ld_geo(&geo[sx.x + a]); xmax = fmaxf(xmax, gx[a].mid); }
         const int cx = gx[0].id_c;
-        if (MODE == BAND_FULL && lane == 0) {        // same-bin pairs a < b (diagonal pixel, Q4)
+        if (lane == 0) {                             // same-bin pairs a < b (diagonal pixel, Q4)
             #pragma unroll
             for (int a = 0; a < 3; a++) for (int b = a + 1; b < 3; b++) if (b < sx.w) {
                 const float s = fabsf(gx[b].mid - gx[a].mid);
@@ -880,33 +854,20 @@ k_band(const int* __restrict__ order, const int* __restrict__ d_count, int count
             const int iy = base + lane;
             bool live = iy < count;
             if (live) {
-                const int y = ord[iy];
-                const float ystart = __int2float_rn(sl[F_START_BP * ld + y]) / 1000.0f;
-                const int4 sy = lv.sub_id[sl[F_ID_D * ld + y]];
-                const Geo gy0 = ld_geo(&gE[sy.x]);
+                const int y = order[iy];
+                const float ystart = __int2float_rn(slot[F_START_BP * ld + y]) / 1000.0f;
+                const int4 sy = lv.sub_id[slot[F_ID_D * ld + y]];
+                const Geo gy0 = ld_geo(&geo[sy.x]);
                 // beyond the band (or next contig): every remaining pair evaluates to the clamp value
                 if (gy0.id_c != cx || (double)ystart - (double)xmax > (double)p.d_max * 1.00001 + 0.05) live = false;
                 else if (eligible(lv, y)) {
                     #pragma unroll
                     for (int b = 0; b < 3; b++) if (b < sy.w) {
-                        const int sub = sy.x + b;
-                        unsigned my = 0u;
-                        if (MODE != BAND_FULL) my = __ldg(&chmask[sub]);
-                        if (MODE == BAND_CAND && !(((mx[0] | mx[1] | mx[2] | my) >> k) & 1u)) continue;
-                        if (MODE == BAND_BASE && !(mx[0] | mx[1] | mx[2] | my)) continue;
-                        const Geo gy = (b == 0) ? gy0 : ld_geo(&gE[sub]);
+                        const Geo gy = (b == 0) ? gy0 : ld_geo(&geo[sy.x + b]);
                         #pragma unroll
                         for (int a = 0; a < 3; a++) if (a < sx.w) {
-                            const unsigned m = mx[a] | my;
-                            if (MODE == BAND_CAND && !((m >> k) & 1u)) continue;
-                            if (MODE == BAND_BASE && !m) continue;
                             const float s = fabsf(gy.mid - gx[a].mid);
-                            if (!(s > 0.0f && s < p.d_max)) continue;
-                            const double v = band_excess(gx[a], gy, s, p);
-                            if (MODE == BAND_BASE) {
-                                #pragma unroll
-                                for (int c = 0; c < GRAAL_N_CANDIDATES; c++) if ((m >> c) & 1u) accs[c] += v;
-                            } else acc += v;
+                            if (s > 0.0f && s < p.d_max) acc += band_excess(gx[a], gy, s, p);
                         }
                     }
                 }
@@ -914,20 +875,10 @@ k_band(const int* __restrict__ order, const int* __restrict__ d_count, int count
             if (!__any_sync(0xffffffffu, live)) break;
         }
     }
-    if (MODE == BAND_BASE) {
-        #pragma unroll
-        for (int c = 0; c < GRAAL_N_CANDIDATES; c++) {
-            const double v = block_sum(accs[c]);
-            if (threadIdx.x == 0) partials[(size_t)c * partial_stride + blockIdx.x] = v;
-        }
-    } else {
-        acc = block_sum(acc);
-        if (threadIdx.x == 0) partials[(size_t)k * partial_stride + blockIdx.x] = acc;
-        if (MODE == BAND_FULL) {
-            acc_diag = block_sum(acc_diag);
-            if (threadIdx.x == 0) partials[(size_t)1 * partial_stride + blockIdx.x] = acc_diag;
-        }
-    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+    acc_diag = block_sum(acc_diag);
+    if (threadIdx.x == 0) partials[(size_t)1 * partial_stride + blockIdx.x] = acc_diag;
 }
 
 // same-bin pairs only (the diagonal pixels): thread per bin
@@ -1082,7 +1033,7 @@ __device__ __forceinline__ void base_order(const int* __restrict__ base, int ld,
 }
 __global__ void k_cand_order(const int* __restrict__ cand0, size_t slot_stride, int ld,
                              const int* __restrict__ sub_index, const int* __restrict__ meta,
-                             const int* __restrict__ piece_len, int* __restrict__ order0, int order_stride, unsigned skip_cands,
+                             const int* __restrict__ piece_len, int order_stride, unsigned skip_cands,
                              LevelView lv, const unsigned* __restrict__ chmask, const Geo* __restrict__ geo0, size_t geo_stride,
                              int4* __restrict__ rec_a0, int4* __restrict__ rec_b0, int* __restrict__ rng,
                              int n_cand, const int* __restrict__ base, const Geo* __restrict__ geo_base,
@@ -1102,7 +1053,6 @@ __global__ void k_cand_order(const int* __restrict__ cand0, size_t slot_stride, 
         if (ps < 0) continue;
         const int idx = off[ps] + sl[F_POS * ld + bin];
         if (idx < 0 || idx >= m) continue;
-        order0[(size_t)k * order_stride + idx] = bin;
         const int4 sid = lv.sub_id[sl[F_ID_D * ld + bin]];
         const int n_sub = eligible(lv, bin) ? sid.w : 0;
         unsigned chg = 0u;
@@ -1332,8 +1282,6 @@ k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restri
 }
 
 // out[dst] = out[src]   /   *total += sel[idx]   (tiny helpers of the incremental bookkeeping)
-__global__ void k_copy_double2(double* p, double* q, int dst, int src) { p[dst] = p[src]; q[dst] = q[src]; }
-__global__ void k_copy_double(double* p, int dst, int src) { p[dst] = p[src]; }
 __global__ void k_add_selected(double* total, const double* v, int idx) { *total += v[idx]; }
 
 // ------------------------------------------------------------------------------------------------
@@ -1629,7 +1577,6 @@ struct Lane {
     int* sub_index = nullptr;                // [n]
     unsigned* chmask = nullptr;              // [W] bit k: record differs from the base slot in candidate k
     Geo* geo_cand = nullptr;                 // [13][W]
-    int* cand_order = nullptr;               // [13][n]
     int4* cand_ordrec = nullptr; int4* base_ordrec = nullptr;   // [13][n] / [n] position-ordered bin records A of U
     int4* cand_ordb = nullptr; int4* base_ordb = nullptr; int4* base_ordc = nullptr;   // records B (mid-points) and C (masks)
     double* partials = nullptr;              // [48][partial_stride]: contacts rows 0..12, candidate band 16..28, base band 32..44
@@ -1868,8 +1815,8 @@ static void free_level_scratch(graal_ctx* c) {
     cudaFree(c->cid16_base); cudaFree(c->mid32_base); cudaFree(c->cm_base); c->cm_base = nullptr; cudaFree(c->group_row); cudaFree(c->band_hist); c->band_hist = nullptr; c->cid16_base = nullptr; c->mid32_base = nullptr; c->group_row = nullptr;
     for (int l = 0; l < GRAAL_MAX_LANES; l++) {
         Lane& L = c->lanes[l];
-        cudaFree(L.sub_index); cudaFree(L.chmask); cudaFree(L.geo_cand); cudaFree(L.cand_order); cudaFree(L.cand_ordrec); cudaFree(L.base_ordrec); cudaFree(L.cand_ordb); cudaFree(L.base_ordb); cudaFree(L.base_ordc); cudaFree(L.rep_in_u);
-        L.sub_index = nullptr; L.chmask = nullptr; L.geo_cand = nullptr; L.cand_order = nullptr; L.cand_ordrec = L.base_ordrec = L.cand_ordb = L.base_ordb = L.base_ordc = nullptr; L.rep_in_u = nullptr;
+        cudaFree(L.sub_index); cudaFree(L.chmask); cudaFree(L.geo_cand); cudaFree(L.cand_ordrec); cudaFree(L.base_ordrec); cudaFree(L.cand_ordb); cudaFree(L.base_ordb); cudaFree(L.base_ordc); cudaFree(L.rep_in_u);
+        L.sub_index = nullptr; L.chmask = nullptr; L.geo_cand = nullptr; L.cand_ordrec = L.base_ordrec = L.cand_ordb = L.base_ordb = L.base_ordc = nullptr; L.rep_in_u = nullptr;
     }
     cudaFree(c->geo_base); cudaFree(c->order);
     cudaFree(c->cont_len); cudaFree(c->cont_off); cudaFree(c->first_idx); cudaFree(c->map); cudaFree(c->keys);
@@ -2068,10 +2015,8 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
         CUDA_OK(cudaMemset(L.base_ordc, 0, (size_t)n * sizeof(int4)));
         CUDA_OK(cudaMalloc(&L.geo_cand, (size_t)GRAAL_N_CANDIDATES * c->W * sizeof(Geo)));
         CUDA_OK(cudaMemset(L.geo_cand, 0, (size_t)GRAAL_N_CANDIDATES * c->W * sizeof(Geo)));
-        CUDA_OK(cudaMalloc(&L.cand_order, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int)));
         CUDA_OK(cudaMalloc(&L.sub_index, (size_t)n * sizeof(int)));
         CUDA_OK(cudaMemset(L.sub_index, 0, (size_t)n * sizeof(int)));
-        CUDA_OK(cudaMemset(L.cand_order, 0, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int)));
         L.pending = false; L.cand_first = -1;
     }
     CUDA_OK(cudaMalloc(&c->band_hist, 16 * GRAAL_N_CANDIDATES * sizeof(double)));
@@ -2318,8 +2263,7 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
             size_t tb = c->cub_tmp_bytes;
             CUDA_OK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, tb, c->cont_len, c->cont_off, c->cap, st)); c->launches += 2;
             k_order_fill<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_off, c->order); CHECK_LAUNCH(c);
-            k_band<BAND_FULL><<<dim3(g2, 1), 256, 0, st>>>(c->order, nullptr, n, s, ld, c->lv, c->geo_base, nullptr, 0, 0, 0, 0u, p,
-                                                         c->partials, ps); CHECK_LAUNCH(c);
+            k_band<<<g2, 256, 0, st>>>(c->order, n, s, ld, c->lv, c->geo_base, p, c->partials, ps); CHECK_LAUNCH(c);
             double* cross = p_override ? c->d_scalars + 41 : c->d_scalars + 40;
             k_reduce_partials<<<1, 256, 0, st>>>(c->partials, g2, 0, 1.0, cross, 0); CHECK_LAUNCH(c);
             k_reduce_partials<<<1, 32, 0, st>>>(cross, 1, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
@@ -2363,7 +2307,7 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
     const int gu = std::min(c->n_sm * 2, nblk(n, 256));
     k_cand_geometry<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->lv, L.sub_index, meta, L.geo_cand, (size_t)c->W, piece_len,
                                                      c->geo_base, L.chmask, skip); CHECK_LAUNCH(c);
-    k_cand_order<<<dim3(gu, n_cand + 1), 256, 0, st>>>(cand0, slot_stride(c), ld, L.sub_index, meta, piece_len, L.cand_order, n, skip,
+    k_cand_order<<<dim3(gu, n_cand + 1), 256, 0, st>>>(cand0, slot_stride(c), ld, L.sub_index, meta, piece_len, n, skip,
                                                       c->lv, L.chmask, L.geo_cand, (size_t)c->W, L.cand_ordrec, L.cand_ordb, rng + 2,
                                                       n_cand, base, c->geo_base, L.base_ordrec, L.base_ordb, L.base_ordc, rng); CHECK_LAUNCH(c);
     // grid-stride kernels over the (device-side) size of U: a few CTAs per SM, not one warp per bin of the level
