@@ -1220,7 +1220,7 @@ k_band_delta(const int4* __restrict__ rec_a0, const int4* __restrict__ rec_b0, c
 // the previous one).  For every stored contact whose partner is in U, in another bin, with a changed
 // record on either side (chmask), the OLD term is evaluated once and the NEW term once per flagged
 // candidate:  accs[k] += ob * (ln ex_k - ln ex_0).
-#define DC_UNROLL 4
+#define DC_UNROLL 2
 __global__ void __launch_bounds__(256)
 k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, LevelView lv,
                       const int* __restrict__ sub_index, const int* __restrict__ meta,
@@ -1263,12 +1263,19 @@ k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restri
                 const unsigned mm = mra | mc[j];
                 if (!mm) continue;                                           // bitwise unchanged in every candidate
                 const float ob = __int_as_float(ce[j].y);
+                // {mid-point, contig id} of the partner in every flagged candidate (the rest of its record -- accu
+                // indices, flags -- does not depend on the candidate): all gathers in flight before the first use
+                int2 pr[GRAAL_N_CANDIDATES];
+                #pragma unroll
+                for (int k = 0; k < GRAAL_N_CANDIDATES; k++)
+                    pr[k] = ((mc[j] >> k) & 1u) ? __ldg(reinterpret_cast<const int2*>(&geo_cand0[(size_t)k * geo_stride + ce[j].x]))
+                                                : make_int2(__float_as_int(g0c.mid), g0c.id_c);
                 const double told = contact_log_term(r0, g0c, ob, p);
                 #pragma unroll
                 for (int k = 0; k < GRAAL_N_CANDIDATES; k++) {
                     if (!((mm >> k) & 1u)) continue;
                     const Geo rk = ((mra >> k) & 1u) ? ld_geo(&geo_cand0[(size_t)k * geo_stride + rowsub]) : r0;
-                    const Geo gc = ((mc[j] >> k) & 1u) ? ld_geo(&geo_cand0[(size_t)k * geo_stride + ce[j].x]) : g0c;
+                    Geo gc = g0c; gc.mid = __int_as_float(pr[k].x); gc.id_c = pr[k].y;
                     accs[k] += contact_log_term(rk, gc, ob, p) - told;
                 }
             }
