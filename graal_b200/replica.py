@@ -99,6 +99,15 @@ class ReplicaExchange:
         self.round_id += 1
         return log
 
+    def warm_up(self):
+        """One all_gather of the exchange's shape that changes nothing: pays the lazy communicator / channel
+        set-up of the backend outside any timed or latency-critical region."""
+        if self.distributed:
+            t = self.torch.zeros((self.n_local, 2), dtype=self.torch.float64, device=self.device)
+            out = [self.torch.empty_like(t) for _ in range(self.world)]
+            self.dist.all_gather(out, t)
+            self.torch.stack(out).cpu()
+
     def maybe_exchange(self, step, local_logliks):
         if self.exchange_every > 0 and step > 0 and step % self.exchange_every == 0:
             return self.exchange(local_logliks)
