@@ -2318,8 +2318,9 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
                                                       c->lv, L.chmask, L.geo_cand, (size_t)c->W, L.cand_ordrec, L.cand_ordb, rng + 2,
                                                       n_cand, base, c->geo_base, L.base_ordrec, L.base_ordb, L.base_ordc, rng); CHECK_LAUNCH(c);
     // grid-stride kernels over the (device-side) size of U: a few CTAs per SM, not one warp per bin of the level
-    const int gw = std::min(ps, std::max(1, std::min(nblk(n, 1), c->n_sm * 8)));
-    const int gb = std::min(ps, std::max(1, std::min(nblk(n, 4), c->n_sm * 4)));
+    const int gw = std::min(ps, std::max(1, std::min(nblk(n, 1), c->n_sm * 2)));      // one resident wave (128 registers: 2 CTAs per SM)
+    // (band: 2 CTAs per SM and one warp per x measured best with three proposals in flight: small grids share the SMs)
+    const int gb = std::min(ps, std::max(1, std::min(nblk(n, 4), c->n_sm * 2)));
     double* p_contacts = L.partials, *p_cand = L.partials + (size_t)16 * ps, *p_base = L.partials + (size_t)32 * ps;
     // contacts: sum over changed contacts of ob * (ln ex_k - ln ex_0): new terms per candidate, old terms once
     c->prof.begin(GRAAL_K_DELTA_CONTACTS, st);
@@ -2328,14 +2329,14 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
     c->prof.end(GRAAL_K_DELTA_CONTACTS, st);
     // band mass: d_band[k] = B_U(S_k) - B_U(S_0) over changed pairs; enters the delta with a minus sign
     c->prof.begin(GRAAL_K_DELTA_BAND, st);
-    if (p.nd == 1) k_band_delta<false, 2, true><<<dim3(gb, n_cand), 256, 0, st>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
+    if (p.nd == 1) k_band_delta<false, 1, true><<<dim3(gb, n_cand), 256, 0, st>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
                                                                               p_cand, ps);
-    else k_band_delta<false, 2, false><<<dim3(gb, n_cand), 256, 0, st>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
+    else k_band_delta<false, 1, false><<<dim3(gb, n_cand), 256, 0, st>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
                                                                      p_cand, ps);
     CHECK_LAUNCH(c);
-    if (p.nd == 1) k_band_delta<true, 8, true><<<dim3(gb, 1), 256, 0, st>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
+    if (p.nd == 1) k_band_delta<true, 4, true><<<dim3(gb, 1), 256, 0, st>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
                                                                         p_base, ps);
-    else k_band_delta<true, 8, false><<<dim3(gb, 1), 256, 0, st>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
+    else k_band_delta<true, 4, false><<<dim3(gb, 1), 256, 0, st>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
                                                                p_base, ps);
     CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_DELTA_BAND, st);
