@@ -243,3 +243,78 @@ def test_size_independent_properties_at_c4_scale():
     g.test_copy_struct(fA, left, 1, -1); g.test_copy_struct(fA, left, 1, -1)
     assert g.eval_likelihood() == like
     g.free_gpu()
+
+
+def _check_full_and_deltas(o, g, rng, n_props, tag):
+    n = o.n_new_frags
+    max_id = o.modify_gl_cuda_buffer(); g.modify_gl_cuda_buffer()
+    fo, fg = o.eval_likelihood(), g.eval_likelihood()
+    assert abs(fo - fg) <= FULL_RTOL * abs(fo), (tag, fo, fg)
+    for it in range(n_props):
+        fA, fB = (int(x) for x in rng.choice(n, 2, replace=False))
+        M.perform_modifications(o.ws, o.cur, fA, fB, max_id)
+        ref = oracle_deltas(o, fA, fB)
+        g.score_neighbours(fA, [fB])
+        got = g._fetch()[16:29].copy()
+        for j in range(13):
+            assert abs(got[j] - ref[j][0]) <= tol(*ref[j]), (tag, fA, fB, j, got[j], ref[j])
+
+
+def test_distances_outside_the_law_table():
+    """The tabulated law (math mode 2) covers 2^-12 .. 2^11 kb.  A 6 Mb contig with d_max = 5000 kb has
+    in-band pairs beyond 2048 kb: they take the general path inside the fast kernels (band, contacts, full
+    pass) and must agree with the oracle like any other pair."""
+    pyr = build_synthetic_pyramid([6_000_000, 900_000], 160, 2, seed=11, cis_rowsum=120.0, v_inter=1e-4, max_band=160)
+    inp = prepare_sampler_inputs(pyr, 1)
+    from graal_b200.sampler import sampler
+    o = H.make_oracle(inp, pyr, d_max=5000.0)
+    g = sampler.from_inputs(inp, rng=np.random.RandomState(1))
+    p, _ = H.default_params(pyr)
+    g.set_parameters(p, 5000.0)
+    assert np.array_equal(np.array(list(g.param_simu[0])), L.params_to_array(o.param_simu))
+    rng = np.random.RandomState(4)
+    _check_full_and_deltas(o, g, rng, 4, "assembled")
+    H.scramble(o, rng, 10, g)
+    _check_full_and_deltas(o, g, rng, 4, "scrambled")
+    g.free_gpu()
+
+
+def test_circular_contig_state(small_pyramid):
+    """A contig closed into a circle (paste of its two ends, mode 12 on the end bins): the circular law
+    (kernels3.cu:135-166) is the general path of every kernel."""
+    inp, o, g = make_pair(small_pyramid, 2)
+    rng = np.random.RandomState(8)
+    from graal_b200.sampler import CUR
+    made = 0
+    for c in np.unique(o.cur["id_c"]):
+        bins = np.nonzero(o.cur["id_c"] == c)[0]
+        if bins.size < 4 or made >= 2:
+            continue
+        head = int(bins[np.argmin(o.cur["pos"][bins])]); tail = int(bins[np.argmax(o.cur["pos"][bins])])
+        max_id = int(o.modify_gl_cuda_buffer()); g.modify_gl_cuda_buffer()
+        for fA, fB in ((tail, head), (head, tail)):         # paste_contigs closes a contig whose two ends it is given
+            new = M.copy_slot(o.cur)
+            M.paste_contigs(new, o.cur, fA, fB, max_id)
+            if new["circ"][head] == 1:
+                for k in M.FIELDS:
+                    o.cur[k][:] = new[k]
+                g.slot_from_host(CUR, new)
+                made += 1
+                break
+    assert made >= 1, "no paste variant produced a circular contig"
+    assert int(np.sum(o.cur["circ"] == 1)) > 0
+    assert H.slots_diff(o.cur, g.slot_to_host(CUR)) == []
+    _check_full_and_deltas(o, g, rng, 6, "circular")
+    # proposals that touch the circle explicitly
+    circ_bins = np.nonzero(o.cur["circ"] == 1)[0]
+    n = o.n_new_frags
+    max_id = o.modify_gl_cuda_buffer(); g.modify_gl_cuda_buffer()
+    for fA in (int(circ_bins[0]), int(circ_bins[-1])):
+        fB = int(rng.choice(np.setdiff1d(np.arange(n), [fA])))
+        M.perform_modifications(o.ws, o.cur, fA, fB, max_id)
+        ref = oracle_deltas(o, fA, fB)
+        g.score_neighbours(fA, [fB])
+        got = g._fetch()[16:29].copy()
+        for j in range(13):
+            assert abs(got[j] - ref[j][0]) <= tol(*ref[j]), (fA, fB, j, got[j], ref[j])
+    g.free_gpu()
