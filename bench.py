@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--neighbours", type=int, default=3)
     ap.add_argument("--exchange-every", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--incremental", action="store_true",
+                    help="carry the likelihood of the current state from the committed candidate (full pass every 256 steps "
+                         "only) instead of recomputing it every step as the reference does; NOT the default workload")
     ap.add_argument("--profile-only", action="store_true", help="short replay for ncu (no CPU baseline, no e2e)")
     return ap.parse_args()
 
@@ -211,6 +214,7 @@ def main():
         g = sampler.from_inputs(inp, device=local_rank, rng=np.random.RandomState(1000 + rank))
         p, d_max = model_params(pyr)
         g.set_parameters(p, d_max)
+    g.incremental_likelihood = bool(args.incremental)
     rex = None
     if world > 1:
         rex = R.ReplicaExchange(1, R.temperature_ladder(world), exchange_every=args.exchange_every, seed=20141217, device=dev)
@@ -278,7 +282,7 @@ def main():
                 nonlocal_t[0] = time.time()
                 l0 = g.gpu_launches
                 ev0.record(g.stream)
-            g.step_device(fA, nb, fB, op)
+            g.step_device(fA, nb, fB, op, full=(not args.incremental) or it % 256 == 0)
             if rex is not None and not profile and (it + 1) % args.exchange_every == 0:
                 like = g._fetch()[0]
                 rex.maybe_exchange(it + 1, [like])
@@ -356,6 +360,8 @@ def main():
                    "contact_list_MB": round(8 * E / 1e6, 1), "neighbours_per_step": k_nb, "candidates_per_neighbour": N_TMP,
                    "state": "assembled genome (%d contigs)" % len(np.unique(init_state["id_c"])),
                    "l2": "inputs larger than L2: the %.0f MB contact list is re-streamed every step" % (8 * E / 1e6),
+                   "full_likelihood": ("incremental: carried from the committed candidate, full pass every 256 steps (NOT the reference's schedule)"
+                                       if args.incremental else "recomputed every step, as the reference does"),
                    "parallelism": "1 replica chain per GPU" + (", replica-exchange all_gather every %d steps" % args.exchange_every if world > 1 else "")},
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_max / args.steps},

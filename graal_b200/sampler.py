@@ -304,6 +304,9 @@ class sampler:
         self.d_dist_skip = t(skip)
         self.param_simu = None
         self.likelihood_t = None
+        self.incremental_likelihood = False     # see step_max_likelihood
+        self.incremental_resync = 256
+        self._inc_valid, self._inc_age = False, 0
         self.score = np.zeros(0)
         self.delta_scores = np.zeros(0)
         self.gpu_launches_at_start = self.lib.graal_launch_count(self.ctx)
@@ -340,6 +343,7 @@ class sampler:
         return {k: a[i].copy() for i, k in enumerate(FRAG_FIELDS)}
 
     def slot_from_host(self, slot, arrays):
+        self._inc_valid = False          # the cached likelihood no longer describes the state / parameters
         n = int(self.n_new_frags)
         self.sync()
         for i, k in enumerate(FRAG_FIELDS):
@@ -378,11 +382,13 @@ class sampler:
     def set_math_mode(self, mode):
         """0: the reference's float32 chain op for op; 1 (default): log-space float64 evaluation of in-band
         pixels (see include/graal_b200.h)."""
+        self._inc_valid = False          # the cached likelihood no longer describes the state / parameters
         check(self.lib.graal_set_math_mode(self.ctx, int(mode)))
         if self.param_simu is not None:
             self._set_device_params(self.param_simu)
 
     def set_parameters(self, param, d_max):
+        self._inc_valid = False          # the cached likelihood no longer describes the state / parameters
         self.param_simu = self.setup_rippe_parameters(param, d_max)
         self._set_device_params(self.param_simu)
 
@@ -440,6 +446,7 @@ class sampler:
     def apply_move(self, src_slot, dst_slot, op, id_fA, id_fB=0, aux=0, max_id=0):
         """One mutation kernel of the reference (``op`` = name in _lib.OPS) between two slots; returns
         max(id_c) of the destination (the ga.max that follows pop_out / split, cuda_lib_gl.py:857,934)."""
+        self._inc_valid = False          # the cached likelihood no longer describes the state / parameters
         check(self.lib.graal_apply_move(self.ctx, int(src_slot), int(dst_slot), _lib.OPS[op], int(id_fA), int(id_fB),
                                         int(aux), int(max_id), self._ptr(self.d_max_id, 1)))
         self.sync()
@@ -447,6 +454,7 @@ class sampler:
 
     def test_copy_struct(self, id_fA, id_f_sampled, mode, max_id):
         """cuda_lib_gl.py:1156-1183: rebuild the sampled candidate, commit it to the current slot."""
+        self._inc_valid = False          # the cached likelihood no longer describes the state / parameters
         mode = int(mode)
         mask = (1 << mode) if mode < 9 else 0x1E00
         self.perform_modifications(id_fA, id_f_sampled, max_id, mask)
@@ -454,6 +462,7 @@ class sampler:
 
     def explode_genome(self, dt=0):
         """cuda_lib_gl.py:1539-1557."""
+        self._inc_valid = False          # the cached likelihood no longer describes the state / parameters
         for i in range(int(self.n_new_frags)):
             check(self.lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
             self.test_copy_struct(i, 0, 0, -1)
@@ -461,6 +470,7 @@ class sampler:
 
     def apply_replay_simu(self, id_fA, id_fB, op_sampled, dt=0):
         """cuda_lib_gl.py:1559-1578."""
+        self._inc_valid = False          # the cached likelihood no longer describes the state / parameters
         check(self.lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
         self.test_copy_struct(id_fA, id_fB, op_sampled, -1)
 
@@ -515,9 +525,16 @@ class sampler:
             # the proposals go to their lanes first; the full likelihood of the current state does not depend
             # on them and runs on the context stream next to them
             self.score_neighbours(id_fA, id_neighbours, with_dist=True)
-            check(lib.graal_full_loglik(self.ctx, CUR, None, self._ptr(self.d_out, 0)))
+            # incremental mode (off by default; the reference recomputes, cuda_lib_gl.py:1828-1848): the score of
+            # the candidate committed by the previous step IS the likelihood of the current state; the full pass
+            # only runs to resynchronise
+            incremental = self.incremental_likelihood and self._inc_valid and self._inc_age < self.incremental_resync
+            if not incremental:
+                check(lib.graal_full_loglik(self.ctx, CUR, None, self._ptr(self.d_out, 0)))
             out = self._fetch()
-            likelihood_t = np.float64(out[0])
+            likelihood_t = np.float64(self.likelihood_t) if incremental else np.float64(out[0])
+            self._inc_age = self._inc_age + 1 if incremental else 0
+            self._inc_valid = True
             self.likelihood_t = likelihood_t
             n_contigs, min_len, mean_len_bp, max_len = int(out[4]), int(out[5]), out[6], int(out[7])
             self.delta_scores = np.array(out[16:16 + n_neighbours * N_TMP_STRUCT], dtype=np.float64)
@@ -552,7 +569,7 @@ class sampler:
         norm_distance = 3.0 * (int(self.n_new_frags) - self.n_frags_4_dist)
         return float(self._fetch()[8]) / norm_distance if norm_distance != 0 else 0.0
 
-    def step_device(self, id_fA, id_neighbours, id_f_sampled, op_sampled):
+    def step_device(self, id_fA, id_neighbours, id_f_sampled, op_sampled, full=True):
         """Device-resident replay of one step: the same kernel sequence as step_max_likelihood with the
         proposal and the sampled candidate supplied by the caller -- nothing is copied to the host and
         the stream is not synchronised (bench.py's resident-input timing, replay of a recorded run)."""
@@ -562,7 +579,8 @@ class sampler:
         if op_sampled < 0:
             return
         self.score_neighbours(id_fA, id_neighbours, with_dist=True)
-        check(lib.graal_full_loglik(self.ctx, CUR, None, self._ptr(self.d_out, 0)))
+        if full:                                   # False: a step of the incremental mode between two resyncs
+            check(lib.graal_full_loglik(self.ctx, CUR, None, self._ptr(self.d_out, 0)))
         x = id_neighbours.index(id_f_sampled) if id_f_sampled in id_neighbours else -1
         check(lib.graal_commit_scored(self.ctx, CUR, CAND0, int(id_fA), int(id_f_sampled), -1, int(op_sampled), x))
 
@@ -590,6 +608,7 @@ class sampler:
 
     # ------------------------------------------------------------------ cuda_lib_gl.py:2022-2107
     def step_nuisance_parameters(self, dt=0, t=0, n_step=1):
+        self._inc_valid = False          # the cached likelihood no longer describes the state / parameters
         curr_param = np.copy(self.param_simu)
         kuhn, lm, c1, slope, d, d_max, fact, d_nuc = curr_param[0]
         self.sigma_fact = 10 ** (np.log10(fact) - 2)

@@ -181,3 +181,22 @@ def test_lanes_and_graphs_match_the_plain_abi(small_pyramid):
         # move on: commit something so that the next round sees another state
         check(lib.graal_commit_scored(ctx, CUR, CAND0, fA, fBs[1], -1, int(rng.randint(13)), 1))
     g.free_gpu()
+
+
+def test_incremental_likelihood_mode(small_pyramid):
+    """incremental_likelihood=True: the likelihood of the current state is carried from the committed
+    candidate's score instead of being recomputed every step (resync every few steps here).  Same accepted
+    moves, likelihood trace within the full-likelihood tolerance."""
+    inp, g = gpu_sampler(small_pyramid, 2, 77)
+    inp2, h = gpu_sampler(small_pyramid, 2, 77)
+    h.incremental_likelihood = True
+    h.incremental_resync = 7
+    tr_g = start_EM(g, 3, 3, scrambled=True, max_steps=120)
+    tr_h = start_EM(h, 3, 3, scrambled=True, max_steps=120)
+    assert np.array_equal(tr_g.mutations(), tr_h.mutations())
+    # full(t) + delta against full(t + 1): equal to the accuracy of a delta (2^-22 of the touched mass, see
+    # test_gpu_likelihood.py), i.e. ~1e-9 of the likelihood per step, bounded by the resync
+    assert np.allclose(tr_g.likelihood, tr_h.likelihood, rtol=2e-8, atol=0)
+    assert np.array_equal(np.array(tr_g.dist_from_init_genome), np.array(tr_h.dist_from_init_genome))
+    assert h.gpu_launches < g.gpu_launches
+    g.free_gpu(); h.free_gpu()
