@@ -70,6 +70,8 @@ _SIGS = {
     "graal_state_stats": (_I, [_P, _I, _P]),
     "graal_dist_genome": (_I, [_P, _I, _P, _P, _P, _P, _P]),
     "graal_dist_candidates": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "graal_score_step": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "graal_fetch": (_I, [_P, _P, _P, C.c_size_t]),
     "graal_dist_histogram": (_I, [_P, _P, _P, _P, _P, _D, _D, _I, _P, _P]),
     "graal_launch_count": (_LL, [_P]),
     "graal_profile_enable": (_I, [_P, _I]),

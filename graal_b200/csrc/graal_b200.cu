@@ -2478,6 +2478,36 @@ int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int i
     return 0;
 }
 
+int graal_dist_candidates(graal_ctx* c, int first_cand_slot, int n_cand, int proposal_index, const int32_t* init_prev, const int32_t* init_next,
+                          const int32_t* init_orientable, const uint8_t* skip, double* d_out);
+
+int graal_score_step(graal_ctx* c, int base_slot, int first_cand_slot, int id_fA, const int32_t* id_fB, int n_proposals, int max_id,
+                     double* d_out, const int32_t* init_prev, const int32_t* init_next, const int32_t* init_orientable,
+                     const uint8_t* skip, double* d_dist) {
+    if (!c || !c->slots) return set_err(-1, "state not bound");
+    if (!id_fB || n_proposals < 0 || n_proposals > 16) return set_err(-1, "need 0..16 proposals");
+    // proposal x uses the candidate slots of lane x % n_lanes when the state block has them, else one shared range
+    const bool per_lane = first_cand_slot + GRAAL_N_CANDIDATES * c->n_lanes <= c->n_slots;
+    for (int x = 0; x < n_proposals; x++) {
+        const int first = first_cand_slot + (per_lane ? GRAAL_N_CANDIDATES * (x % c->n_lanes) : 0);
+        int rc = graal_score_proposal(c, base_slot, first, id_fA, id_fB[x], max_id, x, d_out + (size_t)GRAAL_N_CANDIDATES * x); if (rc) return rc;
+        if (d_dist) {
+            rc = graal_dist_candidates(c, first, GRAAL_N_CANDIDATES, x, init_prev, init_next, init_orientable, skip, d_dist + (size_t)GRAAL_N_CANDIDATES * x);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+int graal_fetch(graal_ctx* c, const void* d_src, void* h_dst, size_t bytes) {
+    if (!c || !d_src || !h_dst) return set_err(-1, "null argument");
+    CUDA_OK(cudaSetDevice(c->device));
+    int rc = join_lanes(c); if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int graal_commit_scored(graal_ctx* c, int base_slot, int first_cand_slot, int id_fA, int id_fB, int max_id, int mode, int proposal_index) {
     NEED_STATE(c);
     if (mode < 0 || mode >= GRAAL_N_CANDIDATES) return set_err(-1, "mode must be 0..12");

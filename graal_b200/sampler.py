@@ -225,6 +225,9 @@ class sampler:
         self.np_id_frag_duplicated = np.asarray(id_frag_duplicated, dtype=I32)
         self._dup_set = set(int(f) for f in self.np_id_frag_duplicated)
         self._n_cand_cache = {}
+        disp = np.asarray(frag_dispatcher).reshape(-1, 2)
+        self._identity_dispatch = bool(len(self._dup_set) == 0 and np.all(disp[:, 1] - disp[:, 0] == 1) and
+                                       np.array_equal(np.asarray(collector_id_repeats)[disp[:, 0]], np.arange(disp.shape[0])))
         self.n_frags, self.n_new_frags = I32(n_frags), I32(n_new_frags)
         self.init_n_sub_frags, self.n_new_sub_frags = I32(init_n_sub_frags), I32(n_new_sub_frags)
         self.uniq_frags = np.setdiff1d(np.arange(n_frags, dtype=I32), self.np_id_frag_duplicated).astype(I32)
@@ -302,11 +305,18 @@ class sampler:
         if self.id_frags_blacklisted:
             skip[np.asarray(self.id_frags_blacklisted, dtype=np.int64)] = 1
         self.d_dist_skip = t(skip)
+        # raw addresses of the buffers the step path passes on every call
+        self._p_out, self._p_hout = self.d_out.data_ptr(), self.h_out.data_ptr()
+        self._n_out_bytes = self.d_out.numel() * self.d_out.element_size()
+        self._h_out_np = self.h_out.numpy()
+        self._p_dist_args = (self.d_init_prev.data_ptr(), self.d_init_next.data_ptr(), self.d_init_orientable.data_ptr(),
+                             self.d_dist_skip.data_ptr())
         self.param_simu = None
         self.likelihood_t = None
         self.incremental_likelihood = False     # see step_max_likelihood
         self.incremental_resync = 256
         self._inc_valid, self._inc_age = False, 0
+        self._remove_cache = {}
         self.score = np.zeros(0)
         self.delta_scores = np.zeros(0)
         self.gpu_launches_at_start = self.lib.graal_launch_count(self.ctx)
@@ -330,11 +340,9 @@ class sampler:
 
     def _fetch(self):
         """One D2H of the whole output block (pinned), after the stream has drained."""
-        check(self.lib.graal_join(self.ctx))          # proposals still on their lanes -> ordered before the copy
-        with self.torch.cuda.stream(self.stream):
-            self.h_out.copy_(self.d_out, non_blocking=True)
-        self.stream.synchronize()
-        return self.h_out.numpy()
+        # (lanes joined, copy on the context stream, wait: one library call instead of torch's stream machinery)
+        check(self.lib.graal_fetch(self.ctx, self._p_out, self._p_hout, self._n_out_bytes))
+        return self._h_out_np
 
     def slot_to_host(self, slot):
         self.sync()
@@ -485,6 +493,8 @@ class sampler:
             n_nonzero = self._n_cand_cache[ori_id] = int(np.count_nonzero(distri))
         n_max_candidates = min(delta, n_nonzero)
         init_id = self.rng.choice(self.distri_xk[ori_id], n_max_candidates, p=distri, replace=False)
+        if self._identity_dispatch:             # no duplicated bins: every dispatcher range is the bin itself
+            return [e for e in init_id.tolist() if e not in self._black_set]
         out = []
         if ori_id in self._dup_set:
             d = self.frag_dispatcher[ori_id]
@@ -500,14 +510,15 @@ class sampler:
     def score_neighbours(self, id_fA, id_neighbours, with_dist=False):
         """stream_likelihood (cuda_lib_gl.py:2392-2546) for every neighbour: candidates + deltas, queued
         on the stream; results land in d_out[16 + 13*x + j]."""
-        for x, id_fB in enumerate(id_neighbours):
-            first = CAND0 + N_TMP_STRUCT * (x % N_LANES)
-            check(self.lib.graal_score_proposal(self.ctx, CUR, first, int(id_fA), int(id_fB), -1, x,
-                                                self._ptr(self.d_out, 16 + N_TMP_STRUCT * x)))
-            if with_dist:       # genome distance of every candidate, fetched with the scores (no second round trip)
-                check(self.lib.graal_dist_candidates(self.ctx, first, N_TMP_STRUCT, x, self._ptr(self.d_init_prev), self._ptr(self.d_init_next),
-                                                     self._ptr(self.d_init_orientable), self._ptr(self.d_dist_skip),
-                                                     self._ptr(self.d_out, OFF_DIST + N_TMP_STRUCT * x)))
+        n = len(id_neighbours)
+        if n == 0:
+            return
+        fbs = (C.c_int32 * n)(*[int(f) for f in id_neighbours])
+        # one call for the whole neighbour loop; with_dist: the genome distance of every candidate comes back with
+        # the scores (no second round trip).  Proposal x is built into the candidate slots of lane x % N_LANES.
+        check(self.lib.graal_score_step(self.ctx, CUR, CAND0, int(id_fA), fbs, n, -1, self._p_out + 8 * 16,
+                                        self._p_dist_args[0], self._p_dist_args[1], self._p_dist_args[2], self._p_dist_args[3],
+                                        (self._p_out + 8 * OFF_DIST) if with_dist else None))
 
     def step_max_likelihood(self, id_fA, delta, size_block=512, dt=0, t=0, n_step=1):
         """cuda_lib_gl.py:1793-1980.  Returns (o, n_contigs, min_len, mean_len_bp, max_len, op_sampled,
@@ -587,7 +598,9 @@ class sampler:
     def _sample(self, score, F_t):
         """Candidate filtering and draw (cuda_lib_gl.py:1899-1947)."""
         nt = N_TMP_STRUCT
-        scores_2_remove = list(range(nt, len(score), nt)) + list(range(nt + 1, len(score), nt))
+        scores_2_remove = self._remove_cache.get(len(score))
+        if scores_2_remove is None:
+            scores_2_remove = self._remove_cache[len(score)] = list(range(nt, len(score), nt)) + list(range(nt + 1, len(score), nt))
         id_max = int(score.argmax())
         filtered_score = score - score.min()
         filtered_score[scores_2_remove] = 0

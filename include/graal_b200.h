@@ -137,6 +137,20 @@ int graal_delta_loglik(graal_ctx* ctx, int base_slot, int first_cand_slot, int n
 int graal_score_proposal(graal_ctx* ctx, int base_slot, int first_cand_slot, int id_fA, int id_fB,
                          int max_id, int proposal_index, double* d_out);
 
+/* The neighbour loop of step_max_likelihood (cuda_lib_gl.py:1866-1895) in one call: graal_score_proposal for
+ * proposals x = 0..n_proposals-1 (id_fA, id_fB[x]; id_fB is a HOST array) -> d_out[13 * x + k], and, if d_dist
+ * is not NULL, graal_dist_candidates -> d_dist[13 * x + k].  Proposal x is built into the candidate slots
+ * first_cand_slot + 13 * (x % lanes) when the state block holds 13 * lanes candidate slots from first_cand_slot
+ * on (the proposals then overlap on the GPU), else into first_cand_slot (serial). */
+int graal_score_step(graal_ctx* ctx, int base_slot, int first_cand_slot, int id_fA, const int32_t* id_fB,
+                     int n_proposals, int max_id, double* d_out,
+                     const int32_t* init_prev, const int32_t* init_next, const int32_t* init_orientable,
+                     const uint8_t* skip, double* d_dist);
+
+/* graal_join + copy `bytes` from device to (pinned) host memory on the context stream + wait: the one device
+ * round trip of a step (the reference's ga.sum / .get() calls, cuda_lib_gl.py:1848,1897). */
+int graal_fetch(graal_ctx* ctx, const void* d_src, void* h_dst, size_t bytes);
+
 /* test_copy_struct (cuda_lib_gl.py:1156-1183): rebuild candidate `mode` of (id_fA, id_fB) and commit it to
  * base_slot.  proposal_index >= 0: the proposal was scored by graal_score_proposal since base_slot last
  * changed, and the cached band total of base_slot is updated with that candidate's band delta (the next
