@@ -595,15 +595,15 @@ k_full_contacts(const long long* __restrict__ rowptr, const int2* __restrict__ c
 // Uniform-accu variant (every sub-frag has the same accu, e.g. level 1): every trans / clamped entry
 // has the SAME log g, so their total is log g * sum(ob) with sum(ob) a level constant; the kernel only
 // CLASSIFIES entries and evaluates the in-band ones, accumulating ob * (ln ex - log g).
-//  * the list is cut into groups of 256 entries; warp w takes groups w, w + n_warps, ... so that at any
-//    time the chip streams ONE contiguous region of the list (DRAM page locality), 8 coalesced 256-B
-//    loads in flight per warp, marked evict-first;
+//  * the list is cut into groups of GROUP = 128 entries; warp w takes groups w, w + n_warps, ... so that at any
+//    time the chip streams ONE contiguous region of the list (DRAM page locality), 4 coalesced 256-B
+//    loads in flight per warp, marked evict-first (measured: 4 loads x 32 warps / SM beats 8 x 24);
 //  * the row of the first entry of every group is precomputed at bind time (no search);
 //  * classification reads the 2-byte contig id of the partner (a W*2-byte table that lives in L1/L2)
 //    and only cis entries -- which sit close to their row, i.e. share cache lines -- fetch the partner
 //    mid-point; all gathers of a group are issued before the first one is used.
-#define UNROLL8 8
-#define GROUP (32 * UNROLL8)
+#define FC_UNROLL 4
+#define GROUP (32 * FC_UNROLL)
 __global__ void k_group_rows(const long long* __restrict__ rowptr, long long E, int W, int n_groups, int* __restrict__ group_row) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
@@ -645,9 +645,9 @@ k_full_contacts_uniform(const long long* __restrict__ rowptr, const int2* __rest
     for (int g = warp; g < n_groups; g += n_warps) {
         const long long e0 = (long long)g * GROUP;
         const int len = (int)min((long long)GROUP, E - e0);
-        int2 ce[UNROLL8];
+        int2 ce[FC_UNROLL];
         #pragma unroll
-        for (int u = 0; u < UNROLL8; u++) {
+        for (int u = 0; u < FC_UNROLL; u++) {
             const int r = u * 32 + lane;
             ce[u] = (r < len) ? ld_stream(&contacts[e0 + r]) : make_int2(0, 0);
         }
@@ -655,13 +655,13 @@ k_full_contacts_uniform(const long long* __restrict__ rowptr, const int2* __rest
         int row_end_rel = (int)min(__ldg(&rowptr[row + 1]) - e0, (long long)INT_MAX);
         const Geo g0 = ld_geo(&geo[row]);
         float r_mid = g0.mid, r_stot = g0.stot; int r_idc = g0.id_c; unsigned r_circ = (unsigned)pk_circ(g0.pk) << 31;
-        unsigned cc[UNROLL8];
+        unsigned cc[FC_UNROLL];
         #pragma unroll
-        for (int u = 0; u < UNROLL8; u++) cc[u] = SMEM_CID ? (unsigned)cid_tab[ce[u].x] : (unsigned)__ldg(&cid16[ce[u].x]);
+        for (int u = 0; u < FC_UNROLL; u++) cc[u] = SMEM_CID ? (unsigned)cid_tab[ce[u].x] : (unsigned)__ldg(&cid16[ce[u].x]);
         // per-lane row of each of its 8 entries (rows are ~100s of entries long: the cursor rarely moves)
-        bool cis[UNROLL8]; float rm[UNROLL8], rs[UNROLL8]; unsigned rc[UNROLL8];
+        bool cis[FC_UNROLL]; float rm[FC_UNROLL], rs[FC_UNROLL]; unsigned rc[FC_UNROLL];
         #pragma unroll
-        for (int u = 0; u < UNROLL8; u++) {
+        for (int u = 0; u < FC_UNROLL; u++) {
             const int r = u * 32 + lane;
             if (r < len && r >= row_end_rel) {
                 long long re;
@@ -675,11 +675,11 @@ k_full_contacts_uniform(const long long* __restrict__ rowptr, const int2* __rest
             cis[u] = c && r < len;
             rm[u] = r_mid; rs[u] = r_stot; rc[u] = r_circ;
         }
-        float pm[UNROLL8];
+        float pm[FC_UNROLL];
         #pragma unroll
-        for (int u = 0; u < UNROLL8; u++) pm[u] = cis[u] ? __ldg(&mid32[ce[u].x]) : 0.0f;
+        for (int u = 0; u < FC_UNROLL; u++) pm[u] = cis[u] ? __ldg(&mid32[ce[u].x]) : 0.0f;
         #pragma unroll
-        for (int u = 0; u < UNROLL8; u++) {
+        for (int u = 0; u < FC_UNROLL; u++) {
             const float s = fabsf(pm[u] - rm[u]);
             const bool inband = cis[u] && s > 0.0f && s < p.d_max;
             const unsigned ballot = __ballot_sync(0xffffffffu, inband);
@@ -709,7 +709,7 @@ k_full_contacts_uniform(const long long* __restrict__ rowptr, const int2* __rest
 // per-warp rings in shared memory filled by 2 KB cp.async.bulk copies + mbarrier (0.212 ms per pass: the per-SM
 // bulk-copy rate is the limit) or by 16-byte cp.async four groups ahead (0.145 ms) against 0.123 ms here --
 // the pass waits on its gathers and on instruction issue, not on the stream.
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 k_full_contacts_direct(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, long long E,
                        const int* __restrict__ group_row, int n_groups,
                        const Geo* __restrict__ geo, const int2* __restrict__ cm,
@@ -727,9 +727,9 @@ k_full_contacts_direct(const long long* __restrict__ rowptr, const int2* __restr
         const long long e0 = (long long)g * GROUP;
         const int len = (int)min((long long)GROUP, E - e0);
         const int2* __restrict__ cg = contacts + e0;
-        int2 ce[UNROLL8];
+        int2 ce[FC_UNROLL];
         #pragma unroll
-        for (int u = 0; u < UNROLL8; u++) {
+        for (int u = 0; u < FC_UNROLL; u++) {
             const int r = u * 32 + lane;
             ce[u] = (r < len) ? ld_stream(&cg[r]) : make_int2(0, 0);
         }
@@ -737,12 +737,12 @@ k_full_contacts_direct(const long long* __restrict__ rowptr, const int2* __restr
         int row_end_rel = (int)min(__ldg(&rowptr[row + 1]) - e0, (long long)GROUP);
         int2 rr = __ldg(&cm[row]);                                  // {contig id, mid-point} of the row
         int r_slow = pk_circ(__ldg(&geo[row].pk));
-        int2 pc[UNROLL8];
+        int2 pc[FC_UNROLL];
         #pragma unroll
-        for (int u = 0; u < UNROLL8; u++) pc[u] = __ldg(&cm[ce[u].x]);
+        for (int u = 0; u < FC_UNROLL; u++) pc[u] = __ldg(&cm[ce[u].x]);
         unsigned slow = 0u;
         #pragma unroll
-        for (int u = 0; u < UNROLL8; u++) {
+        for (int u = 0; u < FC_UNROLL; u++) {
             const int r = u * 32 + lane;
             if (r >= row_end_rel && r < len) {                      // rows are ~100s of entries long: the cursor rarely moves
                 long long re;
@@ -760,7 +760,7 @@ k_full_contacts_direct(const long long* __restrict__ rowptr, const int2* __restr
         }
         if (slow) {                                                 // circular contig / outside the table / non-finite tables
             #pragma unroll
-            for (int u = 0; u < UNROLL8; u++) {
+            for (int u = 0; u < FC_UNROLL; u++) {
                 if (!((slow >> u) & 1u) || u * 32 + lane >= len) continue;
                 const long long e = e0 + u * 32 + lane;             // the row of entry u is not kept per entry: find it again
                 int lo = __ldg(&group_row[g]);
