@@ -63,6 +63,10 @@ struct Params { float kuhn, lm, c1, slope, d, d_max, fact, v_inter, nfpb; int nd
 //          values) | local sub index[26:28) | circ[28]
 struct __align__(16) Geo { float mid; int id_c; float stot; unsigned pk; };
 #define MAX_ACCU_VALUES 256
+// Candidates scored as a second-level delta against their predecessor (3 vs 2, 5 vs 4, 7 vs 6: the same insertion
+// with the other orientation of fA -- only fA's own records differ): bit k set = candidate k is paired with k - 1.
+#define PAIR_MASK 0xA8u
+#define N_BAND_ROWS 16        // 13 candidates + 3 rows "partner of a paired candidate, restricted to the differing records"
 __device__ __forceinline__ int pk_true(unsigned pk) { return pk & 255; }
 __device__ __forceinline__ int pk_quirk(unsigned pk) { return (pk >> 8) & 255; }
 __device__ __forceinline__ int pk_local(unsigned pk) { return (pk >> 26) & 3; }
@@ -296,18 +300,32 @@ __global__ void k_reduce_partials(const double* __restrict__ partials, int n, in
 }
 
 // End of a proposal's delta, one launch for the 13 candidates: second stage of the three reductions and
-//   band[k] = sum(cand band) - sum(base band);   out[k] = sum(contacts) - band[k];   candidate `copy_to` = candidate 0
+//   band[k] = sum(cand band) - sum(base band);   out[k] = sum(contacts) - band[k];   candidate `copy_to` = candidate 0.
+// A paired candidate (bit k of pair_mask) is composed from its partner k - 1:
+//   band[k] = band[k-1] + (T_k - T'_k),  contacts[k] = contacts[k-1] + C_k
+// with T_k / T'_k the band mass of the pairs touching a differing record in candidate k / in its partner (band
+// rows k and 13 + (k-3)/2) and C_k the contact terms over the differing records.
 __global__ void k_finish_delta(const double* __restrict__ p_contacts, int n_contacts, const double* __restrict__ p_cand, const double* __restrict__ p_base,
-                               int n_band, int stride, double* __restrict__ out, double* __restrict__ band, int copy_to) {
+                               int n_band, int stride, double* __restrict__ out, double* __restrict__ band, int copy_to, unsigned pair_mask) {
     const int k = blockIdx.x;
-    const int src = (copy_to > 0 && k == copy_to) ? 0 : k;         // the copied candidate sums candidate 0's partials itself
+    const bool paired = (pair_mask >> k) & 1u;
+    const int src = paired ? k - 1 : ((copy_to > 0 && k == copy_to) ? 0 : k);      // the copied candidate sums candidate 0's partials itself
     double vc = 0.0, vn = 0.0, vb = 0.0;
     for (int j = threadIdx.x; j < n_contacts; j += blockDim.x) vc += p_contacts[(size_t)src * stride + j];
     for (int j = threadIdx.x; j < n_band; j += blockDim.x) { vn += p_cand[(size_t)src * stride + j]; vb += p_base[(size_t)src * stride + j]; }
     vc = block_sum(vc); vn = block_sum(vn); vb = block_sum(vb);
+    double ck = 0.0, tk = 0.0, tp = 0.0;
+    if (paired) {
+        const int prow = GRAAL_N_CANDIDATES + (k - 3) / 2;
+        for (int j = threadIdx.x; j < n_contacts; j += blockDim.x) ck += p_contacts[(size_t)k * stride + j];
+        for (int j = threadIdx.x; j < n_band; j += blockDim.x) { tk += p_cand[(size_t)k * stride + j]; tp += p_cand[(size_t)prow * stride + j]; }
+    }
+    ck = block_sum(ck); tk = block_sum(tk); tp = block_sum(tp);
     if (threadIdx.x == 0) {
         double b = 0.0 + 1.0 * vn; b = b + (-1.0) * vb;
-        double o = 0.0 + 1.0 * vc; o = o + (-1.0) * b;
+        double o = 0.0 + 1.0 * vc;
+        if (paired) { b = b + (tk - tp); o = o + ck; }
+        o = o + (-1.0) * b;
         band[k] = b; out[k] = o;
     }
 }
@@ -949,14 +967,14 @@ k_quirk(const int* __restrict__ quirky, int n_quirky, const int* __restrict__ sl
 //   meta: [0] contig of fA, [1] contig of fB, [2] |A|, [3] |B| (0 if the same contig), [4] |U|, [5] max contig id
 __global__ void k_delta_setup(const int* __restrict__ base, int ld, int fA, int fB, const int* __restrict__ d_max_id,
                               int max_id_host, int* __restrict__ meta, int n, int W, int* __restrict__ sub_index,
-                              unsigned* __restrict__ chmask, int* __restrict__ piece_len, int* __restrict__ rng) {
+                              unsigned* __restrict__ chmask, int* __restrict__ piece_len, int* __restrict__ rng, unsigned* __restrict__ chmask2) {
     const int cA = base[F_ID_C * ld + fA], cB = base[F_ID_C * ld + fB];
     const int lA = base[F_L_CONT * ld + fA], lB = (cB != cA) ? base[F_L_CONT * ld + fB] : 0;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) { meta[0] = cA; meta[1] = cB; meta[2] = lA; meta[3] = lB; meta[4] = lA + lB; meta[5] = (max_id_host >= 0) ? max_id_host : *d_max_id; }
     if (i < GRAAL_N_CANDIDATES * 8) piece_len[i] = 0;
-    if (i < 2 + 2 * GRAAL_N_CANDIDATES) rng[i] = (i & 1) ? -1 : INT_MAX;
-    for (int j = i; j < W; j += gridDim.x * blockDim.x) chmask[j] = 0u;
+    if (i < 2 + 2 * N_BAND_ROWS) rng[i] = (i & 1) ? -1 : INT_MAX;
+    for (int j = i; j < W; j += gridDim.x * blockDim.x) { chmask[j] = 0u; chmask2[j] = 0u; }
     if (i >= n) return;
     const int c = base[F_ID_C * ld + i];
     const int pos = base[F_POS * ld + i];
@@ -1013,7 +1031,7 @@ __device__ __forceinline__ int4 band_record_b(const Geo* __restrict__ g, int sub
 //   C: x, y, z = chmask words of the sub-frags (bit k: differs from the base slot in candidate k)
 __device__ __forceinline__ void base_order(const int* __restrict__ base, int ld, const int* __restrict__ sub_index, const int* __restrict__ meta,
                              LevelView lv, const unsigned* __restrict__ chmask, const Geo* __restrict__ geo_base,
-                             int4* __restrict__ rec_a, int4* __restrict__ rec_b, int4* __restrict__ rec_c, int* __restrict__ rng) {
+                             int4* __restrict__ rec_a, int4* __restrict__ rec_b, int4* __restrict__ rec_c, int* __restrict__ rng, unsigned pair_mask) {
     const int m = meta[4];
     int lo = INT_MAX, hi = -1;
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < m; u += gridDim.x * blockDim.x) {
@@ -1021,7 +1039,7 @@ __device__ __forceinline__ void base_order(const int* __restrict__ base, int ld,
         const int4 sid = lv.sub_id[base[F_ID_D * ld + bin]];
         const int n_sub = eligible(lv, bin) ? sid.w : 0;
         unsigned ms[3] = {0u, 0u, 0u};
-        for (int a = 0; a < n_sub; a++) ms[a] = chmask[sid.x + a];
+        for (int a = 0; a < n_sub; a++) ms[a] = chmask[sid.x + a] & ~pair_mask;      // paired candidates get no old values: they start from their partner
         const unsigned chg = ms[0] | ms[1] | ms[2];
         const float start_kb = __int2float_rn(base[F_START_BP * ld + bin]) / 1000.0f;
         rec_a[u] = make_int4(sid.x | (n_sub << 28), __float_as_int(start_kb), (int)chg, base[F_ID_C * ld + bin]);
@@ -1031,21 +1049,37 @@ __device__ __forceinline__ void base_order(const int* __restrict__ base, int ld,
     }
     if (hi >= 0) { atomicMin(&rng[0], lo); atomicMax(&rng[1], hi); }
 }
+// grid.y: rows 0..12 = candidates, row 13 = the base slot, rows 14..16 = the partners (2, 4, 6) of the paired
+// candidates (3, 5, 7) restricted to the records in which the pair differs -> band rows 13..15.
+//   normal candidate k : changed bits = chmask bit k (differs from the base slot)
+//   paired candidate k : changed bits = differs from candidate k - 1 (also published in chmask2 bit k)
+//   partner row of k   : candidate k - 1's order and records, the same changed bits
 __global__ void k_cand_order(const int* __restrict__ cand0, size_t slot_stride, int ld,
                              const int* __restrict__ sub_index, const int* __restrict__ meta,
                              const int* __restrict__ piece_len, int order_stride, unsigned skip_cands,
                              LevelView lv, const unsigned* __restrict__ chmask, const Geo* __restrict__ geo0, size_t geo_stride,
                              int4* __restrict__ rec_a0, int4* __restrict__ rec_b0, int* __restrict__ rng,
                              int n_cand, const int* __restrict__ base, const Geo* __restrict__ geo_base,
-                             int4* __restrict__ base_a, int4* __restrict__ base_b, int4* __restrict__ base_c, int* __restrict__ base_rng) {
-    const int k = blockIdx.y;
-    if (k == n_cand) { base_order(base, ld, sub_index, meta, lv, chmask, geo_base, base_a, base_b, base_c, base_rng); return; }   // last grid row: the base slot
-    if ((skip_cands >> k) & 1u) return;
+                             int4* __restrict__ base_a, int4* __restrict__ base_b, int4* __restrict__ base_c, int* __restrict__ base_rng,
+                             unsigned pair_mask, unsigned* __restrict__ chmask2) {
+    const int y = blockIdx.y;
+    if (y == n_cand) { base_order(base, ld, sub_index, meta, lv, chmask, geo_base, base_a, base_b, base_c, base_rng, pair_mask); return; }
+    int row = y, src = y, other = -1;                       // output row, candidate whose order / records are written, candidate compared with
+    if (y > n_cand) {                                       // partner row v of paired candidate 3 + 2 v
+        const int v = y - n_cand - 1, kp = 3 + 2 * v;
+        if (!((pair_mask >> kp) & 1u)) return;
+        row = GRAAL_N_CANDIDATES + v; src = kp - 1; other = kp;
+    } else {
+        if ((skip_cands >> y) & 1u) return;
+        if ((pair_mask >> y) & 1u) other = y - 1;
+    }
     const int m = meta[4];
-    const int* sl = cand0 + (size_t)k * slot_stride;
+    const int* sl = cand0 + (size_t)src * slot_stride;
+    const Geo* gs = geo0 + (size_t)src * geo_stride;
+    const Geo* go = (other >= 0) ? geo0 + (size_t)other * geo_stride : nullptr;
     int off[5]; int run = 0;
     #pragma unroll
-    for (int s = 0; s < 5; s++) { off[s] = run; run += piece_len[k * 8 + s]; }
+    for (int s = 0; s < 5; s++) { off[s] = run; run += piece_len[src * 8 + s]; }
     int lo = INT_MAX, hi = -1;
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < m; u += gridDim.x * blockDim.x) {
         const int bin = sub_index[u];
@@ -1056,13 +1090,25 @@ __global__ void k_cand_order(const int* __restrict__ cand0, size_t slot_stride, 
         const int4 sid = lv.sub_id[sl[F_ID_D * ld + bin]];
         const int n_sub = eligible(lv, bin) ? sid.w : 0;
         unsigned chg = 0u;
-        for (int a = 0; a < n_sub; a++) chg |= ((chmask[sid.x + a] >> k) & 1u) << a;
+        for (int a = 0; a < n_sub; a++) {
+            const int sub = sid.x + a;
+            unsigned d;
+            if (other < 0) d = (chmask[sub] >> src) & 1u;
+            else {
+                // a record not flagged in chmask was not rewritten for this proposal: it equals the base record
+                const Geo rs = ((chmask[sub] >> src) & 1u) ? gs[sub] : geo_base[sub];
+                const Geo ro = ((chmask[sub] >> other) & 1u) ? go[sub] : geo_base[sub];
+                d = geo_eq(rs, ro) ? 0u : 1u;
+                if (d && y < n_cand) atomicOr(&chmask2[sub], 1u << y);
+            }
+            chg |= d << a;
+        }
         const float start_kb = __int2float_rn(sl[F_START_BP * ld + bin]) / 1000.0f;
-        rec_a0[(size_t)k * order_stride + idx] = make_int4(sid.x | (n_sub << 28), __float_as_int(start_kb), (int)chg, sl[F_ID_C * ld + bin]);
-        rec_b0[(size_t)k * order_stride + idx] = band_record_b(geo0 + (size_t)k * geo_stride, sid.x, n_sub);
+        rec_a0[(size_t)row * order_stride + idx] = make_int4(sid.x | (n_sub << 28), __float_as_int(start_kb), (int)chg, sl[F_ID_C * ld + bin]);
+        rec_b0[(size_t)row * order_stride + idx] = band_record_b(gs, sid.x, n_sub);
         if (chg) { lo = min(lo, idx); hi = max(hi, idx); }
     }
-    if (hi >= 0) { atomicMin(&rng[2 * k], lo); atomicMax(&rng[2 * k + 1], hi); }
+    if (hi >= 0) { atomicMin(&rng[2 * row], lo); atomicMax(&rng[2 * row + 1], hi); }
 }
 
 // ex - g of an in-band cis pair from its distance, accu table index and (circular contigs) contig length
@@ -1090,7 +1136,8 @@ k_band_delta(const int4* __restrict__ rec_a0, const int4* __restrict__ rec_b0, c
     const int count = *d_count;
     const int4* rec_a = BASE ? rec_a0 : rec_a0 + (size_t)k * order_stride;
     const int4* rec_b = BASE ? rec_b0 : rec_b0 + (size_t)k * order_stride;
-    const Geo* gE = BASE ? geo0 : geo0 + (size_t)k * cand_geo_stride;
+    // band rows 13..15 hold the order / records of candidates 2, 4, 6 (partners of the paired candidates)
+    const Geo* gE = BASE ? geo0 : geo0 + (size_t)(k < GRAAL_N_CANDIDATES ? k : 2 + 2 * (k - GRAAL_N_CANDIDATES)) * cand_geo_stride;
     const int* rng = BASE ? rng0 : rng0 + 2 * k;
     const int lo = rng[0], hi = rng[1];
     const int lane = threadIdx.x & 31;
@@ -1225,7 +1272,7 @@ __global__ void __launch_bounds__(256)
 k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, LevelView lv,
                       const int* __restrict__ sub_index, const int* __restrict__ meta,
                       const Geo* __restrict__ geo_base, const Geo* __restrict__ geo_cand0, size_t geo_stride,
-                      const unsigned* __restrict__ chmask,
+                      const unsigned* __restrict__ chmask, const unsigned* __restrict__ chmask2, unsigned pair_mask,
                       const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
     const int m = meta[4], cA = meta[0], cB = meta[1];
     const int lane = threadIdx.x & 31;
@@ -1244,6 +1291,7 @@ k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restri
         const long long e0 = __ldg(&rowptr[rowsub]), e1 = __ldg(&rowptr[rowsub + 1]);
         const Geo r0 = ld_geo(&geo_base[rowsub]);
         const unsigned mra = __ldg(&chmask[rowsub]);
+        const unsigned mra2 = pair_mask ? (__ldg(&chmask2[rowsub]) & pair_mask) : 0u;   // row differs between a paired candidate and its partner
         for (long long eb = e0 + lane; eb < e1; eb += 32 * DC_UNROLL) {
             int2 ce[DC_UNROLL]; Geo g0[DC_UNROLL]; unsigned mc[DC_UNROLL]; bool ok[DC_UNROLL];
             #pragma unroll
@@ -1260,16 +1308,19 @@ k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restri
                 if (g0c.id_c != cA && g0c.id_c != cB) continue;              // partner outside U
                 if (g0c.pk & PK_EXCLUDED) continue;                          // partner is a duplicated bin: repeat path
                 if (ce[j].x - pk_local(g0c.pk) == sub0) continue;            // same bin: diagonal pixel, not re-scored
-                const unsigned mm = mra | mc[j];
-                if (!mm) continue;                                           // bitwise unchanged in every candidate
+                // paired candidates (bits of pair_mask) are scored against their partner: accs[k] = sum of
+                // ob * (ln ex_k - ln ex_{k-1}) over the contacts with a record that differs between the two
+                const unsigned mm = (mra | mc[j]) & ~pair_mask;
+                const unsigned mm2 = pair_mask ? (mra2 | (__ldg(&chmask2[ce[j].x]) & pair_mask)) : 0u;
+                if (!(mm | mm2)) continue;                                   // bitwise unchanged in every candidate
                 const float ob = __int_as_float(ce[j].y);
                 // {mid-point, contig id} of the partner in every flagged candidate (the rest of its record -- accu
                 // indices, flags -- does not depend on the candidate): all gathers in flight before the first use
                 int2 pr[GRAAL_N_CANDIDATES];
                 #pragma unroll
                 for (int k = 0; k < GRAAL_N_CANDIDATES; k++)
-                    pr[k] = ((mc[j] >> k) & 1u) ? __ldg(reinterpret_cast<const int2*>(&geo_cand0[(size_t)k * geo_stride + ce[j].x]))
-                                                : make_int2(__float_as_int(g0c.mid), g0c.id_c);
+                    pr[k] = ((mc[j] >> k) & mm >> k & 1u) ? __ldg(reinterpret_cast<const int2*>(&geo_cand0[(size_t)k * geo_stride + ce[j].x]))
+                                                          : make_int2(__float_as_int(g0c.mid), g0c.id_c);
                 const double told = contact_log_term(r0, g0c, ob, p);
                 #pragma unroll
                 for (int k = 0; k < GRAAL_N_CANDIDATES; k++) {
@@ -1277,6 +1328,22 @@ k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restri
                     const Geo rk = ((mra >> k) & 1u) ? ld_geo(&geo_cand0[(size_t)k * geo_stride + rowsub]) : r0;
                     Geo gc = g0c; gc.mid = __int_as_float(pr[k].x); gc.id_c = pr[k].y;
                     accs[k] += contact_log_term(rk, gc, ob, p) - told;
+                }
+                if (mm2) {                                                   // rare: the few records in which a pair differs
+                    #pragma unroll
+                    for (int k = 3; k <= 7; k += 2) {
+                        if (!((mm2 >> k) & 1u)) continue;
+                        double t[2];
+                        #pragma unroll
+                        for (int w2 = 0; w2 < 2; w2++) {                     // candidate k, then its partner k - 1
+                            const int kk = k - w2;
+                            const Geo rk = ((mra >> kk) & 1u) ? ld_geo(&geo_cand0[(size_t)kk * geo_stride + rowsub]) : r0;
+                            Geo gc = g0c;
+                            if ((mc[j] >> kk) & 1u) { const Geo q = ld_geo(&geo_cand0[(size_t)kk * geo_stride + ce[j].x]); gc.mid = q.mid; gc.id_c = q.id_c; }
+                            t[w2] = contact_log_term(rk, gc, ob, p);
+                        }
+                        accs[k] += t[0] - t[1];
+                    }
                 }
             }
         }
@@ -1583,6 +1650,7 @@ struct Lane {
     int* ints = nullptr;                     // [256]: [8..16) delta meta, [16..120) piece_len, [160..188) changed ranges
     int* sub_index = nullptr;                // [n]
     unsigned* chmask = nullptr;              // [W] bit k: record differs from the base slot in candidate k
+    unsigned* chmask2 = nullptr;             // [W] bit k (paired candidates): record differs from candidate k - 1
     Geo* geo_cand = nullptr;                 // [13][W]
     int4* cand_ordrec = nullptr; int4* base_ordrec = nullptr;   // [13][n] / [n] position-ordered bin records A of U
     int4* cand_ordb = nullptr; int4* base_ordb = nullptr; int4* base_ordc = nullptr;   // records B (mid-points) and C (masks)
@@ -1622,6 +1690,7 @@ struct graal_ctx {
     Profiler prof;
     FixedGraph g_stats, g_relabel, g_full, g_full_cached;
     Lane lanes[GRAAL_MAX_LANES]; int n_lanes = 3; cudaEvent_t ev_fork = nullptr;
+    int pairing = 1;                         // GRAAL_PAIRING=0: score candidates 3, 5, 7 like the others (A/B runs)
     ProposalGraph graphs[16]; long long version = 0; int use_graphs = 1;      // version: bumped whenever captured arguments go stale
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -1804,6 +1873,7 @@ int graal_ctx_create(int device, graal_ctx** out) {
     c->partial_stride = c->n_sm * 8;
     CUDA_OK(cudaMalloc(&c->partials, (size_t)16 * c->partial_stride * sizeof(double)));
     { const char* e = getenv("GRAAL_GRAPHS"); if (e && e[0] == '0') c->use_graphs = 0; }
+    { const char* e = getenv("GRAAL_PAIRING"); if (e && e[0] == '0') c->pairing = 0; }
     { const char* e = getenv("GRAAL_LANES"); if (e && e[0] >= '1' && e[0] <= '0' + GRAAL_MAX_LANES) c->n_lanes = e[0] - '0'; }
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     for (int l = 0; l < c->n_lanes; l++) {
@@ -1822,7 +1892,7 @@ static void free_level_scratch(graal_ctx* c) {
     cudaFree(c->cid16_base); cudaFree(c->mid32_base); cudaFree(c->cm_base); c->cm_base = nullptr; cudaFree(c->group_row); cudaFree(c->band_hist); c->band_hist = nullptr; c->cid16_base = nullptr; c->mid32_base = nullptr; c->group_row = nullptr;
     for (int l = 0; l < GRAAL_MAX_LANES; l++) {
         Lane& L = c->lanes[l];
-        cudaFree(L.sub_index); cudaFree(L.chmask); cudaFree(L.geo_cand); cudaFree(L.cand_ordrec); cudaFree(L.base_ordrec); cudaFree(L.cand_ordb); cudaFree(L.base_ordb); cudaFree(L.base_ordc); cudaFree(L.rep_in_u);
+        cudaFree(L.sub_index); cudaFree(L.chmask); cudaFree(L.chmask2); L.chmask2 = nullptr; cudaFree(L.geo_cand); cudaFree(L.cand_ordrec); cudaFree(L.base_ordrec); cudaFree(L.cand_ordb); cudaFree(L.base_ordb); cudaFree(L.base_ordc); cudaFree(L.rep_in_u);
         L.sub_index = nullptr; L.chmask = nullptr; L.geo_cand = nullptr; L.cand_ordrec = L.base_ordrec = L.cand_ordb = L.base_ordb = L.base_ordc = nullptr; L.rep_in_u = nullptr;
     }
     cudaFree(c->geo_base); cudaFree(c->order);
@@ -2010,14 +2080,16 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     for (int l = 0; l < c->n_lanes; l++) {
         Lane& L = c->lanes[l];
         CUDA_OK(cudaMalloc(&L.chmask, (size_t)c->W * sizeof(unsigned)));
-        CUDA_OK(cudaMalloc(&L.cand_ordrec, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int4)));
+        CUDA_OK(cudaMalloc(&L.chmask2, (size_t)c->W * sizeof(unsigned)));
+        CUDA_OK(cudaMemset(L.chmask2, 0, (size_t)c->W * sizeof(unsigned)));
+        CUDA_OK(cudaMalloc(&L.cand_ordrec, (size_t)N_BAND_ROWS * n * sizeof(int4)));
         CUDA_OK(cudaMalloc(&L.base_ordrec, (size_t)n * sizeof(int4)));
-        CUDA_OK(cudaMemset(L.cand_ordrec, 0, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int4)));
+        CUDA_OK(cudaMemset(L.cand_ordrec, 0, (size_t)N_BAND_ROWS * n * sizeof(int4)));
         CUDA_OK(cudaMemset(L.base_ordrec, 0, (size_t)n * sizeof(int4)));
-        CUDA_OK(cudaMalloc(&L.cand_ordb, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int4)));
+        CUDA_OK(cudaMalloc(&L.cand_ordb, (size_t)N_BAND_ROWS * n * sizeof(int4)));
         CUDA_OK(cudaMalloc(&L.base_ordb, (size_t)n * sizeof(int4)));
         CUDA_OK(cudaMalloc(&L.base_ordc, (size_t)n * sizeof(int4)));
-        CUDA_OK(cudaMemset(L.cand_ordb, 0, (size_t)GRAAL_N_CANDIDATES * n * sizeof(int4)));
+        CUDA_OK(cudaMemset(L.cand_ordb, 0, (size_t)N_BAND_ROWS * n * sizeof(int4)));
         CUDA_OK(cudaMemset(L.base_ordb, 0, (size_t)n * sizeof(int4)));
         CUDA_OK(cudaMemset(L.base_ordc, 0, (size_t)n * sizeof(int4)));
         CUDA_OK(cudaMalloc(&L.geo_cand, (size_t)GRAAL_N_CANDIDATES * c->W * sizeof(Geo)));
@@ -2301,7 +2373,7 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
 
 // the base slot's geometry must be current (ensure_base_geometry on the context stream) before this runs on `st`
 static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_slot, int first_cand_slot, int n_cand, int id_fA, int id_fB, int max_id,
-                            unsigned skip, double* d_out, double* d_band, int copy_to = 0) {
+                            unsigned skip, double* d_out, double* d_band, int copy_to = 0, unsigned pair_mask = 0u) {
     const int n = c->n_new, ld = c->ld;
     const Params p = c->p;
     int* base = slot_ptr(c, base_slot);
@@ -2310,13 +2382,15 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
     int* piece_len = L.ints + 16;
     const int ps = c->partial_stride;
     int* rng = L.ints + 160;                       // [0,1] base range, [2 + 2k, 3 + 2k] candidate k
-    k_delta_setup<<<nblk(n, 256), 256, 0, st>>>(base, ld, id_fA, id_fB, c->d_ints + 0, max_id, meta, n, c->W, L.sub_index, L.chmask, piece_len, rng); CHECK_LAUNCH(c);
+    k_delta_setup<<<nblk(n, 256), 256, 0, st>>>(base, ld, id_fA, id_fB, c->d_ints + 0, max_id, meta, n, c->W, L.sub_index, L.chmask, piece_len, rng, L.chmask2); CHECK_LAUNCH(c);
     const int gu = std::min(c->n_sm * 2, nblk(n, 256));
     k_cand_geometry<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->lv, L.sub_index, meta, L.geo_cand, (size_t)c->W, piece_len,
                                                      c->geo_base, L.chmask, skip); CHECK_LAUNCH(c);
-    k_cand_order<<<dim3(gu, n_cand + 1), 256, 0, st>>>(cand0, slot_stride(c), ld, L.sub_index, meta, piece_len, n, skip,
+    const int n_rows = pair_mask ? N_BAND_ROWS : n_cand;          // band rows: candidates (+ the partner rows of the paired ones)
+    k_cand_order<<<dim3(gu, n_cand + 1 + (pair_mask ? 3 : 0)), 256, 0, st>>>(cand0, slot_stride(c), ld, L.sub_index, meta, piece_len, n, skip,
                                                       c->lv, L.chmask, L.geo_cand, (size_t)c->W, L.cand_ordrec, L.cand_ordb, rng + 2,
-                                                      n_cand, base, c->geo_base, L.base_ordrec, L.base_ordb, L.base_ordc, rng); CHECK_LAUNCH(c);
+                                                      n_cand, base, c->geo_base, L.base_ordrec, L.base_ordb, L.base_ordc, rng,
+                                                      pair_mask, L.chmask2); CHECK_LAUNCH(c);
     // grid-stride kernels over the (device-side) size of U: a few CTAs per SM, not one warp per bin of the level
     const int gw = std::min(ps, std::max(1, std::min(nblk(n, 1), c->n_sm * 2)));      // one resident wave (128 registers: 2 CTAs per SM)
     // (band: 2 CTAs per SM and one warp per x measured best with three proposals in flight: small grids share the SMs)
@@ -2325,13 +2399,13 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
     // contacts: sum over changed contacts of ob * (ln ex_k - ln ex_0): new terms per candidate, old terms once
     c->prof.begin(GRAAL_K_DELTA_CONTACTS, st);
     k_delta_contacts_rows<<<dim3(gw, 1), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, L.sub_index, meta, c->geo_base, L.geo_cand, (size_t)c->W,
-                                                      L.chmask, p, p_contacts, ps); CHECK_LAUNCH(c);
+                                                      L.chmask, L.chmask2, pair_mask, p, p_contacts, ps); CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_DELTA_CONTACTS, st);
     // band mass: d_band[k] = B_U(S_k) - B_U(S_0) over changed pairs; enters the delta with a minus sign
     c->prof.begin(GRAAL_K_DELTA_BAND, st);
-    if (p.nd == 1) k_band_delta<false, 1, true><<<dim3(gb, n_cand), 256, 0, st>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
+    if (p.nd == 1) k_band_delta<false, 1, true><<<dim3(gb, n_rows), 256, 0, st>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
                                                                               p_cand, ps);
-    else k_band_delta<false, 1, false><<<dim3(gb, n_cand), 256, 0, st>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
+    else k_band_delta<false, 1, false><<<dim3(gb, n_rows), 256, 0, st>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
                                                                      p_cand, ps);
     CHECK_LAUNCH(c);
     if (p.nd == 1) k_band_delta<true, 4, true><<<dim3(gb, 1), 256, 0, st>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
@@ -2341,7 +2415,7 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
     CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_DELTA_BAND, st);
     // second stage of the three reductions, out = contacts - (cand band - base band); candidate 8 (skipped) copies candidate 0
-    k_finish_delta<<<n_cand, 256, 0, st>>>(p_contacts, gw, p_cand, p_base, gb, ps, d_out, d_band, copy_to); CHECK_LAUNCH(c);
+    k_finish_delta<<<n_cand, 256, 0, st>>>(p_contacts, gw, p_cand, p_base, gb, ps, d_out, d_band, copy_to, pair_mask); CHECK_LAUNCH(c);
     if (c->n_rep > 0) {     // ranges 2-4: pixels of the duplicated bins that have a copy in U, new minus old
         CUDA_OK(cudaMemsetAsync(L.rep_in_u, 0, (size_t)c->N, st));
         k_mark_rep_in_u<<<gu, 256, 0, st>>>(base, ld, L.sub_index, meta, c->lv, L.rep_in_u); CHECK_LAUNCH(c);
@@ -2424,7 +2498,8 @@ int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int i
                                                         id_fA, id_fB, c->d_ints + 0, max_id, 0x1FFFu);
         CHECK_LAUNCH(c);
         c->prof.end(GRAAL_K_BUILD, st);
-        return delta_loglik_impl(c, L, st, base_slot, first_cand_slot, GRAAL_N_CANDIDATES, id_fA, id_fB, max_id, skip, d_out, d_band, skip ? 8 : 0);
+        return delta_loglik_impl(c, L, st, base_slot, first_cand_slot, GRAAL_N_CANDIDATES, id_fA, id_fB, max_id, skip, d_out, d_band, skip ? 8 : 0,
+                                 c->pairing ? PAIR_MASK : 0u);
     };
     ProposalGraph& G = c->graphs[proposal_index];
     if (!c->use_graphs || c->prof.on) { rc = enqueue(); if (rc) return rc; }
@@ -2463,8 +2538,8 @@ int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int i
             void* args_build[] = {&a_src, &a_dst, &a_stride, &a_ld, &a_n, &a_fA, &a_fB, &a_dmax, &a_max, &a_mask};
             cudaKernelNodeParams kp = G.kp_build; kp.kernelParams = args_build; kp.extra = nullptr;
             CUDA_OK(cudaGraphExecKernelNodeSetParams(G.exec, G.n_build, &kp));
-            int* a_meta = L.ints + 8; int a_W = c->W; int* a_sub = L.sub_index; unsigned* a_chm = L.chmask; int* a_pl = L.ints + 16; int* a_rng = L.ints + 160;
-            void* args_setup[] = {&a_src, &a_ld, &a_fA, &a_fB, &a_dmax, &a_max, &a_meta, &a_n, &a_W, &a_sub, &a_chm, &a_pl, &a_rng};
+            int* a_meta = L.ints + 8; int a_W = c->W; int* a_sub = L.sub_index; unsigned* a_chm = L.chmask; int* a_pl = L.ints + 16; int* a_rng = L.ints + 160; unsigned* a_chm2 = L.chmask2;
+            void* args_setup[] = {&a_src, &a_ld, &a_fA, &a_fB, &a_dmax, &a_max, &a_meta, &a_n, &a_W, &a_sub, &a_chm, &a_pl, &a_rng, &a_chm2};
             kp = G.kp_setup; kp.kernelParams = args_setup; kp.extra = nullptr;
             CUDA_OK(cudaGraphExecKernelNodeSetParams(G.exec, G.n_setup, &kp));
         }

@@ -171,9 +171,13 @@ def test_lanes_and_graphs_match_the_plain_abi(small_pyramid):
             check(lib.graal_delta_loglik(ctx, CUR, CAND0, N_TMP_STRUCT, fA, fB, -1, g._ptr(g.d_out, 32)))
             ref = g._fetch()[32:32 + N_TMP_STRUCT].copy()
             got = fast[16 + N_TMP_STRUCT * x: 16 + N_TMP_STRUCT * (x + 1)]
-            keep = np.arange(N_TMP_STRUCT) != 8             # candidate 8 is a copy of candidate 0 in the fused path
-            assert np.array_equal(got[keep], ref[keep]), (rnd, x, got, ref)
+            # the fused path copies candidate 8 from candidate 0 and scores candidates 3, 5, 7 as second-level deltas
+            # against 2, 4, 6 (same terms, summed in another order); everything else is the same arithmetic
+            same = np.array([0, 1, 2, 4, 6, 9, 10, 11, 12])
+            assert np.array_equal(got[same], ref[same]), (rnd, x, got, ref)
             assert got[8] == got[0]
+            paired = np.array([3, 5, 7])
+            assert np.allclose(got[paired], ref[paired], rtol=1e-9, atol=1e-7), (rnd, x, got[paired] - ref[paired])
             for k in (0, 5, 12):
                 check(lib.graal_dist_genome(ctx, CAND0 + k, g._ptr(g.d_init_prev), g._ptr(g.d_init_next),
                                             g._ptr(g.d_init_orientable), g._ptr(g.d_dist_skip), g._ptr(g.d_out, 60)))
