@@ -388,8 +388,8 @@ class sampler:
         check(self.lib.graal_set_params(self.ctx, arr))
 
     def set_math_mode(self, mode):
-        """0: the reference's float32 chain op for op; 1 (default): log-space float64 evaluation of in-band
-        pixels (see include/graal_b200.h)."""
+        """0: the reference's float32 chain op for op; 1: log-space float64 evaluation of in-band pixels;
+        2 (default): tabulated law (see include/graal_b200.h)."""
         self._inc_valid = False          # the cached likelihood no longer describes the state / parameters
         check(self.lib.graal_set_math_mode(self.ctx, int(mode)))
         if self.param_simu is not None:

@@ -12,7 +12,14 @@
  *     library owns only its scratch (geometry tables, partial sums, derived level tables).
  *   - a context is bound to one GPU and one CUDA stream and must be used from one thread at a time
  *     (the reference owns its CUDA context from a single Python thread, main_gl.py:690-706).
- *   - results written to device pointers are valid after the context's stream is synchronised.
+ *   - results written to device pointers are valid after the context's stream is synchronised
+ *     (graal_score_proposal / graal_score_step: after graal_join, graal_fetch or graal_sync).
+ *
+ * Environment switches read at graal_ctx_create (A/B measurements; the defaults are the measured best):
+ *   GRAAL_LANES=n    (1..4, default 3)  proposals of a step scored concurrently; 1 = serial on the context stream
+ *   GRAAL_GRAPHS=0   launch every kernel individually instead of replaying captured CUDA graphs
+ *   GRAAL_PAIRING=0  score candidates 3, 5, 7 like the others instead of as deltas against 2, 4, 6
+ *   GRAAL_SMEM_CID=1 contig-id table of the contact pass in shared memory (math modes 0 / 1 only; slower)
  *
  * State layout ("slots"): the reference keeps the genome in a struct of 14 int* (kernels3.cu:9-24,
  * packed by gpustruct.py).  Here a slot is one SoA block of 14 x ld int32, field f of slot s at
@@ -87,9 +94,10 @@ int graal_set_params(graal_ctx* ctx, const float p[8]);
  *      ln v_inter) + ln norm, from the same float32 distance s.  Differs from mode 0 by the float32
  *      roundings of the chain (<= ~1.5e-7 relative per pixel, zero mean), the order of the difference
  *      between two float32 libm implementations.
- *   2  (default) mode 1 with the law tabulated: f(s) and ln f(s) as float64 cubic-Hermite tables with 128
- *      nodes per octave of s (rebuilt on the host for every parameter set), indexed by the float bit
- *      pattern of s; interpolation error < 1e-9 relative.  No log / exp / division per pixel.
+ *   2  (default) mode 1 with the law tabulated: f(s) and ln f(s) as piecewise quadratics, 512 intervals per
+ *      octave of s over 2^-12 .. 2^11 kb, one 16-byte entry {double a0; float a1, a2} per interval (rebuilt on
+ *      the host for every parameter set), indexed by the float bit pattern of s; interpolation error < 2e-9
+ *      relative.  One gather, no log / exp / division per pixel; distances outside the table use mode 1.
  * Circular contigs always use the float32 chain (rippe_contacts_circ, kernels3.cu:135-166). */
 int graal_set_math_mode(graal_ctx* ctx, int mode);
 

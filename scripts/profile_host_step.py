@@ -1,3 +1,5 @@
+"""cProfile of the host side of sampler.step_max_likelihood on the C2 level (run on a GPU box):
+where the time between two device round trips goes (profiles/README.md)."""
 import cProfile, pstats, io, sys, time
 import numpy as np
 sys.argv = ["bench.py"]
