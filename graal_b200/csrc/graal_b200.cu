@@ -1646,6 +1646,9 @@ struct Profiler {
 #define GRAAL_MAX_LANES 4
 struct Lane {
     cudaStream_t st = nullptr; cudaEvent_t done = nullptr; bool pending = false;
+    // side streams of the lane: the contact pass, the candidate band pass and the base band pass of a proposal only
+    // depend on the geometry / order kernels, not on each other (fork / join by events; graph branches when captured)
+    cudaStream_t side[2] = {nullptr, nullptr}; cudaEvent_t ev_ready = nullptr, ev_side[2] = {nullptr, nullptr};
     int cand_first = -1;                     // candidate slots [cand_first, cand_first + 13) in use while pending
     int* ints = nullptr;                     // [256]: [8..16) delta meta, [16..120) piece_len, [160..188) changed ranges
     int* sub_index = nullptr;                // [n]
@@ -1690,6 +1693,7 @@ struct graal_ctx {
     Profiler prof;
     FixedGraph g_stats, g_relabel, g_full, g_full_cached;
     Lane lanes[GRAAL_MAX_LANES]; int n_lanes = 3; cudaEvent_t ev_fork = nullptr;
+    int fork_passes = 1;                     // GRAAL_FORK=0: contact / band passes of a proposal on one stream
     int pairing = 1;                         // GRAAL_PAIRING=0: score candidates 3, 5, 7 like the others (A/B runs)
     ProposalGraph graphs[16]; long long version = 0; int use_graphs = 1;      // version: bumped whenever captured arguments go stale
     int device = 0;
@@ -1874,12 +1878,18 @@ int graal_ctx_create(int device, graal_ctx** out) {
     CUDA_OK(cudaMalloc(&c->partials, (size_t)16 * c->partial_stride * sizeof(double)));
     { const char* e = getenv("GRAAL_GRAPHS"); if (e && e[0] == '0') c->use_graphs = 0; }
     { const char* e = getenv("GRAAL_PAIRING"); if (e && e[0] == '0') c->pairing = 0; }
+    { const char* e = getenv("GRAAL_FORK"); if (e && e[0] == '0') c->fork_passes = 0; }
     { const char* e = getenv("GRAAL_LANES"); if (e && e[0] >= '1' && e[0] <= '0' + GRAAL_MAX_LANES) c->n_lanes = e[0] - '0'; }
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     for (int l = 0; l < c->n_lanes; l++) {
         Lane& L = c->lanes[l];
         CUDA_OK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
         CUDA_OK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&L.ev_ready, cudaEventDisableTiming));
+        for (int i = 0; i < 2; i++) {
+            CUDA_OK(cudaStreamCreateWithFlags(&L.side[i], cudaStreamNonBlocking));
+            CUDA_OK(cudaEventCreateWithFlags(&L.ev_side[i], cudaEventDisableTiming));
+        }
         CUDA_OK(cudaMalloc(&L.ints, 256 * sizeof(int)));
         CUDA_OK(cudaMemset(L.ints, 0, 256 * sizeof(int)));
         CUDA_OK(cudaMalloc(&L.partials, (size_t)48 * c->partial_stride * sizeof(double)));
@@ -1920,6 +1930,8 @@ void graal_ctx_destroy(graal_ctx* c) {
         Lane& L = c->lanes[l];
         cudaFree(L.ints); cudaFree(L.partials);
         if (L.done) cudaEventDestroy(L.done);
+        if (L.ev_ready) cudaEventDestroy(L.ev_ready);
+        for (int i = 0; i < 2; i++) { if (L.ev_side[i]) cudaEventDestroy(L.ev_side[i]); if (L.side[i]) cudaStreamDestroy(L.side[i]); }
         if (L.st) cudaStreamDestroy(L.st);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -2396,6 +2408,15 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
     // (band: 2 CTAs per SM and one warp per x measured best with three proposals in flight: small grids share the SMs)
     const int gb = std::min(ps, std::max(1, std::min(nblk(n, 4), c->n_sm * 2)));
     double* p_contacts = L.partials, *p_cand = L.partials + (size_t)16 * ps, *p_base = L.partials + (size_t)32 * ps;
+    // the three passes are independent: contacts stay on `st`, the two band passes go to the lane's side streams
+    // (one stream when the per-kernel profiler is on, or without side streams)
+    const bool fork = c->fork_passes && !c->prof.on && L.side[0] && L.side[1];
+    cudaStream_t s_cand = fork ? L.side[0] : st, s_base = fork ? L.side[1] : st;
+    if (fork) {
+        CUDA_OK(cudaEventRecord(L.ev_ready, st));
+        CUDA_OK(cudaStreamWaitEvent(s_cand, L.ev_ready, 0));
+        CUDA_OK(cudaStreamWaitEvent(s_base, L.ev_ready, 0));
+    }
     // contacts: sum over changed contacts of ob * (ln ex_k - ln ex_0): new terms per candidate, old terms once
     c->prof.begin(GRAAL_K_DELTA_CONTACTS, st);
     k_delta_contacts_rows<<<dim3(gw, 1), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, L.sub_index, meta, c->geo_base, L.geo_cand, (size_t)c->W,
@@ -2403,17 +2424,21 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
     c->prof.end(GRAAL_K_DELTA_CONTACTS, st);
     // band mass: d_band[k] = B_U(S_k) - B_U(S_0) over changed pairs; enters the delta with a minus sign
     c->prof.begin(GRAAL_K_DELTA_BAND, st);
-    if (p.nd == 1) k_band_delta<false, 1, true><<<dim3(gb, n_rows), 256, 0, st>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
+    if (p.nd == 1) k_band_delta<false, 1, true><<<dim3(gb, n_rows), 256, 0, s_cand>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
                                                                               p_cand, ps);
-    else k_band_delta<false, 1, false><<<dim3(gb, n_rows), 256, 0, st>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
+    else k_band_delta<false, 1, false><<<dim3(gb, n_rows), 256, 0, s_cand>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
                                                                      p_cand, ps);
     CHECK_LAUNCH(c);
-    if (p.nd == 1) k_band_delta<true, 4, true><<<dim3(gb, 1), 256, 0, st>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
+    if (p.nd == 1) k_band_delta<true, 4, true><<<dim3(gb, 1), 256, 0, s_base>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
                                                                         p_base, ps);
-    else k_band_delta<true, 4, false><<<dim3(gb, 1), 256, 0, st>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
+    else k_band_delta<true, 4, false><<<dim3(gb, 1), 256, 0, s_base>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
                                                                p_base, ps);
     CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_DELTA_BAND, st);
+    if (fork) {
+        CUDA_OK(cudaEventRecord(L.ev_side[0], s_cand)); CUDA_OK(cudaEventRecord(L.ev_side[1], s_base));
+        CUDA_OK(cudaStreamWaitEvent(st, L.ev_side[0], 0)); CUDA_OK(cudaStreamWaitEvent(st, L.ev_side[1], 0));
+    }
     // second stage of the three reductions, out = contacts - (cand band - base band); candidate 8 (skipped) copies candidate 0
     k_finish_delta<<<n_cand, 256, 0, st>>>(p_contacts, gw, p_cand, p_base, gb, ps, d_out, d_band, copy_to, pair_mask); CHECK_LAUNCH(c);
     if (c->n_rep > 0) {     // ranges 2-4: pixels of the duplicated bins that have a copy in U, new minus old

@@ -19,6 +19,7 @@
  *   GRAAL_LANES=n    (1..4, default 3)  proposals of a step scored concurrently; 1 = serial on the context stream
  *   GRAAL_GRAPHS=0   launch every kernel individually instead of replaying captured CUDA graphs
  *   GRAAL_PAIRING=0  score candidates 3, 5, 7 like the others instead of as deltas against 2, 4, 6
+ *   GRAAL_FORK=0     contact / band passes of a proposal on one stream instead of three
  *   GRAAL_SMEM_CID=1 contig-id table of the contact pass in shared memory (math modes 0 / 1 only; slower)
  *
  * State layout ("slots"): the reference keeps the genome in a struct of 14 int* (kernels3.cu:9-24,
