@@ -2,8 +2,9 @@
 oracle/ref_emu/cuda_shim.h (TEST INFRASTRUCTURE -- it pins the NumPy oracle against the reference's own code).
 
 Only possible where /root/reference exists (this container); the GPU box uses the golden fixtures generated
-from it (tests/golden/ref_*.npz, tests/golden/make_ref_golden.py).  Nothing of the reference is committed: the
-one-line-patched copy of the kernel file and the library are written to oracle/_ref/ (git-ignored)."""
+from it (tests/golden/ref_*.npz, tests/golden/make_ref_golden.py).  Nothing of the reference is committed or copied: the
+translation unit (shim + the kernel file with one line patched + the launch wrappers) is composed in memory and
+piped to g++; only the library is written, to oracle/_ref/ (git-ignored)."""
 import os
 import subprocess
 import sys
@@ -30,13 +31,14 @@ def build(force=False):
     needle = "extern __shared__ double res[];"
     if text.count(needle) != 1:
         raise RuntimeError("unexpected reference source: %r found %d times" % (needle, text.count(needle)))
-    gen = os.path.join(OUT, "kernels3_emu.cu")
-    with open(gen, "w") as h:
-        # dynamic shared memory of sub_compute_likelihood (one double per thread of the block)
-        h.write(text.replace(needle, "static double res[4096];"))
-    cmd = ["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-w", "-x", "c++", "-I", HERE,
-           '-DREF_KERNELS="%s"' % gen, os.path.join(HERE, "emu_main.cpp"), "-o", LIB]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    # dynamic shared memory of sub_compute_likelihood (one double per thread of the block) -> a static array.
+    # The translation unit is composed in memory and piped to g++: no copy of the reference source is written.
+    main = open(os.path.join(HERE, "emu_main.cpp")).read()
+    marker = "#include REF_KERNELS"
+    assert main.count(marker) == 1
+    unit = main.replace(marker, '#line 1 "%s"\n' % src + text.replace(needle, "static double res[4096];") + '\n#line 1 "emu_main.cpp (after the kernels)"\n')
+    cmd = ["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-w", "-x", "c++", "-I", HERE, "-", "-o", LIB]
+    r = subprocess.run(cmd, input=unit, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("g++ failed:\n%s\n%s" % (" ".join(cmd), r.stderr[-6000:]))
     return LIB

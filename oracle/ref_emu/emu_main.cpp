@@ -1,7 +1,7 @@
-// Host build of the reference kernels (TEST INFRASTRUCTURE, see cuda_shim.h).  REF_KERNELS is the path of the
-// generated copy of kernels3.cu under oracle/_ref/ (the reference source with ONE line changed by build.py:
-// `extern __shared__ double res[];` -> a function-local static array, which the shim's `__shared__` cannot
-// express); everything else is compiled exactly as it lies under /root/reference.
+// Host build of the reference kernels (TEST INFRASTRUCTURE, see cuda_shim.h).  build.py replaces the include line
+// below by the text of /root/reference/kernels3.cu (with ONE line changed: `extern __shared__ double res[];` ->
+// a function-local static array, which the shim's `__shared__` cannot express) and pipes the unit to g++;
+// everything else is compiled exactly as it lies under /root/reference.
 #include "cuda_shim.h"
 #include REF_KERNELS
 
