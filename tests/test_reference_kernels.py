@@ -178,6 +178,42 @@ def test_likelihood_live(pyr):
         assert abs(d - a) <= 1e-6 * abs(a) + 2.0 ** -22 * mass + 1e-9, (j, d, a)
 
 
+@needs_reference
+def test_likelihood_live_circular_contig(pyr):
+    """A contig closed into a circle (rippe_contacts_circ inside both likelihood kernels) and flipped bins
+    (the trans accumulation quirk of the lower data bin)."""
+    o = H.make_oracle(prepare_sampler_inputs(pyr, G.LEVEL), pyr)
+    rng = np.random.RandomState(7)
+    n = o.n_new_frags
+    H.scramble(o, rng, 10, modes=[1, 1, 2, 5])                     # flips and a few insertions
+    max_id = int(o.modify_gl_cuda_buffer())
+    for c in np.unique(o.cur["id_c"]):
+        bins = np.nonzero(o.cur["id_c"] == c)[0]
+        if bins.size >= 4:
+            head = int(bins[np.argmin(o.cur["pos"][bins])]); tail = int(bins[np.argmax(o.cur["pos"][bins])])
+            new = M.copy_slot(o.cur)
+            R.move("paste", new, o.cur, tail, head, max_id=max_id)          # the reference kernel itself closes the circle
+            if new["circ"][head] == 1:
+                for k in M.FIELDS:
+                    o.cur[k][:] = new[k]
+                break
+    assert int((o.cur["circ"] == 1).sum()) >= 4 and int((o.cur["ori"] == -1).sum()) > 0
+    max_id = o.modify_gl_cuda_buffer()
+    ref = R.evaluate_likelihood(o.cur, o.lv, o.param_simu)
+    mine = L.evaluate_likelihood(o.cur, o.lv, o.param_simu)
+    assert np.all(np.abs(mine - ref) <= 2e-6 * (np.abs(ref) + 1.0) + 1e-3)
+    assert abs(mine.sum() - ref.sum()) <= 1e-7 * abs(ref.sum())
+    circ_bins = np.nonzero(o.cur["circ"] == 1)[0]
+    for fA in (int(circ_bins[0]), int(circ_bins[-1]), int(rng.randint(n))):
+        fB = int(rng.choice(np.setdiff1d(np.arange(n), [fA])))
+        M.perform_modifications(o.ws, o.cur, fA, fB, max_id)
+        no_rep, rep = o.candidate_index_sets(fA, fB)
+        for j in range(13):
+            a = R.sub_compute_likelihood(o.ws.collector[j], o.lv, o.param_simu, ref, no_rep, rep, o.uniq_frags)
+            d, mass = oracle_delta_and_mass(o, mine, fA, fB, j)
+            assert abs(d - a) <= 1e-6 * abs(a) + 2.0 ** -22 * mass + 1e-9, (fA, fB, j, d, a)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("tag", ["u", "r"])
 def test_device_vs_reference_kernels(fixture, pyr, tag):
