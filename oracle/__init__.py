@@ -23,5 +23,6 @@ against the same vectors.  Independent anchors kept from before:
  (iii) the reciprocity identities of GRAALprinciple.pdf section B.3.1,
  (iv)  an independent list model of the genome for every mutation (tests/test_oracle_moves.py),
 and the frozen trajectories under ``tests/golden/`` produced by ``tests/golden/make_golden.py``.
-The HOST logic of the sampler (proposal and candidate draws, cuda_lib_gl.py) remains a restatement: Python 2.
+The HOST logic of a step (candidate draw, return_neighbours, setup_distri_frags, dist_inter_genome) is checked
+against the reference's own Python lines executed under Python 3 (tests/test_reference_host_logic.py).
 """

@@ -1,0 +1,55 @@
+"""Run pieces of the reference's HOST code (cuda_lib_gl.py, Python 2) under Python 3 -- TEST INFRASTRUCTURE.
+
+The reference cannot be imported (PyCUDA, OpenGL, print statements), but several of its methods are plain NumPy
+and already valid Python 3 apart from `xrange`.  Their source TEXT is read from /root/reference at test time
+(never copied into the repo), dedented and exec'd; `self` is a mock object prepared by the test."""
+import os
+import textwrap
+import time
+
+import numpy as np
+
+REF = os.environ.get("GRAAL_REFERENCE", "/root/reference")
+PATH = os.path.join(REF, "cuda_lib_gl.py")
+
+
+def available():
+    return os.path.exists(PATH)
+
+
+class _NumpyOfItsTime:
+    """numpy as the reference imported it (1.x): `np.lib.arraysetops.*` was public."""
+    lib = __import__("types").SimpleNamespace(arraysetops=__import__("types").SimpleNamespace(setdiff1d=np.setdiff1d, intersect1d=np.intersect1d))
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+
+NP = _NumpyOfItsTime()
+
+
+def _lines():
+    return open(PATH).read().split("\n")
+
+
+def method(name):
+    """The reference method `name` of class sampler as a Python 3 function f(self, ...)."""
+    lines = _lines()
+    start = next(i for i, l in enumerate(lines) if l.startswith("    def %s(" % name))
+    end = next(i for i in range(start + 1, len(lines)) if lines[i].startswith("    def ") or (lines[i] and not lines[i].startswith(" ")))
+    src = textwrap.dedent("\n".join(lines[start:end]))
+    from scipy import stats
+    ns = {"np": NP, "xrange": range, "time": time, "stats": stats}
+    exec(compile(src, "%s:%s" % (PATH, name), "exec"), ns)
+    return ns[name]
+
+
+def block(after_def, first_marker, last_marker):
+    """The statements of method `after_def` from the first line containing `first_marker` to the first following
+    line containing `last_marker` (inclusive), dedented: returned as a code object to exec in a namespace."""
+    lines = _lines()
+    d = next(i for i, l in enumerate(lines) if l.startswith("    def %s(" % after_def))
+    a = next(i for i in range(d, len(lines)) if first_marker in lines[i])
+    b = next(i for i in range(a, len(lines)) if last_marker in lines[i])
+    src = textwrap.dedent("\n".join(lines[a:b + 1]))
+    return compile(src, "%s:%s[%d:%d]" % (PATH, after_def, a + 1, b + 1), "exec")
