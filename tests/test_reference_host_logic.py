@@ -12,6 +12,7 @@ import helpers as H
 from graal_b200 import sampler as GS
 from graal_b200.level import prepare_sampler_inputs, build_synthetic_pyramid
 from oracle import mutations as M
+from oracle import sampler as OS
 
 pytestmark = pytest.mark.skipif(not RH.available(), reason="reference sources not present")
 NT = 13
@@ -41,6 +42,10 @@ def test_candidate_draw_matches_the_reference_lines():
         got = GS.sampler._sample(mine, score.copy(), F_t)
         got_next = np.random.rand()
         assert got == ref_out and got_next == ref_next, (case, got, ref_out)
+        # the oracle's restatement (what the golden trajectories were generated with) takes an explicit RandomState
+        rs = np.random.RandomState(seed)
+        o_out, _ = OS.sample_candidate(score.copy(), NT, rs, F_t)
+        assert o_out == ref_out and rs.rand() == ref_next, (case, o_out, ref_out)
         n_draws += int(ref_next != np.random.RandomState(seed).rand())
     assert n_draws > 100                                           # the draw path (not only argmax) was exercised
 
