@@ -617,7 +617,15 @@ class sampler:
         self.sub_score = sub_score
         if len(id_ok) <= 1:
             return id_max
-        return int(self.rng.choice(id_ok, 1, p=sub_score)[0])
+        rs = getattr(self.rng, "random_sample", None)
+        if rs is None or not np.all(np.isfinite(sub_score)):
+            return int(self.rng.choice(id_ok, 1, p=sub_score)[0])      # (also raises like the reference on bad weights)
+        # np.random.choice(id_ok, 1, p=sub_score) of a RandomState, without its argument validation: one uniform
+        # draw searched in the normalised cumulative weights (tests/test_reference_host_logic.py: same candidate,
+        # same stream position as the reference's own lines)
+        cdf = sub_score.cumsum()
+        cdf /= cdf[-1]
+        return int(id_ok[int(cdf.searchsorted(rs(), side="right"))])
 
     # ------------------------------------------------------------------ cuda_lib_gl.py:2022-2107
     def step_nuisance_parameters(self, dt=0, t=0, n_step=1):
