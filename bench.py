@@ -8,14 +8,17 @@ candidate committed -> 13 * n_neighbours move evaluations.
 
 Workload at N = 1: BASELINE config C2 -- synthetic T. reesei-shaped pyramid (77 contigs, 33 Mb,
 100,000 level-0 fragments, factor 3), single chain, run at level 1 (33k bins, 100k sub-frags,
-~30 M stored contact entries = 240 MB of contact lists, larger than the 126 MB L2, re-streamed every
-step).  N > 1: one independent replica chain per GPU (weak scaling) with a replica-exchange
+23.7 M stored contact entries = 190 MB of contact lists, larger than the 126 MB L2, re-streamed every
+step).  N > 1: ``--chains-per-gpu`` independent replica chains per GPU (weak scaling) with a replica-exchange
 all_gather of (loglik, temperature index) every --exchange-every steps.
 
     value     device-resident throughput: the recorded proposal schedule replayed with no host round trip
     e2e       the same schedule through the public sampler API (host RNG draws, D2H of scores / state)
-    roofline  the contact-list pass of the full likelihood (k_full_contacts), CUDA events inside the library
-    cpu_baseline / --impl reference: the NumPy oracle (sparse formulation) on the host cores
+    roofline  the contact-list pass of the full likelihood, CUDA events inside the library; ``roofline_delta``: the contact
+              pass of the move deltas; ``roofline_c4``: the same two kernels on BASELINE config C4 (200 k bins, 237 M contacts)
+    parity    the first timed step scored by the NumPy oracle on the host (39 deltas + the full likelihood) against the
+              device's numbers for the same step; the run FAILS (exit code 1) outside the tolerance
+    cpu_baseline / --impl reference: the NumPy oracle (sparse formulation) on all host cores, same schedule
 """
 import argparse
 import json
@@ -42,8 +45,10 @@ def parse():
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c4", "tiny"])
     ap.add_argument("--level", type=int, default=1)
     ap.add_argument("--neighbours", type=int, default=3)
-    ap.add_argument("--exchange-every", type=int, default=20)
+    ap.add_argument("--chains-per-gpu", type=int, default=1)
+    ap.add_argument("--exchange-every", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the roofline_c4 block (C4 level generated and timed in the same run)")
     ap.add_argument("--incremental", action="store_true",
                     help="carry the likelihood of the current state from the committed candidate (full pass every 256 steps "
                          "only) instead of recomputing it every step as the reference does; NOT the default workload")
@@ -75,6 +80,27 @@ def model_params(pyr):
     return [law["kuhn"], law["lm"], law["slope"], law["d"], A], d_max
 
 
+def make_config(name, n_bins, W, E, k_nb, n_contigs, chains, world, exchange_every, incremental=False):
+    """The workload description, identical for both arms (the driver compares the two `config` objects)."""
+    return {"workload": name, "bins": int(n_bins), "sub_frags": int(W), "contact_entries": int(E),
+            "contact_list_MB": round(8 * E / 1e6, 1), "neighbours_per_step": int(k_nb), "candidates_per_neighbour": N_TMP,
+            "state": "assembled genome (%d contigs)" % n_contigs,
+            "schedule": "bins: RandomState(4242).permutation; neighbours: the reference's proposal rule on RandomState(1000 + chain)",
+            "l2": "inputs larger than L2: the %.0f MB contact list is re-streamed every step" % (8 * E / 1e6),
+            "full_likelihood": ("incremental: carried from the committed candidate, full pass every 256 steps (NOT the reference's schedule)"
+                                if incremental else "recomputed every step, as the reference does"),
+            "parallelism": "%d replica chain%s per GPU" % (chains, "" if chains == 1 else "s")
+                           + (", replica-exchange all_gather every %d steps" % exchange_every if world * chains > 1 else "")}
+
+
+def bin_schedule(n, total):
+    sched_rng = np.random.RandomState(4242)          # the same bins on every rank: replicas do statistically identical work
+    frags = sched_rng.permutation(n)[:total]
+    if frags.size < total:
+        frags = np.concatenate([frags, sched_rng.randint(0, n, size=total - frags.size)])
+    return frags
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md)."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -85,7 +111,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -115,90 +141,213 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-_POOL_CTX = {}
+# ------------------------------------------------------------------------------------------------------------------
+# the oracle on the host cores: one step = the 13 x k candidate deltas + the full likelihood of the current state
+# ------------------------------------------------------------------------------------------------------------------
+_W = {}
 
 
-def _pool_delta(args):
+def _w_delta(task):
+    """(fA, fB, j) -> (delta, mass) of candidate j of the proposal; the 13 candidates of a proposal are built once per worker."""
+    from oracle import sparse as S, mutations as M
+    fA, fB, j = task
+    c = _W
+    if c.get("prop") != (fA, fB):
+        if "ws" not in c:
+            c["ws"] = M.Workspace(c["n"])
+        M.perform_modifications(c["ws"], c["cur"], fA, fB, c["max_id"])
+        cur = c["cur"]
+        c["bins_u"] = np.nonzero((cur["id_c"] == cur["id_c"][fA]) | (cur["id_c"] == cur["id_c"][fB]))[0]
+        c["prop"] = (fA, fB)
+    return S.sparse_delta(c["ws"].collector[j], c["cur"], c["lv"], c["par"], c["bins_u"], return_mass=True)
+
+
+def _w_full(task):
+    """One share of the full likelihood: a slice of the stored contacts and a group of contigs of the band mass."""
     from oracle import sparse as S
-    cand, bins_u = args
-    c = _POOL_CTX
-    return S.sparse_delta(cand, c["cur"], c["lv"], c["par"], bins_u)
+    c = _W
+    if "geo" not in c:
+        c["geo"] = S.Geo(c["cur"], c["lv"])
+    kind, arg = task
+    if kind == "contacts":
+        t, _ = S.contact_terms(c["geo"], c["lv"], c["par"], np.arange(arg[0], arg[1]))
+        return float(t.sum())
+    return -S.band_mass(c["geo"], c["lv"], c["par"], arg)
 
 
-def _pool_noop(j):
+def _w_noop(j):
     return j
 
 
-class CpuPort:
-    """The oracle (NumPy port of the reference semantics, sparse formulation) scoring proposals of a level on
-    the host: the level structures are built once; per proposal the 13 candidates are built and scored, by
-    `workers` forked processes when workers > 1 (the candidates are independent, as on the reference's 13
-    streams; the processes inherit the read-only level and are started before any timed region)."""
+class CpuStep:
+    """The oracle (NumPy port of the reference semantics, sparse formulation) scoring whole steps of a level on the host:
+    per step the 13 candidates of every proposal and the full likelihood of the current state, spread over `workers` forked
+    processes (the candidates are independent, as on the reference's 13 streams; the workers inherit the read-only level
+    and are started before any timed region).  The genome stays the initial one (nothing is committed): a bounded sample of
+    the chain's work, same schedule."""
 
-    def __init__(self, inp, pyr, workers=1):
+    def __init__(self, inp, pyr, workers):
         from oracle import mutations as M, sparse as S, likelihood as L
-        self.M, self.S = M, S
+        import multiprocessing as mp
+        self.S = S
         p, d_max = model_params(pyr)
         self.par = L.make_params(p[0], p[1], p[2], p[3], p[4], d_max, inp.mean_value_trans)
-        r, c, v = inp.sub_coo
-        t0 = time.time()
         self.lv = S.SparseLevel(inp.n_frags, inp.np_sub_frags_id, inp.np_sub_frags_len_bp, inp.np_sub_frags_accu,
-                                inp.mean_squared_frags_per_bin, r, c, v)
+                                inp.mean_squared_frags_per_bin, *inp.sub_coo)
         self.cur = {k: np.array(inp.S_o_A_frags[k], dtype=np.int32) for k in M.FIELDS}
         self.cur["ori"][:] = 1
         self.max_id = M.relabel_contigs(self.cur)
-        self.t_setup = time.time() - t0
-        self.ws = M.Workspace(inp.n_new_frags)
-        self.workers, self.pool = int(workers), None
-        if self.workers > 1:
-            import multiprocessing as mp
-            _POOL_CTX.update(cur=self.cur, lv=self.lv, par=self.par)
-            self.pool = mp.get_context("fork").Pool(self.workers)
-            self.pool.map(_pool_noop, range(self.workers))
+        self.workers = max(1, int(workers))
+        _W.clear()
+        _W.update(cur=self.cur, lv=self.lv, par=self.par, n=inp.n_new_frags, max_id=self.max_id)
+        self.pool = mp.get_context("fork").Pool(self.workers)
+        self.pool.map(_w_noop, range(self.workers))
+        # shares of the full likelihood: contact slices of equal size, contigs grouped by band work (~ size)
+        E = int(self.lv.rows.size)
+        n_sl = 2 * self.workers
+        cuts = np.linspace(0, E, n_sl + 1).astype(np.int64)
+        geo = S.Geo(self.cur, self.lv)
+        ids, cnt = np.unique(geo.id_c, return_counts=True)
+        order = np.argsort(-cnt)
+        groups = [[] for _ in range(min(n_sl, ids.size))]
+        load = np.zeros(len(groups))
+        for k in order:
+            g = int(np.argmin(load)); groups[g].append(ids[k]); load[g] += cnt[k]
+        self.full_tasks = [("contacts", (int(a), int(b))) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+        self.full_tasks += [("band", np.nonzero(np.isin(geo.id_c, g))[0]) for g in groups if g]
+        self.const = -(S.g0_mass(self.lv, self.par) + S.quirk_mass(self.cur, self.lv, self.par))
 
     def close(self):
         if self.pool is not None:
             self.pool.terminate()
             self.pool = None
-        _POOL_CTX.clear()
+        _W.clear()
 
-    def score(self, fA, fB, max_seconds=45.0):
-        M, S, cur, lv = self.M, self.S, self.cur, self.lv
-        M.perform_modifications(self.ws, cur, fA, fB, self.max_id)
-        in_u = (cur["id_c"] == cur["id_c"][fA]) | (cur["id_c"] == cur["id_c"][fB])
-        bins_u = np.nonzero(in_u)[0]
-        n_eval = 0
+    def step(self, fA, neighbours, with_full=True):
+        """-> (deltas [(delta, mass)] in proposal-major order, full likelihood or None, seconds)."""
         t0 = time.time()
-        if self.pool is not None:
-            self.pool.map(_pool_delta, [(self.ws.collector[j], bins_u) for j in range(N_TMP)], chunksize=1)
-            n_eval = N_TMP
-        else:
-            for j in range(N_TMP):
-                S.sparse_delta(self.ws.collector[j], cur, lv, self.par, bins_u)
-                n_eval += 1
-                if time.time() - t0 > max_seconds:
-                    break
-        return dict(n_eval=n_eval, t_delta=time.time() - t0, contig_bins=int(bins_u.size))
-
-    def full_sample(self, fA):
-        """The per-step full likelihood, timed on a row sample of the contact list and of the band pairs."""
-        S, lv = self.S, self.lv
-        t0 = time.time()
-        geo = S.Geo(self.cur, lv)
-        sel = np.nonzero(lv.rows % 20 == 0)[0]
-        S.contact_terms(geo, lv, self.par, sel)
-        sub_sample = np.nonzero(geo.id_c == geo.id_c[lv.sub_id[fA, 0]])[0]
-        S.band_mass(geo, lv, self.par, sub_sample)
-        return dict(t_full_sample=time.time() - t0, sample_rows=int(sel.size), sample_subs=int(sub_sample.size))
+        tasks = [(int(fA), int(fB), j) for fB in neighbours for j in range(N_TMP)]
+        r_d = self.pool.map_async(_w_delta, tasks, chunksize=1)
+        r_f = self.pool.map_async(_w_full, self.full_tasks, chunksize=1) if with_full else None
+        deltas = r_d.get()
+        full = (sum(r_f.get()) + self.const) if with_full else None
+        return deltas, full, time.time() - t0
 
 
-def cpu_port_sample(inp, pyr, fA, fB, max_seconds=45.0):
-    """One proposal on one thread + the full-likelihood sample (the `cpu_baseline` of the default run)."""
-    port = CpuPort(inp, pyr, workers=1)
-    r = port.score(fA, fB, max_seconds)
-    r.update(port.full_sample(fA))
-    r.update(t_setup=port.t_setup, n_contacts=int(port.lv.rows.size), W=int(port.lv.W))
-    return r
+class HostProposals:
+    """The reference's proposal rule (return_neighbours, cuda_lib_gl.py:2295-2331) and the one uniform draw of the candidate
+    choice on the host, consuming RandomState(1000 + chain) exactly as graal_b200.sampler does -- the reference arm follows
+    the same (bin, neighbours) schedule without a GPU."""
+
+    def __init__(self, inp, seed):
+        from graal_b200.sampler import neighbour_tables
+        self.rng = np.random.RandomState(seed)
+        self.xk, self.pk = neighbour_tables(inp.level_coo, int(inp.n_frags), [], 10)
+        self.id_d = np.asarray(inp.S_o_A_frags["id_d"])
+
+    def neighbours(self, fA, delta):
+        ori = int(self.id_d[fA])
+        distri = self.pk[ori]
+        n_max = min(min(10, delta), int(np.count_nonzero(distri)))
+        nb = sorted(int(e) for e in self.rng.choice(self.xk[ori], n_max, p=distri, replace=False))
+        self.rng.random_sample()                  # the draw of the sampled candidate
+        return nb
+
+
+def parity_block(deltas_cpu, full_cpu, deltas_gpu, full_gpu):
+    """Device vs oracle on one step: the asserted bound is tests/helpers.delta_check's."""
+    worst_mass, worst_rel, ok = 0.0, 0.0, True
+    for (ref, mass), got in zip(deltas_cpu, deltas_gpu):
+        err = abs(got - ref)
+        worst_mass = max(worst_mass, err / max(mass, 1e-300))
+        if abs(ref) > 0:
+            worst_rel = max(worst_rel, err / abs(ref))
+        ok &= err <= 1e-6 * abs(ref) + 1e-7 * mass + 1e-9
+    full_rel = abs(full_gpu - full_cpu) / abs(full_cpu) if full_cpu else None
+    ok &= full_rel is not None and full_rel <= 1e-7
+    rank_ok = int(np.argmax([d[0] for d in deltas_cpu])) == int(np.argmax(deltas_gpu))
+    return {"n_deltas": len(deltas_gpu), "max_err_over_mass": worst_mass, "max_rel": worst_rel, "full_rel": full_rel,
+            "best_candidate_agrees": bool(rank_ok), "tolerance": "|err| <= 1e-6 |delta| + 1e-7 mass; full 1e-7 relative", "ok": bool(ok)}
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path = the NumPy oracle port (the reference is
+    Python 2 + PyCUDA and cannot run here; its kernels need a GPU), on all host cores, same schedule, same step content."""
+    pyr, inp, name = build_level(args.config, args.level)
+    k_nb = args.neighbours
+    workers = max(1, min(32, os.cpu_count() or 1))
+    port = CpuStep(inp, pyr, workers)
+    props = HostProposals(inp, 1000)
+    total = args.warmup + args.steps
+    frags = bin_schedule(int(inp.n_new_frags), total)
+    vals, t_all, n_ev = [], [], 0
+    t_budget, t_start = 240.0, time.time()                   # the whole run ends within a few minutes
+    for step in range(total):
+        fA = int(frags[step])
+        nb = props.neighbours(fA, k_nb)
+        if not nb:
+            continue
+        if step < args.warmup and time.time() - t_start > 30.0:
+            continue                                          # bounded warm-up
+        _, _, dt = port.step(fA, nb, with_full=True)
+        if step >= args.warmup:
+            vals.append(N_TMP * len(nb) / dt); t_all.append(dt); n_ev += N_TMP * len(nb)
+        if time.time() - t_start > t_budget and vals:
+            break
+    port.close()
+    v = float(n_ev / sum(t_all)) if t_all else 0.0
+    n_contigs = len(np.unique(inp.S_o_A_frags["id_c"]))
+    E = int(port.lv.rows.size)
+    line = {"impl": "reference", "metric": "mcmc_move_loglik_evals_per_s", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(t_all)) * 1e3 if t_all else None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 expected contacts, f64 log-likelihood accumulation",
+            "data": "synthetic",
+            "config": make_config(name, inp.n_frags, inp.init_n_sub_frags, E, k_nb, n_contigs, 1, 1, args.exchange_every),
+            "steps_measured": len(vals),
+            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": workers, "kind": "port",
+                             "sample": "per step: the 13 candidate deltas of each of the %d proposals AND the full likelihood of the current state "
+                                       "(all 23.7 M contacts + band mass), NumPy oracle (sparse formulation) on %d forked workers; the genome "
+                                       "stays the initial one (no commit); %d of %d steps measured inside the 240 s budget"
+                                       % (k_nb, workers, len(vals), args.steps)},
+            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def profile_kernels(g, _lib):
+    import ctypes as C
+    kern = {}
+    for kname, kid in _lib.KERNELS.items():
+        tot, cnt = C.c_double(), C.c_longlong()
+        _lib.check(g.lib.graal_profile_read(g.ctx, kid, C.byref(tot), C.byref(cnt), 1))
+        kern[kname] = {"ms_total": tot.value, "launches": cnt.value, "ms_avg": tot.value / cnt.value if cnt.value else None}
+    cnts = (C.c_longlong * 4)()
+    _lib.check(g.lib.graal_profile_counters(g.ctx, cnts, 1))
+    return kern, [int(x) for x in cnts]
+
+
+def roofline_blocks(kern, counters, E, W, peak, peak_src, traffic):
+    """`roofline` of the contact-list pass of the full likelihood and `roofline_delta` of the delta contact pass
+    (8 B per entry visited, 24 B per row, 16 B per distinct sub-frag, 8 B per candidate)."""
+    fc = kern["FULL_CONTACTS"]
+    alg = 8 * E + 24 * W + 16 * W + 8
+    ach = alg / (fc["ms_avg"] * 1e-3) / 1e9 if fc["ms_avg"] else None
+    roof = {"bound": "hbm", "kernel": "k_full_contacts_win (contact-list pass of the per-step full likelihood)",
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if ach else None,
+            "traffic": traffic.get("full_contacts"), "algorithmic_bytes_per_launch": alg, "avg_launch_ms": fc["ms_avg"],
+            "windows_ms": kern.get("FULL_WINDOWS", {}).get("ms_avg"),
+            "peak_source": peak_src, "contacts_per_s": E / (fc["ms_avg"] * 1e-3) if fc["ms_avg"] else None}
+    dc = kern["DELTA_CONTACTS"]
+    e_u, r_u, b_u, n_p = counters
+    roof_d = None
+    if dc["ms_total"] and n_p:
+        alg_d = 8 * e_u + 24 * r_u + 16 * r_u + 8 * N_TMP * n_p
+        ach_d = alg_d / (dc["ms_total"] * 1e-3) / 1e9
+        roof_d = {"bound": "hbm", "kernel": "delta contact pass (rows of contig(fA) + contig(fB), 13 candidates per launch)",
+                  "achieved": ach_d, "peak": peak, "unit": "GB/s", "frac": ach_d / peak,
+                  "traffic": traffic.get("delta_contacts"), "algorithmic_bytes_per_launch": alg_d / n_p, "avg_launch_ms": dc["ms_avg"],
+                  "proposals": n_p, "mean_entries_in_U": e_u / n_p, "mean_bins_in_U": b_u / n_p,
+                  "candidate_contacts_per_s": N_TMP * e_u / (dc["ms_total"] * 1e-3)}
+    return roof, roof_d
 
 
 def main():
@@ -209,81 +358,64 @@ def main():
     k_nb = args.neighbours
 
     if args.impl == "reference":
-        # the reference's own CPU implementation of the path = the NumPy oracle port (the reference is
-        # Python 2 + PyCUDA and cannot run here; its kernels need a GPU).  Rank 0 only.
-        if rank != 0:
-            return
-        pyr, inp, name = build_level(args.config, args.level)
-        rng = np.random.RandomState(1000)
-        s = inp.S_o_A_frags
-        vals, t_all = [], []
-        workers = max(1, min(N_TMP, os.cpu_count() or 1))        # all the host threads the 13 candidates can use
-        port = CpuPort(inp, pyr, workers=workers)
-        t_budget, t_start = 240.0, time.time()                   # the whole run ends within a few minutes
-        for step in range(args.warmup + args.steps):
-            fA = int(rng.randint(inp.n_new_frags))
-            fB = int(s["next"][fA]) if s["next"][fA] >= 0 else int(s["prev"][fA])
-            r = port.score(fA, fB, max_seconds=20.0)
-            if step >= args.warmup:
-                vals.append(r["n_eval"] / r["t_delta"]); t_all.append(r["t_delta"])
-            if time.time() - t_start > t_budget and vals:
-                break
-        port.close()
-        v = float(np.mean(vals)) if vals else 0.0
-        line = {"impl": "reference", "metric": "mcmc_move_loglik_evals_per_s", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(t_all)) * 1e3 if t_all else None,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 expected / f64 log-likelihood",
-                "data": "synthetic", "config": {"workload": name, "neighbours": k_nb, "steps_measured": len(vals)},
-                "cpu_baseline": {"value": v, "unit": "evals/s", "cores": workers, "kind": "port",
-                                 "sample": "per step: the 13 candidate deltas of ONE proposal of the same level, NumPy oracle (sparse formulation), "
-                                           "one forked worker per candidate up to the host core count; the per-step full likelihood is not included"},
-                "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        if rank == 0:
+            reference_arm(args)
         return
 
     import torch
     import torch.distributed as dist
     from graal_b200 import _lib
-    from graal_b200.sampler import sampler, CUR, FRAG_FIELDS
+    from graal_b200.sampler import sampler, CUR
     from graal_b200 import replica as R
 
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    n_ch = max(1, args.chains_per_gpu)
 
-    if args.config == "c4":
-        # BASELINE config C4: 200k bins / ~200 M stored contacts, generated on the GPU (no CPU baseline: the
-        # NumPy oracle does not fit this size in the time budget)
+    def c4_sampler(seed):
         from graal_b200.level import synthetic_roofline_level
-        inp, lists, tables, info = synthetic_roofline_level(device=dev)
+        inp4, lists, tables, info = synthetic_roofline_level(device=dev)
+        g4 = sampler.from_inputs(inp4, device=local_rank, rng=np.random.RandomState(seed), device_contact_lists=lists, proposal_tables=tables)
+        g4.set_parameters([1.0, 9.6, -1.5, 3.0, 800.0], info["d_max_kb"])
+        return inp4, g4
+
+    chains = []
+    if args.config == "c4":
+        # BASELINE config C4: 200k bins / ~237 M stored contacts, generated on the GPU (no CPU baseline: the NumPy oracle
+        # does not fit this size in the time budget; tests/test_gpu_bench_configs.py checks a row sample of it)
+        inp, g = c4_sampler(1000 + rank * n_ch)
         name = "C4: synthetic 200k-bin / ~200M-contact level (24 contigs, offsets ~ s^-1.5 truncated at d_max = 1000 kb, 5% trans), single chain"
         pyr = None
-        g = sampler.from_inputs(inp, device=local_rank, rng=np.random.RandomState(1000 + rank),
-                                device_contact_lists=lists, proposal_tables=tables)
-        g.set_parameters([1.0, 9.6, -1.5, 3.0, 800.0], info["d_max_kb"])
         args.no_cpu_baseline = True
+        chains = [g]
     else:
         pyr, inp, name = build_level(args.config, args.level)
-        g = sampler.from_inputs(inp, device=local_rank, rng=np.random.RandomState(1000 + rank))
         p, d_max = model_params(pyr)
-        g.set_parameters(p, d_max)
-    g.incremental_likelihood = bool(args.incremental)
+        for ch in range(n_ch):
+            share = chains[0] if chains else None
+            g = sampler.from_inputs(inp, device=local_rank, rng=np.random.RandomState(1000 + rank * n_ch + ch), share_level_with=share)
+            g.set_parameters(p, d_max)
+            chains.append(g)
+    g = chains[0]
+    for gc in chains:
+        gc.incremental_likelihood = bool(args.incremental)
     rex = None
-    if world > 1:
-        rex = R.ReplicaExchange(1, R.temperature_ladder(world), exchange_every=args.exchange_every, seed=20141217, device=dev)
-        R.attach(g, rex, 0)
+    if world * n_ch > 1:
+        rex = R.ReplicaExchange(n_ch, R.temperature_ladder(world * n_ch), exchange_every=args.exchange_every, seed=20141217, device=dev)
+        for ch, gc in enumerate(chains):
+            R.attach(gc, rex, ch)
     n = int(g.n_new_frags)
     init_state = g.slot_to_host(CUR)
     total = args.warmup + args.steps
-    sched_rng = np.random.RandomState(4242)          # the same bins on every rank: replicas do statistically identical work
-    frags = sched_rng.permutation(n)[:total]
-    if frags.size < total:
-        frags = np.concatenate([frags, sched_rng.randint(0, n, size=total - frags.size)])
+    frags = bin_schedule(n, total)
 
     def barrier():
         if world > 1:
             dist.barrier()
+        for gc in chains:
+            gc.sync()
         torch.cuda.synchronize(dev)
 
     clocks = ClockSampler(local_rank)
@@ -291,9 +423,10 @@ def main():
         clocks.start()
     windows = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_mark = [0.0]
 
     # ---------------- pass 1: end to end through the public API (records the schedule) --------------
-    schedule = []
+    schedules = [[] for _ in chains]
     e2e_ms, h2d, d2h = None, 0, 0
     if rex is not None:
         rex.warm_up()                      # NCCL channel set-up for the exchange's all_gather, outside the timed region
@@ -301,86 +434,86 @@ def main():
         for it in range(total):
             if it == args.warmup:
                 barrier()
-                t_w0 = time.time()
+                t_mark[0] = time.time()
                 ev0.record(g.stream)
             fA = int(frags[it])
-            out = g.step_max_likelihood(fA, k_nb)
-            schedule.append((fA, list(g.id_neighbours), int(out[6]), int(out[5])))
+            if n_ch == 1:
+                out = g.step_max_likelihood(fA, k_nb)
+                schedules[0].append((fA, list(g.id_neighbours) if out[5] >= 0 else [], int(out[6]), int(out[5])))
+            else:
+                outs = R.step_chains(chains, fA, k_nb)
+                for ch, (gc, out) in enumerate(zip(chains, outs)):
+                    schedules[ch].append((fA, list(gc.id_neighbours) if out[5] >= 0 else [], int(out[6]), int(out[5])))
             if rex is not None:
-                rex.maybe_exchange(it + 1, [g.likelihood_t])
+                rex.maybe_exchange(it + 1, [gc.likelihood_t for gc in chains])
+        for gc in chains[1:]:
+            gc.sync()
         ev1.record(g.stream)
         barrier()
-        windows.append((t_w0, time.time()))
+        windows.append((t_mark[0], time.time()))
         e2e_ms = ev0.elapsed_time(ev1)
-        # per step: D2H of the pinned output block, twice; H2D: none
-        # (proposal ids travel as kernel arguments)
-        d2h = g.h_out.numel() * 8            # one fetch of the pinned output block per step: scores, stats, candidate distances
-        h2d = 0
+        d2h = g.h_out.numel() * 8 * n_ch     # one fetch of the pinned output block per chain-step: scores, stats, candidate distances
+        h2d = 0                              # proposal ids travel as kernel arguments
     else:
         for it in range(total):
             fA = int(frags[it])
-            nb = g.return_neighbours(fA, k_nb); nb.sort()
-            schedule.append((fA, nb, nb[0] if nb else fA, 6))
+            for ch, gc in enumerate(chains):
+                nb = gc.return_neighbours(fA, k_nb); nb.sort()
+                schedules[ch].append((fA, nb, nb[0] if nb else fA, 6 if nb else -1))
 
     # ---------------- pass 2: device resident replay (no host round trip inside the timed region) ------
     def replay(profile=False):
-        g.slot_from_host(CUR, init_state)
+        for gc in chains:
+            gc.slot_from_host(CUR, init_state)
         if rex is not None:
-            rex.temp_index = np.arange(world, dtype=np.int64); rex.round_id = 0
-        l0 = g.gpu_launches
-        for it, (fA, nb, fB, op) in enumerate(schedule):
+            rex.reset()
+        l0 = sum(gc.gpu_launches for gc in chains)
+        for it in range(total):
             if it == args.warmup:
                 barrier()
                 if profile:
-                    _lib.check(g.lib.graal_profile_enable(g.ctx, 1))
-                nonlocal_t[0] = time.time()
-                l0 = g.gpu_launches
+                    for gc in chains:
+                        _lib.check(gc.lib.graal_profile_enable(gc.ctx, 1))
+                t_mark[0] = time.time()
+                l0 = sum(gc.gpu_launches for gc in chains)
                 ev0.record(g.stream)
-            g.step_device(fA, nb, fB, op, full=(not args.incremental) or it % 256 == 0)
-            if rex is not None and not profile and (it + 1) % args.exchange_every == 0:
-                like = g._fetch()[0]
-                rex.maybe_exchange(it + 1, [like])
+            for gc, sched in zip(chains, schedules):
+                fA, nb, fB, op = sched[it]
+                gc.step_device(fA, nb, fB, op, full=(not args.incremental) or it % 256 == 0)
+            if rex is not None and not profile:
+                rex.maybe_exchange_device(it + 1, chains)
+        for gc in chains[1:]:
+            gc.sync()
         ev1.record(g.stream)
         barrier()
-        ms = ev0.elapsed_time(ev1)
-        return ms, g.gpu_launches - l0
+        return ev0.elapsed_time(ev1), sum(gc.gpu_launches for gc in chains) - l0
 
-    nonlocal_t = [0.0]
     ms, launches = replay(False)
-    windows.append((nonlocal_t[0], time.time()))
+    windows.append((t_mark[0], time.time()))
     if args.profile_only:
         print(json.dumps({"profile_only": True, "ms_per_step": ms / max(1, args.steps), "launches": launches}))
         return
     # ---------------- pass 3: same replay with the library's per-kernel event timers ---------------------
-    prof_ms, _ = replay(True)
-    kern = {}
-    for kname, kid in _lib.KERNELS.items():
-        import ctypes as C
-        tot, cnt = C.c_double(), C.c_longlong()
-        _lib.check(g.lib.graal_profile_read(g.ctx, kid, C.byref(tot), C.byref(cnt), 1))
-        kern[kname] = {"ms_total": tot.value, "launches": cnt.value, "ms_avg": tot.value / cnt.value if cnt.value else None}
-    _lib.check(g.lib.graal_profile_enable(g.ctx, 0))
+    replay(True)
+    kern, counters = profile_kernels(g, _lib)
+    for gc in chains:
+        _lib.check(gc.lib.graal_profile_enable(gc.ctx, 0))
 
     # ---------------- aggregate over ranks -------------------------------------------------------------
-    def max_over_ranks(x):
+    def reduce_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    n_eval = sum(N_TMP * len(nb) for (_, nb, _, _) in schedule[args.warmup:])
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-    tot_eval = sum_over_ranks(float(n_eval))
-    ms_max = max_over_ranks(ms)
-    e2e_max = max_over_ranks(e2e_ms)
+    n_eval = sum(N_TMP * len(nb) for sched in schedules for (_, nb, _, op) in sched[args.warmup:] if op >= 0)
+    tot_eval = reduce_ranks(float(n_eval), dist.ReduceOp.SUM)
+    ms_max, ms_min = reduce_ranks(ms, dist.ReduceOp.MAX), reduce_ranks(ms, dist.ReduceOp.MIN)
+    e2e_max, e2e_min = reduce_ranks(e2e_ms, dist.ReduceOp.MAX), reduce_ranks(e2e_ms, dist.ReduceOp.MIN)
     value = tot_eval / (ms_max * 1e-3)
     e2e_value = tot_eval / (e2e_max * 1e-3)
+    exch = rex.stats() if rex is not None else None
 
     if rank != 0:
         if world > 1:
@@ -394,52 +527,86 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    traffic_all = {}
+    try:
+        traffic_all = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
     E, W = g.n_contacts, int(g.init_n_sub_frags)
-    alg_bytes = 8 * E + 24 * W + 16 * W + 8
-    fc = kern["FULL_CONTACTS"]
-    achieved = alg_bytes / (fc["ms_avg"] * 1e-3) / 1e9 if fc["ms_avg"] else None
-    traffic = None
-    tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr_path):
-        try:
-            traffic = json.load(open(tr_path)).get("k_full_contacts_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    cfg_key = args.config if args.config != "c2" or args.level == 1 else "c2_l%d" % args.level
+    roof, roof_d = roofline_blocks(kern, counters, E, W, peak, peak_src, traffic_all.get(cfg_key, {}))
     line = {
         "metric": "mcmc_move_loglik_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 expected contacts, f64 log-likelihood accumulation",
         "data": "synthetic",
-        "config": {"workload": name, "bins": int(g.n_frags), "sub_frags": W, "contact_entries": E,
-                   "contact_list_MB": round(8 * E / 1e6, 1), "neighbours_per_step": k_nb, "candidates_per_neighbour": N_TMP,
-                   "state": "assembled genome (%d contigs)" % len(np.unique(init_state["id_c"])),
-                   "l2": "inputs larger than L2: the %.0f MB contact list is re-streamed every step" % (8 * E / 1e6),
-                   "full_likelihood": ("incremental: carried from the committed candidate, full pass every 256 steps (NOT the reference's schedule)"
-                                       if args.incremental else "recomputed every step, as the reference does"),
-                   "parallelism": "1 replica chain per GPU" + (", replica-exchange all_gather every %d steps" % args.exchange_every if world > 1 else "")},
+        "config": make_config(name, g.n_frags, W, E, k_nb, len(np.unique(init_state["id_c"])), n_ch, world, args.exchange_every, args.incremental),
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_max / args.steps},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "k_full_contacts (contact-list pass of the per-step full likelihood)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                     "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": fc["ms_avg"],
-                     "peak_source": peak_src, "contacts_per_s": E / (fc["ms_avg"] * 1e-3) if fc["ms_avg"] else None},
+        "roofline": roof,
+        "roofline_delta": roof_d,
         "kernels": kern,
-        "contacts_scored_per_s": {"streamed_full_pass": E / (fc["ms_avg"] * 1e-3) if fc["ms_avg"] else None},
+        "contacts_scored_per_s": {"streamed_full_pass": roof["contacts_per_s"],
+                                  "candidate_contacts_delta_pass": roof_d["candidate_contacts_per_s"] if roof_d else None},
+        "ranks": {"ms_min": ms_min / args.steps, "ms_max": ms_max / args.steps, "e2e_ms_min": e2e_min / args.steps,
+                  "e2e_ms_max": e2e_max / args.steps, "exchange": exch},
     }
-    if world == 1 and not args.no_cpu_baseline:
-        fA, nb, _, _ = schedule[args.warmup]
-        r = cpu_port_sample(inp, pyr, fA, nb[0] if nb else fA, max_seconds=30.0)
-        line["cpu_baseline"] = {"value": r["n_eval"] / r["t_delta"], "unit": "evals/s", "cores": 1, "kind": "port",
-                                "host_cores_visible": os.cpu_count(),
-                                "sample": "the %d candidate deltas of the first timed proposal (contigs of %d bins), NumPy oracle (sparse "
-                                          "formulation), %.1f s; the per-step full likelihood is NOT included (a %d-row / %d-sub-frag sample "
-                                          "of it took %.1f s)" % (r["n_eval"], r["contig_bins"], r["t_delta"], r["sample_rows"],
-                                                                    r["sample_subs"], r["t_full_sample"])}
+    rc = 0
+    if world == 1 and n_ch == 1 and not args.no_cpu_baseline:
+        # the first timed step with neighbours, on the INITIAL genome, by the oracle on the host cores and by the device
+        it0 = next((i for i in range(args.warmup, total) if schedules[0][i][1]), None)
+        if it0 is not None:
+            fA, nb, _, _ = schedules[0][it0]
+            workers = max(1, min(32, os.cpu_count() or 1))
+            port = CpuStep(inp, pyr, workers)
+            port.step(fA, nb[:1], with_full=False)                     # workers warm (imports, first-touch of the level)
+            d_cpu, full_cpu, dt = port.step(fA, nb, with_full=True)
+            port.close()
+            g.slot_from_host(CUR, init_state)
+            g.modify_gl_cuda_buffer()
+            full_gpu = float(g.eval_likelihood())
+            g.score_neighbours(fA, nb)
+            d_gpu = [float(x) for x in g._fetch()[16:16 + N_TMP * len(nb)]]
+            line["parity"] = parity_block(d_cpu, full_cpu, d_gpu, full_gpu)
+            line["cpu_baseline"] = {"value": N_TMP * len(nb) / dt, "unit": "evals/s", "cores": workers, "kind": "port",
+                                    "host_cores_visible": os.cpu_count(),
+                                    "sample": "one whole step (the first timed one, on the initial genome): the %d candidate deltas of its %d "
+                                              "proposals and the full likelihood of the state (all %d contacts + band mass), NumPy oracle "
+                                              "(sparse formulation) on %d forked workers, %.1f s" % (N_TMP * len(nb), len(nb), E, workers, dt)}
+            if not line["parity"]["ok"]:
+                rc = 1
+    if world == 1 and not args.no_c4 and args.config == "c2" and n_ch == 1:
+        # BASELINE config C4 in the same run: the HBM roofline configuration (the contact list is 1.9 GB)
+        for gc in chains:
+            gc.free_gpu()
+        del chains, g
+        torch.cuda.empty_cache()
+        inp4, g4 = c4_sampler(1000)
+        n4 = int(g4.n_new_frags)
+        fr4 = bin_schedule(n4, 13)
+        for it in range(3):
+            g4.step_max_likelihood(int(fr4[it]), k_nb)
+        _lib.check(g4.lib.graal_profile_enable(g4.ctx, 1))
+        t0 = time.time()
+        for it in range(3, 13):
+            g4.step_max_likelihood(int(fr4[it]), k_nb)
+        g4.sync()
+        step_ms = (time.time() - t0) / 10 * 1e3
+        kern4, cnt4 = profile_kernels(g4, _lib)
+        _lib.check(g4.lib.graal_profile_enable(g4.ctx, 0))
+        r4, r4d = roofline_blocks(kern4, cnt4, g4.n_contacts, int(g4.init_n_sub_frags), peak, peak_src, traffic_all.get("c4", {}))
+        r4["workload"] = "C4: synthetic 200k-bin / 237M-contact level (24 contigs), 10 steps of the same chain with the per-kernel timers on"
+        r4["ms_per_step_with_timers"] = step_ms
+        line["roofline_c4"] = r4
+        line["roofline_delta_c4"] = r4d
+        g4.free_gpu()
     print(json.dumps(line))
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
+    if rc:
+        sys.exit(rc)
 
 
 if __name__ == "__main__":

@@ -76,6 +76,7 @@ _SIGS = {
     "graal_launch_count": (_LL, [_P]),
     "graal_profile_enable": (_I, [_P, _I]),
     "graal_profile_read": (_I, [_P, _I, C.POINTER(_D), C.POINTER(_LL), _I]),
+    "graal_profile_counters": (_I, [_P, C.POINTER(_LL), _I]),
 }
 
 
@@ -100,5 +101,5 @@ def check(rc):
         raise GraalError("graal_b200 error %d: %s" % (rc, load().graal_last_error().decode()))
 
 
-KERNELS = dict(FULL_CONTACTS=0, FULL_BAND=1, DELTA_CONTACTS=2, DELTA_BAND=3, BUILD=4, RELABEL=5)
+KERNELS = dict(FULL_CONTACTS=0, FULL_BAND=1, DELTA_CONTACTS=2, DELTA_BAND=3, BUILD=4, RELABEL=5, FULL_WINDOWS=6)
 OPS = dict(COPY=0, FLIP=1, SWAP_ACTIV=2, POP_OUT=3, POP_IN_1=4, POP_IN_2=5, POP_IN_3=6, POP_IN_4=7, SPLIT=8, PASTE=9)

@@ -49,7 +49,11 @@ struct Params { float kuhn, lm, c1, slope, d, d_max, fact, v_inter, nfpb; int nd
                 // tabulated law (math mode 2): piecewise quadratics {double a0; float a1, a2} of ln f(s) and of f(s),
                 // one interval per float bit pattern with LAW_M mantissa bits, s in [2^LAW_EMIN, 2^LAW_EMAX) kb;
                 // v_clamp = v_inter as double (the clamp of f), t_normd = t_norm as double
-                const int4* t_lnf; const int4* t_f; double v_clamp; const double* t_normd; };
+                const int4* t_lnf; const int4* t_f; double v_clamp; const double* t_normd;
+                // uniform-accu levels with a monotone law (windowed contact pass): ln f(s) + ln norm - log g per interval, the
+                // float bit patterns [LAW_SMIN_BITS, LAW_SMIN_BITS + fu_span) it is valid on (below d_max, inside the table,
+                // above the clamp) and the in-band zone beyond the table [fu_zlo, fu_zlo + fu_zspan); fu_ok = 0: not available
+                const int4* t_lnfu; unsigned fu_span, fu_zlo, fu_zspan; int fu_ok; };
 #define LAW_M 9
 #define LAW_EMIN (-12)
 #define LAW_EMAX 11
@@ -793,6 +797,217 @@ k_full_contacts_direct(const long long* __restrict__ rowptr, const int2* __restr
     if (threadIdx.x == 0) partials[blockIdx.x] = acc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Windowed contact pass (uniform-accu levels, math mode 2, monotone law): the default full-likelihood kernel.
+//
+// On a uniform-accu level every entry that is NOT an in-band cis pair contributes the level constant
+// ob * log g, so the pass only has to find the in-band entries.  An entry (row r, column c) can be in band
+// only if c lies inside the SUB-FRAG INDEX HULL of the bins within d_max of r's bin on r's contig in the
+// current genome -- a per-row interval [wlo, wlo + wspan] computed once per pass from the position order
+// (k_windows below).  The test is two integer instructions on the streamed column, no gather: far entries
+// (trans pairs, cis pairs beyond the band: the bulk of a real list) cost the stream load and the test, and
+// only entries inside the window take the exact path (partner {contig id, mid-point} gather, float32
+// distance, table evaluation).  The window is conservative (a superset of the in-band partners, with a
+// margin for the float32 rounding of the mid-points), so the result is the same sum as the gather-everything
+// kernel; a scrambled genome only widens the windows.
+//
+// Work items are rows cut into chunks of <= ITEM_CHUNK entries (static, built at bind): one warp per item,
+// items interleaved over the warps so that the chip streams one region of the list at a time; the row record
+// {contig id, mid-point, window} of the next item is prefetched while the current one is processed.
+// ------------------------------------------------------------------------------------------------
+#define ITEM_CHUNK 2048
+__global__ void k_item_count(const long long* __restrict__ rowptr, int W, int* __restrict__ cnt) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= W) return;
+    const long long len = rowptr[r + 1] - rowptr[r];
+    cnt[r] = (int)((len + ITEM_CHUNK - 1) / ITEM_CHUNK);
+}
+__global__ void k_item_fill(const long long* __restrict__ rowptr, int W, const int* __restrict__ off, int4* __restrict__ items) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= W) return;
+    const long long e0 = rowptr[r], e1 = rowptr[r + 1];
+    int k = off[r];
+    for (long long e = e0; e < e1; e += ITEM_CHUNK, k++)
+        items[k] = make_int4(r, (int)min((long long)ITEM_CHUNK, e1 - e), (int)(unsigned)(e & 0xffffffffll), (int)(e >> 32));
+}
+
+// Position order of a slot with the per-position fields the window pass scans: bin, start (bp), sub-frag index
+// range of the bin, contig.  Unfilled positions (inconsistent state) keep the "everything" hull.
+__global__ void k_order_init(int n, int W, int* __restrict__ order, int* __restrict__ o_start, int2* __restrict__ o_sub, int* __restrict__ o_cid, int* __restrict__ bad) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) *bad = 0;
+    if (k >= n) return;
+    order[k] = -1; o_start[k] = 0; o_sub[k] = make_int2(0, W - 1); o_cid[k] = -1;
+}
+__global__ void k_order_fill2(const int* __restrict__ slot, int ld, int n, int cap, const int* __restrict__ cont_off, LevelView lv,
+                              int* __restrict__ order, int* __restrict__ o_start, int2* __restrict__ o_sub, int* __restrict__ o_cid, int* __restrict__ bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = slot[F_ID_C * ld + i];
+    const int k = (c >= 0 && c < cap) ? cont_off[c] + slot[F_POS * ld + i] : -1;
+    if (k < 0 || k >= n) { *bad = 1; return; }
+    const int4 sid = lv.sub_id[slot[F_ID_D * ld + i]];
+    order[k] = i; o_start[k] = slot[F_START_BP * ld + i]; o_sub[k] = make_int2(sid.x, sid.x + sid.w - 1); o_cid[k] = c;
+}
+// hull of the sub-frag index ranges of every aligned block of 32 order positions
+__global__ void k_hull_blocks(const int2* __restrict__ o_sub, int n, int2* __restrict__ blk) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    int lo = INT_MAX, hi = -1;
+    if (g < n) { const int2 s = o_sub[g]; lo = s.x; hi = s.y; }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((threadIdx.x & 31) == 0 && g < n) blk[g >> 5] = make_int2(lo, hi);
+}
+// Row records of the windowed pass, one per sub-frag: {contig id, mid-point bits, wlo, wspan | slow << 31}.
+// One thread per order position g: the bins [lo, hi] of the same contig that can hold a sub-frag within d_max
+// of a sub-frag of this bin (bin ends compared in bp with a margin of 0.01 % + 100 bp over the float32
+// rounding of the mid-points), then the hull of their sub-frag index ranges from the block table.
+__global__ void __launch_bounds__(256)
+k_windows(const int* __restrict__ order, const int* __restrict__ o_start, const int2* __restrict__ o_sub, const int* __restrict__ o_cid,
+          const int2* __restrict__ blk, const int* __restrict__ cont_off, const int* __restrict__ cont_len,
+          const int* __restrict__ slot, int ld, int n, int W, long long dmax_bp, const int2* __restrict__ cm,
+          int4* __restrict__ hdr, int* __restrict__ bad) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const int bin = order[g];
+    if (bin < 0) { *bad = 1; return; }
+    const int c = o_cid[g];
+    const int cs = cont_off[c], ce = cs + cont_len[c];
+    int wl = 0, wh = W - 1;
+    if (cs <= g && g < ce && ce <= n) {
+        const long long st = o_start[g], en = st + slot[F_LEN_BP * ld + bin];
+        int a = cs, b = g;                      // lo: first position whose bin ends after st - dmax
+        while (a < b) { const int m = (a + b) >> 1; if ((long long)o_start[m + 1] > st - dmax_bp) b = m; else a = m + 1; }
+        const int lo = a;
+        a = g; b = ce - 1;                      // hi: last position whose bin starts before en + dmax
+        while (a < b) { const int m = (a + b + 1) >> 1; if ((long long)o_start[m] < en + dmax_bp) a = m; else b = m - 1; }
+        const int hi = a;
+        wl = INT_MAX; wh = -1;
+        int p = lo;
+        for (; p <= hi && (p & 31); p++) { const int2 s = o_sub[p]; wl = min(wl, s.x); wh = max(wh, s.y); }
+        for (; p + 31 <= hi; p += 32) { const int2 s = blk[p >> 5]; wl = min(wl, s.x); wh = max(wh, s.y); }
+        for (; p <= hi; p++) { const int2 s = o_sub[p]; wl = min(wl, s.x); wh = max(wh, s.y); }
+    } else *bad = 1;
+    const unsigned slow = slot[F_CIRC * ld + bin] == 1 ? 0x80000000u : 0u;
+    const int2 s = o_sub[g];
+    for (int sub = s.x; sub <= s.y; sub++) {
+        const int2 r = cm[sub];
+        hdr[sub] = make_int4(r.x, r.y, wl, (int)((unsigned)(wh - wl) | slow));
+    }
+}
+
+// fast law of the windowed pass: ob * (ln f(s) + ln norm - log g) for SMIN <= s < s_hi from the table whose a0
+// already holds the two constants; [zlo, zlo + zspan): in-band distances beyond the table (general path)
+struct FastLaw { const int4* tab; unsigned smin_bits, span, zlo, zspan; };
+#define LAW_SMIN_BITS ((unsigned)(127 + LAW_EMIN) << 23)
+
+// per-item copy of the row records (item i -> record of its row): the pass then reads items[i] and ihdr[i] with
+// no dependent load between them
+__global__ void k_item_hdr(const int4* __restrict__ items, int n_items, const int4* __restrict__ hdr, int4* __restrict__ ihdr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_items) ihdr[i] = hdr[items[i].x];
+}
+
+// rare paths of the windowed pass, out of line: one in-band entry whose distance is outside the table ...
+__device__ __noinline__ double win_slow_entry(int col, float ob, float r_mid, const int2* __restrict__ cm, const Params& p, double lg) {
+    const float s = fabsf(__int_as_float(__ldg(&cm[col]).y) - r_mid);
+    if (!(s > 0.0f && s < p.d_max)) return 0.0;
+    return inband_log_term(s, ob, 0.0f, 0, 0, p) - (double)ob * lg;
+}
+// ... and a whole item whose row lies on a circular contig (float32 chain of rippe_contacts_circ)
+__device__ __noinline__ double win_circular_item(const int2* __restrict__ cp, int len, int lane, int wlo, unsigned wspan, int r_id, float r_mid,
+                                                 float r_stot, const int2* __restrict__ cm, const Params& p, double lg) {
+    double acc = 0.0;
+    for (int off = lane; off < len; off += 32) {
+        const int2 ce = ld_stream(cp + off);
+        if ((unsigned)(ce.x - wlo) > wspan) continue;
+        const int2 pc = __ldg(&cm[ce.x]);
+        const float s = fabsf(__int_as_float(pc.y) - r_mid);
+        if (pc.x != r_id || !(s > 0.0f && s < p.d_max)) continue;
+        const float ob = __int_as_float(ce.y);
+        acc += inband_log_term(s, ob, r_stot, 0, 1, p) - (double)ob * lg;
+    }
+    return acc;
+}
+
+// UN: stream loads in flight per warp (32 entries each); SUB: the exact path runs on groups of SUB loads behind ONE
+// uniform branch, straight-line inside -- the SUB partner gathers, then the SUB table gathers are in flight together
+// (a branch per load would serialise the two dependent gathers of every load).
+template <int UN, int MINB, int SUB>
+__global__ void __launch_bounds__(256, MINB)
+k_full_contacts_win(const int4* __restrict__ items, const int4* __restrict__ ihdr, int n_items, const int2* __restrict__ contacts,
+                    const int2* __restrict__ cm, const int* __restrict__ bad, int W,
+                    const Geo* __restrict__ geo, const FastLaw fl, const __grid_constant__ Params p, double lg, double* __restrict__ partials) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const bool all_w = *bad != 0;                                   // inconsistent position order: every window is the whole level
+    const int4* __restrict__ tab = fl.tab;
+    const unsigned smin = fl.smin_bits, span = fl.span, zlo = fl.zlo, zspan = fl.zspan;
+    double accd = 0.0;
+    int4 it = make_int4(0, 0, 0, 0), h = it;
+    if (warp < n_items) { it = __ldg(&items[warp]); h = __ldg(&ihdr[warp]); }
+    for (int i = warp; i < n_items; i += n_warps) {
+        int4 itn = make_int4(0, 0, 0, 0), hn = itn;                  // prefetch the next item of this warp
+        if (i + n_warps < n_items) { itn = __ldg(&items[i + n_warps]); hn = __ldg(&ihdr[i + n_warps]); }
+        const int len = it.y;
+        const int2* __restrict__ cp = contacts + (((long long)it.w << 32) | (unsigned)it.z);
+        const int r_id = h.x; const float r_mid = __int_as_float(h.y);
+        const int wlo = all_w ? 0 : h.z; const unsigned wspan = all_w ? (unsigned)W : ((unsigned)h.w & 0x7fffffffu);
+        if (h.w >= 0) {
+            const int idle = wlo - 1;
+            cp += lane;
+            for (int off = 0; off < len; off += 32 * UN) {
+                int2 ce[UN];
+                const int left = len - off - lane;
+                #pragma unroll
+                for (int u = 0; u < UN; u++) ce[u] = (u * 32 < left) ? ld_stream(cp + off + u * 32) : make_int2(idle, 0);
+                #pragma unroll
+                for (int g = 0; g < UN / SUB; g++) {
+                    bool anyw = false;
+                    #pragma unroll
+                    for (int j = 0; j < SUB; j++) anyw |= (unsigned)(ce[g * SUB + j].x - wlo) <= wspan;
+                    if (!__any_sync(0xffffffffu, anyw)) continue;
+                    int2 pc[SUB];
+                    #pragma unroll
+                    for (int j = 0; j < SUB; j++) {
+                        pc[j] = make_int2(-1, 0);                    // (-1 outside the window: never a contig id)
+                        if ((unsigned)(ce[g * SUB + j].x - wlo) <= wspan) pc[j] = __ldg(&cm[ce[g * SUB + j].x]);
+                    }
+                    unsigned bb[SUB]; int4 e[SUB]; unsigned fastm = 0u, slow = 0u;
+                    #pragma unroll
+                    for (int j = 0; j < SUB; j++) {
+                        bb[j] = __float_as_uint(fabsf(__int_as_float(pc[j].y) - r_mid));
+                        const unsigned t = bb[j] - smin;
+                        const bool cis = pc[j].x == r_id;
+                        const bool fast = cis && t < span;
+                        e[j] = __ldg(&tab[(fast ? t : 0u) >> (23 - LAW_M)]);
+                        if (fast) fastm |= 1u << j;
+                        else if (cis && ((bb[j] - 1u) < (smin - 1u) || (bb[j] - zlo) < zspan)) slow |= 1u << j;
+                    }
+                    float accf = 0.0f;
+                    #pragma unroll
+                    for (int j = 0; j < SUB; j++) {
+                        const float uu = __uint_as_float(0x3f800000u | ((bb[j] & ((1u << (23 - LAW_M)) - 1u)) << LAW_M));
+                        const float ob = ((fastm >> j) & 1u) ? __int_as_float(ce[g * SUB + j].y) : 0.0f;
+                        accd = fma((double)ob, __hiloint2double(e[j].y, e[j].x), accd);
+                        accf = fmaf(ob, uu * fmaf(uu, __int_as_float(e[j].w), __int_as_float(e[j].z)), accf);
+                    }
+                    accd += (double)accf;
+                    if (slow) {                                      // in-band distances outside the table (rare)
+                        #pragma unroll
+                        for (int j = 0; j < SUB; j++)
+                            if ((slow >> j) & 1u) accd += win_slow_entry(ce[g * SUB + j].x, __int_as_float(ce[g * SUB + j].y), r_mid, cm, p, lg);
+                    }
+                }
+            }
+        } else accd += win_circular_item(cp, len, lane, wlo, wspan, r_id, r_mid, __ldg(&geo[it.x].stot), cm, p, lg);
+        it = itn; h = hn;
+    }
+    accd = block_sum(accd);
+    if (threadIdx.x == 0) partials[blockIdx.x] = accd;
+}
+
 // (entries touching a duplicated data bin are left to the repeat path: sub_dup marks their sub-frags;
 //  row_of gives the row of each 256-entry group to walk from)
 __device__ __forceinline__ bool entry_excluded(const long long* __restrict__ rowptr, int W, const unsigned char* __restrict__ sub_dup,
@@ -854,7 +1069,7 @@ k_band(const int* __restrict__ order, int count, const int* __restrict__ slot, i
     double acc = 0.0, acc_diag = 0.0;
     for (int ix = warp; ix < count; ix += n_warps) {
         const int x = order[ix];
-        if (!eligible(lv, x)) continue;
+        if (x < 0 || !eligible(lv, x)) continue;
         const int4 sx = lv.sub_id[slot[F_ID_D * ld + x]];
         Geo gx[3];
         float xmax = -1e30f;
@@ -872,7 +1087,7 @@ k_band(const int* __restrict__ order, int count, const int* __restrict__ slot, i
             const int iy = base + lane;
             bool live = iy < count;
             if (live) {
-                const int y = order[iy];
+                const int y = max(order[iy], 0);
                 const float ystart = __int2float_rn(slot[F_START_BP * ld + y]) / 1000.0f;
                 const int4 sy = lv.sub_id[slot[F_ID_D * ld + y]];
                 const Geo gy0 = ld_geo(&geo[sy.x]);
@@ -980,6 +1195,20 @@ __global__ void k_delta_setup(const int* __restrict__ base, int ld, int fA, int 
     const int pos = base[F_POS * ld + i];
     if (c == cA) { if (pos >= 0 && pos < n) sub_index[pos] = i; }
     else if (c == cB) { const int k = lA + pos; if (k >= 0 && k < n) sub_index[k] = i; }
+}
+// profiler only: size of U of this proposal -> counters [0] entries of the rows of U, [1] rows (sub-frags), [2] bins, [3] proposals
+__global__ void k_u_stats(const int* __restrict__ sub_index, const int* __restrict__ meta, LevelView lv, const int* __restrict__ base, int ld,
+                          const long long* __restrict__ rowptr, unsigned long long* __restrict__ counters) {
+    const int m = meta[4];
+    unsigned long long e = 0, r = 0, b = 0;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < m; u += gridDim.x * blockDim.x) {
+        const int4 sid = lv.sub_id[base[F_ID_D * ld + sub_index[u]]];
+        e += (unsigned long long)(rowptr[sid.x + sid.w] - rowptr[sid.x]); r += sid.w; b += 1;
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { e += __shfl_down_sync(0xffffffffu, e, o); r += __shfl_down_sync(0xffffffffu, r, o); b += __shfl_down_sync(0xffffffffu, b, o); }
+    if ((threadIdx.x & 31) == 0 && b) { atomicAdd(&counters[0], e); atomicAdd(&counters[1], r); atomicAdd(&counters[2], b); }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[3], 1ull);
 }
 // candidate geometry (members of U only) + contig lengths of the candidate's pieces of U
 __device__ __forceinline__ int piece_slot(int id_c, const int* meta) {
@@ -1712,7 +1941,7 @@ struct graal_ctx {
     unsigned char* d_accu_idx = nullptr;                // [N*3]
     float* d_tab_norm = nullptr; float* d_tab_g[2] = {nullptr, nullptr}; double* d_tab_logg[2] = {nullptr, nullptr};
     double* d_tab_lnnorm = nullptr; double2* d_tab_log = nullptr; double* d_tab_exp = nullptr;
-    int4* d_tab_lnf[2] = {nullptr, nullptr}; int4* d_tab_f[2] = {nullptr, nullptr}; double* d_tab_normd = nullptr;
+    int4* d_tab_lnf[2] = {nullptr, nullptr}; int4* d_tab_f[2] = {nullptr, nullptr}; int4* d_tab_lnfu[2] = {nullptr, nullptr}; double* d_tab_normd = nullptr;
     std::vector<double> h_law;
     int math_mode = 2;
     std::vector<float> h_tab_g; std::vector<double> h_tab_logg;
@@ -1722,6 +1951,11 @@ struct graal_ctx {
     double lf_total = 0.0, ob_total = 0.0;
     unsigned short* cid16_base = nullptr; float* mid32_base = nullptr; int2* cm_base = nullptr; int smem_optin = 0;
     int* group_row = nullptr; int n_groups = 0;
+    // windowed contact pass: static row items, per-pass order-space arrays and row records
+    int4* items = nullptr; int n_items = 0; int4* row_hdr = nullptr; int4* item_hdr = nullptr;
+    int* o_start = nullptr; int2* o_sub = nullptr; int* o_cid = nullptr; int2* o_blk = nullptr;
+    int full_win = 1;                         // GRAAL_FULL_WIN=0: gather-everything kernel (k_full_contacts_direct) for A/B runs
+    int win_unroll = 8, win_minb = 4, win_sub = 4;   // GRAAL_WIN_SUB=1|2|4|8: loads per exact-path group; GRAAL_WIN_UNROLL=2|4|8: stream loads in flight per warp; GRAAL_WIN_MINB=2..6: CTAs per SM
     int smem_cid = 0;                         // GRAAL_SMEM_CID=1: stage the contig-id table in shared memory (measured: no faster than L1, profiles/README.md)
     double* band_hist = nullptr;              // [16][13] band delta of the proposals scored since the last commit
     int band_slot = -1; int band_age = 0;     // slot whose cross-bin band total is cached in d_scalars[40]
@@ -1739,10 +1973,12 @@ struct graal_ctx {
     void* cub_tmp = nullptr; size_t cub_tmp_bytes = 0; int key_bits = 32;
     int* d_ints = nullptr;                   // [0]=max_id [1]=n_contigs [2]=err [3]=tmp max  [8..16)=delta meta  [16..16+13*8)=piece_len
     unsigned long long* d_stats = nullptr;   // [4]
+    unsigned long long* d_counters = nullptr; // [4] profiler counters (k_u_stats)
     double* partials = nullptr; int partial_stride = 0;   // [14][partial_stride]
     double* d_scalars = nullptr;             // [16] device doubles: [0]=contacts [1]=band [2]=quirk ...
 };
 
+static inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
 static size_t slot_stride(const graal_ctx* c) { return (size_t)N_FIELDS * c->ld; }
 static int* slot_ptr(const graal_ctx* c, int s) { return c->slots + (size_t)s * slot_stride(c); }
 
@@ -1780,13 +2016,14 @@ static int upload_tables(graal_ctx* c, Params& p, int which) {
     p.slope_d = (double)p.slope;
     // tabulated law: f(s) = c1*fact * s^slope * exp((d-2)/(x^2+d)), x = s*lm/kuhn, and ln f, with d/ds, float64
     p.t_lnf = c->d_tab_lnf[which]; p.t_f = c->d_tab_f[which]; p.t_normd = c->d_tab_normd; p.v_clamp = (double)p.v_inter;
+    p.t_lnfu = c->d_tab_lnfu[which]; p.fu_ok = 0; p.fu_span = p.fu_zlo = p.fu_zspan = 0u;
     if (p.mode == 2) {
         if (!(cf > 0.0) || !(p.kuhn > 0.0f) || !(p.lm > 0.0f)) p.mode = 1;      // degenerate parameters: analytic path
         else {
             struct Entry { double a0; float a1, a2; };
             static_assert(sizeof(Entry) == 16, "law table entry");
             const size_t half = (size_t)(LAW_NODES + 2) * 2;          // doubles per table (16 bytes per interval)
-            c->h_law.assign(half * 2, 0.0);
+            c->h_law.assign(half * 3, 0.0);
             Entry* e_ln = reinterpret_cast<Entry*>(c->h_law.data());
             Entry* e_f = reinterpret_cast<Entry*>(c->h_law.data() + half);
             const double K = (double)p.d - 2.0, dd = (double)p.d, q = (double)p.lm / (double)p.kuhn, sl = (double)p.slope;
@@ -1811,6 +2048,39 @@ static int upload_tables(graal_ctx* c, Params& p, int which) {
             }
             CUDA_OK(cudaMemcpyAsync(c->d_tab_lnf[which], c->h_law.data(), half * sizeof(double), cudaMemcpyHostToDevice, c->stream));
             CUDA_OK(cudaMemcpyAsync(c->d_tab_f[which], c->h_law.data() + half, half * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            // Uniform-accu level (one accu value, finite positive clamp): the windowed contact pass adds
+            // ob * (ln f(s) + ln norm - log g) for the in-band entries.  With a law that DECREASES over the table range
+            // the clamp max(f, v_inter) is a threshold on s: beyond s_c the pixel evaluates to exactly g and contributes 0.
+            const float g1 = (nd == 1) ? g_clamp(c->accu_hist[0].first * c->accu_hist[0].first, p.v_inter, p.nfpb) : 0.0f;
+            if (nd == 1 && g1 > 0.0f && p.d_max > 0.0f && p.v_inter > 0.0f) {
+                const float tn = (float)(c->accu_hist[0].first * c->accu_hist[0].first) / p.nfpb;
+                const double cst = log((double)tn) - log((double)g1);
+                auto f2b = [](float f) { unsigned u; memcpy(&u, &f, 4); return u; };
+                auto b2f = [](unsigned u) { float f; memcpy(&f, &u, 4); return f; };
+                const unsigned b_lo = LAW_SMIN_BITS, b_tab = f2b(ldexpf(1.0f, LAW_EMAX)), b_dmax = f2b(p.d_max);
+                bool mono = cst - cst == 0.0;
+                double prev = lnf((double)b2f(b_lo));
+                for (int i = 1; i <= LAW_NODES && mono; i++) {        // decreasing at every interval edge
+                    const double v = lnf(ldexp(1.0 + (double)(i & ((1 << LAW_M) - 1)) / (double)(1 << LAW_M), LAW_EMIN + (i >> LAW_M)));
+                    if (!(v < prev)) mono = false;
+                    prev = v;
+                }
+                if (mono) {
+                    unsigned lo = b_lo, hi = b_tab;                  // smallest pattern in [b_lo, b_tab] with ln f <= ln v (b_tab: none inside the table)
+                    if (lnf((double)b2f(lo)) > p.ln_v) {
+                        while (hi - lo > 1u) { const unsigned m = lo + (hi - lo) / 2u; if (lnf((double)b2f(m)) > p.ln_v) lo = m; else hi = m; }
+                    } else hi = lo;
+                    const unsigned b_sc = (hi >= b_tab && lnf((double)b2f(b_tab)) > p.ln_v) ? 0x7f800000u : hi;
+                    const unsigned b_hi = std::min(std::min(b_dmax, b_tab), b_sc);
+                    p.fu_span = b_hi > b_lo ? b_hi - b_lo : 0u;
+                    const unsigned z_hi = std::min(b_dmax, b_sc);
+                    p.fu_zlo = b_tab; p.fu_zspan = z_hi > b_tab ? z_hi - b_tab : 0u;
+                    Entry* e_u = reinterpret_cast<Entry*>(c->h_law.data() + 2 * half);
+                    for (int i = 0; i < LAW_NODES; i++) { e_u[i] = e_ln[i]; e_u[i].a0 += cst; }
+                    CUDA_OK(cudaMemcpyAsync(c->d_tab_lnfu[which], c->h_law.data() + 2 * half, half * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+                    p.fu_ok = 1;
+                }
+            }
             CUDA_OK(cudaStreamSynchronize(c->stream));      // h_law is reused by the next call
         }
     }
@@ -1873,12 +2143,18 @@ int graal_ctx_create(int device, graal_ctx** out) {
     CUDA_OK(cudaMalloc(&c->d_ints, 256 * sizeof(int)));
     CUDA_OK(cudaMemset(c->d_ints, 0, 256 * sizeof(int)));
     CUDA_OK(cudaMalloc(&c->d_stats, 4 * sizeof(unsigned long long)));
+    CUDA_OK(cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)));
+    CUDA_OK(cudaMemset(c->d_counters, 0, 4 * sizeof(unsigned long long)));
     CUDA_OK(cudaMalloc(&c->d_scalars, 64 * sizeof(double)));
     c->partial_stride = c->n_sm * 8;
     CUDA_OK(cudaMalloc(&c->partials, (size_t)16 * c->partial_stride * sizeof(double)));
     { const char* e = getenv("GRAAL_GRAPHS"); if (e && e[0] == '0') c->use_graphs = 0; }
     { const char* e = getenv("GRAAL_PAIRING"); if (e && e[0] == '0') c->pairing = 0; }
     { const char* e = getenv("GRAAL_FORK"); if (e && e[0] == '0') c->fork_passes = 0; }
+    { const char* e = getenv("GRAAL_FULL_WIN"); if (e && e[0] == '0') c->full_win = 0; }
+    { const char* e = getenv("GRAAL_WIN_UNROLL"); if (e && (e[0] == '2' || e[0] == '4' || e[0] == '8')) c->win_unroll = e[0] - '0'; }
+    { const char* e = getenv("GRAAL_WIN_MINB"); if (e && e[0] >= '2' && e[0] <= '6') c->win_minb = e[0] - '0'; }
+    { const char* e = getenv("GRAAL_WIN_SUB"); if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4' || e[0] == '8')) c->win_sub = e[0] - '0'; }
     { const char* e = getenv("GRAAL_LANES"); if (e && e[0] >= '1' && e[0] <= '0' + GRAAL_MAX_LANES) c->n_lanes = e[0] - '0'; }
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     for (int l = 0; l < c->n_lanes; l++) {
@@ -1905,13 +2181,15 @@ static void free_level_scratch(graal_ctx* c) {
         cudaFree(L.sub_index); cudaFree(L.chmask); cudaFree(L.chmask2); L.chmask2 = nullptr; cudaFree(L.geo_cand); cudaFree(L.cand_ordrec); cudaFree(L.base_ordrec); cudaFree(L.cand_ordb); cudaFree(L.base_ordb); cudaFree(L.base_ordc); cudaFree(L.rep_in_u);
         L.sub_index = nullptr; L.chmask = nullptr; L.geo_cand = nullptr; L.cand_ordrec = L.base_ordrec = L.cand_ordb = L.base_ordb = L.base_ordc = nullptr; L.rep_in_u = nullptr;
     }
+    cudaFree(c->items); cudaFree(c->row_hdr); cudaFree(c->item_hdr); c->item_hdr = nullptr; cudaFree(c->o_start); cudaFree(c->o_sub); cudaFree(c->o_cid); cudaFree(c->o_blk);
+    c->items = nullptr; c->row_hdr = nullptr; c->o_start = nullptr; c->o_sub = nullptr; c->o_cid = nullptr; c->o_blk = nullptr; c->n_items = 0;
     cudaFree(c->geo_base); cudaFree(c->order);
     cudaFree(c->cont_len); cudaFree(c->cont_off); cudaFree(c->first_idx); cudaFree(c->map); cudaFree(c->keys);
     cudaFree(c->keys_sorted); cudaFree(c->cub_tmp); cudaFree(c->d_quirky); cudaFree(c->d_accu_idx);
     cudaFree(c->d_dup); cudaFree(c->d_sub_dup); cudaFree(c->d_rep_bins);
     c->d_dup = c->d_sub_dup = nullptr; c->d_rep_bins = nullptr; c->n_rep = 0;
     cudaFree(c->d_tab_lnnorm); cudaFree(c->d_tab_log); cudaFree(c->d_tab_exp); cudaFree(c->d_tab_normd);
-    for (int w = 0; w < 2; w++) { cudaFree(c->d_tab_lnf[w]); cudaFree(c->d_tab_f[w]); c->d_tab_lnf[w] = nullptr; c->d_tab_f[w] = nullptr; }
+    for (int w = 0; w < 2; w++) { cudaFree(c->d_tab_lnf[w]); cudaFree(c->d_tab_f[w]); cudaFree(c->d_tab_lnfu[w]); c->d_tab_lnf[w] = nullptr; c->d_tab_f[w] = nullptr; c->d_tab_lnfu[w] = nullptr; }
     c->d_tab_normd = nullptr;
     c->d_tab_lnnorm = nullptr; c->d_tab_log = nullptr; c->d_tab_exp = nullptr;
     cudaFree(c->d_tab_norm); cudaFree(c->d_tab_g[0]); cudaFree(c->d_tab_g[1]); cudaFree(c->d_tab_logg[0]); cudaFree(c->d_tab_logg[1]);
@@ -1938,7 +2216,7 @@ void graal_ctx_destroy(graal_ctx* c) {
     for (int i = 0; i < 16; i++) c->graphs[i].reset();
     c->g_stats.reset(); c->g_relabel.reset(); c->g_full.reset(); c->g_full_cached.reset();
     c->prof.destroy();
-    cudaFree(c->d_ints); cudaFree(c->d_stats); cudaFree(c->d_scalars); cudaFree(c->partials);
+    cudaFree(c->d_ints); cudaFree(c->d_stats); cudaFree(c->d_counters); cudaFree(c->d_scalars); cudaFree(c->partials);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1966,6 +2244,15 @@ int graal_profile_enable(graal_ctx* c, int on) {
     CUDA_OK(cudaStreamSynchronize(c->stream));
     for (int k = 0; k < PROF_KERNELS; k++) { c->prof.resolve(k); }
     c->prof.on = on != 0;
+    return 0;
+}
+int graal_profile_counters(graal_ctx* c, int64_t out[4], int reset) {
+    if (!c || !out) return set_err(-1, "null argument");
+    CUDA_OK(cudaSetDevice(c->device));
+    { int rc = join_lanes(c); if (rc) return rc; }
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaMemcpy(out, c->d_counters, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (reset) CUDA_OK(cudaMemset(c->d_counters, 0, 4 * sizeof(unsigned long long)));
     return 0;
 }
 int graal_profile_read(graal_ctx* c, int kernel_id, double* total_ms, int64_t* count, int reset) {
@@ -2055,6 +2342,7 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
         CUDA_OK(cudaMemcpy(c->d_tab_normd, tnd.data(), tnd.size() * sizeof(double), cudaMemcpyHostToDevice));
         for (int w = 0; w < 2; w++) {
             CUDA_OK(cudaMalloc(&c->d_tab_lnf[w], (size_t)(LAW_NODES + 2) * sizeof(int4)));
+            CUDA_OK(cudaMalloc(&c->d_tab_lnfu[w], (size_t)(LAW_NODES + 2) * sizeof(int4)));
             CUDA_OK(cudaMalloc(&c->d_tab_f[w], (size_t)(LAW_NODES + 2) * sizeof(int4)));
         }
         for (int w = 0; w < 2; w++) {
@@ -2133,6 +2421,33 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
         CUDA_OK(cudaMalloc(&c->group_row, (size_t)c->n_groups * sizeof(int)));
         k_group_rows<<<(c->n_groups + 255) / 256, 256, 0, c->stream>>>(c->rowptr, c->E, c->W, c->n_groups, c->group_row); CHECK_LAUNCH(c);
     }
+    // work items of the windowed contact pass: rows cut into chunks of <= ITEM_CHUNK entries
+    CUDA_OK(cudaMalloc(&c->row_hdr, (size_t)c->W * sizeof(int4)));
+    CUDA_OK(cudaMalloc(&c->o_start, ((size_t)n + 1) * sizeof(int)));
+    CUDA_OK(cudaMalloc(&c->o_sub, (size_t)n * sizeof(int2)));
+    CUDA_OK(cudaMalloc(&c->o_cid, (size_t)n * sizeof(int)));
+    CUDA_OK(cudaMalloc(&c->o_blk, ((size_t)n / 32 + 1) * sizeof(int2)));
+    if (c->E > 0) {
+        int* cnt = nullptr; int* off = nullptr; void* tmp = nullptr; size_t tb = 0;
+        CUDA_OK(cudaMalloc(&cnt, (size_t)c->W * sizeof(int)));
+        CUDA_OK(cudaMalloc(&off, (size_t)c->W * sizeof(int)));
+        k_item_count<<<nblk(c->W, 256), 256, 0, c->stream>>>(c->rowptr, c->W, cnt); CHECK_LAUNCH(c);
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, off, c->W, c->stream);
+        CUDA_OK(cudaMalloc(&tmp, tb));
+        CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, off, c->W, c->stream));
+        int last_off = 0, last_cnt = 0;
+        CUDA_OK(cudaMemcpyAsync(&last_off, off + c->W - 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaMemcpyAsync(&last_cnt, cnt + c->W - 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        c->n_items = last_off + last_cnt;
+        if (c->n_items > 0) {
+            CUDA_OK(cudaMalloc(&c->items, (size_t)c->n_items * sizeof(int4)));
+            CUDA_OK(cudaMalloc(&c->item_hdr, (size_t)c->n_items * sizeof(int4)));
+            k_item_fill<<<nblk(c->W, 256), 256, 0, c->stream>>>(c->rowptr, c->W, off, c->items); CHECK_LAUNCH(c);
+        }
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        cudaFree(cnt); cudaFree(off); cudaFree(tmp);
+    }
     // level constant: sum of lf(ob)
     c->lf_total = 0.0;
     if (c->E > 0) {
@@ -2183,7 +2498,6 @@ int graal_state_bind(graal_ctx* c, int32_t* base, int ld, int n_slots) {
 #define NEED_STATE(c) do { if (!(c) || !(c)->slots) return set_err(-1, "state not bound"); CUDA_OK(cudaSetDevice((c)->device)); \
                            { int rcj_ = join_lanes(c); if (rcj_) return rcj_; } } while (0)
 #define NEED_SLOT(c, s) do { if ((s) < 0 || (s) >= (c)->n_slots) return set_err(-1, "slot %d out of range", (s)); } while (0)
-static inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
 
 int graal_relabel_contigs(graal_ctx* c, int slot, int32_t* d_max_id) {
     NEED_STATE(c); NEED_SLOT(c, slot);
@@ -2304,8 +2618,25 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
     // shared-memory classification needs W * 2 B + the queues in one CTA per SM
     const size_t fcs_smem = (size_t)(FCS_THREADS / 32) * QCAP * sizeof(Pending) + (((size_t)c->W + 7) / 8) * 16;
     const bool use_smem = uniform && c->smem_cid && fcs_smem + 1024 <= (size_t)c->smem_optin;
+    const bool use_win = uniform && p.mode == 2 && p.fu_ok && c->full_win && !use_smem && c->n_items > 0;
     int g1 = 0;
-    if (c->E > 0) {
+    typedef void (*win_fn)(const int4*, const int4*, int, const int2*, const int2*, const int*, int, const Geo*, const FastLaw, const Params, double, double*);
+    win_fn k_win = k_full_contacts_win<8, 4, 4>;
+    switch (c->win_unroll * 100 + c->win_minb * 10 + c->win_sub) {
+        case 441: k_win = k_full_contacts_win<4, 4, 1>; break;  case 442: k_win = k_full_contacts_win<4, 4, 2>; break;
+        case 444: k_win = k_full_contacts_win<4, 4, 4>; break;  case 454: k_win = k_full_contacts_win<4, 5, 4>; break;
+        case 841: k_win = k_full_contacts_win<8, 4, 1>; break;  case 842: k_win = k_full_contacts_win<8, 4, 2>; break;
+        case 844: k_win = k_full_contacts_win<8, 4, 4>; break;  case 848: k_win = k_full_contacts_win<8, 4, 8>; break;
+        case 832: k_win = k_full_contacts_win<8, 3, 2>; break;  case 834: k_win = k_full_contacts_win<8, 3, 4>; break;
+        case 838: k_win = k_full_contacts_win<8, 3, 8>; break;  case 852: k_win = k_full_contacts_win<8, 5, 2>; break;
+        case 854: k_win = k_full_contacts_win<8, 5, 4>; break;
+        default: break;
+    }
+    if (c->E > 0 && use_win) {
+        int fc_blocks = 0;
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fc_blocks, k_win, 256, 0));
+        g1 = (int)std::min<long long>(std::min(ps, c->n_sm * std::max(1, fc_blocks)), ((long long)c->n_items + 7) / 8);   // one resident wave
+    } else if (c->E > 0) {
         if (use_smem) {
             CUDA_OK(cudaFuncSetAttribute(k_full_contacts_uniform<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fcs_smem));
             g1 = std::min(ps, c->n_sm);
@@ -2323,7 +2654,32 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
         // d_out = -(lf_total + G0) [+ log g * sum(ob)]   then accumulate the device sums
         const double init = -(c->lf_total + g0) + (uniform ? lg_uniform * c->ob_total : 0.0);
         k_set_double<<<1, 1, 0, st>>>(d_out, init); CHECK_LAUNCH(c);
-        if (g1 > 0) {
+        const bool need_order = (use_win && g1 > 0) || !cached;
+        if (need_order) {                       // contig offsets of the position order (contig by contig, in id order)
+            CUDA_OK(cudaMemsetAsync(c->cont_len, 0, (size_t)c->cap * sizeof(int), st));
+            k_contig_lengths<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_len); CHECK_LAUNCH(c);
+            size_t tb = c->cub_tmp_bytes;
+            CUDA_OK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, tb, c->cont_len, c->cont_off, c->cap, st)); c->launches += 2;
+        }
+        if (use_win && g1 > 0) {                // position order + the per-row windows of this pass
+            c->prof.begin(GRAAL_K_FULL_WINDOWS, st);
+            int* bad = c->d_ints + 4;
+            k_order_init<<<nblk(n, 256), 256, 0, st>>>(n, c->W, c->order, c->o_start, c->o_sub, c->o_cid, bad); CHECK_LAUNCH(c);
+            k_order_fill2<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_off, c->lv, c->order, c->o_start, c->o_sub, c->o_cid, bad); CHECK_LAUNCH(c);
+            k_hull_blocks<<<nblk(n, 256), 256, 0, st>>>(c->o_sub, n, c->o_blk); CHECK_LAUNCH(c);
+            const double dm = (double)p.d_max * 1000.0 * 1.0001 + 100.0;
+            const long long dmax_bp = dm < 4.0e18 ? (long long)ceil(dm) : (long long)4.0e18;
+            k_windows<<<nblk(n, 256), 256, 0, st>>>(c->order, c->o_start, c->o_sub, c->o_cid, c->o_blk, c->cont_off, c->cont_len, s, ld, n, c->W,
+                                                   dmax_bp, c->cm_base, c->row_hdr, bad); CHECK_LAUNCH(c);
+            k_item_hdr<<<nblk(c->n_items, 256), 256, 0, st>>>(c->items, c->n_items, c->row_hdr, c->item_hdr); CHECK_LAUNCH(c);
+            c->prof.end(GRAAL_K_FULL_WINDOWS, st);
+            FastLaw fl; fl.tab = p.t_lnfu; fl.smin_bits = LAW_SMIN_BITS; fl.span = p.fu_span; fl.zlo = p.fu_zlo; fl.zspan = p.fu_zspan;
+            c->prof.begin(GRAAL_K_FULL_CONTACTS, st);
+            k_win<<<g1, 256, 0, st>>>(c->items, c->item_hdr, c->n_items, c->contacts, c->cm_base, bad, c->W, c->geo_base, fl, p, lg_uniform, c->partials);
+            CHECK_LAUNCH(c);
+            c->prof.end(GRAAL_K_FULL_CONTACTS, st);
+            k_reduce_partials<<<1, 256, 0, st>>>(c->partials, g1, 0, 1.0, d_out, 1); CHECK_LAUNCH(c);
+        } else if (g1 > 0) {
             c->prof.begin(GRAAL_K_FULL_CONTACTS, st);
             if (use_smem)
                 k_full_contacts_uniform<true><<<g1, FCS_THREADS, fcs_smem, st>>>(c->rowptr, c->contacts, c->E, c->W, c->group_row, c->n_groups, c->geo_base,
@@ -2348,12 +2704,8 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
             k_reduce_partials<<<1, 256, 0, st>>>(c->partials + (size_t)1 * ps, g3, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
             k_reduce_partials<<<1, 32, 0, st>>>(c->d_scalars + 40, 1, 0, -1.0, d_out, 1); CHECK_LAUNCH(c);
         } else {
-            // position order of the bins, contig by contig
-            CUDA_OK(cudaMemsetAsync(c->cont_len, 0, (size_t)c->cap * sizeof(int), st));
-            k_contig_lengths<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_len); CHECK_LAUNCH(c);
-            size_t tb = c->cub_tmp_bytes;
-            CUDA_OK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, tb, c->cont_len, c->cont_off, c->cap, st)); c->launches += 2;
-            k_order_fill<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_off, c->order); CHECK_LAUNCH(c);
+            // position order of the bins, contig by contig (already filled by the windowed pass)
+            if (!(use_win && g1 > 0)) { k_order_fill<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_off, c->order); CHECK_LAUNCH(c); }
             k_band<<<g2, 256, 0, st>>>(c->order, n, s, ld, c->lv, c->geo_base, p, c->partials, ps); CHECK_LAUNCH(c);
             double* cross = p_override ? c->d_scalars + 41 : c->d_scalars + 40;
             k_reduce_partials<<<1, 256, 0, st>>>(c->partials, g2, 0, 1.0, cross, 0); CHECK_LAUNCH(c);
@@ -2396,6 +2748,7 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
     int* rng = L.ints + 160;                       // [0,1] base range, [2 + 2k, 3 + 2k] candidate k
     k_delta_setup<<<nblk(n, 256), 256, 0, st>>>(base, ld, id_fA, id_fB, c->d_ints + 0, max_id, meta, n, c->W, L.sub_index, L.chmask, piece_len, rng, L.chmask2); CHECK_LAUNCH(c);
     const int gu = std::min(c->n_sm * 2, nblk(n, 256));
+    if (c->prof.on) { k_u_stats<<<gu, 256, 0, st>>>(L.sub_index, meta, c->lv, base, ld, c->rowptr, c->d_counters); CHECK_LAUNCH(c); }
     k_cand_geometry<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->lv, L.sub_index, meta, L.geo_cand, (size_t)c->W, piece_len,
                                                      c->geo_base, L.chmask, skip); CHECK_LAUNCH(c);
     const int n_rows = pair_mask ? N_BAND_ROWS : n_cand;          // band rows: candidates (+ the partner rows of the paired ones)

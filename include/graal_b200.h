@@ -207,10 +207,15 @@ enum {
     GRAAL_K_DELTA_CONTACTS,      /* contact part of graal_delta_loglik */
     GRAAL_K_DELTA_BAND,          /* expected-mass part of graal_delta_loglik (both passes + reductions) */
     GRAAL_K_BUILD,               /* graal_build_candidates */
-    GRAAL_K_RELABEL              /* graal_relabel_contigs */
+    GRAAL_K_RELABEL,             /* graal_relabel_contigs */
+    GRAAL_K_FULL_WINDOWS         /* position order + per-row windows of the windowed contact pass */
 };
 int graal_profile_enable(graal_ctx* ctx, int on);
 int graal_profile_read(graal_ctx* ctx, int kernel_id, double* total_ms, int64_t* count, int reset);
+/* sizes of the proposals scored while the timers were on (what the delta kernels' roofline is computed from):
+ * out[0] = stored contacts in the rows of U (contig(fA) + contig(fB)), [1] = rows (sub-frags) of U, [2] = bins of U,
+ * [3] = proposals counted; summed over the proposals since the last reset. */
+int graal_profile_counters(graal_ctx* ctx, int64_t out[4], int reset);
 
 #ifdef __cplusplus
 }

@@ -194,19 +194,23 @@ def sparse_full(slot, lv, p):
     return float(t.sum()) - (g0_mass(lv, p) + quirk_mass(slot, lv, p) + band_mass(geo, lv, p))
 
 
-def sparse_delta(slot_new, slot_old, lv, p, bins_u):
+def sparse_delta(slot_new, slot_old, lv, p, bins_u, return_mass=False):
     """Delta of sub_compute_likelihood for unique bins: pairs of DISTINCT bins inside ``bins_u``
-    (range 1 of kernels3.cu:3356-3362; diagonal pixels are not re-scored, Q4)."""
+    (range 1 of kernels3.cu:3356-3362; diagonal pixels are not re-scored, Q4).
+    ``return_mass``: also return sum |contact terms| + |band mass| over new and old -- the magnitude the
+    delta is a difference of (the scale of the float32 noise floor of the tolerance)."""
     bins_u = np.unique(np.asarray(bins_u))
     in_u = np.zeros(lv.n_frags, dtype=bool)
     in_u[bins_u] = True
     br, bc = lv.sub2bin[lv.rows], lv.sub2bin[lv.cols]
     sel = np.nonzero(in_u[br] & in_u[bc] & (br != bc))[0]
     subs = np.nonzero(in_u[lv.sub2bin])[0]
-    out = 0.0
+    out, mass = 0.0, 0.0
     for sgn, slot in ((1.0, slot_new), (-1.0, slot_old)):
         geo = Geo(slot, lv)
         t, _ = contact_terms(geo, lv, p, sel)
-        out += sgn * (float(t.sum()) - quirk_mass(slot, lv, p, bins_u)
-                      - band_mass(geo, lv, p, subs, include_same_bin=False))
-    return out
+        q = quirk_mass(slot, lv, p, bins_u)
+        b = band_mass(geo, lv, p, subs, include_same_bin=False)
+        out += sgn * (float(t.sum()) - q - b)
+        mass += float(np.abs(t).sum()) + abs(q) + abs(b)
+    return (out, mass) if return_mass else out

@@ -53,3 +53,53 @@ def delta_tolerance(delta_ref, mass):
     relative 1e-6 as BASELINE.json's north_star states, with a floor for deltas that are small
     next to the float32 expected values (`mass` = sum of |terms| touched) they are differences of."""
     return 1e-6 * max(abs(delta_ref), mass * 2.0 ** -20) + 1e-9
+
+
+MASS_FLOOR = 1e-7      # measured worst |err| / mass: 3.5e-8 (math modes 1, 2) .. 7e-8 (mode 0): float32 libm differences
+
+
+def delta_check(got, ref, mass):
+    """(within the asserted bound, within SURVEY H2's bound).  Asserted: |err| <= 1e-6 |ref| + 1e-7 mass, the
+    relative tolerance of BASELINE.json's north_star plus the MEASURED float32 noise floor of the expected values
+    (powf / expf of CUDA vs NumPy differ by <= 2 ulp per term; `mass` = sum of |terms| the delta is a difference of).
+    H2 (delta_tolerance) is the stricter bound that holds whenever the delta is not a small difference of large sums."""
+    err = abs(got - ref)
+    return err <= 1e-6 * abs(ref) + MASS_FLOOR * mass + 1e-9, err <= delta_tolerance(ref, mass)
+
+
+def ranking_agrees(got, ref, masses):
+    """The candidate order is the one the oracle gives wherever two candidates are further apart than the
+    tolerances of the pair (a tie inside the noise floor may fall either way)."""
+    bad = []
+    for i in range(len(ref)):
+        for j in range(len(ref)):
+            gap = 1e-6 * (abs(ref[i]) + abs(ref[j])) + MASS_FLOOR * (masses[i] + masses[j]) + 2e-9
+            if ref[i] - ref[j] > gap and not got[i] > got[j]:
+                bad.append((i, j))
+    return bad
+
+
+_POOL = {}
+
+
+def _pool_sparse_delta(j):
+    from oracle import sparse as S
+    c = _POOL
+    return S.sparse_delta(c["collector"][j], c["cur"], c["lv"], c["par"], c["bins_u"], return_mass=True)
+
+
+def sparse_deltas(collector, cur, lv, par, bins_u, cands=range(13)):
+    """(delta, mass) of the candidates from the sparse oracle, one forked worker per candidate (the children
+    inherit the read-only level; they never touch CUDA)."""
+    import multiprocessing as mp
+    import os
+    cands = list(cands)
+    workers = max(1, min(len(cands), (os.cpu_count() or 1)))
+    _POOL.update(collector=collector, cur=cur, lv=lv, par=par, bins_u=bins_u)
+    try:
+        if workers == 1:
+            return [_pool_sparse_delta(j) for j in cands]
+        with mp.get_context("fork").Pool(workers) as pool:
+            return pool.map(_pool_sparse_delta, cands, chunksize=1)
+    finally:
+        _POOL.clear()

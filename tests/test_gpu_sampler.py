@@ -132,7 +132,7 @@ def test_repeat_levels(yeast_pyramid):
             new = L.pixel_loglik(o.ws.collector[j], o.lv, o.param_simu, bi, bj, dg)
             old = o.curr_likelihood[glob]
             ref, mass = float(np.sum(new - old)), float(np.abs(new).sum() + np.abs(old).sum())
-            assert abs(got[j] - ref) <= 1e-6 * abs(ref) + 2.0 ** -22 * mass + 1e-9, (fA, fB, j, got[j], ref)
+            assert abs(got[j] - ref) <= 1e-6 * abs(ref) + H.MASS_FLOOR * mass + 1e-9, (fA, fB, j, got[j], ref)
     # de-activate a copy (mode 8) on both sides, then a live trajectory
     M.apply_mutation(o.ws, o.cur, copy, 0, 8, max_id, o.id_contigs)
     g.test_copy_struct(copy, 0, 8, int(max_id))

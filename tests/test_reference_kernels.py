@@ -151,7 +151,7 @@ def test_likelihood_fixture(fixture, pyr, tag):
         M.perform_modifications(o.ws, o.cur, int(fA), int(fB), int(max_id))
         for j in range(13):
             d, mass = oracle_delta_and_mass(o, cur_lls[st], int(fA), int(fB), j)
-            assert abs(d - ref[j]) <= 1e-6 * abs(ref[j]) + 2.0 ** -22 * mass + 1e-9, (tag, st, fA, fB, j, d, ref[j])
+            assert abs(d - ref[j]) <= 1e-6 * abs(ref[j]) + H.MASS_FLOOR * mass + 1e-9, (tag, st, fA, fB, j, d, ref[j])
 
 
 @needs_reference
@@ -175,7 +175,7 @@ def test_likelihood_live(pyr):
     for j in range(13):
         a = R.sub_compute_likelihood(o.ws.collector[j], o.lv, o.param_simu, ref, no_rep, rep, o.uniq_frags)
         d, mass = oracle_delta_and_mass(o, mine, fA, fB, j)
-        assert abs(d - a) <= 1e-6 * abs(a) + 2.0 ** -22 * mass + 1e-9, (j, d, a)
+        assert abs(d - a) <= 1e-6 * abs(a) + H.MASS_FLOOR * mass + 1e-9, (j, d, a)
 
 
 @needs_reference
@@ -211,7 +211,7 @@ def test_likelihood_live_circular_contig(pyr):
         for j in range(13):
             a = R.sub_compute_likelihood(o.ws.collector[j], o.lv, o.param_simu, ref, no_rep, rep, o.uniq_frags)
             d, mass = oracle_delta_and_mass(o, mine, fA, fB, j)
-            assert abs(d - a) <= 1e-6 * abs(a) + 2.0 ** -22 * mass + 1e-9, (fA, fB, j, d, a)
+            assert abs(d - a) <= 1e-6 * abs(a) + H.MASS_FLOOR * mass + 1e-9, (fA, fB, j, d, a)
 
 
 @pytest.mark.gpu
@@ -242,5 +242,5 @@ def test_device_vs_reference_kernels(fixture, pyr, tag):
         got = g._fetch()[16:29].copy()
         for j in range(13):
             _, mass = oracle_delta_and_mass(o, cur_lls[st], int(fA), int(fB), j)
-            assert abs(got[j] - ref[j]) <= 1e-6 * abs(ref[j]) + 2.0 ** -22 * mass + 1e-9, (tag, st, fA, fB, j, got[j], ref[j])
+            assert abs(got[j] - ref[j]) <= 1e-6 * abs(ref[j]) + H.MASS_FLOOR * mass + 1e-9, (tag, st, fA, fB, j, got[j], ref[j])
     g.free_gpu()
