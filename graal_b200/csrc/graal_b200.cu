@@ -53,7 +53,9 @@ struct Params { float kuhn, lm, c1, slope, d, d_max, fact, v_inter, nfpb; int nd
                 // uniform-accu levels with a monotone law (windowed contact pass): ln f(s) + ln norm - log g per interval, the
                 // float bit patterns [LAW_SMIN_BITS, LAW_SMIN_BITS + fu_span) it is valid on (below d_max, inside the table,
                 // above the clamp) and the in-band zone beyond the table [fu_zlo, fu_zlo + fu_zspan); fu_ok = 0: not available
-                const int4* t_lnfu; unsigned fu_span, fu_zlo, fu_zspan; int fu_ok; };
+                const int4* t_lnfu; unsigned fu_span, fu_zlo, fu_zspan; int fu_ok;
+                const int4* t_fu;     // same levels: f(s) * norm - g per interval (band excess of an in-band pair)
+                };
 #define LAW_M 9
 #define LAW_EMIN (-12)
 #define LAW_EMAX 11
@@ -1186,7 +1188,8 @@ __global__ void k_delta_setup(const int* __restrict__ base, int ld, int fA, int 
     const int cA = base[F_ID_C * ld + fA], cB = base[F_ID_C * ld + fB];
     const int lA = base[F_L_CONT * ld + fA], lB = (cB != cA) ? base[F_L_CONT * ld + fB] : 0;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { meta[0] = cA; meta[1] = cB; meta[2] = lA; meta[3] = lB; meta[4] = lA + lB; meta[5] = (max_id_host >= 0) ? max_id_host : *d_max_id; }
+    if (i == 0) { meta[0] = cA; meta[1] = cB; meta[2] = lA; meta[3] = lB; meta[4] = lA + lB; meta[5] = (max_id_host >= 0) ? max_id_host : *d_max_id;
+                  meta[6] = (fA == fB) ? 1 : 0; }        // [6] != 0: the general contact kernel scores this proposal (degenerate proposal / circular contig)
     if (i < GRAAL_N_CANDIDATES * 8) piece_len[i] = 0;
     if (i < 2 + 2 * N_BAND_ROWS) rng[i] = (i & 1) ? -1 : INT_MAX;
     for (int j = i; j < W; j += gridDim.x * blockDim.x) { chmask[j] = 0u; chmask2[j] = 0u; }
@@ -1220,7 +1223,7 @@ __device__ __forceinline__ int piece_slot(int id_c, const int* meta) {
 __global__ void k_cand_geometry(const int* __restrict__ cand0, size_t slot_stride, int ld, LevelView lv,
                                 const int* __restrict__ sub_index, const int* __restrict__ meta,
                                 Geo* __restrict__ geo0, size_t geo_stride, int* __restrict__ piece_len,
-                                const Geo* __restrict__ geo_base, unsigned* __restrict__ chmask, unsigned skip_cands) {
+                                const Geo* __restrict__ geo_base, unsigned* __restrict__ chmask, unsigned skip_cands, int* __restrict__ meta_flag) {
     const int k = blockIdx.y;
     if ((skip_cands >> k) & 1u) return;
     const int m = meta[4];
@@ -1228,6 +1231,7 @@ __global__ void k_cand_geometry(const int* __restrict__ cand0, size_t slot_strid
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < m; u += gridDim.x * blockDim.x) {
         const int bin = sub_index[u];
         bin_geometry(sl, ld, bin, lv, geo0 + (size_t)k * geo_stride);
+        if (sl[F_CIRC * ld + bin] == 1) meta_flag[0] = 1;
         if (eligible(lv, bin)) {   // bit k of chmask[sub]: the candidate's record differs from the base slot's (bitwise)
             const int4 sid = lv.sub_id[sl[F_ID_D * ld + bin]];
             for (int a = 0; a < sid.w; a++)
@@ -1260,7 +1264,8 @@ __device__ __forceinline__ int4 band_record_b(const Geo* __restrict__ g, int sub
 //   C: x, y, z = chmask words of the sub-frags (bit k: differs from the base slot in candidate k)
 __device__ __forceinline__ void base_order(const int* __restrict__ base, int ld, const int* __restrict__ sub_index, const int* __restrict__ meta,
                              LevelView lv, const unsigned* __restrict__ chmask, const Geo* __restrict__ geo_base,
-                             int4* __restrict__ rec_a, int4* __restrict__ rec_b, int4* __restrict__ rec_c, int* __restrict__ rng, unsigned pair_mask) {
+                             int4* __restrict__ rec_a, int4* __restrict__ rec_b, int4* __restrict__ rec_c, int* __restrict__ rng, unsigned pair_mask,
+                             int* __restrict__ meta_flag, const int4* __restrict__ row_hdr, int2* __restrict__ uwin) {
     const int m = meta[4];
     int lo = INT_MAX, hi = -1;
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < m; u += gridDim.x * blockDim.x) {
@@ -1274,6 +1279,8 @@ __device__ __forceinline__ void base_order(const int* __restrict__ base, int ld,
         rec_a[u] = make_int4(sid.x | (n_sub << 28), __float_as_int(start_kb), (int)chg, base[F_ID_C * ld + bin]);
         rec_b[u] = band_record_b(geo_base, sid.x, n_sub);
         rec_c[u] = make_int4((int)ms[0], (int)ms[1], (int)ms[2], 0);
+        if (base[F_CIRC * ld + bin] == 1) meta_flag[0] = 1;
+        if (uwin) { const int4 h = row_hdr[sid.x]; uwin[sid.x] = make_int2(h.z, h.z + (int)((unsigned)h.w & 0x7fffffffu)); }   // union window starts as the base window
         if (chg) { lo = min(lo, u); hi = max(hi, u); }
     }
     if (hi >= 0) { atomicMin(&rng[0], lo); atomicMax(&rng[1], hi); }
@@ -1290,9 +1297,9 @@ __global__ void k_cand_order(const int* __restrict__ cand0, size_t slot_stride, 
                              int4* __restrict__ rec_a0, int4* __restrict__ rec_b0, int* __restrict__ rng,
                              int n_cand, const int* __restrict__ base, const Geo* __restrict__ geo_base,
                              int4* __restrict__ base_a, int4* __restrict__ base_b, int4* __restrict__ base_c, int* __restrict__ base_rng,
-                             unsigned pair_mask, unsigned* __restrict__ chmask2) {
+                             unsigned pair_mask, unsigned* __restrict__ chmask2, int* __restrict__ meta_flag, const int4* __restrict__ row_hdr, int2* __restrict__ uwin) {
     const int y = blockIdx.y;
-    if (y == n_cand) { base_order(base, ld, sub_index, meta, lv, chmask, geo_base, base_a, base_b, base_c, base_rng, pair_mask); return; }
+    if (y == n_cand) { base_order(base, ld, sub_index, meta, lv, chmask, geo_base, base_a, base_b, base_c, base_rng, pair_mask, meta_flag, row_hdr, uwin); return; }
     int row = y, src = y, other = -1;                       // output row, candidate whose order / records are written, candidate compared with
     if (y > n_cand) {                                       // partner row v of paired candidate 3 + 2 v
         const int v = y - n_cand - 1, kp = 3 + 2 * v;
@@ -1491,19 +1498,189 @@ k_band_delta(const int4* __restrict__ rec_a0, const int4* __restrict__ rec_b0, c
     }
 }
 
+// The same band pass for uniform-accu levels with a monotone tabulated law (Params::fu_ok), about half the instructions:
+//  * the range test 0 < s < min(d_max, clamp threshold, table end) is ONE unsigned compare on the bit pattern of s, and
+//    absent sub-frags carry a NaN mid-point, which fails it;
+//  * the table already holds f(s) * norm - g: value = a0 + u * (a1 + u * a2), a0 accumulated in float64, the small
+//    u-part in float32 (flushed per x);
+//  * "pair has a changed record" is folded into the operands: against an unchanged sub-frag of x a lane uses the
+//    mid-points of its CHANGED sub-frags only (the others NaN);
+//  * BASE: the 13 per-candidate accumulators of a thread live in shared memory and are credited by looping over the set
+//    bits of the candidate masks (a bin's sub-frags almost always share one mask: the nine pairs are summed first).
+// Circular contigs and in-band distances outside the table take the general evaluation pair by pair.
+struct FastBand { const int4* tab; unsigned smin_bits, span, zlo, zspan, dmax_bits; };
+template <bool BASE, int PARTS>
+__global__ void __launch_bounds__(256)
+k_band_delta_fast(const int4* __restrict__ rec_a0, const int4* __restrict__ rec_b0, const int4* __restrict__ rec_c, int order_stride,
+                  const int* __restrict__ d_count, const int* __restrict__ rng0,
+                  const Geo* __restrict__ geo0, size_t cand_geo_stride, unsigned skip_cands, const FastBand fb,
+                  const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
+    __shared__ double sacc[BASE ? GRAAL_N_CANDIDATES : 1][BASE ? 256 : 1];
+    const int k = blockIdx.y;
+    const int count = *d_count;
+    const int4* rec_a = BASE ? rec_a0 : rec_a0 + (size_t)k * order_stride;
+    const int4* rec_b = BASE ? rec_b0 : rec_b0 + (size_t)k * order_stride;
+    const Geo* gE = BASE ? geo0 : geo0 + (size_t)(k < GRAAL_N_CANDIDATES ? k : 2 + 2 * (k - GRAAL_N_CANDIDATES)) * cand_geo_stride;
+    const int* rng = BASE ? rng0 : rng0 + 2 * k;
+    const int lo = rng[0], hi = rng[1];
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int4* __restrict__ tab = fb.tab;
+    const float d_max = p.d_max;
+    const float nanf_ = __int_as_float(0x7fc00000);
+    double acc = 0.0;
+    if (BASE) {
+        #pragma unroll
+        for (int c = 0; c < GRAAL_N_CANDIDATES; c++) sacc[c][threadIdx.x] = 0.0;
+    }
+    const bool idle = (!BASE && ((skip_cands >> k) & 1u)) || hi < 0;
+    if (!idle) for (int wx = warp; wx / PARTS <= hi && wx / PARTS < count; wx += n_warps) {
+        const int ix = wx / PARTS, part = wx % PARTS;
+        const int4 rx = rec_a[ix];
+        const int nx = (rx.x >> 28) & 7;
+        if (nx == 0) continue;                                   // duplicated bin: repeat path
+        const unsigned xm = (unsigned)rx.z;
+        const bool xchg = xm != 0u;
+        int y0 = ix + 1, y1 = count;
+        if (!xchg) { y0 = max(y0, lo); y1 = min(y1, hi + 1); }
+        if (y0 >= y1) continue;
+        const int4 xb = rec_b[ix];
+        unsigned mx[3];
+        if (BASE) { const int4 xc = rec_c[ix]; mx[0] = (unsigned)xc.x; mx[1] = (unsigned)xc.y; mx[2] = (unsigned)xc.z; }
+        else { mx[0] = xm & 1u; mx[1] = (xm >> 1) & 1u; mx[2] = (xm >> 2) & 1u; }
+        float xmid[3] = {__int_as_float(xb.x), nx > 1 ? __int_as_float(xb.y) : nanf_, nx > 2 ? __int_as_float(xb.z) : nanf_};
+        float xmax = xmid[0];
+        if (nx > 1) xmax = fmaxf(xmax, xmid[1]);
+        if (nx > 2) xmax = fmaxf(xmax, xmid[2]);
+        const int cx = rx.w;
+        const int circ = (xb.w >> 24) & 1;
+        const float stot = circ ? gE[rx.x & 0x0fffffff].stot : 0.0f;
+        // circular contig: nothing is fast, every in-band pair goes to the general evaluation
+        const unsigned span = circ ? 0u : fb.span, zlo = circ ? 1u : fb.zlo, zspan = circ ? fb.dmax_bits - 1u : fb.zspan, smin = fb.smin_bits;
+        const bool x_uniform = (nx < 2 || mx[1] == mx[0]) && (nx < 3 || mx[2] == mx[0]);
+        double tot = 0.0; float totf = 0.0f, accf = 0.0f;        // BASE: old values credited to the candidates of the whole bin x
+        for (int basei = y0 + 32 * part; basei < y1; basei += 32 * PARTS) {
+            const int iy = basei + lane;
+            bool live = iy < y1;
+            if (live) {
+                const int4 ry = rec_a[iy];
+                // beyond the band (or next contig): every remaining pair evaluates to the clamp value
+                if (ry.w != cx || (double)__int_as_float(ry.y) - (double)xmax > (double)d_max * 1.00001 + 0.05) live = false;
+                else {
+                    const int ny = (ry.x >> 28) & 7;
+                    const unsigned ym = (unsigned)ry.z;
+                    if (ny > 0 && (xchg || ym != 0u)) {
+                        const int4 yb = rec_b[iy];
+                        unsigned my[3];
+                        if (BASE) { const int4 yc = rec_c[iy]; my[0] = (unsigned)yc.x; my[1] = (unsigned)yc.y; my[2] = (unsigned)yc.z; }
+                        else { my[0] = ym & 1u; my[1] = (ym >> 1) & 1u; my[2] = (ym >> 2) & 1u; }
+                        const float ya[3] = {__int_as_float(yb.x), ny > 1 ? __int_as_float(yb.y) : nanf_, ny > 2 ? __int_as_float(yb.z) : nanf_};
+                        const float yc[3] = {my[0] ? ya[0] : nanf_, my[1] ? ya[1] : nanf_, my[2] ? ya[2] : nanf_};   // changed sub-frags only
+                        const bool uniform = BASE && x_uniform && (ny < 2 || my[1] == my[0]) && (ny < 3 || my[2] == my[0]);
+                        unsigned slow = 0u;
+                        double pd = 0.0; float pf = 0.0f;                // sum of the nine pairs
+                        #pragma unroll
+                        for (int b = 0; b < 3; b++) {
+                            #pragma unroll
+                            for (int a = 0; a < 3; a++) {
+                                const float yv = mx[a] ? ya[b] : yc[b];
+                                const unsigned sb = __float_as_uint(fabsf(yv - xmid[a]));
+                                const unsigned t = sb - smin;
+                                const bool fast = t < span;
+                                if ((sb - 1u) < (smin - 1u) || (sb - zlo) < zspan) slow |= 1u << (3 * b + a);
+                                const int4 e = __ldg(&tab[(fast ? t : 0u) >> (23 - LAW_M)]);
+                                const float uu = __uint_as_float(0x3f800000u | ((sb & ((1u << (23 - LAW_M)) - 1u)) << LAW_M));
+                                const double v0 = fast ? __hiloint2double(e.y, e.x) : 0.0;
+                                const float v1 = fast ? uu * fmaf(uu, __int_as_float(e.w), __int_as_float(e.z)) : 0.0f;
+                                if (!BASE || uniform) { pd += v0; pf += v1; }
+                                else {                                    // sub-frags of a bin with different candidate masks (rare)
+                                    const double v = v0 + (double)v1;
+                                    unsigned cm = mx[a] | my[b];
+                                    while (cm) { const int c = __ffs(cm) - 1; cm &= cm - 1u; sacc[BASE ? c : 0][BASE ? threadIdx.x : 0] += v; }
+                                }
+                            }
+                        }
+                        if (slow) {
+                            #pragma unroll
+                            for (int b = 0; b < 3; b++) {
+                                #pragma unroll
+                                for (int a = 0; a < 3; a++) {
+                                    if (!((slow >> (3 * b + a)) & 1u)) continue;
+                                    const float yv = mx[a] ? ya[b] : yc[b];
+                                    const float sv = fabsf(yv - xmid[a]);
+                                    if (!(sv > 0.0f && sv < d_max)) continue;
+                                    const double v = band_excess_general(sv, 0, circ, stot, p);
+                                    if (!BASE || uniform) pd += v;
+                                    else { unsigned cm = mx[a] | my[b]; while (cm) { const int c = __ffs(cm) - 1; cm &= cm - 1u; sacc[BASE ? c : 0][BASE ? threadIdx.x : 0] += v; } }
+                                }
+                            }
+                        }
+                        if (!BASE) { acc += pd; accf += pf; }
+                        else if (uniform) {
+                            tot += pd; totf += pf;                          // candidates of x: credited once per x below
+                            unsigned extra = my[0] & ~mx[0];                // candidates in which only y changed
+                            const double v = pd + (double)pf;
+                            while (extra) { const int c = __ffs(extra) - 1; extra &= extra - 1u; sacc[BASE ? c : 0][BASE ? threadIdx.x : 0] += v; }
+                        }
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, live)) break;
+        }
+        if (BASE) {
+            const double v = tot + (double)totf;
+            unsigned cm = mx[0];                                         // (x_uniform: the mask of the whole bin; else tot == 0)
+            while (cm) { const int c = __ffs(cm) - 1; cm &= cm - 1u; sacc[BASE ? c : 0][BASE ? threadIdx.x : 0] += v; }
+        } else acc += (double)accf;
+    }
+    if (BASE) {
+        __syncthreads();
+        #pragma unroll 1
+        for (int c = 0; c < GRAAL_N_CANDIDATES; c++) {
+            const double v = block_sum(sacc[BASE ? c : 0][BASE ? threadIdx.x : 0]);
+            if (threadIdx.x == 0) partials[(size_t)c * partial_stride + blockIdx.x] = v;
+        }
+    } else {
+        acc = block_sum(acc);
+        if (threadIdx.x == 0) partials[(size_t)k * partial_stride + blockIdx.x] = acc;
+    }
+}
+
 // Contact part of the delta, all candidates in ONE pass over the rows of U: one warp per sub-frag row of a
 // member bin, four 32-entry slices of the row in flight per trip (the loads of a slice do not depend on
 // the previous one).  For every stored contact whose partner is in U, in another bin, with a changed
 // record on either side (chmask), the OLD term is evaluated once and the NEW term once per flagged
 // candidate:  accs[k] += ob * (ln ex_k - ln ex_0).
+// Uniform-accu levels with a monotone tabulated law: the contact term RELATIVE to the far value, ob * (ln ex - log g):
+// exactly 0 for a far pair, one table gather (a0 holds ln norm - log g) for an in-band one; circular contigs and in-band
+// distances outside the table take the general evaluation.
+__device__ __forceinline__ double contact_rel_term(const Geo& a, const Geo& b, float ob, const FastLaw& fl, const Params& p, double lg) {
+    const unsigned sb = __float_as_uint(fabsf(b.mid - a.mid));
+    const unsigned t = sb - fl.smin_bits;
+    const bool cis = a.id_c == b.id_c;
+    const bool circ = pk_circ(a.pk) != 0;
+    if (cis && t < fl.span && !circ) {
+        const int4 e = __ldg(&fl.tab[t >> (23 - LAW_M)]);
+        const float uu = __uint_as_float(0x3f800000u | ((sb & ((1u << (23 - LAW_M)) - 1u)) << LAW_M));
+        return (double)ob * (__hiloint2double(e.y, e.x) + (double)(uu * fmaf(uu, __int_as_float(e.w), __int_as_float(e.z))));
+    }
+    if (cis && (circ || (sb - 1u) < (fl.smin_bits - 1u) || (sb - fl.zlo) < fl.zspan))
+        return contact_log_term_general(a.mid, a.id_c, a.stot, a.pk, b.mid, b.id_c, b.pk, ob, p) - (double)ob * lg;
+    return 0.0;
+}
+
 #define DC_UNROLL 2
+template <bool UNI>
 __global__ void __launch_bounds__(256)
 k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, LevelView lv,
                       const int* __restrict__ sub_index, const int* __restrict__ meta,
                       const Geo* __restrict__ geo_base, const Geo* __restrict__ geo_cand0, size_t geo_stride,
                       const unsigned* __restrict__ chmask, const unsigned* __restrict__ chmask2, unsigned pair_mask,
-                      const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
+                      const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride, const int2* __restrict__ uwin,
+                      const FastLaw fl, double lg) {
     const int m = meta[4], cA = meta[0], cB = meta[1];
+    if (meta[6]) uwin = nullptr;                               // degenerate proposal (fA == fB): the candidate orders are not trusted
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -1521,12 +1698,16 @@ k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restri
         const Geo r0 = ld_geo(&geo_base[rowsub]);
         const unsigned mra = __ldg(&chmask[rowsub]);
         const unsigned mra2 = pair_mask ? (__ldg(&chmask2[rowsub]) & pair_mask) : 0u;   // row differs between a paired candidate and its partner
+        // union window of the row's bin (uniform levels): columns outside it are far in the base and in every candidate
+        int wlo = 0; unsigned wspan = 0xffffffffu;
+        if (uwin) { const int2 uw = __ldg(&uwin[sub0]); wlo = uw.x; wspan = (unsigned)(uw.y - uw.x); }
         for (long long eb = e0 + lane; eb < e1; eb += 32 * DC_UNROLL) {
             int2 ce[DC_UNROLL]; Geo g0[DC_UNROLL]; unsigned mc[DC_UNROLL]; bool ok[DC_UNROLL];
             #pragma unroll
             for (int j = 0; j < DC_UNROLL; j++) {
                 ok[j] = eb + 32 * j < e1;
                 ce[j] = ok[j] ? __ldg(&contacts[eb + 32 * j]) : make_int2(0, 0);   // rows of U recur in the next proposals: keep them in L2
+                ok[j] = ok[j] && (unsigned)(ce[j].x - wlo) <= wspan;
             }
             #pragma unroll
             for (int j = 0; j < DC_UNROLL; j++) if (ok[j]) { g0[j] = ld_geo(&geo_base[ce[j].x]); mc[j] = __ldg(&chmask[ce[j].x]); }
@@ -1550,13 +1731,13 @@ k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restri
                 for (int k = 0; k < GRAAL_N_CANDIDATES; k++)
                     pr[k] = ((mc[j] >> k) & mm >> k & 1u) ? __ldg(reinterpret_cast<const int2*>(&geo_cand0[(size_t)k * geo_stride + ce[j].x]))
                                                           : make_int2(__float_as_int(g0c.mid), g0c.id_c);
-                const double told = contact_log_term(r0, g0c, ob, p);
+                const double told = UNI ? contact_rel_term(r0, g0c, ob, fl, p, lg) : contact_log_term(r0, g0c, ob, p);
                 #pragma unroll
                 for (int k = 0; k < GRAAL_N_CANDIDATES; k++) {
                     if (!((mm >> k) & 1u)) continue;
                     const Geo rk = ((mra >> k) & 1u) ? ld_geo(&geo_cand0[(size_t)k * geo_stride + rowsub]) : r0;
                     Geo gc = g0c; gc.mid = __int_as_float(pr[k].x); gc.id_c = pr[k].y;
-                    accs[k] += contact_log_term(rk, gc, ob, p) - told;
+                    accs[k] += (UNI ? contact_rel_term(rk, gc, ob, fl, p, lg) : contact_log_term(rk, gc, ob, p)) - told;
                 }
                 if (mm2) {                                                   // rare: the few records in which a pair differs
                     #pragma unroll
@@ -1569,7 +1750,7 @@ k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restri
                             const Geo rk = ((mra >> kk) & 1u) ? ld_geo(&geo_cand0[(size_t)kk * geo_stride + rowsub]) : r0;
                             Geo gc = g0c;
                             if ((mc[j] >> kk) & 1u) { const Geo q = ld_geo(&geo_cand0[(size_t)kk * geo_stride + ce[j].x]); gc.mid = q.mid; gc.id_c = q.id_c; }
-                            t[w2] = contact_log_term(rk, gc, ob, p);
+                            t[w2] = UNI ? contact_rel_term(rk, gc, ob, fl, p, lg) : contact_log_term(rk, gc, ob, p);
                         }
                         accs[k] += t[0] - t[1];
                     }
@@ -1581,6 +1762,68 @@ k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restri
     for (int c = 0; c < GRAAL_N_CANDIDATES; c++) {
         const double v = block_sum(accs[c]);
         if (threadIdx.x == 0) partials[(size_t)c * partial_stride + blockIdx.x] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Union windows of the delta contact pass (uniform-accu levels).
+//
+// On a uniform level a contact between two far sub-frags (trans, or cis beyond the band) evaluates to the same ob * log g
+// in every structure, so a stored contact of U only matters for candidate k if the pair is in band in the base structure or
+// in candidate k.  Per bin of U the UNION over the base and the 13 candidates of the sub-frag index hull of the bins within
+// d_max (the base window from the windowed full pass, widened by every candidate's window, computed from the candidate's
+// position-ordered records) bounds the columns that can matter: every other entry of the row costs its stream load and
+// two integer ops in k_delta_contacts_rows -- no partner gather, no evaluation -- and contributes exactly 0 either way.
+// ------------------------------------------------------------------------------------------------
+// hull of the sub-frag index ranges of every aligned block of 32 order positions of every candidate (grid.y)
+__global__ void k_cand_hull_blocks(const int4* __restrict__ rec_a0, int order_stride, const int* __restrict__ meta, int2* __restrict__ blk0, int blk_stride, unsigned skip_cands) {
+    const int k = blockIdx.y;
+    if ((skip_cands >> k) & 1u) return;
+    const int m = meta[4];
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ((m + 31) & ~31); g += gridDim.x * blockDim.x) {
+        int lo = INT_MAX, hi = -1;
+        if (g < m) { const int x = rec_a0[(size_t)k * order_stride + g].x; lo = x & 0x0fffffff; hi = lo + ((x >> 28) & 7) - 1; }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+        if ((threadIdx.x & 31) == 0) blk0[(size_t)k * blk_stride + (g >> 5)] = make_int2(lo, hi);
+    }
+}
+// window of every bin of U in every candidate (grid.y), merged into the union window of the bin (uwin[first sub-frag]).
+// reach_kb = d_max (+ 0.01 %) + the longest bin of the level + 0.1 kb: a bin further than that (start to start) holds no
+// sub-frag within d_max.
+__global__ void __launch_bounds__(256)
+k_cand_windows(const int4* __restrict__ rec_a0, int order_stride, const int* __restrict__ meta, const int* __restrict__ piece_len,
+               const int2* __restrict__ blk0, int blk_stride, unsigned skip_cands, float reach_kb, int2* __restrict__ uwin) {
+    const int k = blockIdx.y;
+    if ((skip_cands >> k) & 1u) return;
+    const int m = meta[4];
+    const int4* __restrict__ ra = rec_a0 + (size_t)k * order_stride;
+    const int2* __restrict__ blk = blk0 + (size_t)k * blk_stride;
+    int off[6]; int run = 0;
+    #pragma unroll
+    for (int q = 0; q < 5; q++) { off[q] = run; run += piece_len[k * 8 + q]; }
+    off[5] = run;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < m; g += gridDim.x * blockDim.x) {
+        const int4 r = ra[g];
+        const int ps = piece_slot(r.w, meta);
+        int cs = 0, ce = m;                                   // the piece (contig of the candidate) that holds position g
+        if (ps >= 0) { cs = off[ps]; ce = min(off[ps + 1], m); }
+        if (!(cs <= g && g < ce)) { cs = 0; ce = m; }
+        const float st = __int_as_float(r.y);
+        int a = cs, b = g;                                    // first position whose bin starts after st - reach
+        while (a < b) { const int mm = (a + b) >> 1; if (__int_as_float(ra[mm].y) > st - reach_kb) b = mm; else a = mm + 1; }
+        const int lo = a;
+        a = g; b = ce - 1;                                    // last position whose bin starts before st + reach
+        while (a < b) { const int mm = (a + b + 1) >> 1; if (__int_as_float(ra[mm].y) < st + reach_kb) a = mm; else b = mm - 1; }
+        const int hi = a;
+        int wl = INT_MAX, wh = -1;
+        int q = lo;
+        for (; q <= hi && (q & 31); q++) { const int x = ra[q].x; const int s0 = x & 0x0fffffff; wl = min(wl, s0); wh = max(wh, s0 + ((x >> 28) & 7) - 1); }
+        for (; q + 31 <= hi; q += 32) { const int2 h = blk[q >> 5]; wl = min(wl, h.x); wh = max(wh, h.y); }
+        for (; q <= hi; q++) { const int x = ra[q].x; const int s0 = x & 0x0fffffff; wl = min(wl, s0); wh = max(wh, s0 + ((x >> 28) & 7) - 1); }
+        int* w = reinterpret_cast<int*>(&uwin[r.x & 0x0fffffff]);
+        if (wl < w[0]) atomicMin(&w[0], wl);
+        if (wh > w[1]) atomicMax(&w[1], wh);
     }
 }
 
@@ -1888,6 +2131,8 @@ struct Lane {
     int4* cand_ordb = nullptr; int4* base_ordb = nullptr; int4* base_ordc = nullptr;   // records B (mid-points) and C (masks)
     double* partials = nullptr;              // [48][partial_stride]: contacts rows 0..12, candidate band 16..28, base band 32..44
     unsigned char* rep_in_u = nullptr;       // [N]
+    int2* uwin = nullptr;                    // [W] union window of the bins of U (first sub-frag of the bin)
+    int2* cand_blk = nullptr;                // [13][n / 32 + 1] block hulls of the candidate orders
 };
 
 // The ~20 launches that score one proposal, captured once per proposal index and replayed with the two
@@ -1941,7 +2186,7 @@ struct graal_ctx {
     unsigned char* d_accu_idx = nullptr;                // [N*3]
     float* d_tab_norm = nullptr; float* d_tab_g[2] = {nullptr, nullptr}; double* d_tab_logg[2] = {nullptr, nullptr};
     double* d_tab_lnnorm = nullptr; double2* d_tab_log = nullptr; double* d_tab_exp = nullptr;
-    int4* d_tab_lnf[2] = {nullptr, nullptr}; int4* d_tab_f[2] = {nullptr, nullptr}; int4* d_tab_lnfu[2] = {nullptr, nullptr}; double* d_tab_normd = nullptr;
+    int4* d_tab_lnf[2] = {nullptr, nullptr}; int4* d_tab_f[2] = {nullptr, nullptr}; int4* d_tab_lnfu[2] = {nullptr, nullptr}; int4* d_tab_fu[2] = {nullptr, nullptr}; double* d_tab_normd = nullptr;
     std::vector<double> h_law;
     int math_mode = 2;
     std::vector<float> h_tab_g; std::vector<double> h_tab_logg;
@@ -1954,8 +2199,15 @@ struct graal_ctx {
     // windowed contact pass: static row items, per-pass order-space arrays and row records
     int4* items = nullptr; int n_items = 0; int4* row_hdr = nullptr; int4* item_hdr = nullptr;
     int* o_start = nullptr; int2* o_sub = nullptr; int* o_cid = nullptr; int2* o_blk = nullptr;
+    int delta_rel = 1;                        // GRAAL_DELTA_REL=0: absolute contact terms in the delta contact pass on every level (A/B runs)
+    int band_fast = 1;                        // GRAAL_BAND_FAST=0: general band delta kernels on every level (A/B runs)
+    int delta_uni = 0;                        // GRAAL_DELTA_UNI=1: union windows in the delta contact pass (measured: no gain -- the pass is bound by the evaluation of the in-band entries)
+    float max_bin_kb = 0.0f;                  // longest bin of the level (reach of the candidate windows)
+    int win_slot = -1; float win_dmax = 0.0f; long long geo_epoch = 0, win_epoch = -1;   // slot / d_max / geometry the row records (row_hdr) describe
+    FixedGraph g_win;
     int full_win = 1;                         // GRAAL_FULL_WIN=0: gather-everything kernel (k_full_contacts_direct) for A/B runs
-    int win_unroll = 8, win_minb = 4, win_sub = 4;   // GRAAL_WIN_SUB=1|2|4|8: loads per exact-path group; GRAAL_WIN_UNROLL=2|4|8: stream loads in flight per warp; GRAAL_WIN_MINB=2..6: CTAs per SM
+    bool win_tuned = false;                   // SUB picked by timing the variants on the bound level (first windowed pass)
+    int win_unroll = 8, win_minb = 4, win_sub = 2;   // GRAAL_WIN_SUB=1|2|4|8: loads per exact-path group; GRAAL_WIN_UNROLL=2|4|8: stream loads in flight per warp; GRAAL_WIN_MINB=2..6: CTAs per SM
     int smem_cid = 0;                         // GRAAL_SMEM_CID=1: stage the contig-id table in shared memory (measured: no faster than L1, profiles/README.md)
     double* band_hist = nullptr;              // [16][13] band delta of the proposals scored since the last commit
     int band_slot = -1; int band_age = 0;     // slot whose cross-bin band total is cached in d_scalars[40]
@@ -2016,14 +2268,14 @@ static int upload_tables(graal_ctx* c, Params& p, int which) {
     p.slope_d = (double)p.slope;
     // tabulated law: f(s) = c1*fact * s^slope * exp((d-2)/(x^2+d)), x = s*lm/kuhn, and ln f, with d/ds, float64
     p.t_lnf = c->d_tab_lnf[which]; p.t_f = c->d_tab_f[which]; p.t_normd = c->d_tab_normd; p.v_clamp = (double)p.v_inter;
-    p.t_lnfu = c->d_tab_lnfu[which]; p.fu_ok = 0; p.fu_span = p.fu_zlo = p.fu_zspan = 0u;
+    p.t_lnfu = c->d_tab_lnfu[which]; p.t_fu = c->d_tab_fu[which]; p.fu_ok = 0; p.fu_span = p.fu_zlo = p.fu_zspan = 0u;
     if (p.mode == 2) {
         if (!(cf > 0.0) || !(p.kuhn > 0.0f) || !(p.lm > 0.0f)) p.mode = 1;      // degenerate parameters: analytic path
         else {
             struct Entry { double a0; float a1, a2; };
             static_assert(sizeof(Entry) == 16, "law table entry");
             const size_t half = (size_t)(LAW_NODES + 2) * 2;          // doubles per table (16 bytes per interval)
-            c->h_law.assign(half * 3, 0.0);
+            c->h_law.assign(half * 4, 0.0);
             Entry* e_ln = reinterpret_cast<Entry*>(c->h_law.data());
             Entry* e_f = reinterpret_cast<Entry*>(c->h_law.data() + half);
             const double K = (double)p.d - 2.0, dd = (double)p.d, q = (double)p.lm / (double)p.kuhn, sl = (double)p.slope;
@@ -2078,6 +2330,12 @@ static int upload_tables(graal_ctx* c, Params& p, int which) {
                     Entry* e_u = reinterpret_cast<Entry*>(c->h_law.data() + 2 * half);
                     for (int i = 0; i < LAW_NODES; i++) { e_u[i] = e_ln[i]; e_u[i].a0 += cst; }
                     CUDA_OK(cudaMemcpyAsync(c->d_tab_lnfu[which], c->h_law.data() + 2 * half, half * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+                    Entry* e_fu = reinterpret_cast<Entry*>(c->h_law.data() + 3 * half);
+                    for (int i = 0; i < LAW_NODES; i++) {
+                        e_fu[i].a0 = e_f[i].a0 * (double)tn - (double)g1;
+                        e_fu[i].a1 = (float)((double)e_f[i].a1 * (double)tn); e_fu[i].a2 = (float)((double)e_f[i].a2 * (double)tn);
+                    }
+                    CUDA_OK(cudaMemcpyAsync(c->d_tab_fu[which], c->h_law.data() + 3 * half, half * sizeof(double), cudaMemcpyHostToDevice, c->stream));
                     p.fu_ok = 1;
                 }
             }
@@ -2152,9 +2410,12 @@ int graal_ctx_create(int device, graal_ctx** out) {
     { const char* e = getenv("GRAAL_PAIRING"); if (e && e[0] == '0') c->pairing = 0; }
     { const char* e = getenv("GRAAL_FORK"); if (e && e[0] == '0') c->fork_passes = 0; }
     { const char* e = getenv("GRAAL_FULL_WIN"); if (e && e[0] == '0') c->full_win = 0; }
+    { const char* e = getenv("GRAAL_DELTA_UNI"); if (e) c->delta_uni = e[0] == '1'; }
+    { const char* e = getenv("GRAAL_BAND_FAST"); if (e && e[0] == '0') c->band_fast = 0; }
+    { const char* e = getenv("GRAAL_DELTA_REL"); if (e && e[0] == '0') c->delta_rel = 0; }
     { const char* e = getenv("GRAAL_WIN_UNROLL"); if (e && (e[0] == '2' || e[0] == '4' || e[0] == '8')) c->win_unroll = e[0] - '0'; }
     { const char* e = getenv("GRAAL_WIN_MINB"); if (e && e[0] >= '2' && e[0] <= '6') c->win_minb = e[0] - '0'; }
-    { const char* e = getenv("GRAAL_WIN_SUB"); if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4' || e[0] == '8')) c->win_sub = e[0] - '0'; }
+    { const char* e = getenv("GRAAL_WIN_SUB"); if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4' || e[0] == '8')) { c->win_sub = e[0] - '0'; c->win_tuned = true; } }
     { const char* e = getenv("GRAAL_LANES"); if (e && e[0] >= '1' && e[0] <= '0' + GRAAL_MAX_LANES) c->n_lanes = e[0] - '0'; }
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     for (int l = 0; l < c->n_lanes; l++) {
@@ -2178,6 +2439,7 @@ static void free_level_scratch(graal_ctx* c) {
     cudaFree(c->cid16_base); cudaFree(c->mid32_base); cudaFree(c->cm_base); c->cm_base = nullptr; cudaFree(c->group_row); cudaFree(c->band_hist); c->band_hist = nullptr; c->cid16_base = nullptr; c->mid32_base = nullptr; c->group_row = nullptr;
     for (int l = 0; l < GRAAL_MAX_LANES; l++) {
         Lane& L = c->lanes[l];
+        cudaFree(L.uwin); cudaFree(L.cand_blk); L.uwin = nullptr; L.cand_blk = nullptr;
         cudaFree(L.sub_index); cudaFree(L.chmask); cudaFree(L.chmask2); L.chmask2 = nullptr; cudaFree(L.geo_cand); cudaFree(L.cand_ordrec); cudaFree(L.base_ordrec); cudaFree(L.cand_ordb); cudaFree(L.base_ordb); cudaFree(L.base_ordc); cudaFree(L.rep_in_u);
         L.sub_index = nullptr; L.chmask = nullptr; L.geo_cand = nullptr; L.cand_ordrec = L.base_ordrec = L.cand_ordb = L.base_ordb = L.base_ordc = nullptr; L.rep_in_u = nullptr;
     }
@@ -2189,7 +2451,7 @@ static void free_level_scratch(graal_ctx* c) {
     cudaFree(c->d_dup); cudaFree(c->d_sub_dup); cudaFree(c->d_rep_bins);
     c->d_dup = c->d_sub_dup = nullptr; c->d_rep_bins = nullptr; c->n_rep = 0;
     cudaFree(c->d_tab_lnnorm); cudaFree(c->d_tab_log); cudaFree(c->d_tab_exp); cudaFree(c->d_tab_normd);
-    for (int w = 0; w < 2; w++) { cudaFree(c->d_tab_lnf[w]); cudaFree(c->d_tab_f[w]); cudaFree(c->d_tab_lnfu[w]); c->d_tab_lnf[w] = nullptr; c->d_tab_f[w] = nullptr; c->d_tab_lnfu[w] = nullptr; }
+    for (int w = 0; w < 2; w++) { cudaFree(c->d_tab_lnf[w]); cudaFree(c->d_tab_f[w]); cudaFree(c->d_tab_lnfu[w]); cudaFree(c->d_tab_fu[w]); c->d_tab_lnf[w] = nullptr; c->d_tab_f[w] = nullptr; c->d_tab_lnfu[w] = nullptr; c->d_tab_fu[w] = nullptr; }
     c->d_tab_normd = nullptr;
     c->d_tab_lnnorm = nullptr; c->d_tab_log = nullptr; c->d_tab_exp = nullptr;
     cudaFree(c->d_tab_norm); cudaFree(c->d_tab_g[0]); cudaFree(c->d_tab_g[1]); cudaFree(c->d_tab_logg[0]); cudaFree(c->d_tab_logg[1]);
@@ -2214,7 +2476,7 @@ void graal_ctx_destroy(graal_ctx* c) {
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (int i = 0; i < 16; i++) c->graphs[i].reset();
-    c->g_stats.reset(); c->g_relabel.reset(); c->g_full.reset(); c->g_full_cached.reset();
+    c->g_stats.reset(); c->g_relabel.reset(); c->g_full.reset(); c->g_full_cached.reset(); c->g_win.reset();
     c->prof.destroy();
     cudaFree(c->d_ints); cudaFree(c->d_stats); cudaFree(c->d_counters); cudaFree(c->d_scalars); cudaFree(c->partials);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -2279,7 +2541,9 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     CUDA_OK(cudaStreamSynchronize(c->stream));
     c->version++;
     for (int i = 0; i < 16; i++) c->graphs[i].reset();
-    c->g_stats.reset(); c->g_relabel.reset(); c->g_full.reset(); c->g_full_cached.reset();
+    c->g_stats.reset(); c->g_relabel.reset(); c->g_full.reset(); c->g_full_cached.reset(); c->g_win.reset();
+    c->win_slot = -1;
+    { const char* e = getenv("GRAAL_WIN_SUB"); c->win_tuned = e != nullptr; }
     free_level_scratch(c);
     c->N = n_frags; c->n_new = n_new_frags; c->W = n_sub_frags; c->E = n_contacts; c->nfpb = nfpb;
     c->lv.sub_id = reinterpret_cast<const int4*>(sub_id); c->lv.sub_len = sub_len_kb; c->lv.sub_accu = sub_accu;
@@ -2295,6 +2559,16 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
         std::vector<int> h_disp((size_t)n_frags * 2);
         CUDA_OK(cudaMemcpy(h_disp.data(), dispatcher, h_disp.size() * sizeof(int), cudaMemcpyDeviceToHost));
         for (int b = 0; b < n_frags; b++) if (h_disp[2 * b + 1] - h_disp[2 * b] > 1) { h_dup[b] = 1; rep_bins.push_back(b); }
+    }
+    {
+        std::vector<float> h_len((size_t)n_frags * 3);
+        CUDA_OK(cudaMemcpy(h_len.data(), sub_len_kb, h_len.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        c->max_bin_kb = 0.0f;
+        for (int b = 0; b < n_frags; b++) {
+            float l = 0.0f;
+            for (int a = 0; a < h_sid[(size_t)b * 4 + 3] && a < 3; a++) l += h_len[(size_t)b * 3 + a];
+            c->max_bin_kb = std::max(c->max_bin_kb, l);
+        }
     }
     std::map<int, long long> hist; std::vector<int> quirky; long long w_check = 0;
     for (int b = 0; b < n_frags; b++) {
@@ -2343,6 +2617,7 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
         for (int w = 0; w < 2; w++) {
             CUDA_OK(cudaMalloc(&c->d_tab_lnf[w], (size_t)(LAW_NODES + 2) * sizeof(int4)));
             CUDA_OK(cudaMalloc(&c->d_tab_lnfu[w], (size_t)(LAW_NODES + 2) * sizeof(int4)));
+            CUDA_OK(cudaMalloc(&c->d_tab_fu[w], (size_t)(LAW_NODES + 2) * sizeof(int4)));
             CUDA_OK(cudaMalloc(&c->d_tab_f[w], (size_t)(LAW_NODES + 2) * sizeof(int4)));
         }
         for (int w = 0; w < 2; w++) {
@@ -2394,6 +2669,9 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
         CUDA_OK(cudaMemset(L.base_ordc, 0, (size_t)n * sizeof(int4)));
         CUDA_OK(cudaMalloc(&L.geo_cand, (size_t)GRAAL_N_CANDIDATES * c->W * sizeof(Geo)));
         CUDA_OK(cudaMemset(L.geo_cand, 0, (size_t)GRAAL_N_CANDIDATES * c->W * sizeof(Geo)));
+        CUDA_OK(cudaMalloc(&L.uwin, (size_t)c->W * sizeof(int2)));
+        CUDA_OK(cudaMemset(L.uwin, 0, (size_t)c->W * sizeof(int2)));
+        CUDA_OK(cudaMalloc(&L.cand_blk, (size_t)GRAAL_N_CANDIDATES * (n / 32 + 1) * sizeof(int2)));
         CUDA_OK(cudaMalloc(&L.sub_index, (size_t)n * sizeof(int)));
         CUDA_OK(cudaMemset(L.sub_index, 0, (size_t)n * sizeof(int)));
         L.pending = false; L.cand_first = -1;
@@ -2579,7 +2857,42 @@ static int ensure_base_geometry(graal_ctx* c, int slot) {
     if (c->geo_base_slot == slot) return 0;
     k_geometry_all<<<nblk(c->n_new, 128), 128, 0, c->stream>>>(slot_ptr(c, slot), c->ld, c->n_new, c->lv, c->geo_base, c->cid16_base, c->mid32_base, c->cm_base);
     CHECK_LAUNCH(c);
-    c->geo_base_slot = slot;
+    c->geo_base_slot = slot; c->geo_epoch++;
+    return 0;
+}
+
+// Position order of `slot` (c->order, cont_off / cont_len) and the row records of the windowed passes (row_hdr, item_hdr)
+// for the band d_max; the geometry of the slot must be current.  Cached per (slot, geometry, d_max).
+static bool windows_current(const graal_ctx* c, int slot, float d_max) {
+    return c->win_slot == slot && c->geo_base_slot == slot && c->win_epoch == c->geo_epoch && c->win_dmax == d_max;
+}
+static int enqueue_base_windows(graal_ctx* c, int slot, float d_max) {
+    cudaStream_t st = c->stream;
+    const int n = c->n_new, ld = c->ld;
+    int* s = slot_ptr(c, slot);
+    int* bad = c->d_ints + 4;
+    c->prof.begin(GRAAL_K_FULL_WINDOWS, st);
+    CUDA_OK(cudaMemsetAsync(c->cont_len, 0, (size_t)c->cap * sizeof(int), st));
+    k_contig_lengths<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_len); CHECK_LAUNCH(c);
+    size_t tb = c->cub_tmp_bytes;
+    CUDA_OK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, tb, c->cont_len, c->cont_off, c->cap, st)); c->launches += 2;
+    k_order_init<<<nblk(n, 256), 256, 0, st>>>(n, c->W, c->order, c->o_start, c->o_sub, c->o_cid, bad); CHECK_LAUNCH(c);
+    k_order_fill2<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_off, c->lv, c->order, c->o_start, c->o_sub, c->o_cid, bad); CHECK_LAUNCH(c);
+    k_hull_blocks<<<nblk(n, 256), 256, 0, st>>>(c->o_sub, n, c->o_blk); CHECK_LAUNCH(c);
+    const double dm = (double)d_max * 1000.0 * 1.0001 + 100.0;
+    const long long dmax_bp = dm < 4.0e18 ? (long long)ceil(dm) : (long long)4.0e18;
+    k_windows<<<nblk(n, 256), 256, 0, st>>>(c->order, c->o_start, c->o_sub, c->o_cid, c->o_blk, c->cont_off, c->cont_len, s, ld, n, c->W,
+                                           dmax_bp, c->cm_base, c->row_hdr, bad); CHECK_LAUNCH(c);
+    if (c->n_items > 0) { k_item_hdr<<<nblk(c->n_items, 256), 256, 0, st>>>(c->items, c->n_items, c->row_hdr, c->item_hdr); CHECK_LAUNCH(c); }
+    c->prof.end(GRAAL_K_FULL_WINDOWS, st);
+    return 0;
+}
+static int ensure_base_windows(graal_ctx* c, int slot, float d_max) {
+    if (windows_current(c, slot, d_max)) return 0;
+    union { float f; unsigned u; } dm; dm.f = d_max;
+    const int rc = run_graphed(c, c->g_win, slot, (long long)dm.u, 0, [&]() -> int { return enqueue_base_windows(c, slot, d_max); });
+    if (rc) return rc;
+    c->win_slot = slot; c->win_epoch = c->geo_epoch; c->win_dmax = d_max;
     return 0;
 }
 
@@ -2649,30 +2962,44 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
         }
     }
     if (c->n_quirky > ps) return set_err(-5, "too many quirky bins (%d > %d)", c->n_quirky, ps);
+    if (use_win && g1 > 0) { rc = ensure_base_windows(c, slot, p.d_max); if (rc) return rc; }
+    if (use_win && g1 > 0 && !c->win_tuned && !p_override && c->win_unroll == 8 && c->win_minb == 4) {
+        // near-diagonal lists want 4 loads per exact-path group, lists dominated by far entries 2: time both once on this level
+        cudaEvent_t e0, e1; CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+        FastLaw fl; fl.tab = p.t_lnfu; fl.smin_bits = LAW_SMIN_BITS; fl.span = p.fu_span; fl.zlo = p.fu_zlo; fl.zspan = p.fu_zspan;
+        float best = 1e30f; int best_sub = c->win_sub;
+        for (int sub = 2; sub <= 4; sub += 2) {
+            win_fn kf = (sub == 2) ? k_full_contacts_win<8, 4, 2> : k_full_contacts_win<8, 4, 4>;
+            float ms = 1e30f;
+            for (int rep = 0; rep < 3; rep++) {
+                CUDA_OK(cudaEventRecord(e0, st));
+                kf<<<g1, 256, 0, st>>>(c->items, c->item_hdr, c->n_items, c->contacts, c->cm_base, c->d_ints + 4, c->W, c->geo_base, fl, p, lg_uniform, c->partials);
+                CHECK_LAUNCH(c);
+                CUDA_OK(cudaEventRecord(e1, st));
+                CUDA_OK(cudaEventSynchronize(e1));
+                float t = 0.f; CUDA_OK(cudaEventElapsedTime(&t, e0, e1));
+                if (rep > 0) ms = std::min(ms, t);
+            }
+            if (ms < best) { best = ms; best_sub = sub; }
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        c->win_sub = best_sub; c->win_tuned = true;
+        k_win = (best_sub == 2) ? k_full_contacts_win<8, 4, 2> : k_full_contacts_win<8, 4, 4>;
+        c->g_full.reset(); c->g_full_cached.reset();
+    }
     const bool cached = !p_override && c->band_slot == slot && c->band_age < GRAAL_BAND_RESYNC;
     auto enqueue = [&]() -> int {
         // d_out = -(lf_total + G0) [+ log g * sum(ob)]   then accumulate the device sums
         const double init = -(c->lf_total + g0) + (uniform ? lg_uniform * c->ob_total : 0.0);
         k_set_double<<<1, 1, 0, st>>>(d_out, init); CHECK_LAUNCH(c);
-        const bool need_order = (use_win && g1 > 0) || !cached;
-        if (need_order) {                       // contig offsets of the position order (contig by contig, in id order)
+        if (!(use_win && g1 > 0) && !cached) {      // contig offsets of the position order (the windowed pass left them behind)
             CUDA_OK(cudaMemsetAsync(c->cont_len, 0, (size_t)c->cap * sizeof(int), st));
             k_contig_lengths<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_len); CHECK_LAUNCH(c);
             size_t tb = c->cub_tmp_bytes;
             CUDA_OK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, tb, c->cont_len, c->cont_off, c->cap, st)); c->launches += 2;
         }
-        if (use_win && g1 > 0) {                // position order + the per-row windows of this pass
-            c->prof.begin(GRAAL_K_FULL_WINDOWS, st);
+        if (use_win && g1 > 0) {
             int* bad = c->d_ints + 4;
-            k_order_init<<<nblk(n, 256), 256, 0, st>>>(n, c->W, c->order, c->o_start, c->o_sub, c->o_cid, bad); CHECK_LAUNCH(c);
-            k_order_fill2<<<nblk(n, 256), 256, 0, st>>>(s, ld, n, c->cap, c->cont_off, c->lv, c->order, c->o_start, c->o_sub, c->o_cid, bad); CHECK_LAUNCH(c);
-            k_hull_blocks<<<nblk(n, 256), 256, 0, st>>>(c->o_sub, n, c->o_blk); CHECK_LAUNCH(c);
-            const double dm = (double)p.d_max * 1000.0 * 1.0001 + 100.0;
-            const long long dmax_bp = dm < 4.0e18 ? (long long)ceil(dm) : (long long)4.0e18;
-            k_windows<<<nblk(n, 256), 256, 0, st>>>(c->order, c->o_start, c->o_sub, c->o_cid, c->o_blk, c->cont_off, c->cont_len, s, ld, n, c->W,
-                                                   dmax_bp, c->cm_base, c->row_hdr, bad); CHECK_LAUNCH(c);
-            k_item_hdr<<<nblk(c->n_items, 256), 256, 0, st>>>(c->items, c->n_items, c->row_hdr, c->item_hdr); CHECK_LAUNCH(c);
-            c->prof.end(GRAAL_K_FULL_WINDOWS, st);
             FastLaw fl; fl.tab = p.t_lnfu; fl.smin_bits = LAW_SMIN_BITS; fl.span = p.fu_span; fl.zlo = p.fu_zlo; fl.zspan = p.fu_zspan;
             c->prof.begin(GRAAL_K_FULL_CONTACTS, st);
             k_win<<<g1, 256, 0, st>>>(c->items, c->item_hdr, c->n_items, c->contacts, c->cm_base, bad, c->W, c->geo_base, fl, p, lg_uniform, c->partials);
@@ -2735,11 +3062,16 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
     return 0;
 }
 
-// the base slot's geometry must be current (ensure_base_geometry on the context stream) before this runs on `st`
+// union windows in the delta contact pass: uniform-accu level (every far pair has the same value) without repeats
+static bool delta_uni_ok(const graal_ctx* c) {
+    return c->delta_uni && c->p.nd == 1 && c->n_rep == 0 && c->n_quirky == 0 && c->E > 0 && c->p.d_max > 0.0f;
+}
+// the base slot's geometry (and, for the windowed delta pass, its row windows) must be current before this runs on `st`
 static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_slot, int first_cand_slot, int n_cand, int id_fA, int id_fB, int max_id,
                             unsigned skip, double* d_out, double* d_band, int copy_to = 0, unsigned pair_mask = 0u) {
     const int n = c->n_new, ld = c->ld;
     const Params p = c->p;
+    const bool uni = delta_uni_ok(c) && windows_current(c, base_slot, p.d_max);
     int* base = slot_ptr(c, base_slot);
     int* cand0 = slot_ptr(c, first_cand_slot);
     int* meta = L.ints + 8;
@@ -2750,12 +3082,18 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
     const int gu = std::min(c->n_sm * 2, nblk(n, 256));
     if (c->prof.on) { k_u_stats<<<gu, 256, 0, st>>>(L.sub_index, meta, c->lv, base, ld, c->rowptr, c->d_counters); CHECK_LAUNCH(c); }
     k_cand_geometry<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->lv, L.sub_index, meta, L.geo_cand, (size_t)c->W, piece_len,
-                                                     c->geo_base, L.chmask, skip); CHECK_LAUNCH(c);
+                                                     c->geo_base, L.chmask, skip, meta + 6); CHECK_LAUNCH(c);
     const int n_rows = pair_mask ? N_BAND_ROWS : n_cand;          // band rows: candidates (+ the partner rows of the paired ones)
     k_cand_order<<<dim3(gu, n_cand + 1 + (pair_mask ? 3 : 0)), 256, 0, st>>>(cand0, slot_stride(c), ld, L.sub_index, meta, piece_len, n, skip,
                                                       c->lv, L.chmask, L.geo_cand, (size_t)c->W, L.cand_ordrec, L.cand_ordb, rng + 2,
                                                       n_cand, base, c->geo_base, L.base_ordrec, L.base_ordb, L.base_ordc, rng,
-                                                      pair_mask, L.chmask2); CHECK_LAUNCH(c);
+                                                      pair_mask, L.chmask2, meta + 6, c->row_hdr, uni ? L.uwin : nullptr); CHECK_LAUNCH(c);
+    const int nblk32 = n / 32 + 1;
+    if (uni) {      // union over the candidates of the window of every bin of U
+        k_cand_hull_blocks<<<dim3(gu, n_cand), 256, 0, st>>>(L.cand_ordrec, n, meta, L.cand_blk, nblk32, skip); CHECK_LAUNCH(c);
+        const float reach = p.d_max * 1.0001f + c->max_bin_kb + 0.1f;
+        k_cand_windows<<<dim3(gu, n_cand), 256, 0, st>>>(L.cand_ordrec, n, meta, piece_len, L.cand_blk, nblk32, skip, reach, L.uwin); CHECK_LAUNCH(c);
+    }
     // grid-stride kernels over the (device-side) size of U: a few CTAs per SM, not one warp per bin of the level
     const int gw = std::min(ps, std::max(1, std::min(nblk(n, 1), c->n_sm * 2)));      // one resident wave (128 registers: 2 CTAs per SM)
     // (band: 2 CTAs per SM and one warp per x measured best with three proposals in flight: small grids share the SMs)
@@ -2772,17 +3110,32 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
     }
     // contacts: sum over changed contacts of ob * (ln ex_k - ln ex_0): new terms per candidate, old terms once
     c->prof.begin(GRAAL_K_DELTA_CONTACTS, st);
-    k_delta_contacts_rows<<<dim3(gw, 1), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, L.sub_index, meta, c->geo_base, L.geo_cand, (size_t)c->W,
-                                                      L.chmask, L.chmask2, pair_mask, p, p_contacts, ps); CHECK_LAUNCH(c);
+    FastLaw flc; flc.tab = p.t_lnfu; flc.smin_bits = LAW_SMIN_BITS; flc.span = p.fu_span; flc.zlo = p.fu_zlo; flc.zspan = p.fu_zspan;
+    const bool rel = c->delta_rel && p.nd == 1 && p.mode == 2 && p.fu_ok && c->n_rep == 0;       // relative contact terms (uniform level, tabulated monotone law)
+    if (rel) {
+        const double lg = log((double)g_clamp(c->accu_hist[0].first * c->accu_hist[0].first, p.v_inter, p.nfpb));
+        k_delta_contacts_rows<true><<<dim3(gw, 1), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, L.sub_index, meta, c->geo_base, L.geo_cand, (size_t)c->W,
+                                                                L.chmask, L.chmask2, pair_mask, p, p_contacts, ps, uni ? L.uwin : nullptr, flc, lg);
+    } else
+        k_delta_contacts_rows<false><<<dim3(gw, 1), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, L.sub_index, meta, c->geo_base, L.geo_cand, (size_t)c->W,
+                                                                 L.chmask, L.chmask2, pair_mask, p, p_contacts, ps, uni ? L.uwin : nullptr, flc, 0.0);
+    CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_DELTA_CONTACTS, st);
     // band mass: d_band[k] = B_U(S_k) - B_U(S_0) over changed pairs; enters the delta with a minus sign
     c->prof.begin(GRAAL_K_DELTA_BAND, st);
-    if (p.nd == 1) k_band_delta<false, 1, true><<<dim3(gb, n_rows), 256, 0, s_cand>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
+    const bool fast_band = c->band_fast && p.nd == 1 && p.mode == 2 && p.fu_ok;
+    FastBand fbd; fbd.tab = p.t_fu; fbd.smin_bits = LAW_SMIN_BITS; fbd.span = p.fu_span; fbd.zlo = p.fu_zlo; fbd.zspan = p.fu_zspan;
+    { union { float f; unsigned u; } dm; dm.f = p.d_max; fbd.dmax_bits = dm.u; }
+    if (fast_band) k_band_delta_fast<false, 1><<<dim3(gb, n_rows), 256, 0, s_cand>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, fbd, p,
+                                                                              p_cand, ps);
+    else if (p.nd == 1) k_band_delta<false, 1, true><<<dim3(gb, n_rows), 256, 0, s_cand>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
                                                                               p_cand, ps);
     else k_band_delta<false, 1, false><<<dim3(gb, n_rows), 256, 0, s_cand>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
                                                                      p_cand, ps);
     CHECK_LAUNCH(c);
-    if (p.nd == 1) k_band_delta<true, 4, true><<<dim3(gb, 1), 256, 0, s_base>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
+    if (fast_band) k_band_delta_fast<true, 4><<<dim3(gb, 1), 256, 0, s_base>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, fbd, p,
+                                                                        p_base, ps);
+    else if (p.nd == 1) k_band_delta<true, 4, true><<<dim3(gb, 1), 256, 0, s_base>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
                                                                         p_base, ps);
     else k_band_delta<true, 4, false><<<dim3(gb, 1), 256, 0, s_base>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
                                                                p_base, ps);
@@ -2830,6 +3183,7 @@ int graal_delta_loglik(graal_ctx* c, int base_slot, int first_cand_slot, int n_c
     if (!c->have_params) return set_err(-1, "parameters not set");
     if (id_fA < 0 || id_fA >= c->n_new || id_fB < 0 || id_fB >= c->n_new) return set_err(-1, "bin id out of range");
     int rc = ensure_base_geometry(c, base_slot); if (rc) return rc;
+    if (delta_uni_ok(c)) { rc = ensure_base_windows(c, base_slot, c->p.d_max); if (rc) return rc; }
     return delta_loglik_impl(c, c->lanes[0], c->stream, base_slot, first_cand_slot, n_cand, id_fA, id_fB, max_id, 0u, d_out, c->d_scalars + 16);
 }
 
@@ -2855,6 +3209,7 @@ int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int i
     int rc;
     if (serial) { rc = join_lanes(c); if (rc) return rc; }
     rc = ensure_base_geometry(c, base_slot); if (rc) return rc;
+    if (delta_uni_ok(c)) { rc = ensure_base_windows(c, base_slot, c->p.d_max); if (rc) return rc; }
     cudaStream_t st = c->stream;
     if (!serial) {
         CUDA_OK(cudaEventRecord(c->ev_fork, c->stream));

@@ -197,13 +197,15 @@ class sampler:
                  mean_squared_frags_per_bin, norm_vect_accu,
                  S_o_A_sub_frags,
                  hic_matrix, mean_value_trans, n_iterations=0, is_simu=False,
-                 device=0, rng=None, sub_sample_factor=0, device_contact_lists=None, proposal_tables=None):
+                 device=0, rng=None, sub_sample_factor=0, device_contact_lists=None, proposal_tables=None, share_level_with=None):
         """Arguments as in cuda_lib_gl.py:33-42 without the GL objects.  ``hic_matrix_sub_sampled``
         (current level) and ``hic_matrix`` (sub level) are upper-triangle COO triples
         (rows, cols, counts) instead of dense arrays.  ``rng``: np.random.RandomState (default: the
         global np.random module, as the reference).  ``device_contact_lists`` = (rowptr int64[W+1],
         contacts int32[E, 2]) torch tensors already on the device and ``proposal_tables`` = (xk, pk) replace
-        the host-side preparation of the two matrices (levels generated on the GPU)."""
+        the host-side preparation of the two matrices (levels generated on the GPU).  ``share_level_with``: another
+        sampler of the SAME level on the same device -- this one reuses its read-only device buffers (contact lists,
+        sub-frag tables) and proposal tables: several chains per GPU hold one copy of the level."""
         if not use_rippe:
             raise GraalError("only the Rippe model exists (kernels4.cu is not part of the reference tree)")
         torch = _torch()
@@ -247,7 +249,10 @@ class sampler:
         for f in self.id_frags_blacklisted:
             da = self.np_sub_frags_id[S_o_A_frags["id_d"][f]]
             black_subs.extend(int(da[k]) for k in range(da[3]))
-        if device_contact_lists is None:
+        if share_level_with is not None:
+            rowptr, contacts = share_level_with.d_rowptr, share_level_with.d_contacts
+            proposal_tables = (share_level_with.distri_xk, share_level_with.distri_pk)
+        elif device_contact_lists is None:
             rowptr, contacts = build_contact_lists(hic_matrix, int(init_n_sub_frags), black_subs, mean_value_trans)
         else:
             rowptr, contacts = device_contact_lists
@@ -262,8 +267,13 @@ class sampler:
         # ---- device buffers (torch owns them)
         dev = self.device
         t = lambda a: a.to(dev) if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-        self.d_sub_id, self.d_sub_len, self.d_sub_accu = t(self.np_sub_frags_id), t(self.np_sub_frags_len_bp), t(self.np_sub_frags_accu)
-        self.d_collector, self.d_dispatcher = t(self.collector_id_repeats), t(self.frag_dispatcher)
+        if share_level_with is not None:
+            o = share_level_with
+            self.d_sub_id, self.d_sub_len, self.d_sub_accu = o.d_sub_id, o.d_sub_len, o.d_sub_accu
+            self.d_collector, self.d_dispatcher = o.d_collector, o.d_dispatcher
+        else:
+            self.d_sub_id, self.d_sub_len, self.d_sub_accu = t(self.np_sub_frags_id), t(self.np_sub_frags_len_bp), t(self.np_sub_frags_accu)
+            self.d_collector, self.d_dispatcher = t(self.collector_id_repeats), t(self.frag_dispatcher)
         self.d_rowptr, self.d_contacts = t(rowptr), t(contacts)
         self.ld = (n + 31) // 32 * 32
         self.n_slots = 1 + N_TMP_STRUCT * N_LANES
@@ -322,14 +332,14 @@ class sampler:
         self.gpu_launches_at_start = self.lib.graal_launch_count(self.ctx)
 
     @classmethod
-    def from_inputs(cls, inp, device=0, rng=None, device_contact_lists=None, proposal_tables=None):
+    def from_inputs(cls, inp, device=0, rng=None, device_contact_lists=None, proposal_tables=None, share_level_with=None):
         """Build from ``graal_b200.level.SamplerInputs`` (what simulation.__init__ assembles)."""
         return cls(True, inp.S_o_A_frags, inp.collector_id_repeats, inp.frag_dispatcher, inp.id_frag_duplicated,
                    inp.id_frags_blacklisted, inp.n_frags, inp.n_new_frags, inp.init_n_sub_frags, inp.n_new_sub_frags,
                    inp.np_rep_sub_frags_id, inp.level_coo, inp.np_sub_frags_len_bp, inp.np_sub_frags_id,
                    inp.np_sub_frags_accu, inp.mean_squared_frags_per_bin, inp.norm_vect_accu, inp.S_o_A_sub_frags,
                    inp.sub_coo, inp.mean_value_trans, device=device, rng=rng,
-                   device_contact_lists=device_contact_lists, proposal_tables=proposal_tables)
+                   device_contact_lists=device_contact_lists, proposal_tables=proposal_tables, share_level_with=share_level_with)
 
     # ------------------------------------------------------------------ plumbing
     def sync(self):
@@ -523,47 +533,79 @@ class sampler:
     def step_max_likelihood(self, id_fA, delta, size_block=512, dt=0, t=0, n_step=1):
         """cuda_lib_gl.py:1793-1980.  Returns (o, n_contigs, min_len, mean_len_bp, max_len, op_sampled,
         id_f_sampled, dist, F_t)."""
+        self.step_begin(id_fA, delta)
+        return self.step_end(t, n_step)
+
+    MAX_PROPOSALS = 16      # proposals scored per device round trip (output block / band-delta history of the library)
+
+    def step_begin(self, id_fA, delta):
+        """First half of step_max_likelihood: everything up to the device round trip is ENQUEUED (statistics, relabel, the
+        proposals on their lanes, the full likelihood beside them); nothing is waited for.  Several chains on one GPU call
+        step_begin on each chain, then step_end on each (graal_b200.replica.step_chains): their kernels overlap."""
         lib = self.lib
-        if id_fA not in self._black_set:
-            check(lib.graal_state_stats(self.ctx, CUR, self._ptr(self.d_out, 4)))
-            check(lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
-            id_neighbours = self.return_neighbours(id_fA, delta)
+        self._step_fA = id_fA
+        check(lib.graal_state_stats(self.ctx, CUR, self._ptr(self.d_out, 4)))
+        check(lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
+        if id_fA in self._black_set:
+            self.id_neighbours = None
+            return
+        id_neighbours = self.return_neighbours(id_fA, delta)
+        id_neighbours.sort()
+        self.id_neighbours = id_neighbours
+        # incremental mode (off by default; the reference recomputes, cuda_lib_gl.py:1828-1848): the score of
+        # the candidate committed by the previous step IS the likelihood of the current state; the full pass
+        # only runs to resynchronise
+        self._step_incremental = self.incremental_likelihood and self._inc_valid and self._inc_age < self.incremental_resync
+        # the proposals go to their lanes first; the full likelihood of the current state does not depend
+        # on them and runs on the context stream next to them
+        self.score_neighbours(id_fA, id_neighbours[:self.MAX_PROPOSALS], with_dist=True)
+        if not self._step_incremental:
+            check(lib.graal_full_loglik(self.ctx, CUR, None, self._ptr(self.d_out, 0)))
+
+    def step_end(self, t=0, n_step=1):
+        """Second half: the one device round trip, the candidate draw (cuda_lib_gl.py:1899-1947), the commit."""
+        lib = self.lib
+        id_fA = self._step_fA
+        if self.id_neighbours is not None:
+            id_neighbours = self.id_neighbours
             n_neighbours = len(id_neighbours)
-            if n_neighbours > 16:
-                raise GraalError("more than 16 neighbours in one step")
-            id_neighbours.sort()
-            self.id_neighbours = id_neighbours
-            # the proposals go to their lanes first; the full likelihood of the current state does not depend
-            # on them and runs on the context stream next to them
-            self.score_neighbours(id_fA, id_neighbours, with_dist=True)
-            # incremental mode (off by default; the reference recomputes, cuda_lib_gl.py:1828-1848): the score of
-            # the candidate committed by the previous step IS the likelihood of the current state; the full pass
-            # only runs to resynchronise
-            incremental = self.incremental_likelihood and self._inc_valid and self._inc_age < self.incremental_resync
-            if not incremental:
-                check(lib.graal_full_loglik(self.ctx, CUR, None, self._ptr(self.d_out, 0)))
             out = self._fetch()
+            incremental = self._step_incremental
             likelihood_t = np.float64(self.likelihood_t) if incremental else np.float64(out[0])
             self._inc_age = self._inc_age + 1 if incremental else 0
             self._inc_valid = True
             self.likelihood_t = likelihood_t
             n_contigs, min_len, mean_len_bp, max_len = int(out[4]), int(out[5]), out[6], int(out[7])
-            self.delta_scores = np.array(out[16:16 + n_neighbours * N_TMP_STRUCT], dtype=np.float64)
+            n_first = min(n_neighbours, self.MAX_PROPOSALS)
+            deltas = [np.array(out[16:16 + n_first * N_TMP_STRUCT], dtype=np.float64)]
+            dists = [np.array(out[OFF_DIST:OFF_DIST + n_first * N_TMP_STRUCT], dtype=np.float64)]
+            last_chunk = 0
+            # more neighbours than one round trip holds (repeats expand every partner to all its copies,
+            # cuda_lib_gl.py:2316-2327): further chunks of <= 16 proposals, one round trip each
+            for c0 in range(self.MAX_PROPOSALS, n_neighbours, self.MAX_PROPOSALS):
+                chunk = id_neighbours[c0:c0 + self.MAX_PROPOSALS]
+                self.score_neighbours(id_fA, chunk, with_dist=True)
+                o2 = self._fetch()
+                deltas.append(np.array(o2[16:16 + len(chunk) * N_TMP_STRUCT], dtype=np.float64))
+                dists.append(np.array(o2[OFF_DIST:OFF_DIST + len(chunk) * N_TMP_STRUCT], dtype=np.float64))
+                last_chunk = c0
+            self.delta_scores = np.concatenate(deltas)
+            dist_all = np.concatenate(dists)
             self.score = self.delta_scores + likelihood_t
             sample_out = self._sample(self.score, self.temperature(t, n_step))
-            id_f_sampled = id_neighbours[sample_out // N_TMP_STRUCT]
+            x = sample_out // N_TMP_STRUCT
+            id_f_sampled = id_neighbours[x]
             op_sampled = sample_out % N_TMP_STRUCT
-            check(lib.graal_commit_scored(self.ctx, CUR, CAND0, int(id_fA), int(id_f_sampled), -1, int(op_sampled),
-                                          int(sample_out // N_TMP_STRUCT)))
+            # the band delta of a scored proposal is only remembered for the chunk scored last
+            x_lib = x - last_chunk if x >= last_chunk else -1
+            check(lib.graal_commit_scored(self.ctx, CUR, CAND0, int(id_fA), int(id_f_sampled), -1, int(op_sampled), int(x_lib)))
             o = self.score[sample_out]
             self.o = o
             # dist_inter_genome of the committed candidate (cuda_lib_gl.py:1962) came back with the scores
             norm_distance = 3.0 * (int(self.n_new_frags) - self.n_frags_4_dist)
-            dist = float(out[OFF_DIST + sample_out]) / norm_distance if norm_distance != 0 else 0.0
+            dist = float(dist_all[sample_out]) / norm_distance if norm_distance != 0 else 0.0
         else:
             o = self.o
-            check(lib.graal_state_stats(self.ctx, CUR, self._ptr(self.d_out, 4)))
-            check(lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
             out = self._fetch()
             n_contigs, min_len, mean_len_bp, max_len = int(out[4]), int(out[5]), out[6], int(out[7])
             op_sampled, id_f_sampled = -1, id_fA
@@ -589,10 +631,13 @@ class sampler:
         check(lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
         if op_sampled < 0:
             return
-        self.score_neighbours(id_fA, id_neighbours, with_dist=True)
+        for c0 in range(0, len(id_neighbours), self.MAX_PROPOSALS):
+            self.score_neighbours(id_fA, id_neighbours[c0:c0 + self.MAX_PROPOSALS], with_dist=True)
         if full:                                   # False: a step of the incremental mode between two resyncs
             check(lib.graal_full_loglik(self.ctx, CUR, None, self._ptr(self.d_out, 0)))
         x = id_neighbours.index(id_f_sampled) if id_f_sampled in id_neighbours else -1
+        last_chunk = (max(len(id_neighbours), 1) - 1) // self.MAX_PROPOSALS * self.MAX_PROPOSALS
+        x = x - last_chunk if x >= last_chunk else -1
         check(lib.graal_commit_scored(self.ctx, CUR, CAND0, int(id_fA), int(id_f_sampled), -1, int(op_sampled), x))
 
     def _sample(self, score, F_t):
@@ -635,21 +680,22 @@ class sampler:
         self.sigma_fact = 10 ** (np.log10(fact) - 2)
         self.sigma_slope, self.sigma_d_max, self.sigma_d_nuc = 0.05, 100, 0.5
         id_modif = self.rng.choice(4)
+        # (the reference ran under NumPy 1.x, where float32 scalar + Python float is float64: cast explicitly, NumPy 2 keeps float32)
         c1f = lambda sl: rippe_c1(kuhn, lm, sl)
         if id_modif == 0:
-            new_fact = fact + self.rng.normal(loc=0.0, scale=self.sigma_fact)
+            new_fact = np.float64(fact) + self.rng.normal(loc=0.0, scale=self.sigma_fact)
             new_d_max = opti.estimate_max_dist_intra([kuhn, lm, slope, d, new_fact], d_nuc)
             out_test_param = [(kuhn, lm, c1f(slope), slope, d, new_d_max, new_fact, d_nuc)]
         elif id_modif == 1:
-            new_slope = slope + self.rng.normal(loc=0.0, scale=self.sigma_slope)
+            new_slope = np.float64(slope) + self.rng.normal(loc=0.0, scale=self.sigma_slope)
             new_d_max = opti.estimate_max_dist_intra([kuhn, lm, new_slope, d, fact], d_nuc)
             out_test_param = [(kuhn, lm, c1f(new_slope), new_slope, d, new_d_max, fact, d_nuc)]
         elif id_modif == 2:
-            new_d_max = d_max + self.rng.normal(loc=0.0, scale=self.sigma_d_max)
+            new_d_max = np.float64(d_max) + self.rng.normal(loc=0.0, scale=self.sigma_d_max)
             new_d_nuc = opti.peval(new_d_max, [kuhn, lm, slope, d, fact])
             out_test_param = [(kuhn, lm, c1f(slope), slope, d, new_d_max, fact, new_d_nuc)]
         else:
-            new_d_nuc = d_nuc + self.rng.normal(loc=0.0, scale=self.sigma_d_nuc)
+            new_d_nuc = np.float64(d_nuc) + self.rng.normal(loc=0.0, scale=self.sigma_d_nuc)
             new_d_max = opti.estimate_max_dist_intra([kuhn, lm, slope, d, fact], new_d_nuc)
             out_test_param = [(kuhn, lm, c1f(slope), slope, d, new_d_max, fact, new_d_nuc)]
         out_test_param = np.array(out_test_param, dtype=PARAM_DTYPE)

@@ -305,19 +305,19 @@ class OracleSampler:
         sigma_fact = 10 ** (np.log10(fact) - 2)
         id_modif = self.rng.choice(4)
         if id_modif == 0:
-            new_fact = fact + self.rng.normal(loc=0.0, scale=sigma_fact)
+            new_fact = np.float64(fact) + self.rng.normal(loc=0.0, scale=sigma_fact)   # NumPy 1.x: float32 + float -> float64
             new_d_max = estimate_max_dist_intra([kuhn, lm, slope, d, new_fact], d_nuc)
             out = (kuhn, lm, slope, d, new_fact, new_d_max, d_nuc)
         elif id_modif == 1:
-            new_slope = slope + self.rng.normal(loc=0.0, scale=0.05)
+            new_slope = np.float64(slope) + self.rng.normal(loc=0.0, scale=0.05)
             new_d_max = estimate_max_dist_intra([kuhn, lm, new_slope, d, fact], d_nuc)
             out = (kuhn, lm, new_slope, d, fact, new_d_max, d_nuc)
         elif id_modif == 2:
-            new_d_max = d_max + self.rng.normal(loc=0.0, scale=100)
+            new_d_max = np.float64(d_max) + self.rng.normal(loc=0.0, scale=100)
             new_d_nuc = peval(new_d_max, [kuhn, lm, slope, d, fact])       # Q10: param[3] = d is the amplitude
             out = (kuhn, lm, slope, d, fact, new_d_max, new_d_nuc)
         else:
-            new_d_nuc = d_nuc + self.rng.normal(loc=0.0, scale=0.5)
+            new_d_nuc = np.float64(d_nuc) + self.rng.normal(loc=0.0, scale=0.5)
             new_d_max = estimate_max_dist_intra([kuhn, lm, slope, d, fact], new_d_nuc)
             out = (kuhn, lm, slope, d, fact, new_d_max, new_d_nuc)
         k_, lm_, sl_, d_, f_, dm_, dn_ = out

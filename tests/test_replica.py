@@ -57,6 +57,8 @@ def _worker(rank, world, port, q):
         logliks = -100.0 * rng.rand(n_local) - 10.0 * np.array([rex.temperature(c) for c in range(n_local)])
         rex.maybe_exchange(step, logliks)
         temps.append([rex.temperature(c) for c in range(n_local)])
+    rex.consume()                                    # the round posted at the last boundary
+    temps[-1] = [rex.temperature(c) for c in range(n_local)]
     q.put((rank, rex.temp_index.tolist(), rex.n_collectives, rex.history, temps[-1]))
     dist.barrier()
     dist.destroy_process_group()
@@ -95,3 +97,21 @@ def test_single_process_fallback_and_attach():
     assert sorted(rex.temp_index.tolist()) == [0, 1, 2] and s.temperature() == R.temperature_ladder(3)[rex.temp_index[2]]
     with pytest.raises(ValueError):
         R.ReplicaExchange(2, R.temperature_ladder(3))
+
+
+def test_exchange_is_applied_one_boundary_later():
+    """post / consume: the table gathered at a boundary decides the labels at the NEXT step boundary (nothing blocks)."""
+    rex = R.ReplicaExchange(2, R.temperature_ladder(2), exchange_every=3, seed=5)
+    L = [-100.0, -1.0]                                # the hotter chain is far better: the swap is certain
+    for step in (1, 2):
+        assert rex.maybe_exchange(step, L) is None
+    assert rex.maybe_exchange(3, L) is None           # posted, not applied yet
+    assert rex.temp_index.tolist() == [0, 1]
+    log = rex.maybe_exchange(4, L)                    # applied at the next boundary
+    assert log is not None and log[0][1] and rex.temp_index.tolist() == [1, 0]
+    st = rex.stats()
+    assert st["posted"] == 1 and st["blocking"] is False
+    rex.warm_up()                                     # changes nothing
+    assert rex.temp_index.tolist() == [1, 0] and rex.round_id == 1 and rex.stats()["posted"] == 1
+    rex.reset()
+    assert rex.temp_index.tolist() == [0, 1] and rex.round_id == 0
