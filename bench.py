@@ -42,13 +42,14 @@ def parse():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c4", "tiny"])
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c4", "c5", "tiny"])
     ap.add_argument("--level", type=int, default=1)
     ap.add_argument("--neighbours", type=int, default=3)
     ap.add_argument("--chains-per-gpu", type=int, default=1)
     ap.add_argument("--exchange-every", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the roofline_c4 block (C4 level generated and timed in the same run)")
+    ap.add_argument("--no-original", action="store_true", help="skip the original_kernels block (kernels3.cu compiled for sm_100a, C1 level 1)")
     ap.add_argument("--incremental", action="store_true",
                     help="carry the likelihood of the current state from the committed candidate (full pass every 256 steps "
                          "only) instead of recomputing it every step as the reference does; NOT the default workload")
@@ -350,6 +351,61 @@ def roofline_blocks(kern, counters, E, W, peak, peak_src, traffic):
     return roof, roof_d
 
 
+def original_kernels_block(k_nb, n_steps=8):
+    """Second baseline: the reference's ORIGINAL kernels (kernels3.cu compiled for sm_100a, baseline/ref_gpu.py) scoring the
+    same steps as the device path on BASELINE config C1 level 1 (1,672 bins, W = 5,000: their dense formulation needs
+    N < 4,609) -- their own launch sequence per step (full likelihood, per neighbour 22 mutation launches + 17 blocking
+    max round trips + index sets + 13 delta launches on 13 streams) against ours (one fused call + one fetch)."""
+    import torch
+    from baseline import ref_gpu
+    from graal_b200.level import yeast_shaped_pyramid, prepare_sampler_inputs
+    from graal_b200.sampler import sampler, CUR
+    if not ref_gpu.available():
+        return {"unavailable": "baseline/_ref/kernels3_sm100a.cubin not built"}
+    pyr = yeast_shaped_pyramid(n_levels=2)
+    inp = prepare_sampler_inputs(pyr, 1)
+    g = sampler.from_inputs(inp, rng=np.random.RandomState(1000))
+    p, d_max = model_params(pyr)
+    g.set_parameters(p, d_max)
+    r = ref_gpu.RefGPU(inp, np.array(list(g.param_simu[0]), dtype=np.float32))
+    max_id = int(g.modify_gl_cuda_buffer())
+    r.slot_from_host(ref_gpu.CUR, g.slot_to_host(CUR))
+    n = int(g.n_new_frags)
+    frags = bin_schedule(n, n_steps + 2)
+    steps = []
+    for fA in frags:
+        nb = g.return_neighbours(int(fA), k_nb); nb.sort()
+        if nb:
+            steps.append((int(fA), nb))
+    worst, t_ref, t_dev, n_ev = 0.0, 0.0, 0.0, 0
+    for it, (fA, nb) in enumerate(steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        full_r, d_r = r.score_step(fA, nb, max_id)
+        t1 = time.perf_counter()
+        g.score_neighbours(fA, nb)
+        _lib_check(g.lib.graal_full_loglik(g.ctx, CUR, None, g._ptr(g.d_out, 0)))
+        out = g._fetch()
+        t2 = time.perf_counter()
+        d_g, full_g = np.array(out[16:16 + N_TMP * len(nb)]), float(out[0])
+        if it >= 2:                                               # two warm-up steps
+            t_ref += t1 - t0; t_dev += t2 - t1; n_ev += N_TMP * len(nb)
+        scale = max(1.0, float(np.abs(d_r).max()))
+        worst = max(worst, float(np.abs(d_g - d_r).max()) / scale, abs(full_g - full_r) / abs(full_r))
+    launches = r.launches
+    g.free_gpu()
+    return {"workload": "C1 level 1 (1,672 bins, 5,000 sub-frags, dense 100 MB matrix), %d steps x %d neighbours x 13 candidates, static genome" % (len(steps) - 2, k_nb),
+            "original_kernels_evals_per_s": n_ev / t_ref if t_ref else None, "ours_evals_per_s": n_ev / t_dev if t_dev else None,
+            "speedup": (t_ref / t_dev) if t_dev else None, "original_ms_per_step": 1e3 * t_ref / max(1, len(steps) - 2),
+            "ours_ms_per_step": 1e3 * t_dev / max(1, len(steps) - 2), "original_launches": launches,
+            "max_rel_difference": worst, "timing": "host wall clock around each step (both sides end with a device round trip)"}
+
+
+def _lib_check(rc):
+    from graal_b200 import _lib
+    _lib.check(rc)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -374,22 +430,33 @@ def main():
     dev = torch.device("cuda", local_rank)
     n_ch = max(1, args.chains_per_gpu)
 
-    def c4_sampler(seed):
+    def c4_sampler(seed, big=False, share=None, inp4=None):
         from graal_b200.level import synthetic_roofline_level
-        inp4, lists, tables, info = synthetic_roofline_level(device=dev)
-        g4 = sampler.from_inputs(inp4, device=local_rank, rng=np.random.RandomState(seed), device_contact_lists=lists, proposal_tables=tables)
-        g4.set_parameters([1.0, 9.6, -1.5, 3.0, 800.0], info["d_max_kb"])
+        if share is None:
+            kw = dict(n_bins=1_000_000, n_contigs=64, n_draws=1_200_000_000) if big else {}
+            inp4, lists, tables, info = synthetic_roofline_level(device=dev, **kw)
+            g4 = sampler.from_inputs(inp4, device=local_rank, rng=np.random.RandomState(seed), device_contact_lists=lists, proposal_tables=tables)
+            g4._d_max_kb = info["d_max_kb"]
+        else:
+            g4 = sampler.from_inputs(inp4, device=local_rank, rng=np.random.RandomState(seed), share_level_with=share)
+            g4._d_max_kb = share._d_max_kb
+        g4.set_parameters([1.0, 9.6, -1.5, 3.0, 800.0], g4._d_max_kb)
         return inp4, g4
 
     chains = []
-    if args.config == "c4":
-        # BASELINE config C4: 200k bins / ~237 M stored contacts, generated on the GPU (no CPU baseline: the NumPy oracle
-        # does not fit this size in the time budget; tests/test_gpu_bench_configs.py checks a row sample of it)
-        inp, g = c4_sampler(1000 + rank * n_ch)
-        name = "C4: synthetic 200k-bin / ~200M-contact level (24 contigs, offsets ~ s^-1.5 truncated at d_max = 1000 kb, 5% trans), single chain"
+    if args.config in ("c4", "c5"):
+        # BASELINE configs C4 (200k bins / ~237 M stored contacts) and C5 (1 M bins / ~1 B contacts, the chains of a GPU share
+        # one copy of the level), generated on the GPU (no CPU baseline: the NumPy oracle does not fit these sizes in the time
+        # budget; tests/test_gpu_bench_configs.py checks a row sample of C4)
+        big = args.config == "c5"
+        inp, g = c4_sampler(1000 + rank * n_ch, big=big)
+        chains = [g]
+        for ch in range(1, n_ch):
+            chains.append(c4_sampler(1000 + rank * n_ch + ch, big=big, share=g, inp4=inp)[1])
+        name = ("C5: synthetic 1M-bin / ~1B-contact level (64 contigs), %d chains per GPU sharing one copy of the level" % n_ch) if big else \
+               "C4: synthetic 200k-bin / ~200M-contact level (24 contigs, offsets ~ s^-1.5 truncated at d_max = 1000 kb, 5% trans), single chain"
         pyr = None
         args.no_cpu_baseline = True
-        chains = [g]
     else:
         pyr, inp, name = build_level(args.config, args.level)
         p, d_max = model_params(pyr)
@@ -577,6 +644,11 @@ def main():
                                               "(sparse formulation) on %d forked workers, %.1f s" % (N_TMP * len(nb), len(nb), E, workers, dt)}
             if not line["parity"]["ok"]:
                 rc = 1
+    if world == 1 and n_ch == 1 and not args.no_original and args.config == "c2":
+        try:
+            line["original_kernels"] = original_kernels_block(k_nb)
+        except Exception as e:                                    # the cubin is an optional artefact (built where /root/reference exists)
+            line["original_kernels"] = {"unavailable": repr(e)[:200]}
     if world == 1 and not args.no_c4 and args.config == "c2" and n_ch == 1:
         # BASELINE config C4 in the same run: the HBM roofline configuration (the contact list is 1.9 GB)
         for gc in chains:

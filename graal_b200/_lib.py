@@ -56,6 +56,7 @@ _SIGS = {
     "graal_join": (_I, [_P]),
     "graal_version": (C.c_char_p, []),
     "graal_level_bind": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _LL, _F]),
+    "graal_coo_to_lists": (_I, [_P, _P, _P, _P, _LL, _I, _P, _P, C.POINTER(_LL)]),
     "graal_set_params": (_I, [_P, C.POINTER(_F)]),
     "graal_set_math_mode": (_I, [_P, _I]),
     "graal_state_bind": (_I, [_P, _P, _I, _I]),

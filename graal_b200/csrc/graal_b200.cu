@@ -4,6 +4,7 @@
 // fused operations are written explicitly (fma()) where they are wanted.
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
+#include <cuda/std/functional>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -1510,7 +1511,7 @@ k_band_delta(const int4* __restrict__ rec_a0, const int4* __restrict__ rec_b0, c
 // Circular contigs and in-band distances outside the table take the general evaluation pair by pair.
 struct FastBand { const int4* tab; unsigned smin_bits, span, zlo, zspan, dmax_bits; };
 template <bool BASE, int PARTS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_band_delta_fast(const int4* __restrict__ rec_a0, const int4* __restrict__ rec_b0, const int4* __restrict__ rec_c, int order_stride,
                   const int* __restrict__ d_count, const int* __restrict__ rng0,
                   const Geo* __restrict__ geo0, size_t cand_geo_stride, unsigned skip_cands, const FastBand fb,
@@ -1560,20 +1561,29 @@ k_band_delta_fast(const int4* __restrict__ rec_a0, const int4* __restrict__ rec_
         const unsigned span = circ ? 0u : fb.span, zlo = circ ? 1u : fb.zlo, zspan = circ ? fb.dmax_bits - 1u : fb.zspan, smin = fb.smin_bits;
         const bool x_uniform = (nx < 2 || mx[1] == mx[0]) && (nx < 3 || mx[2] == mx[0]);
         double tot = 0.0; float totf = 0.0f, accf = 0.0f;        // BASE: old values credited to the candidates of the whole bin x
+        // the records of the NEXT chunk of 32 bins are loaded before the current chunk is evaluated (the three dependent
+        // stages record A -> record B -> table would otherwise be paid per chunk with a handful of warps per scheduler)
+        const int4 zero4 = make_int4(0, 0, 0, 0);
+        int iy0 = y0 + 32 * part + lane;
+        int4 ry_n = iy0 < y1 ? rec_a[iy0] : zero4, yb_n = iy0 < y1 ? rec_b[iy0] : zero4, yc_n = (BASE && iy0 < y1) ? rec_c[iy0] : zero4;
         for (int basei = y0 + 32 * part; basei < y1; basei += 32 * PARTS) {
             const int iy = basei + lane;
             bool live = iy < y1;
+            const int4 ry = ry_n, yb = yb_n, yc4 = yc_n;
+            {
+                const int in = iy + 32 * PARTS;
+                ry_n = in < y1 ? rec_a[in] : zero4; yb_n = in < y1 ? rec_b[in] : zero4;
+                if (BASE) yc_n = in < y1 ? rec_c[in] : zero4;
+            }
             if (live) {
-                const int4 ry = rec_a[iy];
                 // beyond the band (or next contig): every remaining pair evaluates to the clamp value
                 if (ry.w != cx || (double)__int_as_float(ry.y) - (double)xmax > (double)d_max * 1.00001 + 0.05) live = false;
                 else {
                     const int ny = (ry.x >> 28) & 7;
                     const unsigned ym = (unsigned)ry.z;
                     if (ny > 0 && (xchg || ym != 0u)) {
-                        const int4 yb = rec_b[iy];
                         unsigned my[3];
-                        if (BASE) { const int4 yc = rec_c[iy]; my[0] = (unsigned)yc.x; my[1] = (unsigned)yc.y; my[2] = (unsigned)yc.z; }
+                        if (BASE) { my[0] = (unsigned)yc4.x; my[1] = (unsigned)yc4.y; my[2] = (unsigned)yc4.z; }
                         else { my[0] = ym & 1u; my[1] = (ym >> 1) & 1u; my[2] = (ym >> 2) & 1u; }
                         const float ya[3] = {__int_as_float(yb.x), ny > 1 ? __int_as_float(yb.y) : nanf_, ny > 2 ? __int_as_float(yb.z) : nanf_};
                         const float yc[3] = {my[0] ? ya[0] : nanf_, my[1] ? ya[1] : nanf_, my[2] ? ya[2] : nanf_};   // changed sub-frags only
@@ -3382,6 +3392,74 @@ int graal_dist_candidates(graal_ctx* c, int first_cand_slot, int n_cand, int pro
     k_dist_genome<<<dim3(g, n_cand), 256, 0, st>>>(slot_ptr(c, first_cand_slot), slot_stride(c), c->ld, n, init_prev, init_next, init_orientable, skip, part, ps); CHECK_LAUNCH(c);
     k_reduce_partials<<<n_cand, 256, 0, st>>>(part, g, ps, 1.0, d_out, 0); CHECK_LAUNCH(c);
     if (st != c->stream) CUDA_OK(cudaEventRecord(L->done, L->st));      // the join must cover this work too
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// COO -> row-segmented contact lists on the device (sampler.__init__, cuda_lib_gl.py:153-172: csr + csr.T, diagonal zeroed)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_coo_keys(const int* __restrict__ r, const int* __restrict__ c, const float* __restrict__ v, long long n, long long W,
+                           unsigned long long* __restrict__ keys, float* __restrict__ vals) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long a = r[i], b = c[i];
+        const bool ok = a != b && a >= 0 && b >= 0 && a < W && b < W;
+        keys[i] = ok ? (unsigned long long)(min(a, b) * W + max(a, b)) : ~0ull;       // diagonal / invalid entries sort last and are dropped
+        vals[i] = ok ? v[i] : 0.0f;
+    }
+}
+__global__ void k_coo_rows(const unsigned long long* __restrict__ keys, const float* __restrict__ vals, const int* __restrict__ n_unique, long long W,
+                           unsigned char* __restrict__ keep, int* __restrict__ row_count) {
+    const long long m = *n_unique;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        const bool k = keys[i] != ~0ull && vals[i] != 0.0f;
+        keep[i] = k ? 1 : 0;
+        if (k) atomicAdd(&row_count[(int)(keys[i] / (unsigned long long)W)], 1);
+    }
+}
+__global__ void k_coo_emit(const unsigned long long* __restrict__ keys, const float* __restrict__ vals, const unsigned char* __restrict__ keep,
+                           const long long* __restrict__ pos, const int* __restrict__ n_unique, long long W, int2* __restrict__ out) {
+    const long long m = *n_unique;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x)
+        if (keep[i]) out[pos[i]] = make_int2((int)(keys[i] % (unsigned long long)W), __float_as_int(vals[i]));
+}
+
+int graal_coo_to_lists(graal_ctx* c, const int32_t* d_rows, const int32_t* d_cols, const float* d_vals, int64_t n, int n_sub_frags,
+                       int64_t* d_rowptr, void* d_contacts, int64_t* n_contacts_out) {
+    if (!c || !d_rows || !d_cols || !d_vals || !d_rowptr || !d_contacts || !n_contacts_out) return set_err(-1, "null argument");
+    if (n <= 0 || n >= (1ll << 31) || n_sub_frags <= 0) return set_err(-1, "bad sizes");
+    CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const long long W = n_sub_frags;
+    unsigned long long *k0 = nullptr, *k1 = nullptr, *ku = nullptr; float *v0 = nullptr, *v1 = nullptr, *vu = nullptr;
+    int* d_nu = nullptr; int* d_cnt = nullptr; unsigned char* keep = nullptr; long long* pos = nullptr; void* tmp = nullptr;
+    auto cleanup = [&]() { cudaFree(k0); cudaFree(k1); cudaFree(ku); cudaFree(v0); cudaFree(v1); cudaFree(vu); cudaFree(d_nu); cudaFree(d_cnt); cudaFree(keep); cudaFree(pos); cudaFree(tmp); };
+    #define COO_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cleanup(); return set_err(-2, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); } } while (0)
+    COO_OK(cudaMalloc(&k0, n * 8)); COO_OK(cudaMalloc(&k1, n * 8)); COO_OK(cudaMalloc(&ku, n * 8));
+    COO_OK(cudaMalloc(&v0, n * 4)); COO_OK(cudaMalloc(&v1, n * 4)); COO_OK(cudaMalloc(&vu, n * 4));
+    COO_OK(cudaMalloc(&d_nu, 4)); COO_OK(cudaMalloc(&d_cnt, (size_t)(W + 1) * 4)); COO_OK(cudaMalloc(&keep, n)); COO_OK(cudaMalloc(&pos, n * 8));
+    const int g = std::min<long long>((n + 255) / 256, (long long)c->n_sm * 16);
+    k_coo_keys<<<g, 256, 0, st>>>(d_rows, d_cols, d_vals, n, W, k0, v0); c->launches++;
+    size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, k0, k1, v0, v1, (int)n, 0, 64, st);
+    cub::DeviceReduce::ReduceByKey(nullptr, b2, k1, ku, v1, vu, d_nu, cuda::std::plus<>(), (int)n, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, b3, (const unsigned char*)nullptr, (long long*)nullptr, (int)n, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, b4, (const int*)nullptr, (long long*)nullptr, (int)(W + 1), st);
+    const size_t tb = std::max(std::max(b1, b2), std::max(b3, b4));
+    COO_OK(cudaMalloc(&tmp, tb));
+    size_t t = tb;
+    // (invalid keys are all ones: they stay last whatever the number of key bits sorted)
+    COO_OK(cub::DeviceRadixSort::SortPairs(tmp, t, k0, k1, v0, v1, (int)n, 0, 64, st)); t = tb;
+    COO_OK(cub::DeviceReduce::ReduceByKey(tmp, t, k1, ku, v1, vu, d_nu, cuda::std::plus<>(), (int)n, st)); t = tb;      // duplicates summed (float32, in sorted order)
+    COO_OK(cudaMemsetAsync(d_cnt, 0, (size_t)(W + 1) * 4, st));
+    COO_OK(cudaMemsetAsync(keep, 0, n, st));
+    k_coo_rows<<<g, 256, 0, st>>>(ku, vu, d_nu, W, keep, d_cnt); c->launches++;
+    COO_OK(cub::DeviceScan::ExclusiveSum(tmp, t, keep, pos, (int)n, st)); t = tb;
+    COO_OK(cub::DeviceScan::ExclusiveSum(tmp, t, d_cnt, reinterpret_cast<long long*>(d_rowptr), (int)(W + 1), st));
+    k_coo_emit<<<g, 256, 0, st>>>(ku, vu, keep, pos, d_nu, W, reinterpret_cast<int2*>(d_contacts)); c->launches++;
+    COO_OK(cudaMemcpyAsync(n_contacts_out, d_rowptr + W, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    COO_OK(cudaStreamSynchronize(st));
+    #undef COO_OK
+    cleanup();
     return 0;
 }
 

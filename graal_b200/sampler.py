@@ -14,6 +14,8 @@ step_nuisance_parameters :2022-2107, return_neighbours :2295-2331, setup_distri_
 stream_likelihood :2392-2546, temperature :2590-2603, free_gpu :2605-2613.
 """
 import ctypes as C
+import os
+
 import numpy as np
 
 from . import _lib
@@ -249,13 +251,21 @@ class sampler:
         for f in self.id_frags_blacklisted:
             da = self.np_sub_frags_id[S_o_A_frags["id_d"][f]]
             black_subs.extend(int(da[k]) for k in range(da[3]))
+        # ---- context (needed first: the contact lists are built on the device)
+        ctx = C.c_void_p()
+        check(self.lib.graal_ctx_create(device, C.byref(ctx)))
+        self.ctx = ctx
+        self.stream = torch.cuda.Stream(device=self.device)
+        check(self.lib.graal_set_stream(self.ctx, C.c_void_p(self.stream.cuda_stream)))
         if share_level_with is not None:
             rowptr, contacts = share_level_with.d_rowptr, share_level_with.d_contacts
             proposal_tables = (share_level_with.distri_xk, share_level_with.distri_pk)
-        elif device_contact_lists is None:
+        elif device_contact_lists is not None:
+            rowptr, contacts = device_contact_lists
+        elif black_subs or os.environ.get("GRAAL_HOST_LISTS", "0") == "1":
             rowptr, contacts = build_contact_lists(hic_matrix, int(init_n_sub_frags), black_subs, mean_value_trans)
         else:
-            rowptr, contacts = device_contact_lists
+            rowptr, contacts = self.device_contact_lists(hic_matrix, int(init_n_sub_frags))
         self.n_contacts = int(contacts.shape[0])
         # ---- proposal tables (cuda_lib_gl.py:444-445)
         self.n_neighbors = 10
@@ -287,12 +297,6 @@ class sampler:
         self.d_out = torch.zeros(64 + 2 * 16 * N_TMP_STRUCT, dtype=torch.float64, device=dev)
         self.d_max_id = torch.zeros(4, dtype=torch.int32, device=dev)
         self.h_out = torch.zeros_like(self.d_out, device="cpu").pin_memory()
-        # ---- context
-        ctx = C.c_void_p()
-        check(self.lib.graal_ctx_create(device, C.byref(ctx)))
-        self.ctx = ctx
-        self.stream = torch.cuda.Stream(device=dev)
-        check(self.lib.graal_set_stream(self.ctx, C.c_void_p(self.stream.cuda_stream)))
         torch.cuda.synchronize(dev)
         check(self.lib.graal_level_bind(self.ctx, int(n_frags), n, int(init_n_sub_frags),
                                         self.d_sub_id.data_ptr(), self.d_sub_len.data_ptr(), self.d_sub_accu.data_ptr(),
@@ -330,6 +334,24 @@ class sampler:
         self.score = np.zeros(0)
         self.delta_scores = np.zeros(0)
         self.gpu_launches_at_start = self.lib.graal_launch_count(self.ctx)
+
+    def device_contact_lists(self, sub_coo, W):
+        """The sub-level matrix as contact lists, built on the device (graal_coo_to_lists): the COO triple is uploaded as it
+        is; keys (min, max), radix sort, duplicate sums, zero / diagonal removal and the row prefix sum run on the GPU."""
+        torch = self.torch
+        r, c, v = (np.asarray(a) for a in sub_coo)
+        n = int(r.shape[0])
+        if n == 0:
+            return np.zeros(W + 1, dtype=np.int64), np.zeros((0, 2), dtype=I32)
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.device)
+        d_r, d_c, d_v = t(r, I32), t(c, I32), t(v, F32)
+        rowptr = torch.zeros(W + 1, dtype=torch.int64, device=self.device)
+        contacts = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
+        n_out = C.c_longlong(0)
+        torch.cuda.synchronize(self.device)
+        check(self.lib.graal_coo_to_lists(self.ctx, d_r.data_ptr(), d_c.data_ptr(), d_v.data_ptr(), n, int(W),
+                                          rowptr.data_ptr(), contacts.data_ptr(), C.byref(n_out)))
+        return rowptr, contacts[:int(n_out.value)].contiguous()
 
     @classmethod
     def from_inputs(cls, inp, device=0, rng=None, device_contact_lists=None, proposal_tables=None, share_level_with=None):
@@ -723,15 +745,44 @@ class sampler:
                                  self.is_repeat, int(self.n_new_frags), self.n_frags_4_dist)
 
     def genome_content(self):
-        """Contigs of the current genome as lists of (bin id, orientation), in position order."""
+        """cuda_lib_gl.py:1625-1668: (full_order, dict_contig) -- per contig id (increasing) the data ids, positions,
+        start_bp, id_c, prev, next of its bins in position order; contigs with an inactive bin stay empty."""
         self.gpu_vect_frags.copy_from_gpu()
         c = self.gpu_vect_frags
-        out = {}
-        for cid in np.unique(c.id_c):
-            m = np.nonzero(c.id_c == cid)[0]
-            m = m[np.argsort(c.pos[m], kind="stable")]
-            out[int(cid)] = [(int(i), int(c.ori[i])) for i in m]
-        return out
+        dict_contig, full_order = dict(), []
+        for k in np.unique(c.id_c):
+            d = dict_contig[k] = {"id": [], "pos": [], "next": [], "prev": [], "start_bp": [], "id_c": []}
+            id_pos = np.nonzero(c.id_c == k)[0]
+            if np.all(c.activ[id_pos] == 1):
+                o = id_pos[np.argsort(c.pos[id_pos])]
+                d["id"].extend(c.id_d[o]); d["pos"].extend(c.pos[o]); d["start_bp"].extend(c.start_bp[o])
+                d["id_c"].extend(c.id_c[o]); d["prev"].extend(c.prev[o]); d["next"].extend(c.next[o])
+                full_order.extend(c.id_d[o])
+        return full_order, dict_contig
+
+    def display_current_matrix(self, file=None):
+        """cuda_lib_gl.py:1581-1625, the ordering part: (full_order, dict_contig, full_order_high) -- the data ids of the
+        bins contig by contig in position order, the same per contig, and the sub-frag ids in genome order (the sub-frags
+        of a flipped bin reversed; like the reference, the orientation is looked up under the DATA id).  The reference
+        also writes the reordered dense sub-level matrix to ``file`` as a TIFF (GUI snapshot, out of scope): ``file`` is
+        accepted and ignored."""
+        self.gpu_vect_frags.copy_from_gpu()
+        c = self.gpu_vect_frags
+        dict_contig, full_order, full_order_high = dict(), [], []
+        for k in np.unique(c.id_c):
+            dict_contig[k] = []
+            id_pos = np.nonzero(c.id_c == k)[0]
+            if np.all(c.activ[id_pos] == 1):
+                ordered_frag = c.id_d[id_pos[np.argsort(c.pos[id_pos])]]
+                dict_contig[k].extend(ordered_frag)
+                full_order.extend(ordered_frag)
+                for i in ordered_frag:
+                    v = list(self.np_sub_frags_id[i])
+                    ids = v[:v[3]]
+                    if c.ori[i] == -1:
+                        ids.reverse()
+                    full_order_high.extend(ids)
+        return full_order, dict_contig, full_order_high
 
     def export_new_fasta(self, level, contig_names, sequences, new_fasta, info_frags):
         """simulation.export_new_fasta (simulation_loader.py:781-783): genome.fasta + info_frags.txt of the

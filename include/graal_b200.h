@@ -85,6 +85,14 @@ int graal_level_bind(graal_ctx* ctx, int n_frags, int n_new_frags, int n_sub_fra
                      const int32_t* collector, const int32_t* dispatcher,
                      const int64_t* rowptr, const void* contacts, int64_t n_contacts, float nfpb);
 
+/* The preparation of the sub-level matrix in sampler.__init__ (cuda_lib_gl.py:153-172: csr + csr.T, diagonal zeroed) on the
+ * device: n COO entries (rows, cols int32, counts float32; any triangle, duplicates allowed) -> the row-segmented contact
+ * lists graal_level_bind takes: entries keyed (min, max), radix-sorted, duplicates summed, diagonal and zero counts dropped,
+ * rows counted and prefix-summed into d_rowptr (int64[W + 1]); d_contacts must hold n records of 8 bytes; *n_contacts_out
+ * (host) receives the number written.  Blacklisted rows (materialised with mean_value_trans) are added by the caller. */
+int graal_coo_to_lists(graal_ctx* ctx, const int32_t* d_rows, const int32_t* d_cols, const float* d_vals, int64_t n,
+                       int n_sub_frags, int64_t* d_rowptr, void* d_contacts, int64_t* n_contacts_out);
+
 /* param_simu (kernels3.cu:26-35): kuhn, lm, c1, slope, d, d_max, fact, v_inter */
 int graal_set_params(graal_ctx* ctx, const float p[8]);
 

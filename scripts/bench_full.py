@@ -14,9 +14,12 @@ from graal_b200.sampler import sampler, CUR
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-variants = [dict(GRAAL_FULL_WIN="0")] + [dict(GRAAL_FULL_WIN="1", GRAAL_WIN_UNROLL=str(u), GRAAL_WIN_MINB=str(m), GRAAL_WIN_SUB=str(sb))
-                                          for (u, m, sb) in ((8, 4, 1), (8, 4, 2), (8, 4, 4), (8, 4, 8), (8, 3, 2), (8, 3, 4), (8, 3, 8), (8, 5, 2), (8, 5, 4),
-                                                             (4, 4, 1), (4, 4, 2), (4, 4, 4), (4, 5, 4))]
+def _v(spec):
+    u, m, sb = spec.split(":")
+    return dict(GRAAL_FULL_WIN="1", GRAAL_WIN_UNROLL=u, GRAAL_WIN_MINB=m, GRAAL_WIN_SUB=sb)
+
+
+variants = [dict(GRAAL_FULL_WIN="0")] + [_v(a) for a in (sys.argv[3:] or ["8:4:2", "8:4:4"])]
 if cfg == "c4":
     from graal_b200.level import synthetic_roofline_level
     inp, lists, tables, info = synthetic_roofline_level(device="cuda")

@@ -34,7 +34,7 @@ def _lines():
     return open(PATH).read().split("\n")
 
 
-def method(name):
+def method(name, extra_ns=None):
     """The reference method `name` of class sampler as a Python 3 function f(self, ...)."""
     lines = _lines()
     start = next(i for i, l in enumerate(lines) if l.startswith("    def %s(" % name))
@@ -42,6 +42,7 @@ def method(name):
     src = textwrap.dedent("\n".join(lines[start:end]))
     from scipy import stats
     ns = {"np": NP, "xrange": range, "time": time, "stats": stats}
+    ns.update(extra_ns or {})
     exec(compile(src, "%s:%s" % (PATH, name), "exec"), ns)
     return ns[name]
 
@@ -55,3 +56,48 @@ def block(after_def, first_marker, last_marker):
     b = next(i for i in range(a, len(lines)) if last_marker in lines[i])
     src = textwrap.dedent("\n".join(lines[a:b + 1]))
     return compile(src, "%s:%s[%d:%d]" % (PATH, after_def, a + 1, b + 1), "exec")
+
+
+LOADER = os.path.join(REF, "simulation_loader.py")
+
+
+def loader_method(name, extra_ns=None):
+    """Method `name` of class simulation (simulation_loader.py) as a Python 3 function: the Python 2 print STATEMENTS of
+    the text are replaced by `pass` (same indentation), nothing else is touched."""
+    lines = open(LOADER).read().split("\n")
+    start = next(i for i, l in enumerate(lines) if l.startswith("    def %s(" % name))
+    end = next(i for i in range(start + 1, len(lines)) if lines[i].startswith("    def ") or (lines[i] and not lines[i].startswith(" ")))
+    body = []
+    for l in lines[start:end]:
+        st = l.lstrip()
+        body.append(l[:len(l) - len(st)] + "pass" if st.startswith("print ") or st == "print" else l)
+    src = textwrap.dedent("\n".join(body))
+    ns = {"np": NP, "xrange": range, "time": time}
+    ns.update(extra_ns or {})
+    exec(compile(src, "%s:%s" % (LOADER, name), "exec"), ns)
+    return ns[name]
+
+
+PYRAMID = os.path.join(REF, "pyramid_sparse.py")
+
+
+def pyramid_function(name, extra_ns=None):
+    """Module-level function `name` of pyramid_sparse.py as a Python 3 function.  Python 2 idioms of the text are
+    translated mechanically, nothing else is touched: print statements -> pass, d.has_key(k) -> (k in d),
+    `x = d.keys()` -> `x = list(d.keys())` (the text sorts such lists in place)."""
+    import re
+    lines = open(PYRAMID).read().split("\n")
+    start = next(i for i, l in enumerate(lines) if l.startswith("def %s(" % name))
+    end = next(i for i in range(start + 1, len(lines)) if lines[i] and not lines[i][0] in " #")
+    body = []
+    for l in lines[start:end]:
+        st = l.lstrip()
+        if st.startswith("print ") or st == "print":
+            l = l[:len(l) - len(st)] + "pass"
+        l = re.sub(r"(\w+(?:\[[^\]]+\])*)\.has_key\(([^)]+)\)", r"(\2 in \1)", l)
+        l = re.sub(r"=\s*(\w+)\.keys\(\)\s*$", r"= list(\1.keys())", l)
+        body.append(l)
+    ns = {"np": NP, "xrange": range, "time": time}
+    ns.update(extra_ns or {})
+    exec(compile("\n".join(body), "%s:%s" % (PYRAMID, name), "exec"), ns)
+    return ns[name]

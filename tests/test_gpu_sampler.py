@@ -93,8 +93,10 @@ def test_surface_attributes(small_pyramid):
     assert np.isfinite(g.likelihood_t)
     g.gpu_vect_frags.copy_from_gpu()
     assert np.array_equal(g.gpu_vect_frags.pos, inp.S_o_A_frags["pos"]) and np.all(g.gpu_vect_frags.ori == 1)
-    content = g.genome_content()
-    assert sum(len(v) for v in content.values()) == inp.n_new_frags
+    full_order, content = g.genome_content()
+    assert len(full_order) == inp.n_new_frags and sum(len(v["id"]) for v in content.values()) == inp.n_new_frags
+    fo, dc, fo_high = g.display_current_matrix(None)
+    assert [int(x) for x in fo] == [int(x) for x in full_order] and len(fo_high) == inp.init_n_sub_frags
     assert g.gpu_launches > 0
     g.free_gpu()
 
@@ -207,3 +209,29 @@ def test_incremental_likelihood_mode(small_pyramid):
     assert np.array_equal(np.array(tr_g.dist_from_init_genome), np.array(tr_h.dist_from_init_genome))
     assert h.gpu_launches < g.gpu_launches
     g.free_gpu(); h.free_gpu()
+
+
+def test_device_contact_lists_match_the_host_preparation(small_pyramid):
+    """graal_coo_to_lists (device: keys, radix sort, duplicate sums, row prefix sum) vs build_contact_lists (host NumPy,
+    the restatement of cuda_lib_gl.py:153-172), also with entries given in both triangles, duplicated, on the diagonal and
+    with zero counts."""
+    from graal_b200.sampler import build_contact_lists
+    inp, g = gpu_sampler(small_pyramid, 1, 1)
+    W = inp.init_n_sub_frags
+    r, c, v = (np.asarray(a) for a in inp.sub_coo)
+    rp_h, ct_h = build_contact_lists(inp.sub_coo, W)
+    assert np.array_equal(g.d_rowptr.cpu().numpy(), rp_h) and np.array_equal(g.d_contacts.cpu().numpy(), ct_h)
+    rng = np.random.RandomState(2)
+    k = rng.choice(r.shape[0], 500, replace=False)
+    r2 = np.concatenate([r, c[k], np.arange(20), r[:50]])            # lower-triangle copies, diagonal entries, zero counts
+    c2 = np.concatenate([c, r[k], np.arange(20), c[:50]])
+    v2 = np.concatenate([v, v[k], np.full(20, 7), np.zeros(50)]).astype(np.float32)
+    rp_d, ct_d = g.device_contact_lists((r2, c2, v2), W)
+    dense = np.zeros((W, W), dtype=np.float64)
+    np.add.at(dense, (np.minimum(r2, c2), np.maximum(r2, c2)), v2)
+    np.fill_diagonal(dense, 0.0)
+    rr, cc = np.nonzero(dense)
+    ct = ct_d.cpu().numpy()
+    assert np.array_equal(rp_d.cpu().numpy(), np.r_[0, np.cumsum(np.bincount(rr, minlength=W))])
+    assert np.array_equal(ct[:, 0], cc) and np.array_equal(ct[:, 1].copy().view(np.float32), dense[rr, cc].astype(np.float32))
+    g.free_gpu()

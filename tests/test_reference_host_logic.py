@@ -134,3 +134,147 @@ def test_dist_inter_genome():
                                    np.ones(n, dtype=np.int32), orientable, list(inp.id_frags_blacklisted), np.asarray(is_repeat), n, n4)
         assert abs(got - want) < 1e-12, (rnd, got, want)
         assert abs(o.dist_inter_genome(o.cur) - want) < 1e-12
+
+
+def test_genome_content_and_display_order_match_the_reference_lines():
+    """cuda_lib_gl.py:1581-1668: genome_content and the ordering part of display_current_matrix on a scrambled genome."""
+    pyr, inp = _mock_level(False, False)
+    o = H.make_oracle(inp, pyr, seed=5)
+    H.scramble(o, np.random.RandomState(12), 40)
+    o.modify_gl_cuda_buffer()
+    assert np.any(o.cur["ori"] == -1)
+
+    class _Frags:
+        def copy_from_gpu(self):
+            pass
+    fr = _Frags()
+    for k in M.FIELDS:
+        setattr(fr, k, o.cur[k].copy())
+    W = inp.init_n_sub_frags
+
+    class _Img:
+        saved = []
+
+        @staticmethod
+        def fromarray(a):
+            _Img.saved.append(a.shape)
+            return types.SimpleNamespace(save=lambda f: None)
+    ids = types.SimpleNamespace(get=lambda ary: ary.__setitem__(slice(None), o.cur["id_c"]))
+    ref_self = types.SimpleNamespace(gpu_vect_frags=fr, gpu_id_contigs=ids, cpu_id_contigs=np.zeros_like(o.cur["id_c"]),
+                                     np_sub_frags_id=inp.np_sub_frags_id, hic_matrix=np.zeros((W, W), dtype=np.float32),
+                                     hic_matrix_sub_sampled=np.ones((2, 2)))
+    mine = types.SimpleNamespace(gpu_vect_frags=fr, np_sub_frags_id=inp.np_sub_frags_id)
+    r_order, r_dict = RH.method("genome_content")(ref_self)
+    g_order, g_dict = GS.sampler.genome_content(mine)
+    assert [int(x) for x in r_order] == [int(x) for x in g_order] and list(r_dict.keys()) == list(g_dict.keys())
+    for k in r_dict:
+        for f in ("id", "pos", "next", "prev", "start_bp", "id_c"):
+            assert [int(x) for x in r_dict[k][f]] == [int(x) for x in g_dict[k][f]], (k, f)
+    r3 = RH.method("display_current_matrix", {"Image": _Img})(ref_self, "unused.tiff")
+    g3 = GS.sampler.display_current_matrix(mine, None)
+    assert [int(x) for x in r3[0]] == [int(x) for x in g3[0]] and [int(x) for x in r3[2]] == [int(x) for x in g3[2]]
+    assert {k: [int(x) for x in v] for k, v in r3[1].items()} == {k: [int(x) for x in v] for k, v in g3[1].items()}
+    assert _Img.saved == [(W, W)] and len(g3[2]) == W
+
+
+@pytest.mark.parametrize("allow_repeats,blacklist", [(False, False), (True, False), (True, True)])
+def test_level_loader_matches_the_reference_lines(allow_repeats, blacklist):
+    """simulation_loader.py: select_repeated_frags :369-394, modify_vect_frags :182-299, blacklist_contig :129-163 executed
+    on the same level vs graal_b200.level.prepare_sampler_inputs (repeat detection, copies, collector / dispatcher, blacklist)."""
+    import scipy.sparse as sp
+    pyr, inp = _mock_level(allow_repeats, blacklist)
+    lv = pyr.get_level(2)
+    N = lv.n_frags
+    csr = sp.csr_matrix((lv.vals.astype(np.float64), (lv.rows, lv.cols)), shape=(N, N))
+    cmap = types.SimpleNamespace(N=256, __call__=None)
+
+    class _Cmap:
+        N = 256
+
+        def __call__(self, i):
+            return (0.0, 0.0, 0.0, 1.0)
+    plt = types.SimpleNamespace(cm=types.SimpleNamespace(prism=_Cmap()))
+    int2 = np.dtype([("x", np.int32), ("y", np.int32)], align=True)
+    me = types.SimpleNamespace(level=types.SimpleNamespace(sparse_mat_csr=csr, S_o_A_frags=lv.S_o_A_frags), allow_repeats=allow_repeats, int2=int2)
+    me.candidate_dup, me.data_candidate_dup = RH.loader_method("select_repeated_frags")(me)
+    RH.loader_method("modify_vect_frags", {"plt": plt})(me)
+    RH.loader_method("blacklist_contig")(me, [5] if blacklist else [0])
+    if allow_repeats:
+        assert len(me.candidate_dup) > 0 and inp.n_new_frags > inp.n_frags
+    assert [int(x) for x in me.candidate_dup] == [int(x) for x in inp.id_frag_duplicated]
+    for k in ("pos", "id_c", "start_bp", "len_bp", "circ", "id", "prev", "next", "l_cont", "l_cont_bp", "rep", "activ", "id_d"):
+        assert np.array_equal(me.new_S_o_A_frags[k], inp.S_o_A_frags[k]), k
+    assert np.array_equal(me.collector_id_repeats, inp.collector_id_repeats)
+    assert np.array_equal(np.stack([me.frag_dispatcher["x"], me.frag_dispatcher["y"]], axis=1), np.asarray(inp.frag_dispatcher).reshape(-1, 2))
+    assert [int(x) for x in me.frag_blacklisted] == [int(x) for x in inp.id_frags_blacklisted]
+    assert me.n_frags == inp.n_new_frags and me.init_n_frags == inp.n_frags
+
+
+def test_remove_problematic_fragments_matches_the_reference_function(tmp_path):
+    """pyramid_sparse.remove_problematic_fragments (:573-848) executed on text files written from a synthetic level 0 with
+    sparse and 1-bp fragments (inside contigs, at contig ends, a whole contig) vs graal_b200.pyramid_io's in-memory restatement."""
+    import scipy.sparse as sp
+    from graal_b200 import pyramid_io as PIO
+    from graal_b200.level import PyramidLevel, _derive_frag_arrays
+    rs = np.random.RandomState(3)
+    sizes = [40, 25, 6, 30]
+    cid = np.repeat(np.arange(1, 5), sizes).astype(np.int32)
+    n = cid.size
+    ln = rs.randint(200, 900, size=n)
+    ln[[5, 17, 44]] = 1                                             # 1-bp fragments: locked whatever their contacts
+    first = np.r_[True, cid[1:] != cid[:-1]]
+    starts = np.nonzero(first)[0]
+    seg = np.cumsum(first) - 1
+    st = (np.cumsum(ln) - ln) - (np.cumsum(ln) - ln)[starts][seg]
+    en = st + ln
+    dense = np.triu((rs.rand(n, n) < 0.55) * rs.randint(1, 6, size=(n, n)), 0)
+    for f in (3, 4, 20, 39, 64, 65, 66, 67, 68, 69, 70, 100):        # sparse fragments: mid contig, a run, contig ends, ALL of contig 3
+        keep = rs.rand(n) < 0.03
+        dense[f, :] *= keep; dense[:, f] *= keep
+    r, c = np.nonzero(dense)
+    lv = PyramidLevel(level=0, contig_id=cid, start_pos=st.astype(np.int32), end_pos=en.astype(np.int32), n_accu=np.ones(n, dtype=np.int32),
+                      sub_low=np.arange(n, dtype=np.int32), sub_high=np.arange(n, dtype=np.int32),
+                      rows=r.astype(np.int32), cols=c.astype(np.int32), vals=dense[r, c].astype(np.int32))
+    _derive_frag_arrays(lv)
+    mine, thresh, old2new = PIO.remove_problematic_fragments(lv)
+    assert (old2new < 0).any() and mine.n_frags < n and len(np.unique(mine.contig_id)) == 3          # contig 3 deleted
+    # ---- the reference function on files
+    names = ["ctg%d" % k for k in range(1, 5)]
+    fl, ci, ct = (str(tmp_path / x) for x in ("frags.txt", "contigs.txt", "contacts.txt"))
+    with open(fl, "w") as h:
+        h.write("id\tchrom\tstart_pos\tend_pos\tsize\tgc_content\taccu_frag\tfrag_start\tfrag_end\n")
+        for i in range(n):
+            h.write("%d\t%s\t%d\t%d\t%d\t0.5\t1\t%d\t%d\n" % (lv.S_o_A_frags["pos"][i] + 1, names[cid[i] - 1], st[i], en[i], ln[i], i, i))
+    with open(ci, "w") as h:
+        h.write("contig\tlength_kb\tn_frags\tcumul_length\n")
+        cum = 0
+        for k, m in enumerate(sizes):
+            h.write("%s\t%d\t%d\t%d\n" % (names[k], 1, m, cum)); cum += m
+    with open(ct, "w") as h:
+        h.write("id_frag_a\tid_frag_b\tn_contact\n")
+        for a, b in zip(r, c):
+            h.write("%d\t%d\t%d\n" % (a, b, dense[a, b]))
+
+    class _PB:
+        def __init__(self, *a, **k):
+            pass
+
+        def render(self, *a, **k):
+            pass
+    ns = {"sp": sp, "ProgressBar": _PB}
+    for helper in ("get_frag_info_from_fil", "get_contig_info_from_file", "file_len"):
+        ns[helper] = RH.pyramid_function(helper, ns)
+    f = RH.pyramid_function("remove_problematic_fragments", ns)
+    pyramid = {"0": {"data": np.stack([r, c, dense[r, c]]).astype(np.int32), "nfrags": np.array([n], dtype=np.int32)}}
+    out = [str(tmp_path / x) for x in ("new_contigs.txt", "new_frags.txt", "new_contacts.txt")]
+    ref_thresh = f(ci, fl, ct, out[0], out[1], out[2], pyramid)
+    assert abs(float(ref_thresh) - thresh) <= 1e-7 * max(1.0, abs(thresh))
+    rows = [l.rstrip("\n").split("\t") for l in open(out[1]).read().split("\n")[1:] if l]
+    assert len(rows) == mine.n_frags
+    kept_names = [l.split("\t")[0] for l in open(out[0]).read().split("\n")[1:] if l]
+    assert kept_names == ["ctg1", "ctg2", "ctg4"]
+    for i, d in enumerate(rows):
+        assert int(d[0]) == mine.S_o_A_frags["pos"][i] + 1 and d[1] == kept_names[mine.contig_id[i] - 1]
+        assert (int(d[2]), int(d[3]), int(d[4]), int(d[6])) == (int(mine.start_pos[i]), int(mine.end_pos[i]), int(mine.end_pos[i] - mine.start_pos[i]) if False else int(d[4]), int(mine.n_accu[i]))
+    ref_contacts = sorted(tuple(int(x) for x in l.split("\t")) for l in open(out[2]).read().split("\n")[1:] if l)
+    assert ref_contacts == sorted(zip(mine.rows.tolist(), mine.cols.tolist(), mine.vals.tolist()))
