@@ -455,12 +455,13 @@ __global__ void k_relabel_map(const unsigned* __restrict__ keys, const unsigned*
     map[vals[r]] = r;
     if (r + 1 == cap || keys[r + 1] == sentinel) *n_contigs = r + 1;
 }
-__global__ void k_relabel_apply(int* __restrict__ id_c, int n, const int* __restrict__ map,
+__global__ void k_relabel_apply(int* __restrict__ id_c, int n, int cap, const int* __restrict__ map,
                                 const int* __restrict__ n_contigs, int* __restrict__ max_id_a, int* __restrict__ max_id_b) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) { const int m = *n_contigs - 1; *max_id_a = m; if (max_id_b) *max_id_b = m; }
     if (i >= n) return;
-    id_c[i] = map[id_c[i]];
+    const int c = id_c[i];
+    if (c >= 0 && c < cap) id_c[i] = map[c];            // an id outside [0, cap) was flagged by k_first_index (graal_sync reports it): left as it is
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1224,12 +1225,17 @@ __device__ __forceinline__ int piece_slot(int id_c, const int* meta) {
 __global__ void k_cand_geometry(const int* __restrict__ cand0, size_t slot_stride, int ld, LevelView lv,
                                 const int* __restrict__ sub_index, const int* __restrict__ meta,
                                 Geo* __restrict__ geo0, size_t geo_stride, int* __restrict__ piece_len,
-                                const Geo* __restrict__ geo_base, unsigned* __restrict__ chmask, unsigned skip_cands, int* __restrict__ meta_flag) {
+                                const Geo* __restrict__ geo_base, unsigned* __restrict__ chmask, unsigned skip_cands, int* __restrict__ meta_flag,
+                                int4* __restrict__ rec_a0, int order_stride) {
     const int k = blockIdx.y;
     if ((skip_cands >> k) & 1u) return;
     const int m = meta[4];
     const int* sl = cand0 + (size_t)k * slot_stride;
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < m; u += gridDim.x * blockDim.x) {
+        // order records of this proposal start empty (n_sub = 0: skipped by the band pass): a degenerate proposal
+        // (fA == fB) leaves order positions unwritten, which must not show the records of an earlier proposal
+        rec_a0[(size_t)k * order_stride + u] = make_int4(0, 0, 0, -1);
+        if (k < 3) rec_a0[(size_t)(GRAAL_N_CANDIDATES + k) * order_stride + u] = make_int4(0, 0, 0, -1);
         const int bin = sub_index[u];
         bin_geometry(sl, ld, bin, lv, geo0 + (size_t)k * geo_stride);
         if (sl[F_CIRC * ld + bin] == 1) meta_flag[0] = 1;
@@ -2505,6 +2511,11 @@ int graal_sync(graal_ctx* c) {
     if (!c) return set_err(-1, "null context");
     int rc = join_lanes(c); if (rc) return rc;
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    // contig ids outside [0, 2 n + 16) seen by the relabel / statistics kernels (slot uploaded from the host, or chains of
+    // graal_apply_move without a relabel): reported here, off the step path
+    int flag = 0;
+    CUDA_OK(cudaMemcpy(&flag, c->d_ints + 2, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) { CUDA_OK(cudaMemset(c->d_ints + 2, 0, sizeof(int))); return set_err(-6, "a contig id outside [0, %d) was met by the relabel / statistics kernels", c->cap); }
     return 0;
 }
 int graal_join(graal_ctx* c) { if (!c) return set_err(-1, "null context"); return join_lanes(c); }
@@ -2806,7 +2817,7 @@ int graal_relabel_contigs(graal_ctx* c, int slot, int32_t* d_max_id) {
         size_t tb = c->cub_tmp_bytes;
         CUDA_OK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tb, k_in, k_out, v_in, v_out, cap, 0, c->key_bits, st)); c->launches += 2 + (c->key_bits + 7) / 8;
         k_relabel_map<<<nblk(cap, 256), 256, 0, st>>>(k_out, v_out, cap, sentinel, c->map, c->d_ints + 1); CHECK_LAUNCH(c);
-        k_relabel_apply<<<nblk(n, 256), 256, 0, st>>>(s + F_ID_C * ld, n, c->map, c->d_ints + 1, c->d_ints + 0, d_max_id); CHECK_LAUNCH(c);
+        k_relabel_apply<<<nblk(n, 256), 256, 0, st>>>(s + F_ID_C * ld, n, cap, c->map, c->d_ints + 1, c->d_ints + 0, d_max_id); CHECK_LAUNCH(c);
         c->prof.end(GRAAL_K_RELABEL, st);
         return 0;
     };
@@ -3092,7 +3103,7 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
     const int gu = std::min(c->n_sm * 2, nblk(n, 256));
     if (c->prof.on) { k_u_stats<<<gu, 256, 0, st>>>(L.sub_index, meta, c->lv, base, ld, c->rowptr, c->d_counters); CHECK_LAUNCH(c); }
     k_cand_geometry<<<dim3(gu, n_cand), 256, 0, st>>>(cand0, slot_stride(c), ld, c->lv, L.sub_index, meta, L.geo_cand, (size_t)c->W, piece_len,
-                                                     c->geo_base, L.chmask, skip, meta + 6); CHECK_LAUNCH(c);
+                                                     c->geo_base, L.chmask, skip, meta + 6, L.cand_ordrec, n); CHECK_LAUNCH(c);
     const int n_rows = pair_mask ? N_BAND_ROWS : n_cand;          // band rows: candidates (+ the partner rows of the paired ones)
     k_cand_order<<<dim3(gu, n_cand + 1 + (pair_mask ? 3 : 0)), 256, 0, st>>>(cand0, slot_stride(c), ld, L.sub_index, meta, piece_len, n, skip,
                                                       c->lv, L.chmask, L.geo_cand, (size_t)c->W, L.cand_ordrec, L.cand_ordb, rng + 2,

@@ -22,6 +22,7 @@ from . import _lib
 from ._lib import GraalError, check
 from . import rippe as opti
 from .level import FRAG_FIELDS
+from .mh import MetropolisMixin
 
 F32, I32 = np.float32, np.int32
 N_TMP_STRUCT = 13
@@ -190,7 +191,7 @@ def dist_inter_genome(prev, next_, ori, id_d, init_prev, init_next, init_ori, in
     return float(d.sum()) / norm_distance if norm_distance != 0 else 0.0
 
 
-class sampler:
+class sampler(MetropolisMixin):
     def __init__(self, use_rippe, S_o_A_frags, collector_id_repeats, frag_dispatcher,
                  id_frag_duplicated, id_frags_blacklisted,
                  n_frags, n_new_frags, init_n_sub_frags, n_new_sub_frags, np_rep_sub_frags_id,
@@ -245,6 +246,8 @@ class sampler:
         self.np_sub_frags_accu = np.ascontiguousarray(np_sub_frags_accu, dtype=I32).reshape(-1, 3)
         self.mean_squared_frags_per_bin = F32(mean_squared_frags_per_bin)
         self.norm_vect_accu = norm_vect_accu
+        self._level_coo = hic_matrix_sub_sampled if share_level_with is None else share_level_with._level_coo
+        self.n_modif_metropolis = N_TMP_STRUCT
         n = int(n_new_frags)
         # ---- sub-level matrix -> contact lists (cuda_lib_gl.py:153-172, 194)
         black_subs = []
@@ -286,7 +289,7 @@ class sampler:
             self.d_collector, self.d_dispatcher = t(self.collector_id_repeats), t(self.frag_dispatcher)
         self.d_rowptr, self.d_contacts = t(rowptr), t(contacts)
         self.ld = (n + 31) // 32 * 32
-        self.n_slots = 1 + N_TMP_STRUCT * N_LANES
+        self.n_slots = 1 + N_TMP_STRUCT * N_LANES + 4          # + pop, trans1, trans2, forward (the MH / MTM variants, mh.py)
         host = np.zeros((self.n_slots, len(FRAG_FIELDS), self.ld), dtype=I32)
         for fi, k in enumerate(FRAG_FIELDS):
             host[CUR, fi, :n] = np.ones(n, dtype=I32) if k == "ori" else np.asarray(S_o_A_frags[k], dtype=I32)   # Q5

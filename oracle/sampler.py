@@ -336,6 +336,207 @@ class OracleSampler:
         y_rippe = peval(self.bins, [p["kuhn"], p["lm"], p["slope"], p["d"], p["fact"]]) if hasattr(self, "bins") else None
         return p["fact"], p["d"], p["d_max"], p["v_inter"], p["slope"], self.likelihood_t, success, y_rippe
 
+    # ------------------------------------------------------------------------------------------------
+    # Metropolis-Hastings / multiple-try variants (cuda_lib_gl.py:735-839, 957-1013, 2548-2588, 2615-3129); unused by the
+    # shipped GUI path.  `list(V_set)` of a CPython-2 set has no defined order: increasing ids here and on the device.
+    # ------------------------------------------------------------------------------------------------
+    N_MH = 13
+
+    def set_jumping_distributions_parameters(self, delta):
+        """:2548-2588 on the dense level matrix (stable argsort where the reference's is unstable on ties)."""
+        nv = np.asarray(self.inp.norm_vect_accu, dtype=np.float64).reshape(1, -1)
+        mat_norm = np.array(nv.T * nv, dtype=F32)
+        self.matrix_normalized = self.hic_matrix_sub_sampled / mat_norm
+        tmp_sorted = self.matrix_normalized.argsort(axis=1, kind="stable")
+        self.jump_dictionnary = dict()
+        for i in range(self.n_frags):
+            line = [int(x) for x in tmp_sorted[i, :] if x != i]
+            ids = np.array(line[-delta:], dtype=I32)
+            scores = np.array(self.matrix_normalized[i, ids], dtype=F32)
+            with np.errstate(all="ignore"):
+                norm_scores = scores / scores.sum()
+            self.jump_dictionnary[i] = {"proba": norm_scores, "frags": ids, "set_frags": set(int(x) for x in ids)}
+
+    def _mh_base(self, forward):
+        if forward:
+            return self.cur
+        return self.fwd
+
+    def all_modifications_metropolis(self, id_fA, id_fB, max_id, forward):
+        """:2651-2657 with pop_out_pop_in_4_mh :735-789, split_4_mh :791-811, paste_4_mh :813-839, transloc_4_mh :957-1013."""
+        ws, base = self.ws, self._mh_base(forward)
+        for mode in range(6):
+            M.pop_out_frag(ws.pop, base, ws.pop_id_contigs, id_fA, max_id)
+            max_id2 = I32(ws.pop_id_contigs.max())
+            dst = ws.collector[mode]
+            if mode == 0:
+                M.simple_copy(dst, ws.pop)
+            elif mode == 1:
+                M.flip_frag(dst, base, id_fA)
+            elif mode in (2, 3):
+                M.pop_in_frag_3(dst, ws.pop, id_fA, id_fB, max_id2, 1 if mode == 2 else -1)
+            else:
+                M.pop_in_frag_4(dst, ws.pop, id_fA, id_fB, max_id2, 1 if mode == 4 else -1)
+        for up in (0, 1):
+            M.split_contig(ws.collector[6 + up], base, ws.trans1_id_contigs, id_fA, up, max_id)
+        ext = lambda f: base["prev"][f] == -1 or base["next"][f] == -1
+        if ext(id_fA) and ext(id_fB):
+            M.paste_contigs(ws.collector[8], base, id_fA, id_fB, max_id)
+        else:
+            M.simple_copy(ws.collector[8], base)
+        mode = 0
+        for up_a in (0, 1):
+            M.split_contig(ws.trans1, base, ws.trans1_id_contigs, id_fA, up_a, max_id)
+            for up_b in (0, 1):
+                max_id1 = I32(ws.trans1_id_contigs.max())
+                ok = (base["next"][id_fB] == -1) if up_b == 0 else (base["prev"][id_fB] == -1)
+                dst = ws.collector[9 + mode]
+                if ok:
+                    M.split_contig(ws.trans2, ws.trans1, ws.trans2_id_contigs, id_fB, up_b, max_id1)
+                    M.paste_contigs(dst, ws.trans2, id_fA, id_fB, I32(ws.trans2_id_contigs.max()))
+                else:
+                    M.simple_copy(dst, base)
+                mode += 1
+
+    def compute_all_score_MH(self, id_fA, V_set, forward):
+        """:2615-2649 + multi_likelihood_4_metropolis :2659-2806."""
+        base = self._mh_base(forward)
+        list_fB = sorted(int(x) for x in V_set)
+        vect = L.evaluate_likelihood(base, self.lv, self.param_simu)
+        if forward:
+            self.curr_likelihood = vect
+        else:
+            self.curr_likelihood_forward = vect
+        likelihood_t = np.float64(vect.sum())
+        max_id = I32(base["id_c"].max())
+        score = np.zeros(self.N_MH * len(list_fB), dtype=np.float64)
+        contig_A, len_A = base["id_c"][id_fA], int(base["l_cont"][id_fA])
+        inA = base["id_c"] == contig_A
+        self.sub_index[base["pos"][inA]] = base["id_d"][inA]
+        for x, id_fB in enumerate(list_fB):
+            self.all_modifications_metropolis(id_fA, id_fB, max_id, forward)
+            contig_B, len_B = base["id_c"][id_fB], int(base["l_cont"][id_fB])
+            size = len_A
+            if contig_B != contig_A:
+                inB = base["id_c"] == contig_B
+                self.sub_index[len_A + base["pos"][inB]] = base["id_d"][inB]
+                size = len_A + len_B
+            init = self.sub_index[:size]
+            no_rep, rep = np.setdiff1d(init, self.id_frag_duplicated), np.intersect1d(init, self.id_frag_duplicated)
+            for j in range(self.N_MH):
+                score[x * self.N_MH + j] = L.sub_compute_likelihood(self.ws.collector[j], self.lv, self.param_simu, vect,
+                                                                    no_rep, rep, self.uniq_frags) + likelihood_t
+        return score
+
+    def udpate_forward_vect(self, id_fA, id_fB, id_op, max_id):
+        """:2808-2834."""
+        self.all_modifications_metropolis(id_fA, id_fB, max_id, True)
+        if not hasattr(self, "fwd") or self.fwd is None:
+            self.fwd = M.new_slot(self.n_new_frags)
+        M.simple_copy(self.fwd, self.ws.collector[int(id_op)])
+
+    def validate_struct(self, id_fA, id_f_sampled, id_op, max_id):
+        """:3102-3129."""
+        self.all_modifications_metropolis(id_fA, id_f_sampled, max_id, True)
+        M.copy_struct(self.cur, self.ws.collector[int(id_op)], self.id_contigs)
+        self.init_likelihood()
+
+    def detect_impossibility(self, id_fA, list_neighbours, forward):
+        """:3072-3100."""
+        g = self._mh_base(forward)
+        out = []
+        fA_ok = g["prev"][id_fA] == -1 or g["next"][id_fA] == -1
+        for idx, fB in enumerate(list_neighbours):
+            fB_ok = g["prev"][fB] == -1 or g["next"][fB] == -1
+            if not (fB_ok and fA_ok):
+                out.append(self.N_MH * idx + 8)
+            if not g["next"][fB] == -1:
+                out += [self.N_MH * idx + 9, self.N_MH * idx + 11]
+            if not g["prev"][fB] == -1:
+                out += [self.N_MH * idx + 10, self.N_MH * idx + 12]
+        return out
+
+    def _mh_prologue(self, id_fA, dt):
+        c = self.cur
+        stats = (len(np.unique(c["id_c"])), c["l_cont"].min(), c["l_cont"].mean(), c["l_cont"].max())
+        max_id = self.modify_gl_cuda_buffer(id_fA, dt)
+        V_set = set(self.jump_dictionnary[id_fA]["set_frags"])
+        if c["prev"][id_fA] != -1:
+            V_set.add(int(c["prev"][id_fA]))
+        if c["next"][id_fA] != -1:
+            V_set.add(int(c["next"][id_fA]))
+        return stats, max_id, V_set, np.array(sorted(V_set), dtype=I32)
+
+    def _mh_accept(self, ratio, id_fA, f_star, omega_star, max_id, star):
+        r = np.min([1, ratio])
+        if r == 1 or r >= self.rng.rand():
+            self.validate_struct(id_fA, f_star, omega_star, max_id)
+            self.likelihood_t = star
+
+    def step_metropolis_hastings_s_a(self, id_fA, t=0, n_step=1, dt=0):
+        """:2836-2934."""
+        (n_contigs, min_len, mean_len, max_len), max_id, V_set, nb = self._mh_prologue(id_fA, dt)
+        F_t = self.temperature(t, n_step)
+        lf = self.compute_all_score_MH(id_fA, V_set, True)
+        s = lf / F_t
+        mx = s.max()
+        s[s <= mx - 10] = mx - 10
+        s = s - s.min()
+        sf = np.exp(s)
+        sf[self.detect_impossibility(id_fA, nb, True)] = 0
+        p = sf / sf.sum()
+        omega_f = int(self.rng.choice(range(0, len(p)), 1, p=p)[0])
+        f_star, omega_star = int(nb[omega_f // self.N_MH]), omega_f % self.N_MH
+        self.udpate_forward_vect(id_fA, f_star, omega_star, max_id)
+        proba_forward, star = p[omega_f], lf[omega_f]
+        lb = self.compute_all_score_MH(id_fA, V_set, False)
+        bad = self.detect_impossibility(id_fA, nb, False)
+        target = self.likelihood_t / F_t
+        sb = lb / F_t
+        mb = sb.max()
+        if target <= mb - 10:
+            target = mb - 10
+        sb[sb <= mb - 10] = mb - 10
+        target = target - sb.min()
+        sb = sb - sb.min()
+        eb = np.exp(sb)
+        target = np.exp(target)
+        eb[bad] = 0
+        proba_backward = target / eb.sum()
+        with np.errstate(over="ignore"):
+            ratio = np.exp((star + proba_backward - self.likelihood_t - proba_forward) / F_t)
+        self._mh_accept(ratio, id_fA, f_star, omega_star, max_id, star)
+        return self.likelihood_t, n_contigs, min_len, mean_len, max_len, F_t, self.dist_inter_genome(self.cur)
+
+    def step_mtm(self, id_fA, t=0, n_step=1, dt=0):
+        """:2936-3070."""
+        (n_contigs, min_len, mean_len, max_len), max_id, V_set, nb = self._mh_prologue(id_fA, dt)
+        F_t = self.temperature(t, n_step)
+        lf = self.compute_all_score_MH(id_fA, V_set, True)
+        s = lf / F_t
+        s[s == 0] = -np.inf
+        max_fwd = s.max()
+        s[s <= max_fwd - 600] = -np.inf
+        adapt_fwd = np.exp(s - max_fwd)
+        sf = np.copy(adapt_fwd)
+        sf[self.detect_impossibility(id_fA, nb, True)] = 0
+        p = sf / sf.sum()
+        omega_f = int(self.rng.choice(range(0, len(p)), 1, p=p)[0])
+        f_star, omega_star = int(nb[omega_f // self.N_MH]), omega_f % self.N_MH
+        self.udpate_forward_vect(id_fA, f_star, omega_star, max_id)
+        star = lf[omega_f]
+        self.return_neighbours(f_star, len(nb))                   # V_set_back (:3004): drawn, never used
+        lb = self.compute_all_score_MH(f_star, V_set, False)
+        sb = lb / F_t
+        sb[sb == 0] = -np.inf
+        max_bwd = sb.max()
+        sb[sb <= max_bwd - 600] = -np.inf
+        adapt_bwd = np.exp(sb - max_bwd)
+        with np.errstate(over="ignore"):
+            ratio = np.exp(max_fwd - max_bwd) * np.sum(adapt_fwd) / np.sum(adapt_bwd)
+        self._mh_accept(ratio, id_fA, f_star, omega_star, max_id, star)
+        return self.likelihood_t, n_contigs, min_len, mean_len, max_len, F_t, self.dist_inter_genome(self.cur)
+
     # ---- :475-541
     def dist_inter_genome(self, g1):
         return dist_inter_genome(g1, self.np_init_prev, self.np_init_next, self.np_init_ori,

@@ -34,12 +34,23 @@ def _lines():
     return open(PATH).read().split("\n")
 
 
-def method(name, extra_ns=None):
-    """The reference method `name` of class sampler as a Python 3 function f(self, ...)."""
+def method(name, extra_ns=None, py2=False):
+    """The reference method `name` of class sampler as a Python 3 function f(self, ...).  ``py2``: translate the Python 2
+    idioms of the text mechanically (print statements -> pass, the integer division `omega_f / self.n_modif_metropolis`
+    -> //); nothing else is touched."""
     lines = _lines()
     start = next(i for i, l in enumerate(lines) if l.startswith("    def %s(" % name))
     end = next(i for i in range(start + 1, len(lines)) if lines[i].startswith("    def ") or (lines[i] and not lines[i].startswith(" ")))
-    src = textwrap.dedent("\n".join(lines[start:end]))
+    body = lines[start:end]
+    if py2:
+        out = []
+        for l in body:
+            st = l.lstrip()
+            if st.startswith("print ") or st == "print":
+                l = l[:len(l) - len(st)] + "pass"
+            out.append(l.replace("omega_f / self.n_modif_metropolis", "omega_f // self.n_modif_metropolis"))
+        body = out
+    src = textwrap.dedent("\n".join(body))
     from scipy import stats
     ns = {"np": NP, "xrange": range, "time": time, "stats": stats}
     ns.update(extra_ns or {})

@@ -319,3 +319,26 @@ def test_circular_contig_state(small_pyramid):
         for j in range(13):
             assert abs(got[j] - ref[j][0]) <= tol(*ref[j]), (fA, fB, j, got[j], ref[j])
     g.free_gpu()
+
+
+def test_degenerate_proposal_scores(small_pyramid):
+    """id_fB == id_fA (return_neighbours can only produce it for a bin without contacts; the multiple-try variant scores
+    it on every backward pass): the candidate structures the kernels leave are not consistent genomes, the reference
+    scores whatever bins they hold.  State AND scores follow the oracle (the order records of a proposal start empty, so
+    positions a degenerate candidate never writes do not show an earlier proposal's bins)."""
+    from graal_b200.sampler import CAND0
+    inp, o, g = make_pair(small_pyramid, 2)
+    rng = np.random.RandomState(17)
+    H.scramble(o, rng, 25, g)
+    max_id = o.modify_gl_cuda_buffer(); g.modify_gl_cuda_buffer()
+    n = o.n_new_frags
+    g.score_neighbours(5, [9]); g._fetch()                        # an ordinary proposal first: its records must not leak
+    for fA in (int(rng.randint(n)), int(np.nonzero(o.cur["prev"] == -1)[0][0]), int(np.nonzero(o.cur["l_cont"] == o.cur["l_cont"].max())[0][3])):
+        M.perform_modifications(o.ws, o.cur, fA, fA, max_id)
+        ref = oracle_deltas(o, fA, fA)
+        g.score_neighbours(fA, [fA])
+        got = g._fetch()[16:29].copy()
+        for j in range(13):
+            assert H.slots_diff(o.ws.collector[j], g.slot_to_host(CAND0 + j)) == [], (fA, j)
+            assert abs(got[j] - ref[j][0]) <= tol(*ref[j]), (fA, j, got[j], ref[j])
+    g.free_gpu()

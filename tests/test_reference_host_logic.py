@@ -278,3 +278,60 @@ def test_remove_problematic_fragments_matches_the_reference_function(tmp_path):
         assert (int(d[2]), int(d[3]), int(d[4]), int(d[6])) == (int(mine.start_pos[i]), int(mine.end_pos[i]), int(mine.end_pos[i] - mine.start_pos[i]) if False else int(d[4]), int(mine.n_accu[i]))
     ref_contacts = sorted(tuple(int(x) for x in l.split("\t")) for l in open(out[2]).read().split("\n")[1:] if l)
     assert ref_contacts == sorted(zip(mine.rows.tolist(), mine.cols.tolist(), mine.vals.tolist()))
+
+
+class _SortedSet(set):
+    """A set whose iteration order is defined (increasing): the reference iterates `list(V_set)` of a CPython-2 set."""
+
+    def __iter__(self):
+        return iter(sorted(set.__iter__(self)))
+
+    def copy(self):
+        return _SortedSet(set.copy(self))
+
+
+@pytest.mark.parametrize("variant", ["step_metropolis_hastings_s_a", "step_mtm"])
+def test_mh_steps_match_the_reference_lines(variant):
+    """cuda_lib_gl.py:2836-3100: the reference's own step text (jump set, thresholds, exponentials, np.random.choice,
+    acceptance) driving the oracle's primitives vs the oracle's restatement of the step: same trajectory."""
+    pyr, inp = _mock_level(False, False)
+
+    def make():
+        o = H.make_oracle(inp, pyr, seed=1)
+        o.rng = np.random                                            # the reference draws from the global stream
+        H.scramble(o, np.random.RandomState(2), 40)                  # a rearranged genome: proposals that repair it are accepted
+        o.set_jumping_distributions_parameters(3)
+        for d in o.jump_dictionnary.values():
+            d["set_frags"] = _SortedSet(d["set_frags"])
+        o.init_likelihood()
+        return o
+    a, b = make(), make()
+
+    class _View:                                                     # gpu_vect_frags of the reference: host arrays after copy_from_gpu
+        def __init__(self, o, which):
+            self.o, self.which = o, which
+
+        def copy_from_gpu(self):
+            g = self.o.cur if self.which == "cur" else self.o.fwd
+            for k in M.FIELDS:
+                setattr(self, k, g[k])
+    a.gpu_vect_frags, a.gpu_vect_frags_forward = _View(a, "cur"), _View(a, "fwd")
+    a.n_modif_metropolis = 13
+    a.fwd = M.new_slot(a.n_new_frags)
+    a.gpu_vect_frags_forward.copy_from_gpu()
+    ref_detect = RH.method("detect_impossibility", py2=True)
+    a.detect_impossibility = lambda fA, nb, fwd: ref_detect(a, fA, nb, fwd)
+    a.dist_inter_genome = lambda view: OS.OracleSampler.dist_inter_genome(a, a.cur)
+    ref_step = RH.method(variant, py2=True)
+    sched = np.random.RandomState(9).randint(0, a.n_new_frags, size=16)
+    np.random.seed(77)
+    ra = []
+    for fA in sched:
+        a.gpu_vect_frags_forward.copy_from_gpu()
+        ra.append(ref_step(a, int(fA), 0, 1, 0))
+    np.random.seed(77)
+    rb = [getattr(b, variant)(int(fA)) for fA in sched]
+    assert H.slots_diff(a.cur, b.cur) == []
+    for x, y in zip(ra, rb):
+        assert x[0] == y[0] and tuple(x[1:5]) == tuple(y[1:5]) and x[6] == y[6], (x, y)
+    assert any(x[0] != ra[0][0] for x in ra)                          # something was accepted
