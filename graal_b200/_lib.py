@@ -61,6 +61,7 @@ _SIGS = {
     "graal_set_math_mode": (_I, [_P, _I]),
     "graal_state_bind": (_I, [_P, _P, _I, _I]),
     "graal_relabel_contigs": (_I, [_P, _I, _P]),
+    "graal_stats_relabel": (_I, [_P, _I, _P, _P]),
     "graal_apply_move": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "graal_build_candidates": (_I, [_P, _I, _I, _I, _I, _I, _U]),
     "graal_commit": (_I, [_P, _I, _I]),
@@ -74,6 +75,7 @@ _SIGS = {
     "graal_score_step": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "graal_fetch": (_I, [_P, _P, _P, C.c_size_t]),
     "graal_dist_histogram": (_I, [_P, _P, _P, _P, _P, _D, _D, _I, _P, _P]),
+    "graal_candidate_weights": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "graal_launch_count": (_LL, [_P]),
     "graal_profile_enable": (_I, [_P, _I]),
     "graal_profile_read": (_I, [_P, _I, C.POINTER(_D), C.POINTER(_LL), _I]),

@@ -465,6 +465,85 @@ __global__ void k_relabel_apply(int* __restrict__ id_c, int n, int cap, const in
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused step prologue (statistics + relabel) for genomes of at most RL_MAX contigs with ids below RL_RANGE: three
+// launches instead of sixteen.  The per-step chain statistics -> relabel is a latency chain of tiny kernels on the
+// critical path of every step (nothing else can start before the contig ids are final).
+//   k_prologue_scan : per bin, the statistics of graal_state_stats and the first bin of every contig (first[] is kept
+//                     at INT_MAX between calls: k_prologue_rank cleans what it reads)
+//   k_prologue_rank : ONE block: the contigs in use compacted to (length, id) keys, sorted in shared memory (bitonic;
+//                     keys are unique, so the result is the (length, old id) order of the stable sort of
+//                     graal_relabel_contigs), rank -> map, statistics finalised
+//   k_relabel_apply : id_c <- map[id_c]
+// ------------------------------------------------------------------------------------------------
+#define RL_MAX 4096
+#define RL_RANGE 8192
+__global__ void k_prologue_scan(const int* __restrict__ slot, int ld, int n, int* __restrict__ first, unsigned long long* __restrict__ acc, int* __restrict__ err) {
+    unsigned long long heads = 0, sum = 0; int mn = INT_MAX, mx = INT_MIN;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int lc = slot[F_L_CONT * ld + i];
+        mn = min(mn, lc); mx = max(mx, lc);
+        if (slot[F_START_BP * ld + i] == 0) { heads++; sum += (unsigned long long)(long long)slot[F_L_CONT_BP * ld + i]; }
+        const int c = slot[F_ID_C * ld + i];
+        if (c < 0 || c >= RL_RANGE) { atomicExch(err, 1); continue; }
+        const unsigned peers = __match_any_sync(__activemask(), c);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicMin(&first[c], i);
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        heads += __shfl_down_sync(0xffffffffu, heads, o); sum += __shfl_down_sync(0xffffffffu, sum, o);
+        mn = min(mn, __shfl_down_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (heads) { atomicAdd(&acc[0], heads); atomicAdd(&acc[1], sum); }
+        atomicMin((int*)&acc[2], mn); atomicMax((int*)&acc[3], mx);
+    }
+}
+__global__ void __launch_bounds__(1024)
+k_prologue_rank(int* __restrict__ first, const int* __restrict__ l_cont, int range, int* __restrict__ map, int* __restrict__ d_ints,
+                unsigned long long* __restrict__ acc, double* __restrict__ stats_out, int* __restrict__ max_id_out) {
+    __shared__ unsigned long long key[RL_MAX];
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    for (int c = threadIdx.x; c < range; c += blockDim.x) {
+        const int f = first[c];
+        if (f != INT_MAX) {
+            const int p = atomicAdd(&cnt, 1);
+            if (p < RL_MAX) key[p] = ((unsigned long long)(unsigned)l_cont[f] << 32) | (unsigned)c;
+            first[c] = INT_MAX;
+        }
+    }
+    __syncthreads();
+    int k = cnt;
+    if (k > RL_MAX) { if (threadIdx.x == 0) atomicExch(&d_ints[2], 2); k = RL_MAX; }      // more contigs than the fused path holds: flagged
+    int m = 1; while (m < k) m <<= 1;
+    for (int i = k + threadIdx.x; i < m; i += blockDim.x) key[i] = ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= m; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < (m >> 1); i += blockDim.x) {
+                const int lo = ((i / stride) * stride << 1) + (i % stride), hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const unsigned long long a = key[lo], b = key[hi];
+                if ((a > b) == up) { key[lo] = b; key[hi] = a; }
+            }
+            __syncthreads();
+        }
+    for (int r = threadIdx.x; r < k; r += blockDim.x) map[(int)(key[r] & 0xffffffffull)] = r;
+    if (threadIdx.x == 0) {
+        d_ints[1] = k; d_ints[0] = k - 1;
+        if (max_id_out) *max_id_out = k - 1;
+        if (stats_out) {
+            stats_out[0] = (double)k;
+            stats_out[1] = (double)*(const int*)&acc[2];
+            stats_out[2] = acc[0] ? (double)acc[1] / (double)acc[0] : 0.0;
+            stats_out[3] = (double)*(const int*)&acc[3];
+        }
+        acc[0] = 0ull; acc[1] = 0ull; acc[2] = (unsigned long long)(unsigned)INT_MAX; acc[3] = (unsigned long long)(unsigned)INT_MIN;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // geometry: per-sub-frag records of a slot (unique bins: frag index == data bin index)
 // ------------------------------------------------------------------------------------------------
 struct LevelView {
@@ -2234,6 +2313,10 @@ struct graal_ctx {
     // scratch
     Geo* geo_base = nullptr; int geo_base_slot = -1;
     int first_idx_slot = -1;                 // slot whose first-bin-of-contig table (first_idx) is current
+    // fused prologue: host-side bound on the contig ids of `bound_slot` (n_contigs after the last relabel, read back with the
+    // step's fetch, + the ids one committed candidate can add); -1: unknown -> the general path
+    int contig_bound = -1, bound_slot = -1, bound_commits = 0; int* h_ncontigs = nullptr; bool ncontigs_pending = false;
+    bool first_clean = false, stats_clean = false; FixedGraph g_prologue; int fused_prologue = 1;
     int* order = nullptr;                    // [n]
     int* cont_len = nullptr; int* cont_off = nullptr; int cap = 0;   // [cap]
     int* first_idx = nullptr; int* map = nullptr;
@@ -2426,6 +2509,8 @@ int graal_ctx_create(int device, graal_ctx** out) {
     { const char* e = getenv("GRAAL_PAIRING"); if (e && e[0] == '0') c->pairing = 0; }
     { const char* e = getenv("GRAAL_FORK"); if (e && e[0] == '0') c->fork_passes = 0; }
     { const char* e = getenv("GRAAL_FULL_WIN"); if (e && e[0] == '0') c->full_win = 0; }
+    { const char* e = getenv("GRAAL_FUSED_PROLOGUE"); if (e && e[0] == '0') c->fused_prologue = 0; }
+    CUDA_OK(cudaMallocHost(&c->h_ncontigs, sizeof(int)));
     { const char* e = getenv("GRAAL_DELTA_UNI"); if (e) c->delta_uni = e[0] == '1'; }
     { const char* e = getenv("GRAAL_BAND_FAST"); if (e && e[0] == '0') c->band_fast = 0; }
     { const char* e = getenv("GRAAL_DELTA_REL"); if (e && e[0] == '0') c->delta_rel = 0; }
@@ -2491,6 +2576,8 @@ void graal_ctx_destroy(graal_ctx* c) {
         if (L.st) cudaStreamDestroy(L.st);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->h_ncontigs) cudaFreeHost(c->h_ncontigs);
+    c->g_prologue.reset();
     for (int i = 0; i < 16; i++) c->graphs[i].reset();
     c->g_stats.reset(); c->g_relabel.reset(); c->g_full.reset(); c->g_full_cached.reset(); c->g_win.reset();
     c->prof.destroy();
@@ -2563,7 +2650,7 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     c->version++;
     for (int i = 0; i < 16; i++) c->graphs[i].reset();
     c->g_stats.reset(); c->g_relabel.reset(); c->g_full.reset(); c->g_full_cached.reset(); c->g_win.reset();
-    c->win_slot = -1;
+    c->win_slot = -1; c->contig_bound = -1; c->ncontigs_pending = false; c->first_clean = false; c->stats_clean = false; c->g_prologue.reset();
     { const char* e = getenv("GRAAL_WIN_SUB"); c->win_tuned = e != nullptr; }
     free_level_scratch(c);
     c->N = n_frags; c->n_new = n_new_frags; c->W = n_sub_frags; c->E = n_contacts; c->nfpb = nfpb;
@@ -2791,6 +2878,7 @@ int graal_state_bind(graal_ctx* c, int32_t* base, int ld, int n_slots) {
     { int rcj = join_lanes(c); if (rcj) return rcj; }
     c->version++;
     c->slots = base; c->ld = ld; c->n_slots = n_slots; c->geo_base_slot = -1; c->band_slot = -1; c->first_idx_slot = -1;
+    c->contig_bound = -1; c->ncontigs_pending = false;
     return 0;
 }
 
@@ -2824,6 +2912,47 @@ int graal_relabel_contigs(graal_ctx* c, int slot, int32_t* d_max_id) {
     { const int rc = run_graphed(c, c->g_relabel, slot, (long long)(uintptr_t)d_max_id, have_first ? 1 : 0, enqueue); if (rc) return rc; }
     if (c->geo_base_slot == slot) c->geo_base_slot = -1;
     c->first_idx_slot = -1;                  // indexed by the OLD contig ids
+    c->first_clean = false;
+    if (c->bound_slot != slot) { c->bound_slot = slot; c->contig_bound = -1; }
+    c->bound_commits = 0; c->ncontigs_pending = true;      // d_ints[1] = n_contigs of this slot: read back by the next graal_fetch
+    return 0;
+}
+
+// graal_state_stats + graal_relabel_contigs of one slot in three launches when the host knows a bound on the contig ids
+// (see k_prologue_scan); the general sequences otherwise.
+int graal_stats_relabel(graal_ctx* c, int slot, double* d_stats_out, int32_t* d_max_id) {
+    NEED_STATE(c); NEED_SLOT(c, slot);
+    if (!d_stats_out) return set_err(-1, "null output");
+    const bool fused = c->fused_prologue && !c->prof.on && c->bound_slot == slot && c->contig_bound >= 0 && c->contig_bound <= RL_MAX;
+    if (!fused) {
+        int rc = graal_state_stats(c, slot, d_stats_out); if (rc) return rc;
+        rc = graal_relabel_contigs(c, slot, d_max_id); if (rc) return rc;
+        if (c->fused_prologue && !c->prof.on && c->contig_bound < 0 && c->h_ncontigs) {
+            // bound unknown (first step after an upload / a raw mutation): ONE blocking read of the contig count seeds it, the
+            // following steps take the fused path without any (a run that never fetches would otherwise never learn it)
+            CUDA_OK(cudaMemcpyAsync(c->h_ncontigs, c->d_ints + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_OK(cudaStreamSynchronize(c->stream));
+            c->contig_bound = *c->h_ncontigs; c->bound_commits = 0; c->ncontigs_pending = false;
+        }
+        return 0;
+    }
+    const int n = c->n_new, ld = c->ld, cap = c->cap;
+    int* s = slot_ptr(c, slot);
+    cudaStream_t st = c->stream;
+    const bool fill = !c->first_clean, init = !c->stats_clean;
+    auto enqueue = [&]() -> int {
+        if (fill) { k_fill_int<<<nblk(cap, 256), 256, 0, st>>>(c->first_idx, cap, INT_MAX); CHECK_LAUNCH(c); }
+        if (init) { k_init_stats<<<1, 1, 0, st>>>(c->d_stats); CHECK_LAUNCH(c); }
+        k_prologue_scan<<<std::min(nblk(n, 256), c->n_sm * 4), 256, 0, st>>>(s, ld, n, c->first_idx, c->d_stats, c->d_ints + 2); CHECK_LAUNCH(c);
+        k_prologue_rank<<<1, 1024, 0, st>>>(c->first_idx, s + F_L_CONT * ld, std::min(cap, RL_RANGE), c->map, c->d_ints, c->d_stats, d_stats_out, d_max_id); CHECK_LAUNCH(c);
+        k_relabel_apply<<<nblk(n, 256), 256, 0, st>>>(s + F_ID_C * ld, n, cap, c->map, c->d_ints + 1, c->d_ints + 0, d_max_id); CHECK_LAUNCH(c);
+        return 0;
+    };
+    { const int rc = run_graphed(c, c->g_prologue, slot, (long long)(uintptr_t)d_stats_out ^ ((long long)(uintptr_t)d_max_id << 1), (fill ? 1 : 0) | (init ? 2 : 0), enqueue); if (rc) return rc; }
+    c->first_clean = true; c->stats_clean = true;
+    if (c->geo_base_slot == slot) c->geo_base_slot = -1;
+    c->first_idx_slot = -1;
+    c->bound_commits = 0; c->ncontigs_pending = true;
     return 0;
 }
 
@@ -2844,6 +2973,7 @@ int graal_apply_move(graal_ctx* c, int src_slot, int dst_slot, int op, int id_fA
     if (c->geo_base_slot == dst_slot) c->geo_base_slot = -1;
     if (c->first_idx_slot == dst_slot) c->first_idx_slot = -1;
     if (c->band_slot == dst_slot) c->band_slot = -1;
+    if (c->bound_slot == dst_slot) { c->contig_bound = -1; c->ncontigs_pending = false; }
     return 0;
 }
 
@@ -2860,6 +2990,7 @@ int graal_build_candidates(graal_ctx* c, int src_slot, int first_dst_slot, int i
     if (c->geo_base_slot >= first_dst_slot && c->geo_base_slot < first_dst_slot + GRAAL_N_CANDIDATES) c->geo_base_slot = -1;
     if (c->first_idx_slot >= first_dst_slot && c->first_idx_slot < first_dst_slot + GRAAL_N_CANDIDATES) c->first_idx_slot = -1;
     if (c->band_slot >= first_dst_slot && c->band_slot < first_dst_slot + GRAAL_N_CANDIDATES) c->band_slot = -1;
+    if (c->bound_slot >= first_dst_slot && c->bound_slot < first_dst_slot + GRAAL_N_CANDIDATES) { c->contig_bound = -1; c->ncontigs_pending = false; }
     return 0;
 }
 
@@ -2871,6 +3002,8 @@ int graal_commit(graal_ctx* c, int dst_slot, int src_slot) {
     if (c->geo_base_slot == dst_slot) c->geo_base_slot = -1;
     if (c->first_idx_slot == dst_slot) c->first_idx_slot = -1;
     if (c->band_slot == dst_slot) c->band_slot = -1;
+    // a committed candidate of a relabelled genome adds at most 3 contig ids (eject + split insert / two splits)
+    if (c->bound_slot == dst_slot) { c->bound_commits++; if (c->contig_bound >= 0) c->contig_bound += 3; }
     return 0;
 }
 
@@ -3333,7 +3466,12 @@ int graal_fetch(graal_ctx* c, const void* d_src, void* h_dst, size_t bytes) {
     CUDA_OK(cudaSetDevice(c->device));
     int rc = join_lanes(c); if (rc) return rc;
     CUDA_OK(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    const bool pend = c->ncontigs_pending && c->h_ncontigs;
+    if (pend) CUDA_OK(cudaMemcpyAsync(c->h_ncontigs, c->d_ints + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (pend) {     // contig ids of the relabelled slot are < n_contigs (+ 3 per candidate committed since): the fused prologue's bound
+        c->contig_bound = *c->h_ncontigs + 3 * c->bound_commits; c->ncontigs_pending = false;
+    }
     return 0;
 }
 
@@ -3369,7 +3507,7 @@ int graal_state_stats(graal_ctx* c, int slot, double* d_out) {
         return 0;
     };
     { const int rc = run_graphed(c, c->g_stats, slot, (long long)(uintptr_t)d_out, 0, enqueue); if (rc) return rc; }
-    c->first_idx_slot = slot;
+    c->first_idx_slot = slot; c->first_clean = false; c->stats_clean = false;
     return 0;
 }
 
@@ -3472,6 +3610,66 @@ int graal_coo_to_lists(graal_ctx* c, const int32_t* d_rows, const int32_t* d_col
     #undef COO_OK
     cleanup();
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host arithmetic of the candidate draw (cuda_lib_gl.py:1899-1934), float64, in NumPy's operation order -- sums are NumPy's
+// pairwise sums (numpy/core/src/umath/loops_utils.h: plain loop below 8 terms, eight interleaved partial sums up to
+// 128 terms, halves rounded to multiples of 8 above) -- so that the weights are bit-identical to the NumPy statements they
+// replace (tests/test_host.py compares them).  No device work: plain C called between the fetch and the commit of a step.
+// ------------------------------------------------------------------------------------------------
+static double np_pairwise_sum(const double* a, long n) {
+    if (n < 8) { double r = 0.0; for (long i = 0; i < n; i++) r += a[i]; return r; }      // (NumPy starts from a[0]: 0.0 + a[0] == a[0] except -0.0, never a weight)
+    if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; j++) r[j] = a[j];
+        long i;
+        for (i = 8; i < n - (n % 8); i += 8) for (int j = 0; j < 8; j++) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; i++) res += a[i];
+        return res;
+    }
+    long n2 = n / 2; n2 -= n2 % 8;
+    return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+}
+
+// score[n] (n = 13 x neighbours) -> the indices id_ok[n_ok] that may be drawn and their normalised cumulative weights
+// cdf[n_ok] (temperature 1: the power step of the reference is the identity); returns n_ok, *id_max = argmax(score).
+// Returns -1 when a weight is not finite (the caller then runs the NumPy statements, which raise like the reference).
+int graal_candidate_weights(const double* score, int n, int n_tmp, double* work, int32_t* id_ok, double* cdf, int32_t* id_max) {
+    if (!score || !work || !id_ok || !cdf || !id_max || n <= 0 || n_tmp <= 0) return -2;
+    int im = 0; double mn = score[0];
+    bool nan = score[0] != score[0];
+    for (int i = 1; i < n; i++) {
+        if (score[i] != score[i]) nan = true;
+        if (score[i] > score[im]) im = i;
+        if (score[i] < mn) mn = score[i];
+    }
+    if (nan) return -1;
+    *id_max = im;
+    for (int i = 0; i < n; i++) work[i] = score[i] - mn;
+    for (int i = n_tmp; i < n; i += n_tmp) { work[i] = 0.0; if (i + 1 < n) work[i + 1] = 0.0; }     // eject / flip of the later neighbours: duplicates of the first one's
+    double mx = work[0];
+    for (int i = 1; i < n; i++) if (work[i] > mx) mx = work[i];
+    const double shift = mx - 30.0;                                                                 // thresh_overflow
+    int n_ok = 0;
+    for (int i = 0; i < n; i++) {
+        double f = work[i] - shift;
+        if (f < 0.0) f = 0.0;
+        if (f > 0.0) { id_ok[n_ok] = i; cdf[n_ok] = f; n_ok++; }
+    }
+    if (n_ok == 0) return 0;
+    double sum = np_pairwise_sum(cdf, n_ok);
+    for (int i = 0; i < n_ok; i++) cdf[i] = cdf[i] / sum;
+    sum = np_pairwise_sum(cdf, n_ok);                                                               // (power 1 / F_t with F_t == 1: identity) second normalisation
+    for (int i = 0; i < n_ok; i++) cdf[i] = cdf[i] / sum;
+    for (int i = 0; i < n_ok; i++) work[i] = cdf[i];                                                // sub_score (kept for the caller)
+    double run = 0.0;
+    for (int i = 0; i < n_ok; i++) { run += cdf[i]; cdf[i] = run; }
+    const double last = cdf[n_ok - 1];
+    if (!(last - last == 0.0)) return -1;
+    for (int i = 0; i < n_ok; i++) cdf[i] = cdf[i] / last;
+    return n_ok;
 }
 
 int graal_dist_histogram(graal_ctx* c, const int32_t* sub_id_c, const int32_t* sub_start_bp, const int32_t* sub_len_bp,

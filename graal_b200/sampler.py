@@ -230,6 +230,7 @@ class sampler(MetropolisMixin):
         self.np_id_frag_duplicated = np.asarray(id_frag_duplicated, dtype=I32)
         self._dup_set = set(int(f) for f in self.np_id_frag_duplicated)
         self._n_cand_cache = {}
+        self._cdf_cache = {}
         disp = np.asarray(frag_dispatcher).reshape(-1, 2)
         self._identity_dispatch = bool(len(self._dup_set) == 0 and np.all(disp[:, 1] - disp[:, 0] == 1) and
                                        np.array_equal(np.asarray(collector_id_repeats)[disp[:, 0]], np.arange(disp.shape[0])))
@@ -527,7 +528,7 @@ class sampler(MetropolisMixin):
         if n_nonzero is None:
             n_nonzero = self._n_cand_cache[ori_id] = int(np.count_nonzero(distri))
         n_max_candidates = min(delta, n_nonzero)
-        init_id = self.rng.choice(self.distri_xk[ori_id], n_max_candidates, p=distri, replace=False)
+        init_id = self._choice_no_replace(ori_id, n_max_candidates)
         if self._identity_dispatch:             # no duplicated bins: every dispatcher range is the bin itself
             return [e for e in init_id.tolist() if e not in self._black_set]
         out = []
@@ -538,6 +539,38 @@ class sampler(MetropolisMixin):
             d = self.frag_dispatcher[id_fB]
             out.extend(self.collector_id_repeats[d[0]:d[1]])
         return [int(e) for e in out if int(e) not in self._black_set]
+
+    def _choice_no_replace(self, ori_id, size):
+        """``self.rng.choice(self.distri_xk[ori_id], size, p=self.distri_pk[ori_id], replace=False)`` of a legacy
+        RandomState without its argument validation: the same draws in the same order (numpy/random/mtrand.pyx, the
+        replace=False branch: `size - n_found` uniforms per round, searched in the cumulative weights with the bins already
+        found zeroed, first occurrences kept in draw order).  The cumulative weights of the FIRST round only depend on the
+        bin: cached.  Pinned by tests/test_reference_host_logic.py against the reference's own lines."""
+        rs = getattr(self.rng, "random_sample", None)
+        xk = self.distri_xk[ori_id]
+        if rs is None or size <= 0:
+            return self.rng.choice(xk, size, p=self.distri_pk[ori_id], replace=False)
+        ent = self._cdf_cache.get(ori_id)
+        if ent is None:
+            p = np.array(self.distri_pk[ori_id], dtype=np.float64)
+            cdf = np.cumsum(p)
+            cdf /= cdf[-1]
+            ent = self._cdf_cache[ori_id] = (p, cdf)
+        p0, cdf = ent
+        found = []
+        p = None
+        while len(found) < size:
+            x = rs(size - len(found))
+            if found:
+                if p is None:
+                    p = p0.copy()
+                p[found] = 0
+                cdf = np.cumsum(p)
+                cdf /= cdf[-1]
+            for j in cdf.searchsorted(x, side="right").tolist():
+                if j not in found:            # first occurrence of every new index, in draw order (np.unique + sorted first indices);
+                    found.append(j)           # an index found in an earlier round has zero weight now and cannot come back
+        return xk[found]
 
     def temperature(self, t, n_step):
         return 1.0
@@ -569,8 +602,7 @@ class sampler(MetropolisMixin):
         step_begin on each chain, then step_end on each (graal_b200.replica.step_chains): their kernels overlap."""
         lib = self.lib
         self._step_fA = id_fA
-        check(lib.graal_state_stats(self.ctx, CUR, self._ptr(self.d_out, 4)))
-        check(lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
+        check(lib.graal_stats_relabel(self.ctx, CUR, self._ptr(self.d_out, 4), self._ptr(self.d_max_id)))
         if id_fA in self._black_set:
             self.id_neighbours = None
             return
@@ -652,8 +684,7 @@ class sampler(MetropolisMixin):
         proposal and the sampled candidate supplied by the caller -- nothing is copied to the host and
         the stream is not synchronised (bench.py's resident-input timing, replay of a recorded run)."""
         lib = self.lib
-        check(lib.graal_state_stats(self.ctx, CUR, self._ptr(self.d_out, 4)))
-        check(lib.graal_relabel_contigs(self.ctx, CUR, self._ptr(self.d_max_id)))
+        check(lib.graal_stats_relabel(self.ctx, CUR, self._ptr(self.d_out, 4), self._ptr(self.d_max_id)))
         if op_sampled < 0:
             return
         for c0 in range(0, len(id_neighbours), self.MAX_PROPOSALS):
@@ -668,6 +699,25 @@ class sampler(MetropolisMixin):
     def _sample(self, score, F_t):
         """Candidate filtering and draw (cuda_lib_gl.py:1899-1947)."""
         nt = N_TMP_STRUCT
+        rs = getattr(self.rng, "random_sample", None)
+        if F_t == 1.0 and rs is not None and getattr(self, "_fast_weights", True):
+            # the same float64 arithmetic in C (NumPy's operation order, pairwise sums included; graal_candidate_weights):
+            # ~40 microseconds of small-array NumPy calls off the critical path between two steps
+            n = len(score)
+            buf = self._weights_buf.get(n) if hasattr(self, "_weights_buf") else None
+            if buf is None:
+                if not hasattr(self, "_weights_buf"):
+                    self._weights_buf = {}
+                buf = self._weights_buf[n] = (np.empty(n, dtype=np.float64), np.empty(n, dtype=np.int32), np.empty(n, dtype=np.float64),
+                                              C.c_int32(0), _lib.load().graal_candidate_weights)
+            work, ids, cdf, imax, fn = buf
+            sc = score if (score.dtype == np.float64 and score.flags.c_contiguous) else np.ascontiguousarray(score, dtype=np.float64)
+            n_ok = fn(sc.ctypes.data, n, nt, work.ctypes.data, ids.ctypes.data, cdf.ctypes.data, C.byref(imax))
+            if n_ok >= 0:
+                self.sub_score = work[:n_ok].copy()
+                if n_ok <= 1:
+                    return int(imax.value)
+                return int(ids[int(cdf[:n_ok].searchsorted(rs(), side="right"))])
         scores_2_remove = self._remove_cache.get(len(score))
         if scores_2_remove is None:
             scores_2_remove = self._remove_cache[len(score)] = list(range(nt, len(score), nt)) + list(range(nt + 1, len(score), nt))

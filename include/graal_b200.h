@@ -21,6 +21,9 @@
  *   GRAAL_PAIRING=0  score candidates 3, 5, 7 like the others instead of as deltas against 2, 4, 6
  *   GRAAL_FORK=0     contact / band passes of a proposal on one stream instead of three
  *   GRAAL_SMEM_CID=1 contig-id table of the contact pass in shared memory (math modes 0 / 1 only; slower)
+ *   GRAAL_FULL_WIN=0 gather-everything contact pass instead of the windowed one; GRAAL_WIN_UNROLL / _MINB / _SUB: its variants
+ *   GRAAL_DELTA_REL=0 / GRAAL_BAND_FAST=0 general delta kernels on uniform levels; GRAAL_DELTA_UNI=1 union windows in the delta contact pass
+ *   GRAAL_FUSED_PROLOGUE=0 statistics + relabel as the two general launch sequences
  *
  * State layout ("slots"): the reference keeps the genome in a struct of 14 int* (kernels3.cu:9-24,
  * packed by gpustruct.py).  Here a slot is one SoA block of 14 x ld int32, field f of slot s at
@@ -179,6 +182,11 @@ int graal_commit_scored(graal_ctx* ctx, int base_slot, int first_cand_slot, int 
  * n_contigs, min l_cont, mean l_cont_bp over contig heads, max l_cont. */
 int graal_state_stats(graal_ctx* ctx, int slot, double* d_out);
 
+/* graal_state_stats followed by graal_relabel_contigs of the same slot (the head of every step, cuda_lib_gl.py:1801-1816),
+ * fused into three launches when the context knows a bound on the contig ids (read back with graal_fetch after the previous
+ * relabel: at most 4096 contigs); the two general sequences otherwise.  Same outputs as the two calls. */
+int graal_stats_relabel(graal_ctx* ctx, int slot, double* d_stats_out, int32_t* d_max_id);
+
 /* dist_inter_genome (cuda_lib_gl.py:475-541): d_out[0] = sum over the bins with skip[f] == 0 of their
  * distance term (3 minus the neighbour / orientation agreements with the initial genome); the caller
  * divides by 3 * (number of counted bins).  init_prev / init_next / init_orientable: int32[n] device
@@ -202,6 +210,12 @@ int graal_dist_candidates(graal_ctx* ctx, int first_cand_slot, int n_cand, int p
 int graal_dist_histogram(graal_ctx* ctx, const int32_t* sub_id_c, const int32_t* sub_start_bp,
                          const int32_t* sub_len_bp, const int32_t* sub_pos,
                          double max_dist_kb, double bin_kb, int n_bins, double* d_sum, int64_t* d_cnt);
+
+/* Host arithmetic of the candidate draw of step_max_likelihood (cuda_lib_gl.py:1899-1934) at temperature 1, float64, in
+ * NumPy's operation order (pairwise sums included): score[n] (n = n_tmp x neighbours) -> id_ok[n_ok], the normalised weights
+ * (work[0..n_ok)) and their normalised cumulative sums cdf[n_ok]; *id_max = argmax(score).  Returns n_ok, -1 if a weight is
+ * not finite (the caller falls back to the NumPy statements).  No CUDA call. */
+int graal_candidate_weights(const double* score, int n, int n_tmp, double* work, int32_t* id_ok, double* cdf, int32_t* id_max);
 
 /* instrumentation: number of kernel launches issued by this context so far */
 int64_t graal_launch_count(graal_ctx* ctx);

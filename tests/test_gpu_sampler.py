@@ -235,3 +235,35 @@ def test_device_contact_lists_match_the_host_preparation(small_pyramid):
     assert np.array_equal(rp_d.cpu().numpy(), np.r_[0, np.cumsum(np.bincount(rr, minlength=W))])
     assert np.array_equal(ct[:, 0], cc) and np.array_equal(ct[:, 1].copy().view(np.float32), dense[rr, cc].astype(np.float32))
     g.free_gpu()
+
+
+def test_fused_prologue_matches_the_general_sequences(small_pyramid):
+    """graal_stats_relabel: the three-launch prologue (first step: general path + seeded bound; then fused) against the
+    oracle's statistics and relabel over a run of committed moves, and against the general path (GRAAL_FUSED_PROLOGUE=0)."""
+    import os
+    from graal_b200.sampler import CUR
+    inp, g = gpu_sampler(small_pyramid, 2, 3)
+    os.environ["GRAAL_FUSED_PROLOGUE"] = "0"
+    try:
+        inp2, g2 = gpu_sampler(small_pyramid, 2, 3)
+    finally:
+        os.environ.pop("GRAAL_FUSED_PROLOGUE")
+    o = H.make_oracle(inp, small_pyramid, seed=3)
+    rng = np.random.RandomState(1)
+    n = o.n_new_frags
+    for it in range(40):
+        fA = int(rng.randint(n))
+        ro, r1, r2 = o.step_max_likelihood(fA, 3), g.step_max_likelihood(fA, 3), g2.step_max_likelihood(fA, 3)
+        assert tuple(ro[1:7]) == tuple(r1[1:7]) == tuple(r2[1:7]), (it, ro, r1, r2)
+        assert r1[0] == r2[0]
+        assert H.slots_diff(o.cur, g.slot_to_host(CUR)) == [] and H.slots_diff(o.cur, g2.slot_to_host(CUR)) == []
+    # the device-resident replay (no fetch at all) seeds its bound by itself
+    g.slot_from_host(CUR, g2.slot_to_host(CUR))
+    for it in range(5):
+        fA = int(rng.randint(n))
+        nb = g2.return_neighbours(fA, 3); nb.sort()
+        if not nb:
+            continue
+        g.step_device(fA, nb, nb[0], 6); g2.step_device(fA, nb, nb[0], 6)
+        assert H.slots_diff(g.slot_to_host(CUR), g2.slot_to_host(CUR)) == []
+    g.free_gpu(); g2.free_gpu()

@@ -133,3 +133,33 @@ def test_edge_levels():
     # (pop_out_frag is the identity for l_cont == 1, kernels3.cu:545-561)
     assert np.all(o.cur["l_cont"] == 1) and np.all(o.cur["pos"] == 0) and np.all(o.cur["prev"] == -1)
     assert len(np.unique(o.cur["id_c"])) == o.n_new_frags
+
+
+def test_candidate_weights_in_c_match_the_numpy_statements():
+    """graal_candidate_weights (the float64 arithmetic of the candidate draw in C, NumPy's pairwise sums included) against the
+    NumPy statements of sampler._sample: same candidate, same weights bit for bit, same stream position."""
+    import types
+    from graal_b200 import sampler as GS, _lib
+    _lib.build()
+    gen = np.random.RandomState(0)
+    for case in range(3000):
+        n_nb = int(gen.randint(1, 17))
+        score = -1e6 + gen.randn(13 * n_nb) * gen.choice([1e-3, 0.01, 1.0, 5.0, 40.0, 300.0])
+        if case % 7 == 0:
+            score[gen.randint(score.size)] += 100.0
+        if case % 11 == 0:
+            score[:] = score[0]
+        if case % 13 == 0:
+            score[gen.randint(score.size)] = np.nan if case % 2 else np.inf
+        seed = int(gen.randint(1 << 30))
+        a = types.SimpleNamespace(rng=np.random.RandomState(seed), _remove_cache={}, sub_score=None, _fast_weights=False)
+        b = types.SimpleNamespace(rng=np.random.RandomState(seed), _remove_cache={}, sub_score=None, _fast_weights=True)
+        try:
+            ra = GS.sampler._sample(a, score.copy(), 1.0)
+        except ValueError:
+            with pytest.raises(ValueError):
+                GS.sampler._sample(b, score.copy(), 1.0)
+            continue
+        rb = GS.sampler._sample(b, score.copy(), 1.0)
+        assert ra == rb and a.rng.rand() == b.rng.rand(), (case, ra, rb)
+        assert np.array_equal(a.sub_score, b.sub_score, equal_nan=True), case

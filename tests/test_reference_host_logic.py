@@ -98,7 +98,9 @@ def test_neighbour_tables_and_return_neighbours(allow_repeats, blacklist):
                                  _n_cand_cache={}, rng=np.random, _dup_set=dup, _black_set=set(int(f) for f in inp.id_frags_blacklisted),
                                  frag_dispatcher=d2, collector_id_repeats=np.asarray(inp.collector_id_repeats),
                                  _identity_dispatch=bool(len(dup) == 0 and np.all(d2[:, 1] - d2[:, 0] == 1) and
-                                                         np.array_equal(np.asarray(inp.collector_id_repeats)[d2[:, 0]], np.arange(N))))
+                                                         np.array_equal(np.asarray(inp.collector_id_repeats)[d2[:, 0]], np.arange(N))),
+                                 _cdf_cache={})
+    mine._choice_no_replace = lambda ori, size: GS.sampler._choice_no_replace(mine, ori, size)
     gen = np.random.RandomState(3)
     for case in range(300):
         fA = int(gen.randint(n)); delta = int(gen.choice([1, 3, 5, 12])); seed = int(gen.randint(1 << 30))
