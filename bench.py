@@ -86,7 +86,8 @@ def make_config(name, n_bins, W, E, k_nb, n_contigs, chains, world, exchange_eve
     return {"workload": name, "bins": int(n_bins), "sub_frags": int(W), "contact_entries": int(E),
             "contact_list_MB": round(8 * E / 1e6, 1), "neighbours_per_step": int(k_nb), "candidates_per_neighbour": N_TMP,
             "state": "assembled genome (%d contigs)" % n_contigs,
-            "schedule": "bins: RandomState(4242).permutation; neighbours: the reference's proposal rule on RandomState(1000 + chain)",
+            "schedule": "bins: RandomState(4242).permutation; neighbours: the reference's proposal rule on RandomState(1000 + chain)"
+                        + ("; resident replay: rank 0's recorded schedule on every rank" if world > 1 else ""),
             "l2": "inputs larger than L2: the %.0f MB contact list is re-streamed every step" % (8 * E / 1e6),
             "full_likelihood": ("incremental: carried from the committed candidate, full pass every 256 steps (NOT the reference's schedule)"
                                 if incremental else "recomputed every step, as the reference does"),
@@ -303,7 +304,8 @@ def reference_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(t_all)) * 1e3 if t_all else None,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 expected contacts, f64 log-likelihood accumulation",
             "data": "synthetic",
-            "config": make_config(name, inp.n_frags, inp.init_n_sub_frags, E, k_nb, n_contigs, 1, 1, args.exchange_every),
+            "config": make_config(name, inp.n_frags, inp.init_n_sub_frags, E, k_nb, n_contigs, max(1, args.chains_per_gpu),
+                                  int(os.environ.get("WORLD_SIZE", "1")), args.exchange_every),
             "steps_measured": len(vals),
             "cpu_baseline": {"value": v, "unit": "evals/s", "cores": workers, "kind": "port",
                              "sample": "per step: the 13 candidate deltas of each of the %d proposals AND the full likelihood of the current state "
@@ -528,6 +530,12 @@ def main():
                 nb = gc.return_neighbours(fA, k_nb); nb.sort()
                 schedules[ch].append((fA, nb, nb[0] if nb else fA, 6 if nb else -1))
 
+    if world > 1:
+        # the resident replay measures the machine, not the luck of a chain: every rank replays RANK 0's recorded schedule
+        # (same proposals, same committed moves: identical work per GPU); the end-to-end pass above ran the ranks' own chains
+        box = [schedules]
+        dist.broadcast_object_list(box, src=0)
+        schedules = box[0]
     # ---------------- pass 2: device resident replay (no host round trip inside the timed region) ------
     def replay(profile=False):
         for gc in chains:

@@ -2225,6 +2225,7 @@ struct Lane {
     int4* cand_ordrec = nullptr; int4* base_ordrec = nullptr;   // [13][n] / [n] position-ordered bin records A of U
     int4* cand_ordb = nullptr; int4* base_ordb = nullptr; int4* base_ordc = nullptr;   // records B (mid-points) and C (masks)
     double* partials = nullptr;              // [48][partial_stride]: contacts rows 0..12, candidate band 16..28, base band 32..44
+    double* dist_partials = nullptr;         // [13][partial_stride]: genome distance of the candidates
     unsigned char* rep_in_u = nullptr;       // [N]
     int2* uwin = nullptr;                    // [W] union window of the bins of U (first sub-frag of the bin)
     int2* cand_blk = nullptr;                // [13][n / 32 + 1] block hulls of the candidate orders
@@ -2237,7 +2238,7 @@ struct ProposalGraph {
     cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
     cudaGraphNode_t n_build = nullptr, n_setup = nullptr;
     cudaKernelNodeParams kp_build{}, kp_setup{};
-    int base_slot = -1, first_cand = -1; double* d_out = nullptr; unsigned skip = 0u; long long version = -1; cudaStream_t st = nullptr;
+    int base_slot = -1, first_cand = -1; double* d_out = nullptr; double* d_dist = nullptr; unsigned skip = 0u; long long version = -1; cudaStream_t st = nullptr;
     int n_launches = 0;
     void reset() {
         if (exec) cudaGraphExecDestroy(exec);
@@ -2531,6 +2532,7 @@ int graal_ctx_create(int device, graal_ctx** out) {
         CUDA_OK(cudaMalloc(&L.ints, 256 * sizeof(int)));
         CUDA_OK(cudaMemset(L.ints, 0, 256 * sizeof(int)));
         CUDA_OK(cudaMalloc(&L.partials, (size_t)48 * c->partial_stride * sizeof(double)));
+        CUDA_OK(cudaMalloc(&L.dist_partials, (size_t)GRAAL_N_CANDIDATES * c->partial_stride * sizeof(double)));
     }
     *out = c;
     return 0;
@@ -2569,7 +2571,7 @@ void graal_ctx_destroy(graal_ctx* c) {
     free_level_scratch(c);
     for (int l = 0; l < GRAAL_MAX_LANES; l++) {
         Lane& L = c->lanes[l];
-        cudaFree(L.ints); cudaFree(L.partials);
+        cudaFree(L.ints); cudaFree(L.partials); cudaFree(L.dist_partials);
         if (L.done) cudaEventDestroy(L.done);
         if (L.ev_ready) cudaEventDestroy(L.ev_ready);
         for (int i = 0; i < 2; i++) { if (L.ev_side[i]) cudaEventDestroy(L.ev_side[i]); if (L.side[i]) cudaStreamDestroy(L.side[i]); }
@@ -3221,8 +3223,12 @@ static bool delta_uni_ok(const graal_ctx* c) {
     return c->delta_uni && c->p.nd == 1 && c->n_rep == 0 && c->n_quirky == 0 && c->E > 0 && c->p.d_max > 0.0f;
 }
 // the base slot's geometry (and, for the windowed delta pass, its row windows) must be current before this runs on `st`
+// genome distance of the 13 candidates of a proposal (graal_dist_candidates), queued on a side stream of the lane beside the
+// delta passes (it only needs the candidate slots) instead of behind them
+struct DistArgs { const int32_t* init_prev = nullptr; const int32_t* init_next = nullptr; const int32_t* init_orientable = nullptr;
+                  const uint8_t* skip = nullptr; double* d_out = nullptr; };
 static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_slot, int first_cand_slot, int n_cand, int id_fA, int id_fB, int max_id,
-                            unsigned skip, double* d_out, double* d_band, int copy_to = 0, unsigned pair_mask = 0u) {
+                            unsigned skip, double* d_out, double* d_band, int copy_to = 0, unsigned pair_mask = 0u, const DistArgs* dist = nullptr) {
     const int n = c->n_new, ld = c->ld;
     const Params p = c->p;
     const bool uni = delta_uni_ok(c) && windows_current(c, base_slot, p.d_max);
@@ -3261,6 +3267,12 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
         CUDA_OK(cudaEventRecord(L.ev_ready, st));
         CUDA_OK(cudaStreamWaitEvent(s_cand, L.ev_ready, 0));
         CUDA_OK(cudaStreamWaitEvent(s_base, L.ev_ready, 0));
+    }
+    if (dist && dist->d_out) {      // on the stream of the (short) base band pass
+        const int gd = std::min(ps, std::max(1, nblk(n, 256)));
+        k_dist_genome<<<dim3(gd, n_cand), 256, 0, s_base>>>(cand0, slot_stride(c), ld, n, dist->init_prev, dist->init_next, dist->init_orientable, dist->skip,
+                                                           L.dist_partials, ps); CHECK_LAUNCH(c);
+        k_reduce_partials<<<n_cand, 256, 0, s_base>>>(L.dist_partials, gd, ps, 1.0, dist->d_out, 0); CHECK_LAUNCH(c);
     }
     // contacts: sum over changed contacts of ob * (ln ex_k - ln ex_0): new terms per candidate, old terms once
     c->prof.begin(GRAAL_K_DELTA_CONTACTS, st);
@@ -3341,7 +3353,7 @@ int graal_delta_loglik(graal_ctx* c, int base_slot, int first_cand_slot, int n_c
     return delta_loglik_impl(c, c->lanes[0], c->stream, base_slot, first_cand_slot, n_cand, id_fA, id_fB, max_id, 0u, d_out, c->d_scalars + 16);
 }
 
-int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int id_fA, int id_fB, int max_id, int proposal_index, double* d_out) {
+static int score_proposal_impl(graal_ctx* c, int base_slot, int first_cand_slot, int id_fA, int id_fB, int max_id, int proposal_index, double* d_out, const DistArgs* dist) {
     if (!c || !c->slots) return set_err(-1, "state not bound");
     CUDA_OK(cudaSetDevice(c->device));
     if (proposal_index < 0 || proposal_index >= 16) return set_err(-1, "proposal index must be 0..15");
@@ -3386,13 +3398,13 @@ int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int i
         CHECK_LAUNCH(c);
         c->prof.end(GRAAL_K_BUILD, st);
         return delta_loglik_impl(c, L, st, base_slot, first_cand_slot, GRAAL_N_CANDIDATES, id_fA, id_fB, max_id, skip, d_out, d_band, skip ? 8 : 0,
-                                 c->pairing ? PAIR_MASK : 0u);
+                                 c->pairing ? PAIR_MASK : 0u, dist);
     };
     ProposalGraph& G = c->graphs[proposal_index];
     if (!c->use_graphs || c->prof.on) { rc = enqueue(); if (rc) return rc; }
     else {
         const bool hit = G.exec && G.version == c->version && G.base_slot == base_slot && G.first_cand == first_cand_slot &&
-                         G.d_out == d_out && G.skip == skip && G.st == st;
+                         G.d_out == d_out && G.skip == skip && G.st == st && G.d_dist == (dist ? dist->d_out : nullptr);
         if (!hit) {                                             // capture the sequence for this proposal index
             G.reset();
             const int64_t before = c->launches;
@@ -3419,6 +3431,7 @@ int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int i
             if (!G.n_build || !G.n_setup) { G.reset(); return set_err(-2, "proposal graph: parameter nodes not found"); }
             CUDA_OK(cudaGraphInstantiate(&G.exec, graph, 0));
             G.version = c->version; G.base_slot = base_slot; G.first_cand = first_cand_slot; G.d_out = d_out; G.skip = skip; G.st = st;
+            G.d_dist = dist ? dist->d_out : nullptr;
         } else {                                                // same sequence, new (id_fA, id_fB, max_id)
             const int* a_src = slot_ptr(c, base_slot); int* a_dst = slot_ptr(c, first_cand_slot); size_t a_stride = slot_stride(c);
             int a_ld = c->ld, a_n = n, a_fA = id_fA, a_fB = id_fB, a_max = max_id; const int* a_dmax = c->d_ints + 0; unsigned a_mask = 0x1FFFu;
@@ -3440,8 +3453,9 @@ int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int i
     return 0;
 }
 
-int graal_dist_candidates(graal_ctx* c, int first_cand_slot, int n_cand, int proposal_index, const int32_t* init_prev, const int32_t* init_next,
-                          const int32_t* init_orientable, const uint8_t* skip, double* d_out);
+int graal_score_proposal(graal_ctx* c, int base_slot, int first_cand_slot, int id_fA, int id_fB, int max_id, int proposal_index, double* d_out) {
+    return score_proposal_impl(c, base_slot, first_cand_slot, id_fA, id_fB, max_id, proposal_index, d_out, nullptr);
+}
 
 int graal_score_step(graal_ctx* c, int base_slot, int first_cand_slot, int id_fA, const int32_t* id_fB, int n_proposals, int max_id,
                      double* d_out, const int32_t* init_prev, const int32_t* init_next, const int32_t* init_orientable,
@@ -3452,11 +3466,14 @@ int graal_score_step(graal_ctx* c, int base_slot, int first_cand_slot, int id_fA
     const bool per_lane = first_cand_slot + GRAAL_N_CANDIDATES * c->n_lanes <= c->n_slots;
     for (int x = 0; x < n_proposals; x++) {
         const int first = first_cand_slot + (per_lane ? GRAAL_N_CANDIDATES * (x % c->n_lanes) : 0);
-        int rc = graal_score_proposal(c, base_slot, first, id_fA, id_fB[x], max_id, x, d_out + (size_t)GRAAL_N_CANDIDATES * x); if (rc) return rc;
+        DistArgs da;
         if (d_dist) {
-            rc = graal_dist_candidates(c, first, GRAAL_N_CANDIDATES, x, init_prev, init_next, init_orientable, skip, d_dist + (size_t)GRAAL_N_CANDIDATES * x);
-            if (rc) return rc;
+            if (!init_prev || !init_next || !init_orientable || !skip) return set_err(-1, "null argument");
+            da.init_prev = init_prev; da.init_next = init_next; da.init_orientable = init_orientable; da.skip = skip;
+            da.d_out = d_dist + (size_t)GRAAL_N_CANDIDATES * x;
         }
+        // (the genome distance of the candidates rides on a side stream of the proposal's lane, inside its captured graph)
+        int rc = score_proposal_impl(c, base_slot, first, id_fA, id_fB[x], max_id, x, d_out + (size_t)GRAAL_N_CANDIDATES * x, d_dist ? &da : nullptr); if (rc) return rc;
     }
     return 0;
 }
