@@ -1600,7 +1600,7 @@ __global__ void __launch_bounds__(256, 3)
 k_band_delta_fast(const int4* __restrict__ rec_a0, const int4* __restrict__ rec_b0, const int4* __restrict__ rec_c, int order_stride,
                   const int* __restrict__ d_count, const int* __restrict__ rng0,
                   const Geo* __restrict__ geo0, size_t cand_geo_stride, unsigned skip_cands, const FastBand fb,
-                  const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride) {
+                  const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride, int max_parts) {
     __shared__ double sacc[BASE ? GRAAL_N_CANDIDATES : 1][BASE ? 256 : 1];
     const int k = blockIdx.y;
     const int count = *d_count;
@@ -1621,8 +1621,12 @@ k_band_delta_fast(const int4* __restrict__ rec_a0, const int4* __restrict__ rec_
         for (int c = 0; c < GRAAL_N_CANDIDATES; c++) sacc[c][threadIdx.x] = 0.0;
     }
     const bool idle = (!BASE && ((skip_cands >> k) & 1u)) || hi < 0;
-    if (!idle) for (int wx = warp; wx / PARTS <= hi && wx / PARTS < count; wx += n_warps) {
-        const int ix = wx / PARTS, part = wx % PARTS;
+    // a short U leaves most warps without a bin and the others with a chain of dependent trips along the band of theirs:
+    // the band of every x is cut over `parts` warps (a power of two >= PARTS) until every warp has work
+    int parts = PARTS;
+    if (max_parts > PARTS) { const int nx_ = min(hi + 1, count); while (parts < max_parts && nx_ * parts * 2 <= n_warps) parts <<= 1; }
+    if (!idle) for (int wx = warp; wx / parts <= hi && wx / parts < count; wx += n_warps) {
+        const int ix = wx / parts, part = wx - ix * parts;
         const int4 rx = rec_a[ix];
         const int nx = (rx.x >> 28) & 7;
         if (nx == 0) continue;                                   // duplicated bin: repeat path
@@ -1651,12 +1655,12 @@ k_band_delta_fast(const int4* __restrict__ rec_a0, const int4* __restrict__ rec_
         const int4 zero4 = make_int4(0, 0, 0, 0);
         int iy0 = y0 + 32 * part + lane;
         int4 ry_n = iy0 < y1 ? rec_a[iy0] : zero4, yb_n = iy0 < y1 ? rec_b[iy0] : zero4, yc_n = (BASE && iy0 < y1) ? rec_c[iy0] : zero4;
-        for (int basei = y0 + 32 * part; basei < y1; basei += 32 * PARTS) {
+        for (int basei = y0 + 32 * part; basei < y1; basei += 32 * parts) {
             const int iy = basei + lane;
             bool live = iy < y1;
             const int4 ry = ry_n, yb = yb_n, yc4 = yc_n;
             {
-                const int in = iy + 32 * PARTS;
+                const int in = iy + 32 * parts;
                 ry_n = in < y1 ? rec_a[in] : zero4; yb_n = in < y1 ? rec_b[in] : zero4;
                 if (BASE) yc_n = in < y1 ? rec_c[in] : zero4;
             }
@@ -1766,30 +1770,45 @@ __device__ __forceinline__ double contact_rel_term(const Geo& a, const Geo& b, f
 }
 
 #define DC_UNROLL 2
-template <bool UNI>
-__global__ void __launch_bounds__(256)
+#define DC_MAX_SPLIT 8
+// MINB > 2: the 13 accumulators of a thread live in shared memory (26 KB per CTA) and the register budget is 64K / (256 MINB)
+template <bool UNI, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restrict__ contacts, LevelView lv,
                       const int* __restrict__ sub_index, const int* __restrict__ meta,
                       const Geo* __restrict__ geo_base, const Geo* __restrict__ geo_cand0, size_t geo_stride,
                       const unsigned* __restrict__ chmask, const unsigned* __restrict__ chmask2, unsigned pair_mask,
                       const __grid_constant__ Params p, double* __restrict__ partials, int partial_stride, const int2* __restrict__ uwin,
-                      const FastLaw fl, double lg) {
+                      const FastLaw fl, double lg, int max_split) {
     const int m = meta[4], cA = meta[0], cB = meta[1];
     if (meta[6]) uwin = nullptr;                               // degenerate proposal (fA == fB): the candidate orders are not trusted
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    double accs[GRAAL_N_CANDIDATES];
+    constexpr bool SACC = MINB > 2;
+    __shared__ double sacc[SACC ? GRAAL_N_CANDIDATES : 1][SACC ? 256 : 1];
+    double accs[SACC ? 1 : GRAAL_N_CANDIDATES];
     #pragma unroll
-    for (int c = 0; c < GRAAL_N_CANDIDATES; c++) accs[c] = 0.0;
-    for (int w = warp; w < 3 * m; w += n_warps) {
-        const int u = w / 3, a = w - 3 * u;
+    for (int c = 0; c < GRAAL_N_CANDIDATES; c++) { if (SACC) sacc[SACC ? c : 0][SACC ? threadIdx.x : 0] = 0.0; else accs[SACC ? 0 : c] = 0.0; }
+    // a short U leaves most warps without a row and the others with a chain of dependent trips over theirs: the rows are
+    // cut into S slices (a power of two, whole trips each) until every warp has work or a slice is one trip
+    int S = 1;
+    while (S < max_split && 3 * m * S * 2 <= n_warps) S <<= 1;
+    for (int w = warp; w < 3 * m * S; w += n_warps) {
+        const int row = w / S, slice = w - row * S;
+        const int u = row / 3, a = row - 3 * u;
         const int bin = sub_index[u];
         if (!eligible(lv, bin)) continue;                     // duplicated bin: repeat path
         const int4 sid = lv.sub_id[bin];
         if (a >= sid.w) continue;
         const int sub0 = sid.x, rowsub = sid.x + a;
-        const long long e0 = __ldg(&rowptr[rowsub]), e1 = __ldg(&rowptr[rowsub + 1]);
+        long long e0 = __ldg(&rowptr[rowsub]), e1 = __ldg(&rowptr[rowsub + 1]);
+        if (S > 1) {
+            const long long per = (((e1 - e0 + S - 1) / S) + 32 * DC_UNROLL - 1) / (32 * DC_UNROLL) * (32 * DC_UNROLL);
+            e0 += slice * per;
+            e1 = min(e1, e0 + per);
+            if (e0 >= e1) continue;
+        }
         const Geo r0 = ld_geo(&geo_base[rowsub]);
         const unsigned mra = __ldg(&chmask[rowsub]);
         const unsigned mra2 = pair_mask ? (__ldg(&chmask2[rowsub]) & pair_mask) : 0u;   // row differs between a paired candidate and its partner
@@ -1832,7 +1851,8 @@ k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restri
                     if (!((mm >> k) & 1u)) continue;
                     const Geo rk = ((mra >> k) & 1u) ? ld_geo(&geo_cand0[(size_t)k * geo_stride + rowsub]) : r0;
                     Geo gc = g0c; gc.mid = __int_as_float(pr[k].x); gc.id_c = pr[k].y;
-                    accs[k] += (UNI ? contact_rel_term(rk, gc, ob, fl, p, lg) : contact_log_term(rk, gc, ob, p)) - told;
+                    const double dv = (UNI ? contact_rel_term(rk, gc, ob, fl, p, lg) : contact_log_term(rk, gc, ob, p)) - told;
+                    if (SACC) sacc[SACC ? k : 0][SACC ? threadIdx.x : 0] += dv; else accs[SACC ? 0 : k] += dv;
                 }
                 if (mm2) {                                                   // rare: the few records in which a pair differs
                     #pragma unroll
@@ -1847,7 +1867,7 @@ k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restri
                             if ((mc[j] >> kk) & 1u) { const Geo q = ld_geo(&geo_cand0[(size_t)kk * geo_stride + ce[j].x]); gc.mid = q.mid; gc.id_c = q.id_c; }
                             t[w2] = UNI ? contact_rel_term(rk, gc, ob, fl, p, lg) : contact_log_term(rk, gc, ob, p);
                         }
-                        accs[k] += t[0] - t[1];
+                        if (SACC) sacc[SACC ? k : 0][SACC ? threadIdx.x : 0] += t[0] - t[1]; else accs[SACC ? 0 : k] += t[0] - t[1];
                     }
                 }
             }
@@ -1855,7 +1875,7 @@ k_delta_contacts_rows(const long long* __restrict__ rowptr, const int2* __restri
     }
     #pragma unroll
     for (int c = 0; c < GRAAL_N_CANDIDATES; c++) {
-        const double v = block_sum(accs[c]);
+        const double v = block_sum(SACC ? sacc[SACC ? c : 0][SACC ? threadIdx.x : 0] : accs[SACC ? 0 : c]);
         if (threadIdx.x == 0) partials[(size_t)c * partial_stride + blockIdx.x] = v;
     }
 }
@@ -2295,6 +2315,9 @@ struct graal_ctx {
     // windowed contact pass: static row items, per-pass order-space arrays and row records
     int4* items = nullptr; int n_items = 0; int4* row_hdr = nullptr; int4* item_hdr = nullptr;
     int* o_start = nullptr; int2* o_sub = nullptr; int* o_cid = nullptr; int2* o_blk = nullptr;
+    int band_split = 1;                       // GRAAL_BAND_SPLIT=1..32: most warps the band of one bin of a short U is cut over in the fast band delta kernels
+    int delta_minb = 2;                       // GRAAL_DELTA_MINB=2|3|4: resident CTAs per SM the delta contact pass is compiled for (3, 4: accumulators in shared memory)
+    int delta_split = DC_MAX_SPLIT;           // GRAAL_DELTA_SPLIT=1|2|4|8: most slices a row of a short U is cut into in the delta contact pass
     int delta_rel = 1;                        // GRAAL_DELTA_REL=0: absolute contact terms in the delta contact pass on every level (A/B runs)
     int band_fast = 1;                        // GRAAL_BAND_FAST=0: general band delta kernels on every level (A/B runs)
     int delta_uni = 0;                        // GRAAL_DELTA_UNI=1: union windows in the delta contact pass (measured: no gain -- the pass is bound by the evaluation of the in-band entries)
@@ -2515,6 +2538,9 @@ int graal_ctx_create(int device, graal_ctx** out) {
     { const char* e = getenv("GRAAL_DELTA_UNI"); if (e) c->delta_uni = e[0] == '1'; }
     { const char* e = getenv("GRAAL_BAND_FAST"); if (e && e[0] == '0') c->band_fast = 0; }
     { const char* e = getenv("GRAAL_DELTA_REL"); if (e && e[0] == '0') c->delta_rel = 0; }
+    { const char* e = getenv("GRAAL_BAND_SPLIT"); if (e && atoi(e) >= 1 && atoi(e) <= 32) c->band_split = atoi(e); }
+    { const char* e = getenv("GRAAL_DELTA_MINB"); if (e && atoi(e) >= 2 && atoi(e) <= 4) c->delta_minb = atoi(e); }
+    { const char* e = getenv("GRAAL_DELTA_SPLIT"); if (e && atoi(e) >= 1 && atoi(e) <= 32) c->delta_split = atoi(e); }
     { const char* e = getenv("GRAAL_WIN_UNROLL"); if (e && (e[0] == '2' || e[0] == '4' || e[0] == '8')) c->win_unroll = e[0] - '0'; }
     { const char* e = getenv("GRAAL_WIN_MINB"); if (e && e[0] >= '2' && e[0] <= '6') c->win_minb = e[0] - '0'; }
     { const char* e = getenv("GRAAL_WIN_SUB"); if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4' || e[0] == '8')) { c->win_sub = e[0] - '0'; c->win_tuned = true; } }
@@ -3255,7 +3281,7 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
         k_cand_windows<<<dim3(gu, n_cand), 256, 0, st>>>(L.cand_ordrec, n, meta, piece_len, L.cand_blk, nblk32, skip, reach, L.uwin); CHECK_LAUNCH(c);
     }
     // grid-stride kernels over the (device-side) size of U: a few CTAs per SM, not one warp per bin of the level
-    const int gw = std::min(ps, std::max(1, std::min(nblk(n, 1), c->n_sm * 2)));      // one resident wave (128 registers: 2 CTAs per SM)
+    const int gw = std::min(ps, std::max(1, std::min(nblk(n, 1), c->n_sm * c->delta_minb)));      // one resident wave (128 registers: 2 CTAs per SM)
     // (band: 2 CTAs per SM and one warp per x measured best with three proposals in flight: small grids share the SMs)
     const int gb = std::min(ps, std::max(1, std::min(nblk(n, 4), c->n_sm * 2)));
     double* p_contacts = L.partials, *p_cand = L.partials + (size_t)16 * ps, *p_base = L.partials + (size_t)32 * ps;
@@ -3278,13 +3304,12 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
     c->prof.begin(GRAAL_K_DELTA_CONTACTS, st);
     FastLaw flc; flc.tab = p.t_lnfu; flc.smin_bits = LAW_SMIN_BITS; flc.span = p.fu_span; flc.zlo = p.fu_zlo; flc.zspan = p.fu_zspan;
     const bool rel = c->delta_rel && p.nd == 1 && p.mode == 2 && p.fu_ok && c->n_rep == 0;       // relative contact terms (uniform level, tabulated monotone law)
-    if (rel) {
-        const double lg = log((double)g_clamp(c->accu_hist[0].first * c->accu_hist[0].first, p.v_inter, p.nfpb));
-        k_delta_contacts_rows<true><<<dim3(gw, 1), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, L.sub_index, meta, c->geo_base, L.geo_cand, (size_t)c->W,
-                                                                L.chmask, L.chmask2, pair_mask, p, p_contacts, ps, uni ? L.uwin : nullptr, flc, lg);
-    } else
-        k_delta_contacts_rows<false><<<dim3(gw, 1), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, L.sub_index, meta, c->geo_base, L.geo_cand, (size_t)c->W,
-                                                                 L.chmask, L.chmask2, pair_mask, p, p_contacts, ps, uni ? L.uwin : nullptr, flc, 0.0);
+    const double lg = rel ? log((double)g_clamp(c->accu_hist[0].first * c->accu_hist[0].first, p.v_inter, p.nfpb)) : 0.0;
+#define DC_LAUNCH(U_, B_) k_delta_contacts_rows<U_, B_><<<dim3(gw, 1), 256, 0, st>>>(c->rowptr, c->contacts, c->lv, L.sub_index, meta, c->geo_base, L.geo_cand, (size_t)c->W, \
+                                                                L.chmask, L.chmask2, pair_mask, p, p_contacts, ps, uni ? L.uwin : nullptr, flc, lg, c->delta_split)
+    if (rel) { if (c->delta_minb == 4) DC_LAUNCH(true, 4); else if (c->delta_minb == 3) DC_LAUNCH(true, 3); else DC_LAUNCH(true, 2); }
+    else     { if (c->delta_minb == 4) DC_LAUNCH(false, 4); else if (c->delta_minb == 3) DC_LAUNCH(false, 3); else DC_LAUNCH(false, 2); }
+#undef DC_LAUNCH
     CHECK_LAUNCH(c);
     c->prof.end(GRAAL_K_DELTA_CONTACTS, st);
     // band mass: d_band[k] = B_U(S_k) - B_U(S_0) over changed pairs; enters the delta with a minus sign
@@ -3293,14 +3318,14 @@ static int delta_loglik_impl(graal_ctx* c, Lane& L, cudaStream_t st, int base_sl
     FastBand fbd; fbd.tab = p.t_fu; fbd.smin_bits = LAW_SMIN_BITS; fbd.span = p.fu_span; fbd.zlo = p.fu_zlo; fbd.zspan = p.fu_zspan;
     { union { float f; unsigned u; } dm; dm.f = p.d_max; fbd.dmax_bits = dm.u; }
     if (fast_band) k_band_delta_fast<false, 1><<<dim3(gb, n_rows), 256, 0, s_cand>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, fbd, p,
-                                                                              p_cand, ps);
+                                                                              p_cand, ps, c->band_split);
     else if (p.nd == 1) k_band_delta<false, 1, true><<<dim3(gb, n_rows), 256, 0, s_cand>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
                                                                               p_cand, ps);
     else k_band_delta<false, 1, false><<<dim3(gb, n_rows), 256, 0, s_cand>>>(L.cand_ordrec, L.cand_ordb, nullptr, n, meta + 4, rng + 2, L.geo_cand, (size_t)c->W, skip, p,
                                                                      p_cand, ps);
     CHECK_LAUNCH(c);
     if (fast_band) k_band_delta_fast<true, 4><<<dim3(gb, 1), 256, 0, s_base>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, fbd, p,
-                                                                        p_base, ps);
+                                                                        p_base, ps, c->band_split);
     else if (p.nd == 1) k_band_delta<true, 4, true><<<dim3(gb, 1), 256, 0, s_base>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,
                                                                         p_base, ps);
     else k_band_delta<true, 4, false><<<dim3(gb, 1), 256, 0, s_base>>>(L.base_ordrec, L.base_ordb, L.base_ordc, n, meta + 4, rng, c->geo_base, 0, skip, p,

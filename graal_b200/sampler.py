@@ -11,7 +11,8 @@ eval_likelihood :543-631, setup_texture :637-665, test_copy_struct :1156-1183,
 setup_rippe_parameters :1203-1214, estimate_parameters :1229-1294, explode_genome :1539-1557,
 apply_replay_simu :1559-1578, modify_gl_cuda_buffer :1695-1788, step_max_likelihood :1793-1980,
 step_nuisance_parameters :2022-2107, return_neighbours :2295-2331, setup_distri_frags :2363-2390,
-stream_likelihood :2392-2546, temperature :2590-2603, free_gpu :2605-2613.
+stream_likelihood :2392-2546, temperature :2590-2603, free_gpu :2605-2613.  The MH / MTM steps are in mh.py, the remaining
+entry points of the class (per-mode builders, validation step, older proposal rule, scramblers, local_flip) in variants.py.
 """
 import ctypes as C
 import os
@@ -23,6 +24,7 @@ from ._lib import GraalError, check
 from . import rippe as opti
 from .level import FRAG_FIELDS
 from .mh import MetropolisMixin
+from .variants import VariantsMixin
 
 F32, I32 = np.float32, np.int32
 N_TMP_STRUCT = 13
@@ -191,7 +193,7 @@ def dist_inter_genome(prev, next_, ori, id_d, init_prev, init_next, init_ori, in
     return float(d.sum()) / norm_distance if norm_distance != 0 else 0.0
 
 
-class sampler(MetropolisMixin):
+class sampler(MetropolisMixin, VariantsMixin):
     def __init__(self, use_rippe, S_o_A_frags, collector_id_repeats, frag_dispatcher,
                  id_frag_duplicated, id_frags_blacklisted,
                  n_frags, n_new_frags, init_n_sub_frags, n_new_sub_frags, np_rep_sub_frags_id,
@@ -774,6 +776,7 @@ class sampler(MetropolisMixin):
             new_d_max = opti.estimate_max_dist_intra([kuhn, lm, slope, d, fact], new_d_nuc)
             out_test_param = [(kuhn, lm, c1f(slope), slope, d, new_d_max, fact, new_d_nuc)]
         out_test_param = np.array(out_test_param, dtype=PARAM_DTYPE)
+        self.param_simu_test = out_test_param                 # (gpu_param_simu_test, cuda_lib_gl.py:2088)
         test_likelihood = self.eval_likelihood(out_test_param)
         F_t = self.temperature(t, n_step)
         with np.errstate(over="ignore"):

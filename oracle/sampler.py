@@ -22,6 +22,7 @@ from scipy.optimize import leastsq, fsolve
 
 from . import mutations as M
 from . import likelihood as L
+from .variants import OracleVariants
 
 F32 = np.float32
 I32 = np.int32
@@ -100,7 +101,7 @@ def distance_histogram(sub_soa, hic_matrix, max_dist_kb, size_bin_kb):
 
 
 # ---------------------------------------------------------------- the sampler
-class OracleSampler:
+class OracleSampler(OracleVariants):
     N_TMP = 13
 
     def __init__(self, inp, rng, hic_matrix=None, hic_matrix_sub_sampled=None):
