@@ -55,12 +55,18 @@ struct Params { float kuhn, lm, c1, slope, d, d_max, fact, v_inter, nfpb; int nd
                 // float bit patterns [LAW_SMIN_BITS, LAW_SMIN_BITS + fu_span) it is valid on (below d_max, inside the table,
                 // above the clamp) and the in-band zone beyond the table [fu_zlo, fu_zlo + fu_zspan); fu_ok = 0: not available
                 const int4* t_lnfu; unsigned fu_span, fu_zlo, fu_zspan; int fu_ok;
+                // the same relative law on LAW7_OCT octaves below the end of the fast range, 2^LAW7_M intervals per octave
+                // (32 KB: staged in shared memory by the windowed full pass); fu7_smin = bit pattern of its first distance
+                const int4* t_lnfu7; unsigned fu7_smin, fu7_span;
                 const int4* t_fu;     // same levels: f(s) * norm - g per interval (band excess of an in-band pair)
                 };
 #define LAW_M 9
 #define LAW_EMIN (-12)
 #define LAW_EMAX 11
 #define LAW_NODES (((LAW_EMAX) - (LAW_EMIN)) << LAW_M)
+#define LAW7_M 7
+#define LAW7_OCT 16
+#define LAW7_NODES (LAW7_OCT << LAW7_M)
 
 // per-sub-frag geometry record of one slot (16 B, one 128-bit load):
 //   mid  : mid-point in kb (float32, reference op order kernels3.cu:2997-3060)
@@ -1016,7 +1022,9 @@ __device__ __noinline__ double win_circular_item(const int2* __restrict__ cp, in
 // UN: stream loads in flight per warp (32 entries each); SUB: the exact path runs on groups of SUB loads behind ONE
 // uniform branch, straight-line inside -- the SUB partner gathers, then the SUB table gathers are in flight together
 // (a branch per load would serialise the two dependent gathers of every load).
-template <int UN, int MINB, int SUB>
+// TM: mantissa bits of the law table index.  LAW_M: the global table (L1 / L2 gathers); LAW7_M: the coarse table, staged
+// in shared memory by every CTA (the table gather leaves the global load path; |error| of ln f <= 1e-8, oscillating)
+template <int UN, int MINB, int SUB, int TM = LAW_M>
 __global__ void __launch_bounds__(256, MINB)
 k_full_contacts_win(const int4* __restrict__ items, const int4* __restrict__ ihdr, int n_items, const int2* __restrict__ contacts,
                     const int2* __restrict__ cm, const int* __restrict__ bad, int W,
@@ -1025,6 +1033,12 @@ k_full_contacts_win(const int4* __restrict__ items, const int4* __restrict__ ihd
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const bool all_w = *bad != 0;                                   // inconsistent position order: every window is the whole level
+    constexpr bool STAB = TM != LAW_M;
+    __shared__ int4 stab[STAB ? LAW7_NODES : 1];
+    if (STAB) {
+        for (int k = threadIdx.x; k < LAW7_NODES; k += blockDim.x) stab[STAB ? k : 0] = __ldg(&fl.tab[k]);
+        __syncthreads();
+    }
     const int4* __restrict__ tab = fl.tab;
     const unsigned smin = fl.smin_bits, span = fl.span, zlo = fl.zlo, zspan = fl.zspan;
     double accd = 0.0;
@@ -1064,14 +1078,14 @@ k_full_contacts_win(const int4* __restrict__ items, const int4* __restrict__ ihd
                         const unsigned t = bb[j] - smin;
                         const bool cis = pc[j].x == r_id;
                         const bool fast = cis && t < span;
-                        e[j] = __ldg(&tab[(fast ? t : 0u) >> (23 - LAW_M)]);
+                        e[j] = STAB ? stab[STAB ? ((fast ? t : 0u) >> (23 - TM)) : 0] : __ldg(&tab[(fast ? t : 0u) >> (23 - TM)]);
                         if (fast) fastm |= 1u << j;
                         else if (cis && ((bb[j] - 1u) < (smin - 1u) || (bb[j] - zlo) < zspan)) slow |= 1u << j;
                     }
                     float accf = 0.0f;
                     #pragma unroll
                     for (int j = 0; j < SUB; j++) {
-                        const float uu = __uint_as_float(0x3f800000u | ((bb[j] & ((1u << (23 - LAW_M)) - 1u)) << LAW_M));
+                        const float uu = __uint_as_float(0x3f800000u | ((bb[j] & ((1u << (23 - TM)) - 1u)) << TM));
                         const float ob = ((fastm >> j) & 1u) ? __int_as_float(ce[g * SUB + j].y) : 0.0f;
                         accd = fma((double)ob, __hiloint2double(e[j].y, e[j].x), accd);
                         accf = fmaf(ob, uu * fmaf(uu, __int_as_float(e[j].w), __int_as_float(e[j].z)), accf);
@@ -2302,8 +2316,8 @@ struct graal_ctx {
     unsigned char* d_accu_idx = nullptr;                // [N*3]
     float* d_tab_norm = nullptr; float* d_tab_g[2] = {nullptr, nullptr}; double* d_tab_logg[2] = {nullptr, nullptr};
     double* d_tab_lnnorm = nullptr; double2* d_tab_log = nullptr; double* d_tab_exp = nullptr;
-    int4* d_tab_lnf[2] = {nullptr, nullptr}; int4* d_tab_f[2] = {nullptr, nullptr}; int4* d_tab_lnfu[2] = {nullptr, nullptr}; int4* d_tab_fu[2] = {nullptr, nullptr}; double* d_tab_normd = nullptr;
-    std::vector<double> h_law;
+    int4* d_tab_lnf[2] = {nullptr, nullptr}; int4* d_tab_f[2] = {nullptr, nullptr}; int4* d_tab_lnfu[2] = {nullptr, nullptr}; int4* d_tab_lnfu7[2] = {nullptr, nullptr}; int4* d_tab_fu[2] = {nullptr, nullptr}; double* d_tab_normd = nullptr;
+    std::vector<double> h_law, h_law7;
     int math_mode = 2;
     std::vector<float> h_tab_g; std::vector<double> h_tab_logg;
     int* d_quirky = nullptr; int n_quirky = 0;
@@ -2325,6 +2339,7 @@ struct graal_ctx {
     int win_slot = -1; float win_dmax = 0.0f; long long geo_epoch = 0, win_epoch = -1;   // slot / d_max / geometry the row records (row_hdr) describe
     FixedGraph g_win;
     int full_win = 1;                         // GRAAL_FULL_WIN=0: gather-everything kernel (k_full_contacts_direct) for A/B runs
+    int win_stab = 0; bool win_stab_allowed = true;   // law table of the windowed full pass in shared memory (coarse copy); GRAAL_WIN_STAB=0: never, =1: always (no timing)
     bool win_tuned = false;                   // SUB picked by timing the variants on the bound level (first windowed pass)
     int win_unroll = 8, win_minb = 4, win_sub = 2;   // GRAAL_WIN_SUB=1|2|4|8: loads per exact-path group; GRAAL_WIN_UNROLL=2|4|8: stream loads in flight per warp; GRAAL_WIN_MINB=2..6: CTAs per SM
     int smem_cid = 0;                         // GRAAL_SMEM_CID=1: stage the contig-id table in shared memory (measured: no faster than L1, profiles/README.md)
@@ -2392,6 +2407,7 @@ static int upload_tables(graal_ctx* c, Params& p, int which) {
     // tabulated law: f(s) = c1*fact * s^slope * exp((d-2)/(x^2+d)), x = s*lm/kuhn, and ln f, with d/ds, float64
     p.t_lnf = c->d_tab_lnf[which]; p.t_f = c->d_tab_f[which]; p.t_normd = c->d_tab_normd; p.v_clamp = (double)p.v_inter;
     p.t_lnfu = c->d_tab_lnfu[which]; p.t_fu = c->d_tab_fu[which]; p.fu_ok = 0; p.fu_span = p.fu_zlo = p.fu_zspan = 0u;
+    p.t_lnfu7 = c->d_tab_lnfu7[which]; p.fu7_smin = 0u; p.fu7_span = 0u;
     if (p.mode == 2) {
         if (!(cf > 0.0) || !(p.kuhn > 0.0f) || !(p.lm > 0.0f)) p.mode = 1;      // degenerate parameters: analytic path
         else {
@@ -2453,6 +2469,26 @@ static int upload_tables(graal_ctx* c, Params& p, int which) {
                     Entry* e_u = reinterpret_cast<Entry*>(c->h_law.data() + 2 * half);
                     for (int i = 0; i < LAW_NODES; i++) { e_u[i] = e_ln[i]; e_u[i].a0 += cst; }
                     CUDA_OK(cudaMemcpyAsync(c->d_tab_lnfu[which], c->h_law.data() + 2 * half, half * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+                    // coarse copy for shared memory: the LAW7_OCT octaves that end where the fast range ends (shorter in-band
+                    // distances, if any, take the exact evaluation)
+                    if (p.fu_span > 0u) {
+                        const int e_top = (int)((b_hi - 1u) >> 23) - 127;                 // octave of the last fast distance
+                        const int e_lo7 = std::max(LAW_EMIN, std::min(e_top - LAW7_OCT + 1, LAW_EMAX - LAW7_OCT));
+                        c->h_law7.resize((size_t)LAW7_NODES * 2);
+                        Entry* e7 = reinterpret_cast<Entry*>(c->h_law7.data());
+                        for (int i = 0; i < LAW7_NODES; i++) {
+                            const int e = e_lo7 + (i >> LAW7_M);
+                            const double lo7 = ldexp(1.0 + (double)(i & ((1 << LAW7_M) - 1)) / (double)(1 << LAW7_M), e), h7 = ldexp(1.0, e - LAW7_M);
+                            double al[3] = {0, 0, 0};
+                            for (int j = 0; j < 3; j++) { const double v = lnf(lo7 + h7 * (un[j] - 1.0)); for (int k = 0; k < 3; k++) al[k] += v * w[j][k]; }
+                            e7[i].a0 = al[0] + cst; e7[i].a1 = (float)al[1]; e7[i].a2 = (float)al[2];
+                        }
+                        CUDA_OK(cudaMemcpyAsync(c->d_tab_lnfu7[which], c->h_law7.data(), (size_t)LAW7_NODES * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+                        p.fu7_smin = (unsigned)(127 + e_lo7) << 23;
+                        const unsigned b_top7 = (unsigned)(127 + e_lo7 + LAW7_OCT) << 23;
+                        const unsigned b_hi7 = std::min(b_hi, b_top7);
+                        p.fu7_span = b_hi7 > p.fu7_smin ? b_hi7 - p.fu7_smin : 0u;
+                    }
                     Entry* e_fu = reinterpret_cast<Entry*>(c->h_law.data() + 3 * half);
                     for (int i = 0; i < LAW_NODES; i++) {
                         e_fu[i].a0 = e_f[i].a0 * (double)tn - (double)g1;
@@ -2544,6 +2580,7 @@ int graal_ctx_create(int device, graal_ctx** out) {
     { const char* e = getenv("GRAAL_WIN_UNROLL"); if (e && (e[0] == '2' || e[0] == '4' || e[0] == '8')) c->win_unroll = e[0] - '0'; }
     { const char* e = getenv("GRAAL_WIN_MINB"); if (e && e[0] >= '2' && e[0] <= '6') c->win_minb = e[0] - '0'; }
     { const char* e = getenv("GRAAL_WIN_SUB"); if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4' || e[0] == '8')) { c->win_sub = e[0] - '0'; c->win_tuned = true; } }
+    { const char* e = getenv("GRAAL_WIN_STAB"); if (e && e[0] == '0') c->win_stab_allowed = false; if (e && e[0] == '1') { c->win_stab = 1; c->win_tuned = true; } }
     { const char* e = getenv("GRAAL_LANES"); if (e && e[0] >= '1' && e[0] <= '0' + GRAAL_MAX_LANES) c->n_lanes = e[0] - '0'; }
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     for (int l = 0; l < c->n_lanes; l++) {
@@ -2580,7 +2617,7 @@ static void free_level_scratch(graal_ctx* c) {
     cudaFree(c->d_dup); cudaFree(c->d_sub_dup); cudaFree(c->d_rep_bins);
     c->d_dup = c->d_sub_dup = nullptr; c->d_rep_bins = nullptr; c->n_rep = 0;
     cudaFree(c->d_tab_lnnorm); cudaFree(c->d_tab_log); cudaFree(c->d_tab_exp); cudaFree(c->d_tab_normd);
-    for (int w = 0; w < 2; w++) { cudaFree(c->d_tab_lnf[w]); cudaFree(c->d_tab_f[w]); cudaFree(c->d_tab_lnfu[w]); cudaFree(c->d_tab_fu[w]); c->d_tab_lnf[w] = nullptr; c->d_tab_f[w] = nullptr; c->d_tab_lnfu[w] = nullptr; c->d_tab_fu[w] = nullptr; }
+    for (int w = 0; w < 2; w++) { cudaFree(c->d_tab_lnf[w]); cudaFree(c->d_tab_f[w]); cudaFree(c->d_tab_lnfu[w]); cudaFree(c->d_tab_lnfu7[w]); c->d_tab_lnfu7[w] = nullptr; cudaFree(c->d_tab_fu[w]); c->d_tab_lnf[w] = nullptr; c->d_tab_f[w] = nullptr; c->d_tab_lnfu[w] = nullptr; c->d_tab_fu[w] = nullptr; }
     c->d_tab_normd = nullptr;
     c->d_tab_lnnorm = nullptr; c->d_tab_log = nullptr; c->d_tab_exp = nullptr;
     cudaFree(c->d_tab_norm); cudaFree(c->d_tab_g[0]); cudaFree(c->d_tab_g[1]); cudaFree(c->d_tab_logg[0]); cudaFree(c->d_tab_logg[1]);
@@ -2679,7 +2716,7 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     for (int i = 0; i < 16; i++) c->graphs[i].reset();
     c->g_stats.reset(); c->g_relabel.reset(); c->g_full.reset(); c->g_full_cached.reset(); c->g_win.reset();
     c->win_slot = -1; c->contig_bound = -1; c->ncontigs_pending = false; c->first_clean = false; c->stats_clean = false; c->g_prologue.reset();
-    { const char* e = getenv("GRAAL_WIN_SUB"); c->win_tuned = e != nullptr; }
+    { const char* e = getenv("GRAAL_WIN_SUB"); const char* e2 = getenv("GRAAL_WIN_STAB"); c->win_tuned = e != nullptr || (e2 && e2[0] == '1'); }
     free_level_scratch(c);
     c->N = n_frags; c->n_new = n_new_frags; c->W = n_sub_frags; c->E = n_contacts; c->nfpb = nfpb;
     c->lv.sub_id = reinterpret_cast<const int4*>(sub_id); c->lv.sub_len = sub_len_kb; c->lv.sub_accu = sub_accu;
@@ -2753,6 +2790,7 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
         for (int w = 0; w < 2; w++) {
             CUDA_OK(cudaMalloc(&c->d_tab_lnf[w], (size_t)(LAW_NODES + 2) * sizeof(int4)));
             CUDA_OK(cudaMalloc(&c->d_tab_lnfu[w], (size_t)(LAW_NODES + 2) * sizeof(int4)));
+            CUDA_OK(cudaMalloc(&c->d_tab_lnfu7[w], (size_t)LAW7_NODES * sizeof(int4)));
             CUDA_OK(cudaMalloc(&c->d_tab_fu[w], (size_t)(LAW_NODES + 2) * sizeof(int4)));
             CUDA_OK(cudaMalloc(&c->d_tab_f[w], (size_t)(LAW_NODES + 2) * sizeof(int4)));
         }
@@ -3145,13 +3183,26 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
     }
     if (c->n_quirky > ps) return set_err(-5, "too many quirky bins (%d > %d)", c->n_quirky, ps);
     if (use_win && g1 > 0) { rc = ensure_base_windows(c, slot, p.d_max); if (rc) return rc; }
+    auto win_variant = [&](int sub, int stab) -> win_fn {
+        if (stab) return (sub == 2) ? k_full_contacts_win<8, 4, 2, LAW7_M> : k_full_contacts_win<8, 4, 4, LAW7_M>;
+        return (sub == 2) ? k_full_contacts_win<8, 4, 2> : k_full_contacts_win<8, 4, 4>;
+    };
+    auto win_law = [&](int stab) {
+        FastLaw fl; fl.zlo = p.fu_zlo; fl.zspan = p.fu_zspan;
+        if (stab) { fl.tab = p.t_lnfu7; fl.smin_bits = p.fu7_smin; fl.span = p.fu7_span; }
+        else { fl.tab = p.t_lnfu; fl.smin_bits = LAW_SMIN_BITS; fl.span = p.fu_span; }
+        return fl;
+    };
+    const bool stab_ok = c->win_stab_allowed && p.fu7_span > 0u;
     if (use_win && g1 > 0 && !c->win_tuned && !p_override && c->win_unroll == 8 && c->win_minb == 4) {
-        // near-diagonal lists want 4 loads per exact-path group, lists dominated by far entries 2: time both once on this level
+        // near-diagonal lists want 4 loads per exact-path group, lists dominated by far entries 2; the law table from shared
+        // memory or through L1: the four combinations are timed once on this level
         cudaEvent_t e0, e1; CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
-        FastLaw fl; fl.tab = p.t_lnfu; fl.smin_bits = LAW_SMIN_BITS; fl.span = p.fu_span; fl.zlo = p.fu_zlo; fl.zspan = p.fu_zspan;
-        float best = 1e30f; int best_sub = c->win_sub;
+        float best = 1e30f; int best_sub = c->win_sub, best_stab = 0;
+        for (int stab = 0; stab <= (stab_ok ? 1 : 0); stab++)
         for (int sub = 2; sub <= 4; sub += 2) {
-            win_fn kf = (sub == 2) ? k_full_contacts_win<8, 4, 2> : k_full_contacts_win<8, 4, 4>;
+            win_fn kf = win_variant(sub, stab);
+            const FastLaw fl = win_law(stab);
             float ms = 1e30f;
             for (int rep = 0; rep < 3; rep++) {
                 CUDA_OK(cudaEventRecord(e0, st));
@@ -3162,12 +3213,29 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
                 float t = 0.f; CUDA_OK(cudaEventElapsedTime(&t, e0, e1));
                 if (rep > 0) ms = std::min(ms, t);
             }
-            if (ms < best) { best = ms; best_sub = sub; }
+            if (ms < (stab ? 0.97f * best : best)) { best = ms; best_sub = sub; best_stab = stab; }     // the coarse table only for a real gain (> 3 %)
         }
         cudaEventDestroy(e0); cudaEventDestroy(e1);
-        c->win_sub = best_sub; c->win_tuned = true;
-        k_win = (best_sub == 2) ? k_full_contacts_win<8, 4, 2> : k_full_contacts_win<8, 4, 4>;
+        c->win_sub = best_sub; c->win_stab = best_stab; c->win_tuned = true;
         c->g_full.reset(); c->g_full_cached.reset();
+    }
+    int use_stab = (c->win_stab && stab_ok && c->win_unroll == 8 && c->win_minb == 4 && (c->win_sub == 2 || c->win_sub == 4)) ? 1 : 0;
+    if (use_win && c->win_unroll == 8 && c->win_minb == 4 && (c->win_sub == 2 || c->win_sub == 4)) k_win = win_variant(c->win_sub, use_stab);
+    if (use_win && c->win_stab && stab_ok && !use_stab) {           // other shapes of the shared-memory variant (A/B runs through the environment)
+        switch (c->win_unroll * 100 + c->win_minb * 10 + c->win_sub) {
+            case 848: k_win = k_full_contacts_win<8, 4, 8, LAW7_M>; use_stab = 1; break;
+            case 834: k_win = k_full_contacts_win<8, 3, 4, LAW7_M>; use_stab = 1; break;
+            case 854: k_win = k_full_contacts_win<8, 5, 4, LAW7_M>; use_stab = 1; break;
+            case 864: k_win = k_full_contacts_win<8, 6, 4, LAW7_M>; use_stab = 1; break;
+            case 444: k_win = k_full_contacts_win<4, 4, 4, LAW7_M>; use_stab = 1; break;
+            case 464: k_win = k_full_contacts_win<4, 6, 4, LAW7_M>; use_stab = 1; break;
+            default: break;
+        }
+        if (use_stab) {
+            int fc_blocks = 0;
+            CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fc_blocks, k_win, 256, 0));
+            g1 = (int)std::min<long long>(std::min(ps, c->n_sm * std::max(1, fc_blocks)), ((long long)c->n_items + 7) / 8);
+        }
     }
     const bool cached = !p_override && c->band_slot == slot && c->band_age < GRAAL_BAND_RESYNC;
     auto enqueue = [&]() -> int {
@@ -3182,7 +3250,7 @@ int graal_full_loglik(graal_ctx* c, int slot, const float* p_override, double* d
         }
         if (use_win && g1 > 0) {
             int* bad = c->d_ints + 4;
-            FastLaw fl; fl.tab = p.t_lnfu; fl.smin_bits = LAW_SMIN_BITS; fl.span = p.fu_span; fl.zlo = p.fu_zlo; fl.zspan = p.fu_zspan;
+            const FastLaw fl = win_law(use_stab);
             c->prof.begin(GRAAL_K_FULL_CONTACTS, st);
             k_win<<<g1, 256, 0, st>>>(c->items, c->item_hdr, c->n_items, c->contacts, c->cm_base, bad, c->W, c->geo_base, fl, p, lg_uniform, c->partials);
             CHECK_LAUNCH(c);

@@ -15,8 +15,12 @@ from graal_b200.sampler import sampler, CUR
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 def _v(spec):
-    u, m, sb = spec.split(":")
-    return dict(GRAAL_FULL_WIN="1", GRAAL_WIN_UNROLL=u, GRAAL_WIN_MINB=m, GRAAL_WIN_SUB=sb)
+    """unroll:minb:sub[:stab]  (stab = GRAAL_WIN_STAB: law table of the windowed pass from shared memory 1 / through L1 0)"""
+    u, m, sb = spec.split(":")[:3]
+    d = dict(GRAAL_FULL_WIN="1", GRAAL_WIN_UNROLL=u, GRAAL_WIN_MINB=m, GRAAL_WIN_SUB=sb)
+    if len(spec.split(":")) > 3:
+        d["GRAAL_WIN_STAB"] = spec.split(":")[3]
+    return d
 
 
 variants = [dict(GRAAL_FULL_WIN="0")] + [_v(a) for a in (sys.argv[3:] or ["8:4:2", "8:4:4"])]
@@ -34,7 +38,7 @@ else:
 ref = None
 sched = None
 for v in variants:
-    for k in ("GRAAL_FULL_WIN", "GRAAL_WIN_UNROLL", "GRAAL_WIN_MINB", "GRAAL_WIN_SUB"):
+    for k in ("GRAAL_FULL_WIN", "GRAAL_WIN_UNROLL", "GRAAL_WIN_MINB", "GRAAL_WIN_SUB", "GRAAL_WIN_STAB"):
         os.environ.pop(k, None)
     os.environ.update(v)
     g = mk()

@@ -47,7 +47,7 @@ def test_builders_and_per_neighbour_scores(small_pyramid):
         o.stream_likelihood(fA, fB, 1, o.likelihood_t, max_id)
         g.stream_likelihood(fA, None, None, fB, 1, g.likelihood_t, max_id)
         assert np.all(g.score[:13] == 0)
-        assert np.allclose(o.score[13:], g.score[13:], rtol=1e-9, atol=1e-5), (fA, fB, np.abs(o.score - g.score).max())
+        assert np.allclose(o.score[13:], g.score[13:], rtol=1e-8), (fA, fB, np.abs(o.score - g.score).max())
         # the MH builders one family at a time == all_modifications_metropolis
         o.all_modifications_metropolis(fA, fB, max_id, True)
         for mode in range(6):
@@ -60,7 +60,7 @@ def test_builders_and_per_neighbour_scores(small_pyramid):
         so = o.compute_all_score_MH(fA, {fB}, True)
         sg = np.zeros(13)
         g.multi_likelihood_4_metropolis(fA, None, None, fB, 0, None, g.compute_likelihood(True), None, max_id, sg, True)
-        assert np.allclose(so, sg, rtol=1e-9, atol=1e-5), (fA, fB, np.abs(so - sg).max())
+        assert np.allclose(so, sg, rtol=1e-8), (fA, fB, np.abs(so - sg).max())
     g.free_gpu()
 
 
@@ -79,17 +79,29 @@ def test_validation_step_scores_by_full_likelihoods(small_pyramid):
         assert np.allclose(o.score, g.score, rtol=3e-7), (it, np.abs(o.score - g.score).max())
         assert tuple(ro[1:]) == tuple(rg[1:]) and abs(float(ro[0]) - float(rg[0])) <= 3e-7 * abs(float(ro[0])), (it, ro, rg)
         assert H.slots_diff(o.cur, g.slot_to_host(CUR)) == [], it
-    # full(candidate) == likelihood_t + delta(candidate) on the device alone
+    # full(candidate) vs likelihood_t + delta(candidate): the device gives the oracle's value for both, and the identity holds
+    # wherever it holds in the reference (it does not for every translocation: the delta kernel only revisits the pixels of
+    # the two touched contigs of the CURRENT structure, kernels3.cu:3225-3249)
+    from graal_b200.sampler import CAND0
+    from oracle import likelihood as L
     fA = int(sched[0])
-    max_id = int(g.modify_gl_cuda_buffer(fA))
-    lt = g.eval_likelihood()
-    nb = g.return_neighbours(fA, 2)
-    g.score = np.zeros(13 * len(nb))
+    max_id = int(g.modify_gl_cuda_buffer(fA)); assert max_id == int(o.modify_gl_cuda_buffer(fA))
+    lt, lo = g.eval_likelihood(), o.eval_likelihood()
+    nb = g.return_neighbours(fA, 2); assert nb == o.return_neighbours(fA, 2)
+    g.score = np.zeros(13 * len(nb)); o.score = np.zeros(13 * len(nb)); o.delta = np.zeros(13 * len(nb))
+    held = 0
     for x, fB in enumerate(nb):
         g.stream_likelihood(fA, None, None, fB, x, lt, max_id)
-        from graal_b200.sampler import CAND0
-        full = np.array([g.full_likelihood_of_slot(CAND0 + j) for j in range(13)])
-        assert np.allclose(full, g.score[13 * x:13 * x + 13], rtol=1e-9, atol=1e-4), (fB, np.abs(full - g.score[13 * x:13 * x + 13]).max())
+        o.stream_likelihood(fA, fB, x, lo, max_id)
+        full_g = np.array([g.full_likelihood_of_slot(CAND0 + j) for j in range(13)])
+        full_o = np.array([L.evaluate_likelihood(o.ws.collector[j], o.lv, o.param_simu).sum() for j in range(13)])
+        sl = slice(13 * x, 13 * x + 13)
+        assert np.allclose(full_g, full_o, rtol=1e-8), (fB, np.abs(full_g - full_o).max())
+        assert np.allclose(g.score[sl], o.score[sl], rtol=1e-8), (fB, np.abs(g.score[sl] - o.score[sl]).max())
+        ok = np.abs(full_o - o.score[sl]) < 1e-2
+        assert np.allclose(full_g[ok], g.score[sl][ok], rtol=1e-8), fB
+        held += int(ok.sum())
+    assert held >= 9 * len(nb)
     g.free_gpu()
 
 
