@@ -349,7 +349,9 @@ def roofline_blocks(kern, counters, E, W, peak, peak_src, traffic):
                   "achieved": ach_d, "peak": peak, "unit": "GB/s", "frac": ach_d / peak,
                   "traffic": traffic.get("delta_contacts"), "algorithmic_bytes_per_launch": alg_d / n_p, "avg_launch_ms": dc["ms_avg"],
                   "proposals": n_p, "mean_entries_in_U": e_u / n_p, "mean_bins_in_U": b_u / n_p,
-                  "candidate_contacts_per_s": N_TMP * e_u / (dc["ms_total"] * 1e-3)}
+                  "candidate_contacts_per_s": N_TMP * e_u / (dc["ms_total"] * 1e-3),
+                  "limiter": "not HBM: dependent instruction chains per entry (14 evaluations) at 16 warps per SM -- ncu: issue "
+                             "26-30 %, 5-10 warps per issue waiting on memory, L2 / L1 throughput 33-35 % (DESIGN.md section 11)"}
     return roof, roof_d
 
 
