@@ -8,8 +8,10 @@ on the synthetic yeast-shaped pyramid (BASELINE config C1, generator seed 201412
   traj_c1_l3.npz       the first 10^4 steps of start_EM from the exploded genome (3 neighbours,
                        RandomState(20141217)): list_mutations (id_fA, id_fB, id_mutation), scores
   traj_c1_l2_nuis.npz  600 steps at level 2 with nuisance-parameter sampling
+  traj_c1_l1.npz       one whole cycle (1,672 steps) at level 1 -- 1,672 bins, 5,000 sub-frags, the size the original
+                       kernels are benchmarked on (about 40 minutes of the dense oracle)
 
-usage: python tests/golden/make_golden.py [like|traj3|traj2|all]
+usage: python tests/golden/make_golden.py [like|traj3|traj2|traj1|all]
 """
 import os
 import sys
@@ -100,3 +102,5 @@ if __name__ == "__main__":
         make_traj(pyr, 3, 10000, False, "traj_c1_l3.npz")
     if what in ("traj2", "all"):
         make_traj(pyr, 2, 600, True, "traj_c1_l2_nuis.npz")
+    if what in ("traj1", "all"):
+        make_traj(pyr, 1, 1672, False, "traj_c1_l1.npz")

@@ -71,6 +71,27 @@ def test_golden_trajectory_10k_steps(yeast_pyramid, tmp_path):
     g.free_gpu(); g2.free_gpu()
 
 
+def test_golden_trajectory_level1_one_cycle(yeast_pyramid):
+    """The same identity on the largest C1 level (1,672 bins, 5,000 sub-frags -- the size the original kernels are
+    benchmarked on): one whole cycle from the exploded genome, against the frozen oracle trajectory."""
+    from graal_b200.sampler import CUR
+    path = os.path.join(GOLD, "traj_c1_l1.npz")
+    z = np.load(path)
+    inp, g = gpu_sampler(yeast_pyramid, int(z["level"]), int(z["seed"]))
+    n_steps = z["mutations"].shape[0]
+    tr = start_EM(g, n_steps // g.n_new_frags + 1, 3, scrambled=True, max_steps=n_steps)
+    got = tr.mutations()
+    same = np.all(got == z["mutations"], axis=1)
+    first_bad = int(np.argmin(same)) if not same.all() else -1
+    assert first_bad < 0, "diverged at step %d (draw-to-boundary margin %s)" % (first_bad, z["margins"][first_bad])
+    assert np.allclose(tr.likelihood, z["likelihood"], rtol=1e-7, atol=0)
+    assert np.array_equal(np.array(tr.n_contigs), z["n_contigs"])
+    final = g.slot_to_host(CUR)
+    for k in M.FIELDS:
+        assert np.array_equal(final[k], z["state_" + k]), k
+    g.free_gpu()
+
+
 def test_golden_trajectory_with_nuisance_parameters(yeast_pyramid):
     z = np.load(os.path.join(GOLD, "traj_c1_l2_nuis.npz"))
     inp, g = gpu_sampler(yeast_pyramid, int(z["level"]), int(z["seed"]))
