@@ -636,20 +636,26 @@ class sampler(MetropolisMixin, VariantsMixin):
             self.likelihood_t = likelihood_t
             n_contigs, min_len, mean_len_bp, max_len = int(out[4]), int(out[5]), out[6], int(out[7])
             n_first = min(n_neighbours, self.MAX_PROPOSALS)
-            deltas = [np.array(out[16:16 + n_first * N_TMP_STRUCT], dtype=np.float64)]
-            dists = [np.array(out[OFF_DIST:OFF_DIST + n_first * N_TMP_STRUCT], dtype=np.float64)]
             last_chunk = 0
-            # more neighbours than one round trip holds (repeats expand every partner to all its copies,
-            # cuda_lib_gl.py:2316-2327): further chunks of <= 16 proposals, one round trip each
-            for c0 in range(self.MAX_PROPOSALS, n_neighbours, self.MAX_PROPOSALS):
-                chunk = id_neighbours[c0:c0 + self.MAX_PROPOSALS]
-                self.score_neighbours(id_fA, chunk, with_dist=True)
-                o2 = self._fetch()
-                deltas.append(np.array(o2[16:16 + len(chunk) * N_TMP_STRUCT], dtype=np.float64))
-                dists.append(np.array(o2[OFF_DIST:OFF_DIST + len(chunk) * N_TMP_STRUCT], dtype=np.float64))
-                last_chunk = c0
-            self.delta_scores = np.concatenate(deltas)
-            dist_all = np.concatenate(dists)
+            if n_neighbours <= self.MAX_PROPOSALS:
+                # one round trip (the usual case): nothing but the draw stands between the fetch and the commit -- the pinned
+                # block is only overwritten by the next fetch, copies are taken from it once
+                self.delta_scores = np.array(out[16:16 + n_first * N_TMP_STRUCT], dtype=np.float64)
+                dist_all = out[OFF_DIST:OFF_DIST + n_first * N_TMP_STRUCT]
+            else:
+                deltas = [np.array(out[16:16 + n_first * N_TMP_STRUCT], dtype=np.float64)]
+                dists = [np.array(out[OFF_DIST:OFF_DIST + n_first * N_TMP_STRUCT], dtype=np.float64)]
+                # more neighbours than one round trip holds (repeats expand every partner to all its copies,
+                # cuda_lib_gl.py:2316-2327): further chunks of <= 16 proposals, one round trip each
+                for c0 in range(self.MAX_PROPOSALS, n_neighbours, self.MAX_PROPOSALS):
+                    chunk = id_neighbours[c0:c0 + self.MAX_PROPOSALS]
+                    self.score_neighbours(id_fA, chunk, with_dist=True)
+                    o2 = self._fetch()
+                    deltas.append(np.array(o2[16:16 + len(chunk) * N_TMP_STRUCT], dtype=np.float64))
+                    dists.append(np.array(o2[OFF_DIST:OFF_DIST + len(chunk) * N_TMP_STRUCT], dtype=np.float64))
+                    last_chunk = c0
+                self.delta_scores = np.concatenate(deltas)
+                dist_all = np.concatenate(dists)
             self.score = self.delta_scores + likelihood_t
             sample_out = self._sample(self.score, self.temperature(t, n_step))
             x = sample_out // N_TMP_STRUCT

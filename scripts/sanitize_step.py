@@ -1,5 +1,6 @@
 """compute-sanitizer target: BASELINE config C1 level 2 (563 bins), lanes + CUDA graphs on -- full likelihood, four
-step_max_likelihood steps (3 proposals x 13 candidates each, commit), one nuisance-parameter step, one MH step."""
+step_max_likelihood steps (3 proposals x 13 candidates each, commit), one nuisance-parameter step, one MH step, the validation
+step, the older step, local_flip.  GRAAL_WIN_STAB=1 forces the shared-memory law table of the full pass."""
 import os
 import sys
 
@@ -22,5 +23,9 @@ for fA in (5, 77, 300, 412):
 print(g.step_nuisance_parameters()[:7])
 g.set_jumping_distributions_parameters(3)
 print(g.step_mtm(40)[:3])
+# the rest of the class surface (variants.py): validation step, older proposal rule, local_flip
+print(g.debug_step_max_likelihood(123, 2)[:3])
+print(g.step_max_likelihood_4_visu(200, 2)[:3])
+g.local_flip(250, 13, int(g.modify_gl_cuda_buffer()))
 print("launches", g.gpu_launches)
 g.free_gpu()
