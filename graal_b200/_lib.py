@@ -76,6 +76,9 @@ _SIGS = {
     "graal_fetch": (_I, [_P, _P, _P, C.c_size_t]),
     "graal_dist_histogram": (_I, [_P, _P, _P, _P, _P, _D, _D, _I, _P, _P]),
     "graal_candidate_weights": (_I, [_P, _I, _I, _P, _P, _P, _P]),
+    "graal_draw_candidates": (_I, [_P, _P, _P, _D, _I, _I, _P, _D, _P, _P, _P]),
+    "graal_draw_commit": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _P, _D, _I, _D, _P, _P, _P, _P, _P, C.c_size_t]),
+    "graal_fetch_wait": (_I, [_P]),
     "graal_launch_count": (_LL, [_P]),
     "graal_profile_enable": (_I, [_P, _I]),
     "graal_profile_read": (_I, [_P, _I, C.POINTER(_D), C.POINTER(_LL), _I]),

@@ -382,9 +382,9 @@ __global__ void k_set_double(double* p, double v) { *p = v; }
 __global__ void k_init_stats(unsigned long long* a) { a[0] = 0ull; a[1] = 0ull; a[2] = (unsigned long long)(unsigned)INT_MAX; a[3] = (unsigned long long)(unsigned)INT_MIN; }
 
 // the 13 candidates of new_perform_modificationS (cuda_lib_gl.py:841-954) in one pass.
-__global__ void k_build_candidates(const int* __restrict__ src, int* __restrict__ dst0, size_t slot_stride,
-                                   int ld, int n, int fA, int fB, const int* __restrict__ d_max_id,
-                                   int max_id_host, unsigned mask) {
+__device__ __forceinline__ void build_candidates_body(const int* __restrict__ src, int* __restrict__ dst0, size_t slot_stride,
+                                                      int ld, int n, int fA, int fB, const int* __restrict__ d_max_id,
+                                                      int max_id_host, unsigned mask) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int M = (max_id_host >= 0) ? max_id_host : *d_max_id;
@@ -425,6 +425,30 @@ __global__ void k_build_candidates(const int* __restrict__ src, int* __restrict_
             }
         }
     }
+}
+__global__ void k_build_candidates(const int* __restrict__ src, int* __restrict__ dst0, size_t slot_stride,
+                                   int ld, int n, int fA, int fB, const int* __restrict__ d_max_id,
+                                   int max_id_host, unsigned mask) {
+    build_candidates_body(src, dst0, slot_stride, ld, n, fA, fB, d_max_id, max_id_host, mask);
+}
+// the candidate drawn ON THE DEVICE (k_draw_candidates): sel = {sample_out, n_ok, status, id_f_sampled, op}; rebuilds candidate
+// `op` of (fA, id_f_sampled) like test_copy_struct (cuda_lib_gl.py:1156-1183).  status != 0: no draw, nothing is built.
+__global__ void k_build_candidates_sel(const int* __restrict__ src, int* __restrict__ dst0, size_t slot_stride,
+                                       int ld, int n, int fA, const int* __restrict__ sel, const int* __restrict__ d_max_id, int max_id_host) {
+    if (sel[2] != 0) return;
+    const int op = sel[4];
+    build_candidates_body(src, dst0, slot_stride, ld, n, fA, sel[3], d_max_id, max_id_host, op < 9 ? (1u << op) : 0x1E00u);
+}
+// commit of the drawn candidate: slot (first candidate slot + op) -> the current slot
+__global__ void k_commit_sel(const int* __restrict__ cand0, size_t slot_stride, int* __restrict__ dst, int ld, int n, const int* __restrict__ sel) {
+    if (sel[2] != 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    store_bin(dst, ld, i, load_bin(cand0 + (size_t)sel[4] * slot_stride, ld, i));
+}
+__global__ void k_add_selected_sel(double* total, const double* band_hist, const int* __restrict__ sel) {
+    if (sel[2] != 0) return;
+    *total += band_hist[sel[0]];          // band_hist[proposal][candidate] flat == sample_out
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2296,7 +2320,7 @@ struct FixedGraph {
 struct graal_ctx {
     Profiler prof;
     FixedGraph g_stats, g_relabel, g_full, g_full_cached;
-    Lane lanes[GRAAL_MAX_LANES]; int n_lanes = 3; cudaEvent_t ev_fork = nullptr;
+    Lane lanes[GRAAL_MAX_LANES]; int n_lanes = 3; cudaEvent_t ev_fork = nullptr, ev_fetch = nullptr; bool fetch_pending = false, fetch_ncontigs = false;
     int fork_passes = 1;                     // GRAAL_FORK=0: contact / band passes of a proposal on one stream
     int pairing = 1;                         // GRAAL_PAIRING=0: score candidates 3, 5, 7 like the others (A/B runs)
     ProposalGraph graphs[16]; long long version = 0; int use_graphs = 1;      // version: bumped whenever captured arguments go stale
@@ -2583,6 +2607,7 @@ int graal_ctx_create(int device, graal_ctx** out) {
     { const char* e = getenv("GRAAL_WIN_STAB"); if (e && e[0] == '0') c->win_stab_allowed = false; if (e && e[0] == '1') { c->win_stab = 1; c->win_tuned = true; } }
     { const char* e = getenv("GRAAL_LANES"); if (e && e[0] >= '1' && e[0] <= '0' + GRAAL_MAX_LANES) c->n_lanes = e[0] - '0'; }
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_fetch, cudaEventDisableTiming));
     for (int l = 0; l < c->n_lanes; l++) {
         Lane& L = c->lanes[l];
         CUDA_OK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
@@ -2641,6 +2666,7 @@ void graal_ctx_destroy(graal_ctx* c) {
         if (L.st) cudaStreamDestroy(L.st);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_fetch) cudaEventDestroy(c->ev_fetch);
     if (c->h_ncontigs) cudaFreeHost(c->h_ncontigs);
     c->g_prologue.reset();
     for (int i = 0; i < 16; i++) c->graphs[i].reset();
@@ -3728,6 +3754,163 @@ int graal_coo_to_lists(graal_ctx* c, const int32_t* d_rows, const int32_t* d_col
 // 128 terms, halves rounded to multiples of 8 above) -- so that the weights are bit-identical to the NumPy statements they
 // replace (tests/test_host.py compares them).  No device work: plain C called between the fetch and the commit of a step.
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// The candidate draw of step_max_likelihood (cuda_lib_gl.py:1899-1947) on the device: the arithmetic of
+// graal_candidate_weights below (NumPy's operation order, pairwise sums included) by one warp, then the search of the uniform
+// `u` (drawn by the host from the reference's stream, consumed only if more than one candidate is left) in the cumulative
+// weights.  score = deltas + likelihood_t.  sel = {sample_out, n_ok, status (0 ok, 1 NaN / non-finite weights: the host path
+// decides), id_f_sampled, op}; out_sub = the n_ok normalised weights (sub_score), out_score = {score of the drawn candidate,
+// sample_out, n_ok, status} as doubles (one block for the host to fetch).
+// ------------------------------------------------------------------------------------------------
+#define DRAW_MAX (16 * GRAAL_N_CANDIDATES)
+struct NbList { int id[16]; };
+__device__ double dev_np_sum128(const double* a, int n, int lane) {       // n <= 128, all lanes call, result in every lane
+    double res;
+    if (n < 8) { res = 0.0; for (int i = 0; i < n; i++) res += a[i]; return res; }
+    double r = 0.0;
+    const int n8 = n - (n % 8);
+    if (lane < 8) { r = a[lane]; for (int i = 8; i < n8; i += 8) r += a[i + lane]; }
+    const double r0 = __shfl_sync(0xffffffffu, r, 0), r1 = __shfl_sync(0xffffffffu, r, 1), r2 = __shfl_sync(0xffffffffu, r, 2), r3 = __shfl_sync(0xffffffffu, r, 3);
+    const double r4 = __shfl_sync(0xffffffffu, r, 4), r5 = __shfl_sync(0xffffffffu, r, 5), r6 = __shfl_sync(0xffffffffu, r, 6), r7 = __shfl_sync(0xffffffffu, r, 7);
+    res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (int i = n8; i < n; i++) res += a[i];
+    return res;
+}
+__device__ double dev_np_pairwise_sum(const double* a, int n, int lane) {   // n <= 256
+    if (n <= 128) return dev_np_sum128(a, n, lane);
+    int n2 = n / 2; n2 -= n2 % 8;
+    const double x = dev_np_sum128(a, n2, lane), y = dev_np_sum128(a + n2, n - n2, lane);
+    return x + y;
+}
+__global__ void __launch_bounds__(32)
+k_draw_candidates(const double* __restrict__ d_delta, const double* __restrict__ d_full, double likelihood_host, int use_host_likelihood,
+                  int n, int n_tmp, double u, NbList nb, int* __restrict__ sel, double* __restrict__ out_sub, double* __restrict__ out_score) {
+    __shared__ double score[DRAW_MAX], work[DRAW_MAX], cdf[DRAW_MAX];
+    __shared__ int ids[DRAW_MAX];
+    const int lane = threadIdx.x;
+    const double lt = use_host_likelihood ? likelihood_host : *d_full;
+    bool nan = false;
+    for (int i = lane; i < n; i += 32) { const double v = d_delta[i] + lt; score[i] = v; if (v != v) nan = true; }
+    __syncwarp();
+    nan = __any_sync(0xffffffffu, nan);
+    // argmax (first occurrence) and min
+    int im = 0; double mn = score[0];
+    if (lane == 0) for (int i = 1; i < n; i++) { if (score[i] > score[im]) im = i; if (score[i] < mn) mn = score[i]; }
+    im = __shfl_sync(0xffffffffu, im, 0); mn = __shfl_sync(0xffffffffu, mn, 0);
+    for (int i = lane; i < n; i += 32) {
+        double w = score[i] - mn;
+        if (i >= n_tmp && (i % n_tmp == 0 || i % n_tmp == 1)) w = 0.0;      // eject / flip of the later neighbours: duplicates
+        work[i] = w;
+    }
+    __syncwarp();
+    double mx = work[0];
+    if (lane == 0) for (int i = 1; i < n; i++) if (work[i] > mx) mx = work[i];
+    mx = __shfl_sync(0xffffffffu, mx, 0);
+    const double shift = mx - 30.0;
+    int n_ok = 0;
+    for (int base = 0; base < n; base += 32) {                               // ordered compaction of the positive weights
+        const int i = base + lane;
+        double f = 0.0;
+        if (i < n) { f = work[i] - shift; if (f < 0.0) f = 0.0; }
+        const unsigned m = __ballot_sync(0xffffffffu, f > 0.0);
+        if (f > 0.0) { const int k = n_ok + __popc(m & ((1u << lane) - 1u)); ids[k] = i; cdf[k] = f; }
+        n_ok += __popc(m);
+    }
+    __syncwarp();
+    int status = nan ? 1 : 0, sample = im;
+    if (!nan && n_ok > 0) {
+        double sum = dev_np_pairwise_sum(cdf, n_ok, lane);
+        __syncwarp();
+        for (int i = lane; i < n_ok; i += 32) cdf[i] = cdf[i] / sum;
+        __syncwarp();
+        sum = dev_np_pairwise_sum(cdf, n_ok, lane);
+        __syncwarp();
+        for (int i = lane; i < n_ok; i += 32) { cdf[i] = cdf[i] / sum; out_sub[i] = cdf[i]; }
+        __syncwarp();
+        if (lane == 0) { double run = 0.0; for (int i = 0; i < n_ok; i++) { run += cdf[i]; cdf[i] = run; } }
+        __syncwarp();
+        const double last = cdf[n_ok - 1];
+        if (!(last - last == 0.0)) status = 1;
+        else if (n_ok > 1) {
+            int cnt = 0;
+            for (int i = lane; i < n_ok; i += 32) if (cdf[i] / last <= u) cnt++;          // searchsorted(cdf / last, u, side='right')
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            sample = ids[min(cnt, n_ok - 1)];
+        }
+    }
+    if (lane == 0) {
+        sel[0] = sample; sel[1] = n_ok; sel[2] = status;
+        sel[3] = nb.id[sample / n_tmp]; sel[4] = sample % n_tmp;
+        out_score[0] = score[sample]; out_score[1] = (double)sample; out_score[2] = (double)n_ok; out_score[3] = (double)status;
+    }
+}
+
+int graal_draw_candidates(graal_ctx* c, const double* d_delta, const double* d_full, double likelihood_host, int use_host_likelihood,
+                          int n_proposals, const int32_t* id_fB, double u, int32_t* d_sel, double* d_sub_score, double* d_score) {
+    NEED_STATE(c);
+    if (!d_delta || !id_fB || !d_sel || !d_sub_score || !d_score || (!use_host_likelihood && !d_full)) return set_err(-1, "null argument");
+    if (n_proposals < 1 || n_proposals > 16) return set_err(-1, "need 1..16 proposals");
+    int rc = join_lanes(c); if (rc) return rc;
+    NbList nb;
+    for (int x = 0; x < 16; x++) nb.id[x] = x < n_proposals ? id_fB[x] : 0;
+    k_draw_candidates<<<1, 32, 0, c->stream>>>(d_delta, d_full, likelihood_host, use_host_likelihood, n_proposals * GRAAL_N_CANDIDATES, GRAAL_N_CANDIDATES,
+                                               u, nb, d_sel, d_sub_score, d_score);
+    CHECK_LAUNCH(c);
+    return 0;
+}
+int graal_draw_commit(graal_ctx* c, int base_slot, int first_cand_slot, int id_fA, const int32_t* id_fB, int n_proposals, int max_id,
+                      const double* d_delta, const double* d_full, double likelihood_host, int use_host_likelihood, double u,
+                      int32_t* d_sel, double* d_sub_score, double* d_score, const void* d_fetch_src, void* h_fetch_dst, size_t fetch_bytes) {
+    NEED_STATE(c); NEED_SLOT(c, base_slot); NEED_SLOT(c, first_cand_slot); NEED_SLOT(c, first_cand_slot + GRAAL_N_CANDIDATES - 1);
+    const int n = c->n_new;
+    if (id_fA < 0 || id_fA >= n) return set_err(-1, "bin id out of range");
+    if (base_slot >= first_cand_slot && base_slot < first_cand_slot + GRAAL_N_CANDIDATES) return set_err(-1, "source slot inside the destination range");
+    for (int x = 0; x < n_proposals && id_fB; x++) if (id_fB[x] < 0 || id_fB[x] >= n) return set_err(-1, "bin id out of range");
+    int rc = graal_draw_candidates(c, d_delta, d_full, likelihood_host, use_host_likelihood, n_proposals, id_fB, u, d_sel, d_sub_score, d_score); if (rc) return rc;
+    const int keep = c->band_slot;
+    cudaStream_t st = c->stream;
+    if (d_fetch_src && h_fetch_dst && fetch_bytes) {
+        // the step's results leave for the host right behind the draw, BEFORE the commit kernels: graal_fetch_wait returns while
+        // the commit runs (contig ids of the relabelled slot are < n_contigs, + 3 for the candidate committed below)
+        CUDA_OK(cudaMemcpyAsync(h_fetch_dst, d_fetch_src, fetch_bytes, cudaMemcpyDeviceToHost, st));
+        c->fetch_ncontigs = c->ncontigs_pending && c->h_ncontigs;
+        if (c->fetch_ncontigs) CUDA_OK(cudaMemcpyAsync(c->h_ncontigs, c->d_ints + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaEventRecord(c->ev_fetch, st));
+        c->fetch_pending = true;
+    }
+    // test_copy_struct (cuda_lib_gl.py:1156-1183) of the candidate the device drew: rebuild it, copy it over the current slot
+    k_build_candidates_sel<<<nblk(n, 128), 128, 0, st>>>(slot_ptr(c, base_slot), slot_ptr(c, first_cand_slot), slot_stride(c), c->ld, n, id_fA, d_sel, c->d_ints + 0, max_id);
+    CHECK_LAUNCH(c);
+    k_commit_sel<<<nblk(n, 128), 128, 0, st>>>(slot_ptr(c, first_cand_slot), slot_stride(c), slot_ptr(c, base_slot), c->ld, n, d_sel);
+    CHECK_LAUNCH(c);
+    for (int k = 0; k < GRAAL_N_CANDIDATES; k++) {
+        const int sl = first_cand_slot + k;
+        if (c->geo_base_slot == sl) c->geo_base_slot = -1;
+        if (c->first_idx_slot == sl) c->first_idx_slot = -1;
+        if (c->band_slot == sl) c->band_slot = -1;
+        if (c->bound_slot == sl) { c->contig_bound = -1; c->ncontigs_pending = false; }
+    }
+    if (c->geo_base_slot == base_slot) c->geo_base_slot = -1;
+    if (c->first_idx_slot == base_slot) c->first_idx_slot = -1;
+    if (c->band_slot == base_slot) c->band_slot = -1;
+    if (c->bound_slot == base_slot) { c->bound_commits++; if (c->contig_bound >= 0) c->contig_bound += 3; }
+    if (keep == base_slot) {              // keep the cached band total in step with the committed candidate
+        k_add_selected_sel<<<1, 1, 0, st>>>(c->d_scalars + 40, c->band_hist, d_sel); CHECK_LAUNCH(c);
+        c->band_slot = base_slot;
+    }
+    return 0;
+}
+int graal_fetch_wait(graal_ctx* c) {
+    if (!c) return set_err(-1, "null argument");
+    if (!c->fetch_pending) return set_err(-1, "no fetch posted by graal_draw_commit");
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaEventSynchronize(c->ev_fetch));
+    c->fetch_pending = false;
+    if (c->fetch_ncontigs && c->ncontigs_pending) { c->contig_bound = *c->h_ncontigs + 3 * c->bound_commits; c->ncontigs_pending = false; }
+    c->fetch_ncontigs = false;
+    return 0;
+}
 static double np_pairwise_sum(const double* a, long n) {
     if (n < 8) { double r = 0.0; for (long i = 0; i < n; i++) r += a[i]; return r; }      // (NumPy starts from a[0]: 0.0 + a[0] == a[0] except -0.0, never a weight)
     if (n <= 128) {

@@ -31,6 +31,8 @@ N_TMP_STRUCT = 13
 CUR = 0            # slot of the current genome (reference: gpu_vect_frags)
 CAND0 = 1          # first of the 13 collector slots (reference: collector_gpu_vect_frags)
 OFF_DIST = 16 + 16 * 13   # offset of the candidates' genome distances in the output block
+OFF_SUB = 16 + 2 * 16 * 13   # device draw: the normalised weights of the candidates left (sub_score)
+OFF_DRAW = OFF_SUB + 16 * 13   # device draw: {score of the drawn candidate, sample_out, n_ok, status}
 N_LANES = 3        # proposals of one step scored concurrently: lane q owns candidate slots CAND0 + 13*q .. +13
 PARAM_FIELDS = ("kuhn", "lm", "c1", "slope", "d", "d_max", "fact", "v_inter")
 PARAM_DTYPE = np.dtype([(k if k != "d_max" else "l_max", F32) for k in PARAM_FIELDS], align=True)
@@ -299,9 +301,13 @@ class sampler(MetropolisMixin, VariantsMixin):
         host[CAND0:, FRAG_FIELDS.index("ori"), :] = 1           # collector initial content (cuda_lib_gl.py:269-287)
         host[CAND0:, FRAG_FIELDS.index("activ"), :] = 1
         self.d_slots = t(host)
-        # [0] full, [1] test, [4:8] stats, [8] dist, [16:224] deltas of <= 16 proposals, [224:432] their genome distances
-        self.d_out = torch.zeros(64 + 2 * 16 * N_TMP_STRUCT, dtype=torch.float64, device=dev)
+        # [0] full, [1] test, [4:8] stats, [8] dist, [16:224] deltas of <= 16 proposals, [224:432] their genome distances,
+        # [432:640] sub_score and [640:644] {score, sample_out, n_ok, status} of the draw made on the device
+        self.d_out = torch.zeros(OFF_DRAW + 16, dtype=torch.float64, device=dev)
         self.d_max_id = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.d_sel = torch.zeros(8, dtype=torch.int32, device=dev)
+        # the candidate draw and the commit on the device, right behind the scores (GRAAL_DEVICE_DRAW=0: on the host after the fetch)
+        self.device_draw = os.environ.get("GRAAL_DEVICE_DRAW", "1") != "0"
         self.h_out = torch.zeros_like(self.d_out, device="cpu").pin_memory()
         torch.cuda.synchronize(dev)
         check(self.lib.graal_level_bind(self.ctx, int(n_frags), n, int(init_n_sub_frags),
@@ -593,12 +599,12 @@ class sampler(MetropolisMixin, VariantsMixin):
     def step_max_likelihood(self, id_fA, delta, size_block=512, dt=0, t=0, n_step=1):
         """cuda_lib_gl.py:1793-1980.  Returns (o, n_contigs, min_len, mean_len_bp, max_len, op_sampled,
         id_f_sampled, dist, F_t)."""
-        self.step_begin(id_fA, delta)
+        self.step_begin(id_fA, delta, t, n_step)
         return self.step_end(t, n_step)
 
     MAX_PROPOSALS = 16      # proposals scored per device round trip (output block / band-delta history of the library)
 
-    def step_begin(self, id_fA, delta):
+    def step_begin(self, id_fA, delta, t=0, n_step=1):
         """First half of step_max_likelihood: everything up to the device round trip is ENQUEUED (statistics, relabel, the
         proposals on their lanes, the full likelihood beside them); nothing is waited for.  Several chains on one GPU call
         step_begin on each chain, then step_end on each (graal_b200.replica.step_chains): their kernels overlap."""
@@ -620,6 +626,21 @@ class sampler(MetropolisMixin, VariantsMixin):
         self.score_neighbours(id_fA, id_neighbours[:self.MAX_PROPOSALS], with_dist=True)
         if not self._step_incremental:
             check(lib.graal_full_loglik(self.ctx, CUR, None, self._ptr(self.d_out, 0)))
+        # the draw (cuda_lib_gl.py:1899-1947) and the commit (:1952) follow on the device without waiting for the host: the
+        # NEXT uniform of the stream goes along, and is only consumed if the draw needed it (known after the fetch)
+        self._drawn_on_device = False
+        rs = getattr(self.rng, "random_sample", None)
+        n_nb = len(id_neighbours)
+        if (self.device_draw and 0 < n_nb <= self.MAX_PROPOSALS and rs is not None and hasattr(self.rng, "get_state")
+                and self.temperature(t, n_step) == 1.0 and getattr(self, "_fast_weights", True)):
+            self._rng_before_draw = self.rng.get_state()
+            u = float(rs())
+            fbs = (C.c_int32 * n_nb)(*id_neighbours)
+            check(lib.graal_draw_commit(self.ctx, CUR, CAND0, int(id_fA), fbs, n_nb, -1, self._p_out + 8 * 16, self._p_out,
+                                        float(self.likelihood_t) if self._step_incremental else 0.0, 1 if self._step_incremental else 0, u,
+                                        self.d_sel.data_ptr(), self._p_out + 8 * OFF_SUB, self._p_out + 8 * OFF_DRAW,
+                                        self._p_out, self._p_hout, self._n_out_bytes))
+            self._drawn_on_device = True
 
     def step_end(self, t=0, n_step=1):
         """Second half: the one device round trip, the candidate draw (cuda_lib_gl.py:1899-1947), the commit."""
@@ -628,7 +649,11 @@ class sampler(MetropolisMixin, VariantsMixin):
         if self.id_neighbours is not None:
             id_neighbours = self.id_neighbours
             n_neighbours = len(id_neighbours)
-            out = self._fetch()
+            if self._drawn_on_device:                 # the block left for the host before the commit kernels: wait for the copy only
+                check(lib.graal_fetch_wait(self.ctx))
+                out = self._h_out_np
+            else:
+                out = self._fetch()
             incremental = self._step_incremental
             likelihood_t = np.float64(self.likelihood_t) if incremental else np.float64(out[0])
             self._inc_age = self._inc_age + 1 if incremental else 0
@@ -657,13 +682,25 @@ class sampler(MetropolisMixin, VariantsMixin):
                 self.delta_scores = np.concatenate(deltas)
                 dist_all = np.concatenate(dists)
             self.score = self.delta_scores + likelihood_t
-            sample_out = self._sample(self.score, self.temperature(t, n_step))
-            x = sample_out // N_TMP_STRUCT
-            id_f_sampled = id_neighbours[x]
-            op_sampled = sample_out % N_TMP_STRUCT
-            # the band delta of a scored proposal is only remembered for the chunk scored last
-            x_lib = x - last_chunk if x >= last_chunk else -1
-            check(lib.graal_commit_scored(self.ctx, CUR, CAND0, int(id_fA), int(id_f_sampled), -1, int(op_sampled), int(x_lib)))
+            drawn = self._drawn_on_device and out[OFF_DRAW + 3] == 0.0
+            if self._drawn_on_device and not drawn:
+                self.rng.set_state(self._rng_before_draw)        # NaN scores: nothing was drawn or committed, the host path decides
+            if drawn:
+                sample_out, n_ok = int(out[OFF_DRAW + 1]), int(out[OFF_DRAW + 2])
+                if n_ok <= 1:
+                    self.rng.set_state(self._rng_before_draw)    # one candidate left: the reference draws nothing (:1936-1939)
+                self.sub_score = np.array(out[OFF_SUB:OFF_SUB + n_ok], dtype=np.float64)
+                x = sample_out // N_TMP_STRUCT
+                id_f_sampled = id_neighbours[x]
+                op_sampled = sample_out % N_TMP_STRUCT
+            else:
+                sample_out = self._sample(self.score, self.temperature(t, n_step))
+                x = sample_out // N_TMP_STRUCT
+                id_f_sampled = id_neighbours[x]
+                op_sampled = sample_out % N_TMP_STRUCT
+                # the band delta of a scored proposal is only remembered for the chunk scored last
+                x_lib = x - last_chunk if x >= last_chunk else -1
+                check(lib.graal_commit_scored(self.ctx, CUR, CAND0, int(id_fA), int(id_f_sampled), -1, int(op_sampled), int(x_lib)))
             o = self.score[sample_out]
             self.o = o
             # dist_inter_genome of the committed candidate (cuda_lib_gl.py:1962) came back with the scores

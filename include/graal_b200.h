@@ -24,6 +24,7 @@
  *   GRAAL_FULL_WIN=0 gather-everything contact pass instead of the windowed one; GRAAL_WIN_UNROLL / _MINB / _SUB: its variants
  *   GRAAL_DELTA_REL=0 / GRAAL_BAND_FAST=0 general delta kernels on uniform levels; GRAAL_DELTA_UNI=1 union windows in the delta contact pass
  *   GRAAL_FUSED_PROLOGUE=0 statistics + relabel as the two general launch sequences
+ *   (Python side: GRAAL_DEVICE_DRAW=0 candidate draw and commit on the host after the fetch instead of graal_draw_commit)
  *   GRAAL_WIN_STAB=0|1 law table of the windowed contact pass through L1 / from a 32 KB coarse copy in shared memory (default: timed once per level)
  *   GRAAL_DELTA_SPLIT=n (1..32, default 8) slices a row is cut into when U is short; GRAAL_DELTA_MINB=2|3|4 CTAs per SM of the delta contact pass
  *   GRAAL_BAND_SPLIT=n (1..32, default 1) warps the band of one bin of a short U is cut over in the fast band delta kernels
@@ -219,6 +220,25 @@ int graal_dist_histogram(graal_ctx* ctx, const int32_t* sub_id_c, const int32_t*
  * (work[0..n_ok)) and their normalised cumulative sums cdf[n_ok]; *id_max = argmax(score).  Returns n_ok, -1 if a weight is
  * not finite (the caller falls back to the NumPy statements).  No CUDA call. */
 int graal_candidate_weights(const double* score, int n, int n_tmp, double* work, int32_t* id_ok, double* cdf, int32_t* id_max);
+
+/* The same draw ON THE DEVICE, and the commit that follows it, without a host round trip (cuda_lib_gl.py:1899-1952):
+ * score = d_delta[0 : 13 n_proposals] + likelihood (d_full[0], or likelihood_host when use_host_likelihood), the weights in
+ * NumPy's operation order as in graal_candidate_weights, `u` = the NEXT uniform of the caller's RandomState -- it is consumed
+ * by the draw only if more than one candidate is left (n_ok > 1): the caller advances its stream accordingly after the fetch.
+ * d_sel (5 int32, device) = {sample_out, n_ok, status, id_f_sampled, op}; status 1 = NaN / non-finite weights: nothing is
+ * drawn or committed, the host path decides (the reference raises there).  d_sub_score: >= 13 n_proposals doubles (the n_ok
+ * normalised weights, `sampler.sub_score`); d_score: 4 doubles {score of the drawn candidate, sample_out, n_ok, status}.
+ * graal_draw_commit then rebuilds candidate `op` of (id_fA, id_f_sampled) and copies it over base_slot like
+ * graal_commit_scored (test_copy_struct, cuda_lib_gl.py:1156-1183), all enqueued on the context stream behind the lanes. */
+int graal_draw_candidates(graal_ctx* ctx, const double* d_delta, const double* d_full, double likelihood_host, int use_host_likelihood,
+                          int n_proposals, const int32_t* id_fB, double u, int32_t* d_sel, double* d_sub_score, double* d_score);
+int graal_draw_commit(graal_ctx* ctx, int base_slot, int first_cand_slot, int id_fA, const int32_t* id_fB, int n_proposals, int max_id,
+                      const double* d_delta, const double* d_full, double likelihood_host, int use_host_likelihood, double u,
+                      int32_t* d_sel, double* d_sub_score, double* d_score, const void* d_fetch_src, void* h_fetch_dst, size_t fetch_bytes);
+/* d_fetch_src / h_fetch_dst / fetch_bytes (optional): the D2H copy of the step's output block is enqueued between the draw and
+ * the commit; graal_fetch_wait blocks until it has landed (the commit kernels may still be running) and does graal_fetch's
+ * bookkeeping. */
+int graal_fetch_wait(graal_ctx* ctx);
 
 /* instrumentation: number of kernel launches issued by this context so far */
 int64_t graal_launch_count(graal_ctx* ctx);

@@ -290,3 +290,69 @@ def test_fused_prologue_matches_the_general_sequences(small_pyramid):
         g.step_device(fA, nb, nb[0], 6); g2.step_device(fA, nb, nb[0], 6)
         assert H.slots_diff(g.slot_to_host(CUR), g2.slot_to_host(CUR)) == []
     g.free_gpu(); g2.free_gpu()
+
+
+def test_device_draw_is_the_host_draw(small_pyramid):
+    """The candidate draw made on the device (k_draw_candidates, right behind the scores) against the host draw
+    (sampler._sample, pinned to the reference's lines by tests/test_reference_host_logic.py): same candidate, same number of
+    candidates left, same normalised weights bit for bit, on thousands of score vectors -- and the same steps, tuples, genome and
+    RandomState position when whole steps run either way."""
+    import ctypes as C
+    import types
+    import torch
+    from graal_b200 import _lib
+    from graal_b200.sampler import sampler, CUR, OFF_SUB, OFF_DRAW
+    inp, g = gpu_sampler(small_pyramid, 2, 3)
+    gen = np.random.RandomState(17)
+    checked_draws = 0
+    for case in range(1500):
+        n_nb = int(gen.randint(1, 17))
+        n = 13 * n_nb
+        delta = gen.randn(n) * gen.choice([0.01, 1.0, 5.0, 40.0, 400.0])
+        lt = -1e6 * gen.rand()
+        if case % 7 == 0:
+            delta[gen.randint(n)] += 100.0
+        if case % 11 == 0:
+            delta[:] = delta[0]
+        if case % 97 == 0:
+            delta[gen.randint(n)] = np.nan
+        u = float(gen.rand())
+        nb = gen.randint(0, int(g.n_new_frags), size=n_nb).astype(np.int32)
+        g.d_out[16:16 + n] = torch.from_numpy(delta).to(g.device)
+        g.d_out[0] = lt
+        fbs = (C.c_int32 * n_nb)(*[int(x) for x in nb])
+        _lib.check(g.lib.graal_draw_candidates(g.ctx, g._p_out + 8 * 16, g._p_out, 0.0, 0, n_nb, fbs, u, g.d_sel.data_ptr(),
+                                                g._p_out + 8 * OFF_SUB, g._p_out + 8 * OFF_DRAW))
+        out = g._fetch()
+        sel = g.d_sel.cpu().numpy()
+        score = delta + np.float64(lt)
+        stub = types.SimpleNamespace(rng=types.SimpleNamespace(random_sample=lambda: u), _remove_cache={}, sub_score=None, _fast_weights=True)
+        if np.isnan(score).any():
+            assert sel[2] == 1 and out[OFF_DRAW + 3] == 1.0, case
+            continue
+        want = sampler._sample(stub, score.copy(), 1.0)
+        n_ok = len(stub.sub_score)
+        assert sel[2] == 0 and sel[0] == want == int(out[OFF_DRAW + 1]), (case, sel, want)
+        assert sel[1] == n_ok == int(out[OFF_DRAW + 2]), (case, sel, n_ok)
+        assert sel[3] == nb[want // 13] and sel[4] == want % 13
+        assert np.array_equal(out[OFF_SUB:OFF_SUB + n_ok], stub.sub_score), case
+        assert out[OFF_DRAW] == score[want]
+        checked_draws += int(n_ok > 1)
+    assert checked_draws > 500
+    g.free_gpu()
+    # whole steps either way
+    runs = []
+    for dev in (False, True):
+        inp, g = gpu_sampler(small_pyramid, 2, 29)
+        g.device_draw = dev
+        H.scramble(H.make_oracle(inp, small_pyramid, seed=1), np.random.RandomState(4), 25, g)
+        sched = np.random.RandomState(6).randint(0, int(g.n_new_frags), size=60)
+        tuples = [g.step_max_likelihood(int(fA), 3) for fA in sched]
+        runs.append((tuples, g.slot_to_host(CUR), g.rng.rand(), [np.array(g.sub_score)]))
+        g.free_gpu()
+    (ta, sa, ra, wa), (tb, sb, rb, wb) = runs
+    assert ra == rb                                                  # the stream advanced by the same number of draws
+    assert H.slots_diff(sa, sb) == []
+    for a, b in zip(ta, tb):
+        assert tuple(a[1:6]) == tuple(b[1:6]) and a[6] == b[6] and a[0] == b[0] and a[7] == b[7], (a, b)
+    assert np.array_equal(wa[0], wb[0])
