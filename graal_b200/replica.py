@@ -228,8 +228,11 @@ class ReplicaExchange:
 def step_chains(chains, id_fA, delta, t=0, n_step=1):
     """One step of several chains that share a GPU: every chain's work is enqueued first (its kernels run on its own
     streams and overlap with the other chains'), then each chain's round trip / draw / commit is finished in turn."""
+    # (chains that draw from ONE generator keep the host draw: the device draw hands the next uniform over before it knows
+    # whether it is consumed, which only one pending step per generator can do)
+    own_rng = len({id(g.rng) for g in chains}) == len(chains)
     for g in chains:
-        g.step_begin(id_fA, delta)
+        g.step_begin(id_fA, delta, t, n_step, device_draw=own_rng)
     return [g.step_end(t, n_step) for g in chains]
 
 

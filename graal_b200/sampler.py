@@ -604,7 +604,7 @@ class sampler(MetropolisMixin, VariantsMixin):
 
     MAX_PROPOSALS = 16      # proposals scored per device round trip (output block / band-delta history of the library)
 
-    def step_begin(self, id_fA, delta, t=0, n_step=1):
+    def step_begin(self, id_fA, delta, t=0, n_step=1, device_draw=True):
         """First half of step_max_likelihood: everything up to the device round trip is ENQUEUED (statistics, relabel, the
         proposals on their lanes, the full likelihood beside them); nothing is waited for.  Several chains on one GPU call
         step_begin on each chain, then step_end on each (graal_b200.replica.step_chains): their kernels overlap."""
@@ -631,7 +631,7 @@ class sampler(MetropolisMixin, VariantsMixin):
         self._drawn_on_device = False
         rs = getattr(self.rng, "random_sample", None)
         n_nb = len(id_neighbours)
-        if (self.device_draw and 0 < n_nb <= self.MAX_PROPOSALS and rs is not None and hasattr(self.rng, "get_state")
+        if (self.device_draw and device_draw and 0 < n_nb <= self.MAX_PROPOSALS and rs is not None and hasattr(self.rng, "get_state")
                 and self.temperature(t, n_step) == 1.0 and getattr(self, "_fast_weights", True)):
             self._rng_before_draw = self.rng.get_state()
             u = float(rs())
