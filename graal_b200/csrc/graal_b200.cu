@@ -2321,6 +2321,8 @@ struct graal_ctx {
     Profiler prof;
     FixedGraph g_stats, g_relabel, g_full, g_full_cached;
     Lane lanes[GRAAL_MAX_LANES]; int n_lanes = 3; cudaEvent_t ev_fork = nullptr, ev_fetch = nullptr; bool fetch_pending = false, fetch_ncontigs = false;
+    int fetch_seq = 0; bool fetch_published = false, publish_enable = true;     // results written by a kernel into mapped pinned memory + a sequence word the host polls
+    long long commits_total = 0, fetch_mark = 0;                 // commits on the bound slot, and their count when the pending readback left
     int fork_passes = 1;                     // GRAAL_FORK=0: contact / band passes of a proposal on one stream
     int pairing = 1;                         // GRAAL_PAIRING=0: score candidates 3, 5, 7 like the others (A/B runs)
     ProposalGraph graphs[16]; long long version = 0; int use_graphs = 1;      // version: bumped whenever captured arguments go stale
@@ -2594,11 +2596,13 @@ int graal_ctx_create(int device, graal_ctx** out) {
     { const char* e = getenv("GRAAL_FORK"); if (e && e[0] == '0') c->fork_passes = 0; }
     { const char* e = getenv("GRAAL_FULL_WIN"); if (e && e[0] == '0') c->full_win = 0; }
     { const char* e = getenv("GRAAL_FUSED_PROLOGUE"); if (e && e[0] == '0') c->fused_prologue = 0; }
-    CUDA_OK(cudaMallocHost(&c->h_ncontigs, sizeof(int)));
+    CUDA_OK(cudaHostAlloc(&c->h_ncontigs, 64, cudaHostAllocMapped));      // [0] n_contigs readback, [8] sequence number of the last published fetch
+    c->h_ncontigs[0] = 0; c->h_ncontigs[8] = 0;
     { const char* e = getenv("GRAAL_DELTA_UNI"); if (e) c->delta_uni = e[0] == '1'; }
     { const char* e = getenv("GRAAL_BAND_FAST"); if (e && e[0] == '0') c->band_fast = 0; }
     { const char* e = getenv("GRAAL_DELTA_REL"); if (e && e[0] == '0') c->delta_rel = 0; }
     { const char* e = getenv("GRAAL_BAND_SPLIT"); if (e && atoi(e) >= 1 && atoi(e) <= 32) c->band_split = atoi(e); }
+    { const char* e = getenv("GRAAL_PUBLISH"); if (e && e[0] == '0') c->publish_enable = false; }
     { const char* e = getenv("GRAAL_DELTA_MINB"); if (e && atoi(e) >= 2 && atoi(e) <= 4) c->delta_minb = atoi(e); }
     { const char* e = getenv("GRAAL_DELTA_SPLIT"); if (e && atoi(e) >= 1 && atoi(e) <= 32) c->delta_split = atoi(e); }
     { const char* e = getenv("GRAAL_WIN_UNROLL"); if (e && (e[0] == '2' || e[0] == '4' || e[0] == '8')) c->win_unroll = e[0] - '0'; }
@@ -2741,7 +2745,7 @@ int graal_level_bind(graal_ctx* c, int n_frags, int n_new_frags, int n_sub_frags
     c->version++;
     for (int i = 0; i < 16; i++) c->graphs[i].reset();
     c->g_stats.reset(); c->g_relabel.reset(); c->g_full.reset(); c->g_full_cached.reset(); c->g_win.reset();
-    c->win_slot = -1; c->contig_bound = -1; c->ncontigs_pending = false; c->first_clean = false; c->stats_clean = false; c->g_prologue.reset();
+    c->win_slot = -1; c->contig_bound = -1; c->ncontigs_pending = false; c->fetch_ncontigs = false; c->first_clean = false; c->stats_clean = false; c->g_prologue.reset();
     { const char* e = getenv("GRAAL_WIN_SUB"); const char* e2 = getenv("GRAAL_WIN_STAB"); c->win_tuned = e != nullptr || (e2 && e2[0] == '1'); }
     free_level_scratch(c);
     c->N = n_frags; c->n_new = n_new_frags; c->W = n_sub_frags; c->E = n_contacts; c->nfpb = nfpb;
@@ -2970,7 +2974,7 @@ int graal_state_bind(graal_ctx* c, int32_t* base, int ld, int n_slots) {
     { int rcj = join_lanes(c); if (rcj) return rcj; }
     c->version++;
     c->slots = base; c->ld = ld; c->n_slots = n_slots; c->geo_base_slot = -1; c->band_slot = -1; c->first_idx_slot = -1;
-    c->contig_bound = -1; c->ncontigs_pending = false;
+    c->contig_bound = -1; c->ncontigs_pending = false; c->fetch_ncontigs = false;
     return 0;
 }
 
@@ -3005,7 +3009,7 @@ int graal_relabel_contigs(graal_ctx* c, int slot, int32_t* d_max_id) {
     if (c->geo_base_slot == slot) c->geo_base_slot = -1;
     c->first_idx_slot = -1;                  // indexed by the OLD contig ids
     c->first_clean = false;
-    if (c->bound_slot != slot) { c->bound_slot = slot; c->contig_bound = -1; }
+    if (c->bound_slot != slot) { c->bound_slot = slot; c->contig_bound = -1; c->fetch_ncontigs = false; }
     c->bound_commits = 0; c->ncontigs_pending = true;      // d_ints[1] = n_contigs of this slot: read back by the next graal_fetch
     return 0;
 }
@@ -3065,7 +3069,7 @@ int graal_apply_move(graal_ctx* c, int src_slot, int dst_slot, int op, int id_fA
     if (c->geo_base_slot == dst_slot) c->geo_base_slot = -1;
     if (c->first_idx_slot == dst_slot) c->first_idx_slot = -1;
     if (c->band_slot == dst_slot) c->band_slot = -1;
-    if (c->bound_slot == dst_slot) { c->contig_bound = -1; c->ncontigs_pending = false; }
+    if (c->bound_slot == dst_slot) { c->contig_bound = -1; c->ncontigs_pending = false; c->fetch_ncontigs = false; }
     return 0;
 }
 
@@ -3082,7 +3086,7 @@ int graal_build_candidates(graal_ctx* c, int src_slot, int first_dst_slot, int i
     if (c->geo_base_slot >= first_dst_slot && c->geo_base_slot < first_dst_slot + GRAAL_N_CANDIDATES) c->geo_base_slot = -1;
     if (c->first_idx_slot >= first_dst_slot && c->first_idx_slot < first_dst_slot + GRAAL_N_CANDIDATES) c->first_idx_slot = -1;
     if (c->band_slot >= first_dst_slot && c->band_slot < first_dst_slot + GRAAL_N_CANDIDATES) c->band_slot = -1;
-    if (c->bound_slot >= first_dst_slot && c->bound_slot < first_dst_slot + GRAAL_N_CANDIDATES) { c->contig_bound = -1; c->ncontigs_pending = false; }
+    if (c->bound_slot >= first_dst_slot && c->bound_slot < first_dst_slot + GRAAL_N_CANDIDATES) { c->contig_bound = -1; c->ncontigs_pending = false; c->fetch_ncontigs = false; }
     return 0;
 }
 
@@ -3095,7 +3099,7 @@ int graal_commit(graal_ctx* c, int dst_slot, int src_slot) {
     if (c->first_idx_slot == dst_slot) c->first_idx_slot = -1;
     if (c->band_slot == dst_slot) c->band_slot = -1;
     // a committed candidate of a relabelled genome adds at most 3 contig ids (eject + split insert / two splits)
-    if (c->bound_slot == dst_slot) { c->bound_commits++; if (c->contig_bound >= 0) c->contig_bound += 3; }
+    if (c->bound_slot == dst_slot) { c->bound_commits++; c->commits_total++; if (c->contig_bound >= 0) c->contig_bound += 3; }
     return 0;
 }
 
@@ -3762,6 +3766,17 @@ int graal_coo_to_lists(graal_ctx* c, const int32_t* d_rows, const int32_t* d_col
 // decides), id_f_sampled, op}; out_sub = the n_ok normalised weights (sub_score), out_score = {score of the drawn candidate,
 // sample_out, n_ok, status} as doubles (one block for the host to fetch).
 // ------------------------------------------------------------------------------------------------
+// The step's output block straight into the caller's pinned host buffer (mapped: the device sees the same address), the contig
+// count beside it, then -- behind a system-wide fence -- the sequence number graal_fetch_wait polls: no copy-engine operation
+// between the draw and the commit kernels, no event.
+__global__ void k_publish(const double* __restrict__ d_src, double* __restrict__ h_dst, int n_doubles, const int* __restrict__ d_ncontigs,
+                          volatile int* __restrict__ h_ints, int with_ncontigs, int seq) {
+    for (int i = threadIdx.x; i < n_doubles; i += blockDim.x) h_dst[i] = d_src[i];
+    if (threadIdx.x == 0 && with_ncontigs) h_ints[0] = *d_ncontigs;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) { h_ints[8] = seq; __threadfence_system(); }
+}
 #define DRAW_MAX (16 * GRAAL_N_CANDIDATES)
 struct NbList { int id[16]; };
 __device__ double dev_np_sum128(const double* a, int n, int lane) {       // n <= 128, all lanes call, result in every lane
@@ -3873,11 +3888,22 @@ int graal_draw_commit(graal_ctx* c, int base_slot, int first_cand_slot, int id_f
     if (d_fetch_src && h_fetch_dst && fetch_bytes) {
         // the step's results leave for the host right behind the draw, BEFORE the commit kernels: graal_fetch_wait returns while
         // the commit runs (contig ids of the relabelled slot are < n_contigs, + 3 for the candidate committed below)
-        CUDA_OK(cudaMemcpyAsync(h_fetch_dst, d_fetch_src, fetch_bytes, cudaMemcpyDeviceToHost, st));
         c->fetch_ncontigs = c->ncontigs_pending && c->h_ncontigs;
-        if (c->fetch_ncontigs) CUDA_OK(cudaMemcpyAsync(c->h_ncontigs, c->d_ints + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CUDA_OK(cudaEventRecord(c->ev_fetch, st));
-        c->fetch_pending = true;
+        void* h_dev = nullptr;
+        const bool publish = c->publish_enable && (fetch_bytes % 8 == 0) && cudaHostGetDevicePointer(&h_dev, h_fetch_dst, 0) == cudaSuccess && h_dev == h_fetch_dst;
+        if (!publish) (void)cudaGetLastError();
+        if (publish) {
+            c->fetch_seq++;
+            k_publish<<<1, 256, 0, st>>>(static_cast<const double*>(d_fetch_src), static_cast<double*>(h_fetch_dst), (int)(fetch_bytes / 8), c->d_ints + 1,
+                                         c->h_ncontigs, c->fetch_ncontigs ? 1 : 0, c->fetch_seq);
+            CHECK_LAUNCH(c);
+        } else {
+            CUDA_OK(cudaMemcpyAsync(h_fetch_dst, d_fetch_src, fetch_bytes, cudaMemcpyDeviceToHost, st));
+            if (c->fetch_ncontigs) CUDA_OK(cudaMemcpyAsync(c->h_ncontigs, c->d_ints + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_OK(cudaEventRecord(c->ev_fetch, st));
+        }
+        if (c->fetch_ncontigs) { c->fetch_mark = c->commits_total; c->ncontigs_pending = false; }
+        c->fetch_pending = true; c->fetch_published = publish;
     }
     // test_copy_struct (cuda_lib_gl.py:1156-1183) of the candidate the device drew: rebuild it, copy it over the current slot
     k_build_candidates_sel<<<nblk(n, 128), 128, 0, st>>>(slot_ptr(c, base_slot), slot_ptr(c, first_cand_slot), slot_stride(c), c->ld, n, id_fA, d_sel, c->d_ints + 0, max_id);
@@ -3889,12 +3915,12 @@ int graal_draw_commit(graal_ctx* c, int base_slot, int first_cand_slot, int id_f
         if (c->geo_base_slot == sl) c->geo_base_slot = -1;
         if (c->first_idx_slot == sl) c->first_idx_slot = -1;
         if (c->band_slot == sl) c->band_slot = -1;
-        if (c->bound_slot == sl) { c->contig_bound = -1; c->ncontigs_pending = false; }
+        if (c->bound_slot == sl) { c->contig_bound = -1; c->ncontigs_pending = false; c->fetch_ncontigs = false; }
     }
     if (c->geo_base_slot == base_slot) c->geo_base_slot = -1;
     if (c->first_idx_slot == base_slot) c->first_idx_slot = -1;
     if (c->band_slot == base_slot) c->band_slot = -1;
-    if (c->bound_slot == base_slot) { c->bound_commits++; if (c->contig_bound >= 0) c->contig_bound += 3; }
+    if (c->bound_slot == base_slot) { c->bound_commits++; c->commits_total++; if (c->contig_bound >= 0) c->contig_bound += 3; }
     if (keep == base_slot) {              // keep the cached band total in step with the committed candidate
         k_add_selected_sel<<<1, 1, 0, st>>>(c->d_scalars + 40, c->band_hist, d_sel); CHECK_LAUNCH(c);
         c->band_slot = base_slot;
@@ -3905,9 +3931,20 @@ int graal_fetch_wait(graal_ctx* c) {
     if (!c) return set_err(-1, "null argument");
     if (!c->fetch_pending) return set_err(-1, "no fetch posted by graal_draw_commit");
     CUDA_OK(cudaSetDevice(c->device));
-    CUDA_OK(cudaEventSynchronize(c->ev_fetch));
+    if (c->fetch_published) {
+        volatile int* seq = c->h_ncontigs + 8;
+        for (long long spin = 0; *seq != c->fetch_seq; spin++) {
+            if ((spin & 0xfffff) == 0xfffff) {                  // every ~1M polls: has the stream failed or drained without publishing?
+                const cudaError_t q = cudaStreamQuery(c->stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady) return set_err(-2, "stream failed while waiting for the step's results: %s", cudaGetErrorString(q));
+                if (q == cudaSuccess && *seq != c->fetch_seq) return set_err(-2, "the step's results were never published");
+            }
+        }
+        __sync_synchronize();
+    } else CUDA_OK(cudaEventSynchronize(c->ev_fetch));
     c->fetch_pending = false;
-    if (c->fetch_ncontigs && c->ncontigs_pending) { c->contig_bound = *c->h_ncontigs + 3 * c->bound_commits; c->ncontigs_pending = false; }
+    // contig ids were < n_contigs when the readback left; every candidate committed since adds at most 3 (relabels only lower them)
+    if (c->fetch_ncontigs) c->contig_bound = *c->h_ncontigs + 3 * (int)(c->commits_total - c->fetch_mark);
     c->fetch_ncontigs = false;
     return 0;
 }

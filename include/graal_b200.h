@@ -24,6 +24,7 @@
  *   GRAAL_FULL_WIN=0 gather-everything contact pass instead of the windowed one; GRAAL_WIN_UNROLL / _MINB / _SUB: its variants
  *   GRAAL_DELTA_REL=0 / GRAAL_BAND_FAST=0 general delta kernels on uniform levels; GRAAL_DELTA_UNI=1 union windows in the delta contact pass
  *   GRAAL_FUSED_PROLOGUE=0 statistics + relabel as the two general launch sequences
+ *   GRAAL_PUBLISH=0  graal_draw_commit hands the results over with cudaMemcpyAsync + an event instead of k_publish into mapped memory
  *   (Python side: GRAAL_DEVICE_DRAW=0 candidate draw and commit on the host after the fetch instead of graal_draw_commit)
  *   GRAAL_WIN_STAB=0|1 law table of the windowed contact pass through L1 / from a 32 KB coarse copy in shared memory (default: timed once per level)
  *   GRAAL_DELTA_SPLIT=n (1..32, default 8) slices a row is cut into when U is short; GRAAL_DELTA_MINB=2|3|4 CTAs per SM of the delta contact pass
